@@ -1,0 +1,294 @@
+// dspeed_b200 -- device-side building blocks shared by the per-processor kernels and
+// the fused waveform-resident chain kernel (sm_100a).
+//
+// Execution model: one CTA owns one waveform ("row") at a time.  The row is staged
+// once from HBM into shared memory (padded layout below) and every processor is a
+// block-wide routine over shared-memory "slots"; scalars travel in registers /
+// a small shared scalar file.  Reductions and searches use warp shuffles, the
+// recursive filters of the reference (pole-zero, trapezoids, moving averages) are
+// evaluated as prefix sums: each thread owns a contiguous chunk (sequential, in
+// registers, float64 accumulator), chunks are stitched with one shuffle scan.
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include "dspeed_b200.h"
+
+namespace dspb {
+
+constexpr int NT = 256;          // threads per CTA for row-resident kernels
+constexpr int NW = NT / 32;      // warps per CTA
+constexpr int SCRATCH_BYTES = 1024;  // block-primitive scratch at the start of dynamic smem
+
+// Padded shared-memory index: one pad word per 32 elements.  With a thread-contiguous
+// chunk of C in {4,8,16,32} elements, lane l at step j touches bank (l*C + j + (l*C+j)/32) % 32,
+// which is a permutation of the 32 banks; unit-stride (thread-strided) access stays
+// conflict-free as well.
+__device__ __forceinline__ int sidx(int i) { return i + (i >> 5); }
+__host__ __device__ __forceinline__ int slot_words(int n) { return n + (n >> 5) + 1; }
+
+template <typename T> __device__ __forceinline__ T nan_of();
+template <> __device__ __forceinline__ float nan_of<float>() { return CUDART_NAN_F; }
+template <> __device__ __forceinline__ double nan_of<double>() { return CUDART_NAN; }
+
+// Per-row scalar argument: device array (stride 0 = broadcast, 1 = per row) or immediate.
+template <typename T>
+struct Scalar {
+  const T* ptr;
+  long long stride;
+  T imm;
+  __device__ __forceinline__ T get(long long row) const { return ptr ? ptr[row * stride] : imm; }
+};
+
+// A waveform operand in global memory.
+struct Wave {
+  const void* ptr;
+  long long row_stride;  // elements
+  int dtype;             // DSPB_F32 / DSPB_F64 / DSPB_U16 / ...
+};
+
+struct Scratch {
+  double d[NW * 4 + 4];
+  int i[NW * 4 + 4];
+};
+static_assert(sizeof(Scratch) <= SCRATCH_BYTES, "scratch too large");
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ int warp_id() { return threadIdx.x >> 5; }
+
+// ---- block-wide primitives (all threads of the CTA must call) -------------------
+
+// Exclusive prefix sum of one double per thread; returns the exclusive prefix,
+// writes the block total.
+__device__ __forceinline__ double block_excl_scan(double v, double& total, Scratch* sc) {
+  const int lane = lane_id(), w = warp_id();
+  double incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    double t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  __syncthreads();  // protect scratch reuse
+  if (lane == 31) sc->d[w] = incl;
+  __syncthreads();
+  double woff = 0.0, tot = 0.0;
+#pragma unroll
+  for (int k = 0; k < NW; k++) {
+    double s = sc->d[k];
+    if (k < w) woff += s;
+    tot += s;
+  }
+  total = tot;
+  return woff + (incl - v);
+}
+
+// Same, scanning from the last thread towards the first (suffix sums).
+__device__ __forceinline__ double block_excl_scan_rev(double v, double& total, Scratch* sc) {
+  const int lane = lane_id(), w = warp_id();
+  double incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    double t = __shfl_down_sync(0xffffffffu, incl, o);
+    if (lane + o < 32) incl += t;
+  }
+  __syncthreads();
+  if (lane == 0) sc->d[w] = incl;
+  __syncthreads();
+  double woff = 0.0, tot = 0.0;
+#pragma unroll
+  for (int k = 0; k < NW; k++) {
+    double s = sc->d[k];
+    if (k > w) woff += s;
+    tot += s;
+  }
+  total = tot;
+  return woff + (incl - v);
+}
+
+__device__ __forceinline__ double block_sum(double v, Scratch* sc) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if (lane_id() == 0) sc->d[warp_id()] = v;
+  __syncthreads();
+  double tot = 0.0;
+#pragma unroll
+  for (int k = 0; k < NW; k++) tot += sc->d[k];
+  return tot;
+}
+
+// two sums at once (saves barriers)
+__device__ __forceinline__ void block_sum2(double& a, double& b, Scratch* sc) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  __syncthreads();
+  if (lane_id() == 0) {
+    sc->d[warp_id()] = a;
+    sc->d[NW + warp_id()] = b;
+  }
+  __syncthreads();
+  double ta = 0.0, tb = 0.0;
+#pragma unroll
+  for (int k = 0; k < NW; k++) {
+    ta += sc->d[k];
+    tb += sc->d[NW + k];
+  }
+  a = ta;
+  b = tb;
+}
+
+__device__ __forceinline__ int block_or(int pred) { return __syncthreads_or(pred); }
+
+// Smallest int over the block (INT_MAX = none).
+__device__ __forceinline__ int block_min_int(int v, Scratch* sc) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+  __syncthreads();
+  if (lane_id() == 0) sc->i[warp_id()] = v;
+  __syncthreads();
+  int r = sc->i[0];
+#pragma unroll
+  for (int k = 1; k < NW; k++) r = min(r, sc->i[k]);
+  return r;
+}
+__device__ __forceinline__ int block_max_int(int v, Scratch* sc) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+  __syncthreads();
+  if (lane_id() == 0) sc->i[warp_id()] = v;
+  __syncthreads();
+  int r = sc->i[0];
+#pragma unroll
+  for (int k = 1; k < NW; k++) r = max(r, sc->i[k]);
+  return r;
+}
+
+// First-occurrence arg-min and arg-max (strict comparisons, as min_max.py:73-77).
+template <typename T>
+__device__ __forceinline__ void block_argminmax(T& vmin, int& imin, T& vmax, int& imax, Scratch* sc) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    T ov = __shfl_xor_sync(0xffffffffu, vmin, o);
+    int oi = __shfl_xor_sync(0xffffffffu, imin, o);
+    if (ov < vmin || (ov == vmin && oi < imin)) { vmin = ov; imin = oi; }
+    ov = __shfl_xor_sync(0xffffffffu, vmax, o);
+    oi = __shfl_xor_sync(0xffffffffu, imax, o);
+    if (ov > vmax || (ov == vmax && oi < imax)) { vmax = ov; imax = oi; }
+  }
+  __syncthreads();
+  if (lane_id() == 0) {
+    sc->d[warp_id()] = (double)vmin;
+    sc->d[NW + warp_id()] = (double)vmax;
+    sc->i[warp_id()] = imin;
+    sc->i[NW + warp_id()] = imax;
+  }
+  __syncthreads();
+  T bmin = (T)sc->d[0], bmax = (T)sc->d[NW];
+  int bimin = sc->i[0], bimax = sc->i[NW];
+#pragma unroll
+  for (int k = 1; k < NW; k++) {
+    T ov = (T)sc->d[k];
+    int oi = sc->i[k];
+    if (ov < bmin || (ov == bmin && oi < bimin)) { bmin = ov; bimin = oi; }
+    ov = (T)sc->d[NW + k];
+    oi = sc->i[NW + k];
+    if (ov > bmax || (ov == bmax && oi < bimax)) { bmax = ov; bimax = oi; }
+  }
+  vmin = bmin; imin = bimin; vmax = bmax; imax = bimax;
+}
+
+// ---- row staging -----------------------------------------------------------------
+
+template <typename T, typename TIn>
+__device__ __forceinline__ int stage_row_typed(T* s, const TIn* g, int n) {
+  int has_nan = 0;
+  for (int i = threadIdx.x; i < n; i += NT) {
+    T v = (T)g[i];
+    if (v != v) has_nan = 1;
+    s[sidx(i)] = v;
+  }
+  return has_nan;
+}
+
+// 128-bit path for uint16 rows whose start is 16-byte aligned (always true for the
+// 8192-sample LEGEND records): 8 samples per load, coalesced.
+template <typename T>
+__device__ __forceinline__ void stage_row_u16_vec(T* s, const uint16_t* g, int n) {
+  const int nv = n >> 3;
+  const uint4* gv = reinterpret_cast<const uint4*>(g);
+  for (int v = threadIdx.x; v < nv; v += NT) {
+    uint4 q;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w)
+                 : "l"(gv + v));
+    const int i = v << 3;
+    const int b = sidx(i);  // the 8 samples share one 32-group (i % 8 == 0)
+    s[b + 0] = (T)(q.x & 0xffffu);
+    s[b + 1] = (T)(q.x >> 16);
+    s[b + 2] = (T)(q.y & 0xffffu);
+    s[b + 3] = (T)(q.y >> 16);
+    s[b + 4] = (T)(q.z & 0xffffu);
+    s[b + 5] = (T)(q.z >> 16);
+    s[b + 6] = (T)(q.w & 0xffffu);
+    s[b + 7] = (T)(q.w >> 16);
+  }
+  for (int i = (nv << 3) + threadIdx.x; i < n; i += NT) s[sidx(i)] = (T)g[i];
+}
+
+// Stage one row of a global waveform operand into a shared slot, converting to T.
+// Returns (per thread) whether this thread saw a NaN; caller ORs over the block.
+template <typename T>
+__device__ __forceinline__ int stage_row(T* s, const Wave& w, long long row, int n) {
+  switch (w.dtype) {
+    case DSPB_U16: {
+      const uint16_t* g = reinterpret_cast<const uint16_t*>(w.ptr) + row * w.row_stride;
+      if ((reinterpret_cast<uintptr_t>(g) & 15) == 0) stage_row_u16_vec<T>(s, g, n);
+      else stage_row_typed<T, uint16_t>(s, g, n);
+      return 0;
+    }
+    case DSPB_F32: return stage_row_typed<T, float>(s, reinterpret_cast<const float*>(w.ptr) + row * w.row_stride, n);
+    case DSPB_F64: return stage_row_typed<T, double>(s, reinterpret_cast<const double*>(w.ptr) + row * w.row_stride, n);
+    case DSPB_I16: return stage_row_typed<T, int16_t>(s, reinterpret_cast<const int16_t*>(w.ptr) + row * w.row_stride, n);
+    case DSPB_I32: return stage_row_typed<T, int32_t>(s, reinterpret_cast<const int32_t*>(w.ptr) + row * w.row_stride, n);
+    case DSPB_U32: return stage_row_typed<T, uint32_t>(s, reinterpret_cast<const uint32_t*>(w.ptr) + row * w.row_stride, n);
+  }
+  return 0;
+}
+
+template <typename T>
+__device__ __forceinline__ void store_row(T* g, const T* s, int n) {
+  for (int i = threadIdx.x; i < n; i += NT) g[i] = s[sidx(i)];
+}
+template <typename T>
+__device__ __forceinline__ void store_row_nan(T* g, int n) {
+  const T v = nan_of<T>();
+  for (int i = threadIdx.x; i < n; i += NT) g[i] = v;
+}
+template <typename T>
+__device__ __forceinline__ void fill_slot_nan(T* s, int n) {
+  const T v = nan_of<T>();
+  for (int i = threadIdx.x; i < n; i += NT) s[sidx(i)] = v;
+}
+
+// Record the first data-dependent fatal condition (the reference's DSPFatal) of a launch.
+__device__ __forceinline__ void raise_fatal(int* fatal, int code, long long row) {
+  if (fatal && code) {
+    if (atomicCAS(fatal, 0, code) == 0) {
+      fatal[1] = (int)(row & 0x7fffffff);
+      fatal[2] = (int)(row >> 31);
+    }
+  }
+}
+
+// Thread-contiguous chunk of a row of n samples.
+__device__ __forceinline__ void chunk_range(int n, int& lo, int& hi) {
+  const int c = (n + NT - 1) / NT;
+  lo = min(n, (int)threadIdx.x * c);
+  hi = min(n, lo + c);
+}
+
+}  // namespace dspb

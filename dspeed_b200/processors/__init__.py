@@ -1,0 +1,651 @@
+"""``dspeed_b200.processors`` -- the hot-path processors of ``dspeed.processors`` as
+hand-written sm_100a CUDA kernels behind the reference's gufunc protocol.
+
+Every processor keeps the reference's name, argument order and meaning
+(src/dspeed/processors/__init__.py:66-159) and exposes what the chain's
+``ProcessorManager`` needs (processing_chain.py:1528-1543): ``__name__``,
+``.signature``, ``.types``, and a void call ``proc(*inputs, *outputs)`` that writes
+caller-owned output arrays in place.
+
+Arrays are ``torch`` CUDA tensors (the chain's block buffers).  NumPy arrays are also
+accepted, exactly like the reference's gufuncs: they are staged to the device, the same
+kernels run, and the outputs are copied back into the caller's arrays -- there is NO
+CPU implementation behind these functions; without the CUDA library they raise.
+
+Data-dependent ``DSPFatal`` conditions are recorded on the device.  Called stand-alone
+a processor synchronises and raises immediately (reference behaviour); the processing
+chain instead passes ``fatal=<int32[4] device tensor>`` and checks once per block.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from .. import _lib
+from ..errors import DSPFatal
+
+__all__: list[str] = []
+
+_DT_CODE = {
+    torch.float32: 0, torch.float64: 1, torch.uint16: 2, torch.int16: 3, torch.int32: 4, torch.uint32: 5,
+}
+_vp = C.c_void_p
+_i64 = C.c_int64
+_i32 = C.c_int32
+_f64 = C.c_double
+
+
+class _Call:
+    """Marshals one processor call into the C ABI of include/dspeed_b200.h."""
+
+    def __init__(self, T: torch.dtype, device: torch.device):
+        self.T = T
+        self.device = device
+        self.n_rows = 1
+        self.keep = []  # keep temporaries alive until the launch is enqueued
+
+    # -- row count -----------------------------------------------------------------
+    def rows_from(self, *arrs):
+        n = 1
+        for a in arrs:
+            if isinstance(a, torch.Tensor) and a.ndim >= 1:
+                lead = a.shape[0]
+                if lead != 1:
+                    if n != 1 and lead != n:
+                        raise ValueError(f"cannot broadcast leading dimensions {n} and {lead}")
+                    n = lead
+        self.n_rows = n
+        return n
+
+    # -- operand marshalling ---------------------------------------------------------
+    def wave_in(self, w: torch.Tensor):
+        """-> (ptr, row_stride, dtype code), n"""
+        if w.ndim == 1:
+            w = w.unsqueeze(0)
+        if w.ndim != 2:
+            w = w.reshape(-1, w.shape[-1])
+        if w.dtype not in _DT_CODE:
+            w = w.to(self.T)
+        if w.shape[-1] > 1 and w.stride(-1) != 1:
+            w = w.contiguous()
+        self.keep.append(w)
+        rs = 0 if w.shape[0] == 1 and self.n_rows > 1 else w.stride(0)
+        return [_vp(w.data_ptr()), _i64(rs), _i32(_DT_CODE[w.dtype])], w.shape[-1]
+
+    def wave_out(self, w: torch.Tensor, n: int | None = None):
+        if w.ndim == 1:
+            w = w.unsqueeze(0)
+        if w.dtype != self.T:
+            raise TypeError(f"output dtype {w.dtype} does not match the {self.T} type loop")
+        if w.shape[-1] > 1 and w.stride(-1) != 1:
+            raise ValueError("output waveforms must be contiguous along the sample axis")
+        if n is not None and w.shape[-1] != n:
+            raise DSPFatal(f"Output waveform has length {w.shape[-1]}; expect {n}")
+        return [_vp(w.data_ptr()), _i64(w.stride(0))], w.shape[-1]
+
+    def scalar_in(self, x):
+        """per-row scalar: python/numpy number -> immediate; tensor -> device array"""
+        if isinstance(x, torch.Tensor):
+            t = x.reshape(-1)
+            if t.dtype != self.T:
+                t = t.to(self.T)
+            if t.numel() == 1:
+                stride = 0
+            else:
+                if t.numel() != self.n_rows:
+                    raise ValueError(f"scalar argument has {t.numel()} entries for {self.n_rows} rows")
+                stride = t.stride(0)
+            self.keep.append(t)
+            return [_vp(t.data_ptr()), _i64(stride), _f64(0.0)]
+        return [_vp(None), _i64(0), _f64(float(x))]
+
+    def scalar_out(self, x: torch.Tensor):
+        t = x.reshape(-1) if x.ndim != 1 else x
+        if t.dtype != self.T:
+            raise TypeError(f"output dtype {t.dtype} does not match the {self.T} type loop")
+        if t.numel() != self.n_rows or (t.numel() > 1 and t.stride(0) != 1):
+            raise ValueError("scalar outputs must be contiguous [n_rows] arrays")
+        return _vp(t.data_ptr())
+
+
+def _as_int(x) -> int:
+    if isinstance(x, torch.Tensor):
+        x = x.reshape(-1)[0].item()
+    if isinstance(x, np.ndarray):
+        x = x.reshape(-1)[0]
+    if isinstance(x, (str, bytes)):
+        return ord(x)
+    return int(x)
+
+
+def _as_float(x) -> float:
+    if isinstance(x, torch.Tensor):
+        x = x.reshape(-1)[0].item()
+    if isinstance(x, np.ndarray):
+        x = x.reshape(-1)[0]
+    return float(x)
+
+
+def _stream_ptr(device) -> _vp:
+    return _vp(torch.cuda.current_stream(device).cuda_stream)
+
+
+def raise_if_fatal(fatal: torch.Tensor, processor: str | None = None, wf_range=None) -> None:
+    """Synchronise on the device fatal record and raise the reference's DSPFatal."""
+    rec = fatal.cpu()
+    code = int(rec[0])
+    if code:
+        e = DSPFatal(_lib.fatal_message(code))
+        e.code = code
+        e.row = int(rec[1]) | (int(rec[2]) << 31)
+        e.processor = processor
+        e.wf_range = wf_range
+        raise e
+
+
+class DeviceProcessor:
+    """A CUDA processor obeying the gufunc protocol of the reference."""
+
+    def __init__(self, name, signature, types, impl, nout, doc=""):
+        self.__name__ = name
+        self.__doc__ = doc
+        self.signature = signature
+        self.types = list(types)
+        self.impl = impl
+        self.nout = nout
+        self.nin = signature.count("(") - nout if signature else None
+        self.device_processor = True
+
+    def __repr__(self):
+        return f"<dspeed_b200 processor {self.__name__} {self.signature}>"
+
+    def __call__(self, *args, fatal: torch.Tensor | None = None, **kwargs):
+        host = [isinstance(a, np.ndarray) and a.ndim > 0 for a in args]
+        any_dev = any(isinstance(a, torch.Tensor) for a in args)
+        if any(host) or not any_dev:
+            return self._call_host(args, kwargs)
+        dev = next(a.device for a in args if isinstance(a, torch.Tensor))
+        if dev.type != "cuda":
+            raise RuntimeError(f"{self.__name__}: tensors must live on a CUDA device (no CPU fallback)")
+        own_fatal = fatal is None
+        if own_fatal:
+            fatal = torch.zeros(4, dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            rc = self.impl(*args, fatal=fatal, **kwargs)
+        if rc:
+            if rc < 0:
+                raise RuntimeError(f"{self.__name__}: CUDA error {-rc}")
+            e = DSPFatal(_lib.fatal_message(rc))
+            e.code = rc
+            raise e
+        if own_fatal:
+            raise_if_fatal(fatal, self.__name__)
+
+    def _call_host(self, args, kwargs):
+        """NumPy front door: stage to the device, run the same kernels, copy back."""
+        if not torch.cuda.is_available():
+            raise RuntimeError(
+                f"{self.__name__}: no CUDA device available and dspeed_b200 has no CPU fallback"
+            )
+        dev = torch.device("cuda", torch.cuda.current_device())
+        nargs = len(args)
+        dargs = []
+        outs = []
+        for i, a in enumerate(args):
+            is_out = i >= nargs - self.nout
+            if isinstance(a, np.ndarray) and a.ndim > 0:
+                if is_out:
+                    if not a.flags.writeable:
+                        raise ValueError("output array is read-only")
+                    t = torch.empty(a.shape, dtype=_torch_dtype(a.dtype), device=dev)
+                    outs.append((a, t))
+                else:
+                    t = torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+                dargs.append(t)
+            elif isinstance(a, np.ndarray):
+                dargs.append(a.item())
+            else:
+                dargs.append(a)
+        self.__call__(*dargs, **kwargs)
+        for a, t in outs:
+            np.copyto(a, t.cpu().numpy())
+
+
+def _torch_dtype(dt) -> torch.dtype:
+    return {
+        np.dtype("float32"): torch.float32, np.dtype("float64"): torch.float64,
+        np.dtype("uint16"): torch.uint16, np.dtype("int16"): torch.int16,
+        np.dtype("int32"): torch.int32, np.dtype("uint32"): torch.uint32,
+        np.dtype("int64"): torch.int64, np.dtype("uint8"): torch.uint8, np.dtype("int8"): torch.int8,
+        np.dtype("bool"): torch.bool,
+    }[np.dtype(dt)]
+
+
+def _sfx(T):
+    return "_f32" if T == torch.float32 else "_f64"
+
+
+def _out_T(*outs):
+    for o in outs:
+        if isinstance(o, torch.Tensor) and o.dtype in (torch.float32, torch.float64):
+            return o.dtype
+    raise TypeError("outputs must be float32 or float64 device tensors")
+
+
+def _fn(name, T):
+    return getattr(_lib.lib(), name + _sfx(T))
+
+
+def _tail(fatal, dev):
+    return [_vp(fatal.data_ptr() if fatal is not None else None), _stream_ptr(dev)]
+
+
+_REGISTRY: dict[str, DeviceProcessor] = {}
+
+
+def _register(name, signature, types, nout):
+    def deco(f):
+        p = DeviceProcessor(name, signature, types, f, nout, f.__doc__ or "")
+        _REGISTRY[name] = p
+        globals()[name] = p
+        __all__.append(name)
+        return p
+
+    return deco
+
+
+_FD = ["f->f", "d->d"]  # placeholder, replaced per processor
+
+
+# ---------------------------------------------------------------------------------------
+# processors
+# ---------------------------------------------------------------------------------------
+@_register("bl_subtract", "(n),()->(n)", ["ff->f", "dd->d"], 1)
+def _bl_subtract(w_in, a_baseline, w_out, fatal=None):
+    """bl_subtract.py:11-46"""
+    T = _out_T(w_out)
+    c = _Call(T, w_out.device)
+    c.rows_from(w_in, a_baseline, w_out)
+    wi, n = c.wave_in(w_in)
+    wo, _ = c.wave_out(w_out, n)
+    return _fn("dspb_bl_subtract", T)(*wi, _i64(c.n_rows), _i64(n), *c.scalar_in(a_baseline), *wo, *_tail(fatal, w_out.device))
+
+
+@_register("min_max", "(n)->(),(),(),()", ["f->ffff", "d->dddd"], 4)
+def _min_max(w_in, t_min, t_max, a_min, a_max, fatal=None):
+    """min_max.py:11-82"""
+    T = _out_T(a_min)
+    c = _Call(T, a_min.device)
+    c.rows_from(w_in, a_min)
+    wi, n = c.wave_in(w_in)
+    return _fn("dspb_min_max", T)(*wi, _i64(c.n_rows), _i64(n), c.scalar_out(t_min), c.scalar_out(t_max),
+                                  c.scalar_out(a_min), c.scalar_out(a_max), *_tail(fatal, a_min.device))
+
+
+@_register("amax", "(n),()->()", ["fi->f", "di->d"], 1)
+def _amax(w_in, axis, a_max, fatal=None):
+    """numpy.amax(w, axis, out) as configured in icpc-dsp-config.json:123-129"""
+    T = _out_T(a_max)
+    c = _Call(T, a_max.device)
+    c.rows_from(w_in, a_max)
+    wi, n = c.wave_in(w_in)
+    return _fn("dspb_amax", T)(*wi, _i64(c.n_rows), _i64(n), c.scalar_out(a_max), *_tail(fatal, a_max.device))
+
+
+@_register("min_max_norm", "(n),(),()->(n)", ["fff->f", "ddd->d"], 1)
+def _min_max_norm(w_in, a_min, a_max, w_out, fatal=None):
+    """min_max.py:85-140"""
+    T = _out_T(w_out)
+    c = _Call(T, w_out.device)
+    c.rows_from(w_in, a_min, a_max, w_out)
+    wi, n = c.wave_in(w_in)
+    wo, _ = c.wave_out(w_out, n)
+    return _fn("dspb_min_max_norm", T)(*wi, _i64(c.n_rows), _i64(n), *c.scalar_in(a_min), *c.scalar_in(a_max), *wo,
+                                       *_tail(fatal, w_out.device))
+
+
+@_register("linear_slope_fit", "(n)->(),(),(),()", ["f->ffff", "d->dddd"], 4)
+def _linear_slope_fit(w_in, mean, stdev, slope, intercept, fatal=None):
+    """linear_slope_fit.py:11-90 (the reference's mean/stdev baseline processor)"""
+    T = _out_T(mean)
+    c = _Call(T, mean.device)
+    c.rows_from(w_in, mean)
+    wi, n = c.wave_in(w_in)
+    return _fn("dspb_linear_slope_fit", T)(*wi, _i64(c.n_rows), _i64(n), c.scalar_out(mean), c.scalar_out(stdev),
+                                           c.scalar_out(slope), c.scalar_out(intercept), *_tail(fatal, mean.device))
+
+
+@_register("mean_stdev", "(n)->(),()", ["f->ff", "d->dd"], 2)
+def _mean_stdev(w_in, mean, stdev, fatal=None):
+    """Two-output alias of linear_slope_fit (BASELINE.json names the baseline processor
+    ``mean_stdev``; the reference snapshot only has linear_slope_fit.py:11-90)."""
+    slope = torch.empty_like(mean)
+    icpt = torch.empty_like(mean)
+    return _linear_slope_fit.impl(w_in, mean, stdev, slope, icpt, fatal=fatal)
+
+
+@_register("linear_slope_diff", "(n),(),()->(),()", ["fff->ff", "ddd->dd"], 2)
+def _linear_slope_diff(w_in, slope, intercept, mean, rms, fatal=None):
+    """linear_slope_fit.py:93-158"""
+    T = _out_T(mean)
+    c = _Call(T, mean.device)
+    c.rows_from(w_in, slope, intercept, mean)
+    wi, n = c.wave_in(w_in)
+    return _fn("dspb_linear_slope_diff", T)(*wi, _i64(c.n_rows), _i64(n), *c.scalar_in(slope), *c.scalar_in(intercept),
+                                            c.scalar_out(mean), c.scalar_out(rms), *_tail(fatal, mean.device))
+
+
+@_register("mean_below_threshold", "(n),()->()", ["ff->f", "dd->d"], 1)
+def _mean_below_threshold(w_in, threshold, result, fatal=None):
+    """arithmetic.py:9-62"""
+    T = _out_T(result)
+    c = _Call(T, result.device)
+    c.rows_from(w_in, threshold, result)
+    wi, n = c.wave_in(w_in)
+    return _fn("dspb_mean_below_threshold", T)(*wi, _i64(c.n_rows), _i64(n), *c.scalar_in(threshold),
+                                               c.scalar_out(result), *_tail(fatal, result.device))
+
+
+@_register("pole_zero", "(n),()->(n)", ["ff->f", "dd->d"], 1)
+def _pole_zero(w_in, t_tau, w_out, fatal=None):
+    """pole_zero.py:24-77"""
+    T = _out_T(w_out)
+    c = _Call(T, w_out.device)
+    c.rows_from(w_in, t_tau, w_out)
+    wi, n = c.wave_in(w_in)
+    wo, _ = c.wave_out(w_out, n)
+    return _fn("dspb_pole_zero", T)(*wi, _i64(c.n_rows), _i64(n), *c.scalar_in(t_tau), *wo, *_tail(fatal, w_out.device))
+
+
+@_register("double_pole_zero", "(n),(),(),()->(n)", ["ffff->f", "dddd->d"], 1)
+def _double_pole_zero(w_in, t_tau1, t_tau2, frac, w_out, fatal=None):
+    """pole_zero.py:82-198"""
+    T = _out_T(w_out)
+    c = _Call(T, w_out.device)
+    c.rows_from(w_in, t_tau1, t_tau2, frac, w_out)
+    wi, n = c.wave_in(w_in)
+    wo, _ = c.wave_out(w_out, n)
+    return _fn("dspb_double_pole_zero", T)(*wi, _i64(c.n_rows), _i64(n), *c.scalar_in(t_tau1), *c.scalar_in(t_tau2),
+                                           *c.scalar_in(frac), *wo, *_tail(fatal, w_out.device))
+
+
+def _trap_common(w_in, rise, flat, w_out, norm, fatal):
+    T = _out_T(w_out)
+    c = _Call(T, w_out.device)
+    c.rows_from(w_in, w_out)
+    wi, n = c.wave_in(w_in)
+    wo, _ = c.wave_out(w_out, n)
+    return _fn("dspb_trap_filter", T)(*wi, _i64(c.n_rows), _i64(n), _i32(_as_int(rise)), _i32(_as_int(flat)), _i32(norm),
+                                      *wo, *_tail(fatal, w_out.device))
+
+
+@_register("trap_filter", "(n),(),()->(n)", ["fii->f", "dii->d"], 1)
+def _trap_filter(w_in, rise, flat, w_out, fatal=None):
+    """trap_filters.py:12-76"""
+    return _trap_common(w_in, rise, flat, w_out, 0, fatal)
+
+
+@_register("trap_norm", "(n),(),()->(n)", ["fii->f", "dii->d"], 1)
+def _trap_norm(w_in, rise, flat, w_out, fatal=None):
+    """trap_filters.py:79-149"""
+    return _trap_common(w_in, rise, flat, w_out, 1, fatal)
+
+
+@_register("asym_trap_filter", "(n),(),(),()->(n)", ["fiii->f", "diii->d"], 1)
+def _asym_trap_filter(w_in, rise, flat, fall, w_out, fatal=None):
+    """trap_filters.py:152-227"""
+    T = _out_T(w_out)
+    c = _Call(T, w_out.device)
+    c.rows_from(w_in, w_out)
+    wi, n = c.wave_in(w_in)
+    wo, _ = c.wave_out(w_out, n)
+    return _fn("dspb_asym_trap_filter", T)(*wi, _i64(c.n_rows), _i64(n), _i32(_as_int(rise)), _i32(_as_int(flat)),
+                                           _i32(_as_int(fall)), *wo, *_tail(fatal, w_out.device))
+
+
+@_register("trap_pickoff", "(n),(),(),()->()", ["fiif->f", "diid->d"], 1)
+def _trap_pickoff(w_in, rise, flat, t_pickoff, a_out, fatal=None):
+    """trap_filters.py:230-301"""
+    T = _out_T(a_out)
+    c = _Call(T, a_out.device)
+    c.rows_from(w_in, t_pickoff, a_out)
+    wi, n = c.wave_in(w_in)
+    return _fn("dspb_trap_pickoff", T)(*wi, _i64(c.n_rows), _i64(n), _i32(_as_int(rise)), _i32(_as_int(flat)),
+                                       *c.scalar_in(t_pickoff), c.scalar_out(a_out), *_tail(fatal, a_out.device))
+
+
+def _mw_common(w_in, length, w_out, kind, fatal):
+    T = _out_T(w_out)
+    c = _Call(T, w_out.device)
+    c.rows_from(w_in, w_out)
+    wi, n = c.wave_in(w_in)
+    wo, _ = c.wave_out(w_out, n)
+    return _fn("dspb_moving_window", T)(*wi, _i64(c.n_rows), _i64(n), _f64(_as_float(length)), _i32(kind), *wo,
+                                        *_tail(fatal, w_out.device))
+
+
+@_register("moving_window_left", "(n),()->(n)", ["ff->f", "dd->d"], 1)
+def _moving_window_left(w_in, length, w_out, fatal=None):
+    """moving_windows.py:12-61"""
+    return _mw_common(w_in, length, w_out, 0, fatal)
+
+
+@_register("moving_window_right", "(n),()->(n)", ["ff->f", "dd->d"], 1)
+def _moving_window_right(w_in, length, w_out, fatal=None):
+    """moving_windows.py:64-114"""
+    return _mw_common(w_in, length, w_out, 1, fatal)
+
+
+@_register("moving_window_multi", "(n),(),(),()->(n)", ["fffi->f", "dddi->d"], 1)
+def _moving_window_multi(w_in, length, num_mw, mw_type, w_out, fatal=None):
+    """moving_windows.py:117-203"""
+    T = _out_T(w_out)
+    c = _Call(T, w_out.device)
+    c.rows_from(w_in, w_out)
+    wi, n = c.wave_in(w_in)
+    wo, _ = c.wave_out(w_out, n)
+    return _fn("dspb_moving_window_multi", T)(*wi, _i64(c.n_rows), _i64(n), _f64(_as_float(length)),
+                                              _f64(_as_float(num_mw)), _i32(_as_int(mw_type)), *wo,
+                                              *_tail(fatal, w_out.device))
+
+
+@_register("avg_current", "(n),(),(m)", ["fff->", "ddd->"], 1)
+def _avg_current(w_in, length, w_out, fatal=None):
+    """moving_windows.py:206-249"""
+    T = _out_T(w_out)
+    c = _Call(T, w_out.device)
+    c.rows_from(w_in, w_out)
+    wi, n = c.wave_in(w_in)
+    wo, m = c.wave_out(w_out)
+    return _fn("dspb_avg_current", T)(*wi, _i64(c.n_rows), _i64(n), _f64(_as_float(length)), *wo, _i64(m),
+                                      *_tail(fatal, w_out.device))
+
+
+@_register("time_point_thresh", "(n),(),(),()->()", ["ffff->f", "dddd->d"], 1)
+def _time_point_thresh(w_in, a_threshold, t_start, walk_forward, t_out, fatal=None):
+    """time_point_thresh.py:12-92"""
+    T = _out_T(t_out)
+    c = _Call(T, t_out.device)
+    c.rows_from(w_in, a_threshold, t_start, walk_forward, t_out)
+    wi, n = c.wave_in(w_in)
+    return _fn("dspb_time_point_thresh", T)(*wi, _i64(c.n_rows), _i64(n), *c.scalar_in(a_threshold), *c.scalar_in(t_start),
+                                            *c.scalar_in(walk_forward), c.scalar_out(t_out), *_tail(fatal, t_out.device))
+
+
+@_register("interpolated_time_point_thresh", "(n),(),(),(),()->()", ["ffflb->f", "dddlb->d"], 1)
+def _interpolated_time_point_thresh(w_in, a_threshold, t_start, walk_forward, mode_in, t_out, fatal=None):
+    """time_point_thresh.py:95-222"""
+    T = _out_T(t_out)
+    c = _Call(T, t_out.device)
+    c.rows_from(w_in, a_threshold, t_start, t_out)
+    wi, n = c.wave_in(w_in)
+    return _fn("dspb_interpolated_time_point_thresh", T)(
+        *wi, _i64(c.n_rows), _i64(n), *c.scalar_in(a_threshold), *c.scalar_in(t_start), _i64(_as_int(walk_forward)),
+        _i32(_as_int(mode_in)), c.scalar_out(t_out), *_tail(fatal, t_out.device))
+
+
+@_register("multi_time_point_thresh", "(n),(m),(),(),()->(m)", ["ffffb->f", "ddddb->d"], 1)
+def _multi_time_point_thresh(w_in, a_threshold, t_start, polarity, mode_in, t_out, fatal=None):
+    """time_point_thresh.py:225-401"""
+    T = _out_T(t_out)
+    c = _Call(T, t_out.device)
+    c.rows_from(w_in, t_start, t_out)
+    wi, n = c.wave_in(w_in)
+    thr = a_threshold.to(T)
+    if thr.ndim == 1:
+        thr = thr.unsqueeze(0)
+    thr = thr.contiguous()
+    c.keep.append(thr)
+    m = thr.shape[-1]
+    rs = m if thr.shape[0] == c.n_rows and c.n_rows > 1 else (m if thr.shape[0] == c.n_rows else 0)
+    if thr.shape[0] == 1:
+        rs = 0
+    to = t_out if t_out.ndim == 2 else t_out.unsqueeze(0)
+    assert to.is_contiguous() and to.shape[-1] == m
+    return _fn("dspb_multi_time_point_thresh", T)(
+        *wi, _i64(c.n_rows), _i64(n), _vp(thr.data_ptr()), _i64(m), _i64(rs), *c.scalar_in(t_start),
+        _f64(_as_float(polarity)), _i32(_as_int(mode_in)), _vp(to.data_ptr()), *_tail(fatal, t_out.device))
+
+
+@_register("fixed_time_pickoff", "(n),(),()->()", ["ffb->f", "ddb->d"], 1)
+def _fixed_time_pickoff(w_in, t_in, mode_in, a_out, fatal=None):
+    """fixed_time_pickoff.py:12-125"""
+    T = _out_T(a_out)
+    c = _Call(T, a_out.device)
+    c.rows_from(w_in, t_in, a_out)
+    wi, n = c.wave_in(w_in)
+    return _fn("dspb_fixed_time_pickoff", T)(*wi, _i64(c.n_rows), _i64(n), *c.scalar_in(t_in), _i32(_as_int(mode_in)),
+                                             c.scalar_out(a_out), *_tail(fatal, a_out.device))
+
+
+@_register("windower", "(n),(),(m)", ["fff->", "ddd->"], 1)
+def _windower(w_in, t0_in, w_out, fatal=None):
+    """windower.py:12-54"""
+    T = _out_T(w_out)
+    c = _Call(T, w_out.device)
+    c.rows_from(w_in, t0_in, w_out)
+    wi, n = c.wave_in(w_in)
+    wo, m = c.wave_out(w_out)
+    return _fn("dspb_windower", T)(*wi, _i64(c.n_rows), _i64(n), *c.scalar_in(t0_in), *wo, _i64(m),
+                                   *_tail(fatal, w_out.device))
+
+
+@_register("upsampler", "(n),(),(m)", ["fff->", "ddd->"], 1)
+def _upsampler(w_in, upsample, w_out, fatal=None):
+    """upsampler.py:14-49"""
+    T = _out_T(w_out)
+    c = _Call(T, w_out.device)
+    c.rows_from(w_in, w_out)
+    wi, n = c.wave_in(w_in)
+    wo, m = c.wave_out(w_out)
+    return _fn("dspb_upsampler", T)(*wi, _i64(c.n_rows), _i64(n), _f64(_as_float(upsample)), *wo, _i64(m),
+                                    *_tail(fatal, w_out.device))
+
+
+def _convolve_common(w_in, kernel, mode_in, w_out, fatal):
+    T = _out_T(w_out)
+    c = _Call(T, w_out.device)
+    c.rows_from(w_in, w_out)
+    wi, n = c.wave_in(w_in)
+    wo, p = c.wave_out(w_out)
+    k = kernel.reshape(-1).to(T).contiguous()
+    c.keep.append(k)
+    return _fn("dspb_convolve_wf", T)(*wi, _i64(c.n_rows), _i64(n), _vp(k.data_ptr()), _i64(k.numel()),
+                                      _i32(_as_int(mode_in)), *wo, _i64(p), *_tail(fatal, w_out.device))
+
+
+@_register("convolve_wf", "(n),(m),(),(p)", ["ffbf->", "ddbd->"], 1)
+def _convolve_wf(w_in, kernel, mode_in, w_out, fatal=None):
+    """convolutions.py:14-72"""
+    return _convolve_common(w_in, kernel, mode_in, w_out, fatal)
+
+
+@_register("fft_convolve_wf", "(n),(m),(),(p)", ["ffbf", "ddbd"], 1)
+def _fft_convolve_wf(w_in, kernel, mode_in, w_out, fatal=None):
+    """convolutions.py:75-119 -- same sums as convolve_wf, evaluated directly on the
+    device (the reference's in-place zeroing of NaN input rows is not reproduced; NaN
+    rows give NaN outputs)."""
+    return _convolve_common(w_in, kernel, mode_in, w_out, fatal)
+
+
+@_register("get_multi_local_extrema", "(n),(),(),(),(),(),(m),(m),(),()", ["ffffffffII->", "ddddddddII->"], 4)
+def _get_multi_local_extrema(w_in, a_delta_max_in, a_delta_min_in, search_direction, a_abs_max_in, a_abs_min_in,
+                             vt_max_out, vt_min_out, n_max_out, n_min_out, fatal=None):
+    """get_multi_local_extrema.py:12-306"""
+    T = _out_T(vt_max_out)
+    c = _Call(T, vt_max_out.device)
+    c.rows_from(w_in, vt_max_out)
+    wi, n = c.wave_in(w_in)
+    vmx = vt_max_out if vt_max_out.ndim == 2 else vt_max_out.unsqueeze(0)
+    vmn = vt_min_out if vt_min_out.ndim == 2 else vt_min_out.unsqueeze(0)
+    assert vmx.is_contiguous() and vmn.is_contiguous() and vmx.shape == vmn.shape
+    assert n_max_out.dtype == torch.uint32 and n_min_out.dtype == torch.uint32
+    m = vmx.shape[-1]
+    return _fn("dspb_get_multi_local_extrema", T)(
+        *wi, _i64(c.n_rows), _i64(n), _f64(_as_float(a_delta_max_in)), _f64(_as_float(a_delta_min_in)),
+        _f64(_as_float(search_direction)), _f64(_as_float(a_abs_max_in)), _f64(_as_float(a_abs_min_in)),
+        _vp(vmx.data_ptr()), _vp(vmn.data_ptr()), _i64(m), _vp(n_max_out.data_ptr()), _vp(n_min_out.data_ptr()),
+        *_tail(fatal, vt_max_out.device))
+
+
+@_register("recursive_filter", "(n),(p),(q),(),()->(n)", ["fddff->f", "ddddd->d"], 1)
+def _recursive_filter(w_in, a, b, init_in, init_out, w_out, fatal=None):
+    """recursive_filter.py:12-93 (len(b) <= 3)"""
+    T = _out_T(w_out)
+    c = _Call(T, w_out.device)
+    c.rows_from(w_in, init_in, init_out, w_out)
+    wi, n = c.wave_in(w_in)
+    wo, _ = c.wave_out(w_out, n)
+    av = np.ascontiguousarray(np.asarray(a.cpu() if isinstance(a, torch.Tensor) else a, np.float64).reshape(-1))
+    bv = np.ascontiguousarray(np.asarray(b.cpu() if isinstance(b, torch.Tensor) else b, np.float64).reshape(-1))
+    if np.isnan(av).any() or np.isnan(bv).any():
+        w_out.fill_(float("nan"))
+        return 0
+    return _fn("dspb_recursive_filter", T)(
+        *wi, _i64(c.n_rows), _i64(n), av.ctypes.data_as(_vp), _i64(av.size), bv.ctypes.data_as(_vp), _i64(bv.size),
+        *c.scalar_in(init_in), *c.scalar_in(init_out), *wo, *_tail(fatal, w_out.device))
+
+
+# ---- set-up time kernel generators (const-folded by the chain compiler) ------------------
+def _kernel_out(kernel):
+    T = _out_T(kernel)
+    k = kernel.reshape(-1)
+    assert k.is_contiguous()
+    return T, k
+
+
+@_register("cusp_filter", "(),(),(),(n)", ["ffff->", "dddd->"], 1)
+def _cusp_filter(sigma, flat, decay, kernel, fatal=None):
+    """energy_kernels.py:12-73"""
+    T, k = _kernel_out(kernel)
+    r = (lambda v: float(np.float32(_as_float(v)))) if T == torch.float32 else _as_float
+    return _fn("dspb_cusp_filter", T)(_f64(r(sigma)), _f64(r(flat)), _f64(r(decay)), _vp(k.data_ptr()), _i64(k.numel()),
+                                      _stream_ptr(kernel.device))
+
+
+@_register("zac_filter", "(),(),(),(n)", ["ffff->", "dddd->"], 1)
+def _zac_filter(sigma, flat, decay, kernel, fatal=None):
+    """energy_kernels.py:76-157"""
+    T, k = _kernel_out(kernel)
+    r = (lambda v: float(np.float32(_as_float(v)))) if T == torch.float32 else _as_float
+    return _fn("dspb_zac_filter", T)(_f64(r(sigma)), _f64(r(flat)), _f64(r(decay)), _vp(k.data_ptr()), _i64(k.numel()),
+                                     _stream_ptr(kernel.device))
+
+
+@_register("t0_filter", "(),(),(n)", ["fff->", "ddd->"], 1)
+def _t0_filter(rise, fall, kernel, fatal=None):
+    """kernels.py:12-61"""
+    T, k = _kernel_out(kernel)
+    r = (lambda v: float(np.float32(_as_float(v)))) if T == torch.float32 else _as_float
+    return _fn("dspb_t0_filter", T)(_f64(r(rise)), _f64(r(fall)), _vp(k.data_ptr()), _i64(k.numel()),
+                                    _stream_ptr(kernel.device))
+
+
+def __getattr__(name):
+    raise AttributeError(
+        f"module {__name__} has no attribute {name}: not on the B200 hot path "
+        "(see DESIGN.md 'out of scope'); there is no CPU fallback"
+    )

@@ -1,0 +1,212 @@
+/*
+ * dspeed_b200 -- C ABI of the B200 (sm_100a) implementation of dspeed's
+ * ProcessingChain block-execution hot path.
+ *
+ * This is the drop-in boundary: one `extern "C"` launcher per processor of
+ * `dspeed.processors` on the hot path (reference: src/dspeed/processors/, cited per
+ * function), plus the fused waveform-resident chain program (dspb_chain_*), which is
+ * what `ProcessingChain.execute` (src/dspeed/processing_chain.py:665-673,1144-1163)
+ * launches once per block instead of one numba gufunc call per processor.
+ *
+ * Conventions (all launchers):
+ *  - every pointer is a DEVICE pointer owned by the caller (PyTorch tensors); the
+ *    library never allocates, frees or retains them.  Launches are asynchronous on
+ *    `stream` (a cudaStream_t passed as void*); the caller keeps buffers alive until
+ *    the stream reaches the launch.
+ *  - a waveform operand is (ptr, row_stride, dtype): `n_rows` rows of `n` samples,
+ *    consecutive rows `row_stride` ELEMENTS apart (views/slices of a larger block are
+ *    expressed by offsetting ptr), element type `dtype` = DSPB_F32/F64/U16/I16/I32/U32.
+ *    Integer waveforms are converted on load exactly like numpy casts them into the
+ *    reference's float loop.
+ *  - the suffix _f32 / _f64 is the reference's type loop ("f" / "d"): the dtype of all
+ *    outputs and of every per-row scalar array.
+ *  - a per-row scalar argument is (ptr, stride, imm): if ptr != NULL the value for row r
+ *    is ptr[r*stride] (stride 0 broadcasts one device value), else the immediate `imm`.
+ *  - outputs are written in place into caller-allocated arrays (gufunc convention,
+ *    reference processors/__init__.py:47-59); waveform outputs take (ptr, row_stride).
+ *  - NaN convention of the reference (docs/source/manuals/build_dsp.rst:152-175): if any
+ *    input sample or scalar of a row is NaN all outputs of that row are NaN.
+ *  - errors: return 0 on success; > 0 = a DSPFatal condition detectable from the
+ *    arguments alone (DSPB_FATAL_*, same messages as the reference); < 0 = -cudaError_t.
+ *    Data-dependent DSPFatal conditions are recorded on the device in `fatal`
+ *    (int32[4]: code, row low 31 bits, row high bits, reserved; first writer wins;
+ *    may be NULL) and raised by the host wrapper after the block completes, mirroring
+ *    processing_chain.py:1156-1159.
+ *  - re-entrant: no global mutable state; any stream, any device (current device =
+ *    the one owning the pointers).
+ */
+#ifndef DSPEED_B200_H
+#define DSPEED_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* element types of waveform operands */
+enum { DSPB_F32 = 0, DSPB_F64 = 1, DSPB_U16 = 2, DSPB_I16 = 3, DSPB_I32 = 4, DSPB_U32 = 5 };
+
+/* DSPFatal conditions (reference file:line) */
+enum {
+  DSPB_OK = 0,
+  DSPB_FATAL_PZ_NAN = 1,            /* pole_zero.py:76-77 */
+  DSPB_FATAL_DPZ_SHORT = 2,         /* pole_zero.py:145-148 */
+  DSPB_FATAL_RISE_NEG = 3,          /* trap_filters.py:53-54 */
+  DSPB_FATAL_FLAT_NEG = 4,          /* trap_filters.py:56-57 */
+  DSPB_FATAL_FALL_NEG = 5,          /* trap_filters.py:205-206 */
+  DSPB_FATAL_TRAP_WIDE = 6,         /* trap_filters.py:59-60 */
+  DSPB_FATAL_PICKOFF_NONINT = 7,    /* trap_filters.py:278-279 */
+  DSPB_FATAL_MW_RANGE = 8,          /* moving_windows.py:52-55 */
+  DSPB_FATAL_MWM_LEN_NONINT = 9,    /* moving_windows.py:167-168 */
+  DSPB_FATAL_MWM_NUM_NONINT = 10,   /* moving_windows.py:170-171 */
+  DSPB_FATAL_MWM_RANGE = 11,        /* moving_windows.py:173-174 */
+  DSPB_FATAL_MWM_NUM_NEG = 12,      /* moving_windows.py:176-177 */
+  DSPB_FATAL_TSTART_NONINT = 13,    /* time_point_thresh.py:67-68 */
+  DSPB_FATAL_WALK_NONINT = 14,      /* time_point_thresh.py:70-71 */
+  DSPB_FATAL_TSTART_RANGE = 15,     /* time_point_thresh.py:73-74 */
+  DSPB_FATAL_INTERP_MODE = 16,      /* time_point_thresh.py:222, fixed_time_pickoff.py:125 */
+  DSPB_FATAL_POLARITY_ZERO = 17,    /* time_point_thresh.py:314 */
+  DSPB_FATAL_FTP_INT = 18,          /* fixed_time_pickoff.py:85 */
+  DSPB_FATAL_WINDOWER_LEN = 19,     /* windower.py:42-43 */
+  DSPB_FATAL_UPSAMPLE = 20,         /* upsampler.py:41-42 */
+  DSPB_FATAL_CONV_KERNEL_LONG = 21, /* convolutions.py:48-49 */
+  DSPB_FATAL_CONV_MODE = 22,        /* convolutions.py:70 */
+  DSPB_FATAL_CONV_OUTLEN = 23,      /* convolutions.py:53-68 */
+  DSPB_FATAL_GMLE_LEN = 24,         /* get_multi_local_extrema.py:126-129 */
+  DSPB_FATAL_GMLE_DELTA = 25,       /* get_multi_local_extrema.py:130-131 */
+  DSPB_FATAL_GMLE_DIR = 26,         /* get_multi_local_extrema.py:305-306 */
+  DSPB_FATAL_RF_B_SCALAR = 27,      /* recursive_filter.py:66-67 */
+  DSPB_FATAL_RF_SHORT = 28,         /* recursive_filter.py:68-71 */
+  DSPB_FATAL_SHAPE = 29,            /* gufunc core-dimension mismatch (numpy raises) */
+  DSPB_FATAL_KERNEL_ARGS = 30,      /* energy_kernels.py:51-61, kernels.py:49-56 */
+  DSPB_ERR_ROW_TOO_LONG = 100,      /* waveform does not fit the shared-memory resident layout */
+  DSPB_ERR_UNSUPPORTED = 101
+};
+
+/* library / device information */
+int dspb_version(void);
+/* largest waveform length (samples of the compute dtype) `n_slots` resident copies allow */
+int64_t dspb_max_row_len(int elem_bytes, int n_slots);
+const char* dspb_fatal_message(int code);
+
+#define DSPB_WAVE_IN(name) const void* name, int64_t name##_row_stride, int32_t name##_dtype
+#define DSPB_WAVE_OUT(name) void* name, int64_t name##_row_stride
+#define DSPB_SCALAR(name) const void* name, int64_t name##_stride, double name##_imm
+#define DSPB_TAIL int32_t* fatal, void* stream
+
+#define DSPB_DECLARE(SFX)                                                                          \
+  /* bl_subtract.py:11-46   w_out = w_in - a_baseline */                                           \
+  int dspb_bl_subtract##SFX(DSPB_WAVE_IN(w_in), int64_t n_rows, int64_t n, DSPB_SCALAR(a_baseline), \
+                            DSPB_WAVE_OUT(w_out), DSPB_TAIL);                                      \
+  /* min_max.py:11-82       first arg-min / arg-max (as floats) and the extreme values */          \
+  int dspb_min_max##SFX(DSPB_WAVE_IN(w_in), int64_t n_rows, int64_t n, void* t_min, void* t_max,   \
+                        void* a_min, void* a_max, DSPB_TAIL);                                      \
+  /* numpy.amax(w, axis=1) as used by the configs (icpc-dsp-config.json:123-129) */                \
+  int dspb_amax##SFX(DSPB_WAVE_IN(w_in), int64_t n_rows, int64_t n, void* a_max, DSPB_TAIL);       \
+  /* min_max.py:85-140 */                                                                          \
+  int dspb_min_max_norm##SFX(DSPB_WAVE_IN(w_in), int64_t n_rows, int64_t n, DSPB_SCALAR(a_min),    \
+                             DSPB_SCALAR(a_max), DSPB_WAVE_OUT(w_out), DSPB_TAIL);                 \
+  /* linear_slope_fit.py:11-90   mean, stdev(ddof=1), slope, intercept */                          \
+  int dspb_linear_slope_fit##SFX(DSPB_WAVE_IN(w_in), int64_t n_rows, int64_t n, void* mean,        \
+                                 void* stdev, void* slope, void* intercept, DSPB_TAIL);            \
+  /* linear_slope_fit.py:93-158 */                                                                 \
+  int dspb_linear_slope_diff##SFX(DSPB_WAVE_IN(w_in), int64_t n_rows, int64_t n,                   \
+                                  DSPB_SCALAR(slope), DSPB_SCALAR(intercept), void* mean,          \
+                                  void* rms, DSPB_TAIL);                                           \
+  /* arithmetic.py:9-62 */                                                                         \
+  int dspb_mean_below_threshold##SFX(DSPB_WAVE_IN(w_in), int64_t n_rows, int64_t n,                \
+                                     DSPB_SCALAR(threshold), void* result, DSPB_TAIL);             \
+  /* pole_zero.py:24-77 */                                                                         \
+  int dspb_pole_zero##SFX(DSPB_WAVE_IN(w_in), int64_t n_rows, int64_t n, DSPB_SCALAR(t_tau),       \
+                          DSPB_WAVE_OUT(w_out), DSPB_TAIL);                                        \
+  /* pole_zero.py:82-198 */                                                                        \
+  int dspb_double_pole_zero##SFX(DSPB_WAVE_IN(w_in), int64_t n_rows, int64_t n,                    \
+                                 DSPB_SCALAR(t_tau1), DSPB_SCALAR(t_tau2), DSPB_SCALAR(frac),      \
+                                 DSPB_WAVE_OUT(w_out), DSPB_TAIL);                                 \
+  /* trap_filters.py:12-76 (norm=0) and :79-149 (norm=1) */                                        \
+  int dspb_trap_filter##SFX(DSPB_WAVE_IN(w_in), int64_t n_rows, int64_t n, int32_t rise,           \
+                            int32_t flat, int32_t norm, DSPB_WAVE_OUT(w_out), DSPB_TAIL);          \
+  /* trap_filters.py:152-227 */                                                                    \
+  int dspb_asym_trap_filter##SFX(DSPB_WAVE_IN(w_in), int64_t n_rows, int64_t n, int32_t rise,      \
+                                 int32_t flat, int32_t fall, DSPB_WAVE_OUT(w_out), DSPB_TAIL);     \
+  /* trap_filters.py:230-301 */                                                                    \
+  int dspb_trap_pickoff##SFX(DSPB_WAVE_IN(w_in), int64_t n_rows, int64_t n, int32_t rise,          \
+                             int32_t flat, DSPB_SCALAR(t_pickoff), void* a_out, DSPB_TAIL);        \
+  /* moving_windows.py:12-61 (kind 0 = left), :64-114 (kind 1 = right) */                          \
+  int dspb_moving_window##SFX(DSPB_WAVE_IN(w_in), int64_t n_rows, int64_t n, double length,        \
+                              int32_t kind, DSPB_WAVE_OUT(w_out), DSPB_TAIL);                      \
+  /* moving_windows.py:117-203 */                                                                  \
+  int dspb_moving_window_multi##SFX(DSPB_WAVE_IN(w_in), int64_t n_rows, int64_t n, double length,  \
+                                    double num_mw, int32_t mw_type, DSPB_WAVE_OUT(w_out),          \
+                                    DSPB_TAIL);                                                    \
+  /* moving_windows.py:206-249 ; w_out has n_out = n - int(length) samples */                      \
+  int dspb_avg_current##SFX(DSPB_WAVE_IN(w_in), int64_t n_rows, int64_t n, double length,          \
+                            DSPB_WAVE_OUT(w_out), int64_t n_out, DSPB_TAIL);                       \
+  /* time_point_thresh.py:12-92 */                                                                 \
+  int dspb_time_point_thresh##SFX(DSPB_WAVE_IN(w_in), int64_t n_rows, int64_t n,                   \
+                                  DSPB_SCALAR(a_threshold), DSPB_SCALAR(t_start),                  \
+                                  DSPB_SCALAR(walk_forward), void* t_out, DSPB_TAIL);              \
+  /* time_point_thresh.py:95-222 ; mode_in is the interpolation character */                       \
+  int dspb_interpolated_time_point_thresh##SFX(DSPB_WAVE_IN(w_in), int64_t n_rows, int64_t n,      \
+                                               DSPB_SCALAR(a_threshold), DSPB_SCALAR(t_start),     \
+                                               int64_t walk_forward, int32_t mode_in, void* t_out, \
+                                               DSPB_TAIL);                                         \
+  /* time_point_thresh.py:225-401 ; thresholds [n_rows or 1, m], t_out [n_rows, m] */              \
+  int dspb_multi_time_point_thresh##SFX(DSPB_WAVE_IN(w_in), int64_t n_rows, int64_t n,             \
+                                        const void* a_threshold, int64_t m, int64_t thr_row_stride,\
+                                        DSPB_SCALAR(t_start), double polarity, int32_t mode_in,    \
+                                        void* t_out, DSPB_TAIL);                                   \
+  /* fixed_time_pickoff.py:12-125 */                                                               \
+  int dspb_fixed_time_pickoff##SFX(DSPB_WAVE_IN(w_in), int64_t n_rows, int64_t n,                  \
+                                   DSPB_SCALAR(t_in), int32_t mode_in, void* a_out, DSPB_TAIL);    \
+  /* windower.py:12-54 ; w_out has m samples */                                                    \
+  int dspb_windower##SFX(DSPB_WAVE_IN(w_in), int64_t n_rows, int64_t n, DSPB_SCALAR(t0_in),        \
+                         DSPB_WAVE_OUT(w_out), int64_t m, DSPB_TAIL);                              \
+  /* upsampler.py:14-49 ; w_out has m samples */                                                   \
+  int dspb_upsampler##SFX(DSPB_WAVE_IN(w_in), int64_t n_rows, int64_t n, double upsample,          \
+                          DSPB_WAVE_OUT(w_out), int64_t m, DSPB_TAIL);                             \
+  /* convolutions.py:14-72 (convolve_wf) and :75-119 (fft_convolve_wf: same sums, evaluated        \
+   * directly); kernel [m] of the output dtype on the device; mode_in 'f'|'v'|'s'; w_out has p. */ \
+  int dspb_convolve_wf##SFX(DSPB_WAVE_IN(w_in), int64_t n_rows, int64_t n, const void* kernel,     \
+                            int64_t m, int32_t mode_in, DSPB_WAVE_OUT(w_out), int64_t p,           \
+                            DSPB_TAIL);                                                            \
+  /* get_multi_local_extrema.py:12-306 ; vt_max/vt_min [n_rows, m], n_max/n_min uint32 [n_rows] */ \
+  int dspb_get_multi_local_extrema##SFX(DSPB_WAVE_IN(w_in), int64_t n_rows, int64_t n,             \
+                                        double a_delta_max, double a_delta_min,                    \
+                                        double search_direction, double a_abs_max,                 \
+                                        double a_abs_min, void* vt_max, void* vt_min, int64_t m,   \
+                                        uint32_t* n_max, uint32_t* n_min, DSPB_TAIL);              \
+  /* recursive_filter.py:12-93 ; a[p], b[q] host doubles (q <= 3) */                               \
+  int dspb_recursive_filter##SFX(DSPB_WAVE_IN(w_in), int64_t n_rows, int64_t n, const double* a,   \
+                                 int64_t p, const double* b, int64_t q, DSPB_SCALAR(init_in),      \
+                                 DSPB_SCALAR(init_out), DSPB_WAVE_OUT(w_out), DSPB_TAIL);          \
+  /* set-up time kernel synthesis on the device (const-folded by the chain compiler,               \
+   * processing_chain.py:2775-2820): energy_kernels.py:12-73, :76-157, kernels.py:12-61 */         \
+  int dspb_cusp_filter##SFX(double sigma, double flat, double decay, void* kernel, int64_t length, \
+                            void* stream);                                                         \
+  int dspb_zac_filter##SFX(double sigma, double flat, double decay, void* kernel, int64_t length,  \
+                           void* stream);                                                          \
+  int dspb_t0_filter##SFX(double rise, double fall, void* kernel, int64_t length, void* stream);
+
+DSPB_DECLARE(_f32)
+DSPB_DECLARE(_f64)
+
+/* ---- fused waveform-resident chain program (see DESIGN.md "chain compiler") ---------
+ * A program is a flat int32/double blob produced by the host chain compiler
+ * (dspeed_b200/fusion.py); the kernel interprets it with one CTA per waveform: the raw
+ * row is read from HBM once, all intermediates live in shared-memory slots / a
+ * per-row scalar file, only requested outputs are written back. */
+typedef struct dspb_chain dspb_chain;
+int dspb_chain_create(const int32_t* code, int64_t n_code, const double* consts, int64_t n_consts,
+                      dspb_chain** out);
+/* ptrs: device pointer table indexed by the program (inputs, outputs, kernels) */
+int dspb_chain_launch(dspb_chain* chain, const void* const* ptrs, int64_t n_ptrs, int64_t n_rows,
+                      int32_t* fatal, void* stream);
+int64_t dspb_chain_smem_bytes(const dspb_chain* chain);
+void dspb_chain_destroy(dspb_chain* chain);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DSPEED_B200_H */

@@ -550,10 +550,8 @@ static int FN(orc1_fixed_time_pickoff)(const REAL *w, int64_t n, REAL t_in, int8
       for (int64_t i = 1; i < n - 1; i++) {
         double p = 0.5 * w2[i - 1] + 2.0;
         w2[i] = -0.5 / p;
-        /* REAL arithmetic: w[i+1] - 2*w[i] + w[i-1]  (int*REAL stays REAL in numba) */
-        REAL a = (REAL)((REAL)2 * w[i]);
-        REAL b = (REAL)(w[i + 1] - a);
-        u[i] = (double)(REAL)(b + w[i - 1]);
+        /* 2 * w[i] is int64 * REAL -> float64 in numba */
+        u[i] = ((double)w[i + 1] - 2.0 * (double)w[i]) + (double)w[i - 1];
         u[i] = (3.0 * u[i] - 0.5 * u[i - 1]) / p;
       }
       for (int64_t i = n - 2; i > i_in - 1; i--) w2[i] = w2[i] * w2[i + 1] + u[i];
