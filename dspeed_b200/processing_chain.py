@@ -1,0 +1,1756 @@
+"""Device-resident ``ProcessingChain``: the variable/buffer manager, the expression and
+recipe compiler, and the block executor of dspeed, rebuilt for B200.
+
+Interface and semantics follow the reference (src/dspeed/processing_chain.py; cited
+per class): the same JSON/YAML recipe schema, ``get_variable`` expression grammar, type /
+shape / unit / coordinate-grid deduction, unit-to-sample conversion and constant
+folding.  What changes is *where things live and run*:
+
+* every variable is a ``torch`` CUDA tensor ``[block_width, *shape]`` carrying the
+  reference's metadata (dtype, shape, grid, unit, is_coord) -- reference
+  ``ProcChainVar`` :147-377;
+* processors are the CUDA processors of :mod:`dspeed_b200.processors` (numpy ufuncs used
+  as glue map to device element-wise ops, :mod:`dspeed_b200.numpy_bridge`); a processor
+  without a device implementation is a set-up error -- there is no CPU fallback;
+* ``execute`` streams blocks: pinned host -> device copy of the input columns, all
+  processor launches of the block on one CUDA stream, device -> pinned host copy of the
+  output columns; data-dependent ``DSPFatal`` conditions are collected in a device-side
+  record and raised once per block (reference :1144-1163);
+* ``block_width`` keeps its meaning (rows per execute step) but defaults to a large
+  value: results do not depend on it.
+
+When :mod:`dspeed_b200.fusion` recognises the chain (or a prefix of it) it replaces the
+per-processor launches by ONE waveform-resident kernel per block; see DESIGN.md.
+"""
+
+from __future__ import annotations
+
+import ast
+import importlib
+import itertools as it
+import json
+import logging
+import re
+import time
+from collections.abc import Collection, MutableMapping
+from copy import deepcopy
+from dataclasses import dataclass
+from functools import partial
+from numbers import Real
+from typing import Any
+
+import numpy as np
+import torch
+
+from . import numpy_bridge, tables
+from . import processors as device_processors
+from .errors import DSPFatal, ProcessingChainError
+from .tables import kind_of
+from .units import Quantity, Unit, as_unit, from_foreign, is_in_registry, to_period_units, ureg
+
+log = logging.getLogger("dspeed")
+
+auto = "auto"
+
+MAX_FATAL_SLOTS = 1024
+
+#: rows per execute step when the caller does not choose (reference default is 16 rows of
+#: numpy work; a B200 wants tens of thousands of waveforms in flight)
+DEFAULT_BLOCK_WIDTH = 16384
+
+
+class EndExecute(Exception):
+    """raised by an input manager when the chunk is exhausted (reference :41-42)"""
+
+
+ast_ops_dict = {
+    ast.Add: (np.add, "{}+{}"),
+    ast.Sub: (np.subtract, "{}-{}"),
+    ast.Mult: (np.multiply, "{}*{}"),
+    ast.Div: (np.divide, "{}/{}"),
+    ast.FloorDiv: (np.floor_divide, "{}//{}"),
+    ast.USub: (np.negative, "-{}"),
+    ast.Eq: (np.equal, "{}=={}"),
+    ast.NotEq: (np.not_equal, "{}!={}"),
+    ast.Lt: (np.less, "{}<{}"),
+    ast.LtE: (np.less_equal, "{}<={}"),
+    ast.Gt: (np.greater, "{}>{}"),
+    ast.GtE: (np.greater_equal, "{}>={}"),
+}
+
+
+def fatal_message(code: int) -> str:
+    extra = {numpy_bridge.FATAL_CONVERT_INT: "Cannot convert to integer. Use round or astype",
+             numpy_bridge.FATAL_GET_RANGE: "i is out of range"}
+    return extra.get(code) or device_processors._lib.fatal_message(code)
+
+
+def _np2t(dt) -> torch.dtype:
+    return tables._np_to_torch(dt)
+
+
+# ======================================================================================
+# coordinate grids and variables
+# ======================================================================================
+@dataclass
+class CoordinateGrid:
+    """Period and offset of the sample grid a time coordinate is measured on
+    (reference :67-144).  ``offset`` is a Quantity or a per-event variable (the
+    waveform's ``t0``)."""
+
+    period: Any
+    offset: Any = 0
+
+    def __post_init__(self) -> None:
+        if isinstance(self.period, CoordinateGrid):
+            self.offset = self.period.offset
+            self.period = self.period.period
+        elif isinstance(self.period, ProcChainVar):
+            if self.period.grid in (None, auto):
+                raise ProcessingChainError(f"{self.period} does not have an assigned coordinate grid")
+            self.offset = self.period.offset
+            self.period = self.period.period
+        elif isinstance(self.period, Collection) and not isinstance(self.period, str):
+            self.period, self.offset = self.period
+        self.period = from_foreign(self.period)
+        self.offset = from_foreign(self.offset)
+        if isinstance(self.period, str):
+            self.period = Quantity(1.0, self.period)
+        elif isinstance(self.period, Unit):
+            self.period = Quantity(1.0, self.period)
+        if isinstance(self.offset, Real):
+            self.offset = self.offset * self.period
+        if not isinstance(self.period, Quantity) or not isinstance(self.offset, (Quantity, ProcChainVar)):
+            raise ProcessingChainError(f"invalid coordinate grid ({self.period}, {self.offset})")
+
+    def __eq__(self, other) -> bool:
+        if not isinstance(other, CoordinateGrid):
+            return False
+        return self.period == other.period and (
+            self.offset is other.offset if isinstance(self.offset, ProcChainVar) else self.offset == other.offset
+        )
+
+    def unit_str(self) -> str:
+        return format(self.period.u, "~") or str(self.period.u)
+
+    def get_period(self, unit) -> float:
+        if isinstance(unit, str):
+            unit = ureg.Quantity(unit)
+        return float(self.period / unit)
+
+    def get_offset(self, unit=None):
+        """offset in ``unit`` (default: in periods): a float, or the device buffer of the
+        offset variable converted to that unit"""
+        if unit is None:
+            unit = self.period
+        elif isinstance(unit, str):
+            unit = ureg.Quantity(unit)
+        if isinstance(self.offset, ProcChainVar):
+            return self.offset.get_buffer(CoordinateGrid(unit))
+        return float(self.offset / unit)
+
+    def __str__(self) -> str:
+        off = self.offset.name if isinstance(self.offset, ProcChainVar) else str(self.offset)
+        return f"({self.period},{off})"
+
+
+class ProcChainVar:
+    """A named chain variable and its device block buffer(s) (reference :147-377).
+
+    Coordinate variables (times) keep one buffer per unit system they are requested in;
+    the extra buffers are filled by conversion processors appended to the chain."""
+
+    def __init__(self, proc_chain, name, shape=auto, dtype=auto, grid=auto, unit=auto, is_coord=auto,
+                 vector_len=None, is_const=False):
+        assert isinstance(proc_chain, ProcessingChain) and isinstance(name, str)
+        self.proc_chain = proc_chain
+        self.name = name
+        self._buffer = None
+        self.shape = shape
+        self.dtype = dtype
+        self.grid = grid
+        self.unit = unit
+        self.is_coord = is_coord
+        self.vector_len = vector_len
+        self.is_const = is_const
+        log.debug(f"added variable: {self.description()}")
+
+    def __setattr__(self, name: str, value: Any) -> None:
+        if value is auto:
+            pass
+        elif name == "shape":
+            value = tuple(int(d) for d in value) if hasattr(value, "__iter__") else (int(value),)
+        elif name == "dtype" and not isinstance(value, np.dtype):
+            value = np.dtype(value)
+        elif name == "grid" and not isinstance(value, CoordinateGrid) and value is not None:
+            if isinstance(value, str):
+                value = CoordinateGrid(value, 0)
+            elif isinstance(value, Collection):
+                value = CoordinateGrid(*value)
+            else:
+                value = CoordinateGrid(value, 0)
+        elif name == "unit" and value is not None:
+            value = from_foreign(value)
+        elif name == "is_coord":
+            value = bool(value)
+        elif name == "vector_len" and value is not None:
+            if not isinstance(value, ProcChainVar):
+                value = self.proc_chain.get_variable(value)
+            value.update_auto(shape=(), grid=None, unit=None, is_coord=False)
+        super().__setattr__(name, value)
+
+    # -- buffers -------------------------------------------------------------------
+    def _make_buffer(self) -> torch.Tensor:
+        lead = 1 if self.is_const else self.proc_chain._block_width
+        return torch.zeros((lead,) + self.shape, dtype=_np2t(self.dtype), device=self.proc_chain.device)
+
+    def get_buffer(self, unit=None) -> torch.Tensor:
+        if self._buffer is None:
+            if self.shape is auto:
+                raise ProcessingChainError(f"cannot deduce shape of {self.name}")
+            if self.dtype is auto:
+                raise ProcessingChainError(f"cannot deduce dtype of {self.name}")
+            self._buffer = self._make_buffer()
+
+        if unit is None:
+            unit = self.grid if self.is_coord else self.unit
+        if not isinstance(unit, CoordinateGrid) and is_in_registry(unit):
+            unit = CoordinateGrid(unit)
+
+        if isinstance(self._buffer, torch.Tensor):
+            if self.is_coord is True:
+                if not isinstance(self.grid, CoordinateGrid) and unit is not None:
+                    self.grid = CoordinateGrid(unit)
+            if not isinstance(unit, CoordinateGrid):
+                return self._buffer
+            # first request in a unit system: remember which one the native buffer is in
+            self._buffer = [(self._buffer, unit)]
+
+        if not isinstance(unit, CoordinateGrid):
+            return self._buffer[0][0]
+        for buff, buf_u in self._buffer:
+            if buf_u == unit:
+                return buff
+        conversion_manager = UnitConversionManager(self, unit)
+        self._buffer.append((conversion_manager.out_buffer, unit))
+        self.proc_chain._proc_managers.append(conversion_manager)
+        log.debug(f"added conversion: {conversion_manager}")
+        return conversion_manager.out_buffer
+
+    @property
+    def buffer(self):
+        return self.get_buffer()
+
+    @property
+    def period(self):
+        return self.grid.period if self.grid else None
+
+    @property
+    def offset(self):
+        return self.grid.offset if self.grid else None
+
+    def description(self) -> str:
+        return (f"{self.name}(shape: {self.shape}, dtype: {self.dtype}, grid: {self.grid}, "
+                f"unit: {self.unit}, is_coord: {self.is_coord})")
+
+    def update_auto(self, shape=auto, dtype=auto, grid=auto, unit=auto, is_coord=auto, period=None, offset=0,
+                    vector_len=None) -> None:
+        """fill in attributes that are still ``auto`` (reference :334-374)"""
+        if grid is auto and period is not None:
+            if isinstance(offset, str):
+                offset = self.proc_chain.get_variable(offset, expr_only=True)
+            grid = CoordinateGrid(period, offset)
+        if self.shape is auto and shape is not auto:
+            self.shape = shape
+        if self.dtype is auto and dtype is not auto:
+            self.dtype = dtype
+        if self.grid is auto and grid is not auto:
+            self.grid = grid
+        if self.unit is auto and unit is not auto:
+            self.unit = unit
+        if self.is_coord is auto and is_coord is not auto:
+            self.is_coord = is_coord
+        if self.vector_len is None and vector_len is not None:
+            self.vector_len = vector_len
+
+    def __str__(self) -> str:
+        return self.name
+
+
+# ======================================================================================
+# the chain
+# ======================================================================================
+class ProcessingChain:
+    """Variables, processors and I/O links of one DSP chain, executed block by block on
+    one CUDA device (reference :380-1482)."""
+
+    def __init__(self, block_width: int = None, buffer_len: int = None, device=None) -> None:
+        self._vars_dict: dict[str, ProcChainVar] = {}
+        self._proc_managers: list = []
+        self._input_managers: dict = {}
+        self._output_managers: dict = {}
+        self._block_width = int(block_width) if block_width else DEFAULT_BLOCK_WIDTH
+        self._buffer_len = buffer_len
+        if device is None:
+            if not torch.cuda.is_available():
+                raise RuntimeError("dspeed_b200.ProcessingChain needs a CUDA device (there is no CPU fallback)")
+            device = torch.device("cuda", torch.cuda.current_device())
+        self.device = torch.device(device)
+        if self.device.type not in ("cuda", "meta"):
+            # "meta" = plan-only build (no data, nothing executes): used to inspect / test the
+            # compiled chain without a GPU.  There is deliberately no "cpu" execution device.
+            raise RuntimeError(f"unsupported device {self.device}: dspeed_b200 executes on CUDA only")
+        #: device-side DSPFatal records, one int32[4] row per bound processor
+        self.fatal = torch.zeros((MAX_FATAL_SLOTS, 4), dtype=torch.int32, device=self.device)
+        self._fatal_owner: list = []
+        self._fused = None  # set by fusion.try_fuse()
+        self.stats = {"launches": 0, "blocks": 0, "h2d_bytes": 0, "d2h_bytes": 0}
+
+    # -- variables -----------------------------------------------------------------
+    def add_variable(self, name, dtype=auto, shape=auto, grid=auto, unit=auto, is_coord=auto, period=None, offset=0,
+                     vector_len=None) -> ProcChainVar:
+        self._validate_name(name, raise_exception=True)
+        if name in self._vars_dict:
+            raise ProcessingChainError(name + " is already in variable list")
+        if grid is auto and period is not None:
+            if isinstance(offset, str):
+                offset = self.get_variable(offset, expr_only=True)
+            grid = CoordinateGrid(period, offset)
+        var = ProcChainVar(self, name, shape=shape, dtype=dtype, grid=grid, unit=unit, is_coord=is_coord,
+                           vector_len=vector_len)
+        self._vars_dict[name] = var
+        return var
+
+    def set_constant(self, varname, val, dtype=None, unit=None) -> ProcChainVar:
+        """make a variable a constant with the given value (reference :487-524)"""
+        param = self.get_variable(varname)
+        if not param.is_const and param._buffer is not None:
+            raise ProcessingChainError(f"{param} is already defined, cannot set_constant")
+        param.is_const = True
+        val = from_foreign(val)
+        if isinstance(val, Quantity):
+            unit = val.u
+            val = val.m
+        if isinstance(val, torch.Tensor):
+            val = val.detach().cpu().numpy()
+        val = np.array(val, dtype=dtype)
+        param.update_auto(shape=val.shape, dtype=val.dtype, unit=unit, is_coord=False)
+        buf = param.get_buffer()
+        buf.copy_(torch.from_numpy(np.ascontiguousarray(val).astype(param.dtype, casting="unsafe")).reshape(buf.shape))
+        log.debug(f"set constant: {param.description()} = {val}")
+        return param
+
+    # -- I/O links -----------------------------------------------------------------
+    def link_io_buffer(self, varname, buff=None, output=False):
+        """link a variable to a host/device column (reference :526-621)"""
+        self._validate_name(varname, raise_exception=True)
+        var = self.get_variable(varname, expr_only=True)
+        if var is None:
+            var = self.add_variable(varname)
+        io_managers = self._output_managers if output else self._input_managers
+        if not isinstance(var, ProcChainVar):
+            raise ProcessingChainError("Must link an input buffer to a processing chain variable")
+
+        if buff is None:
+            dtype = var.dtype
+            n = self._buffer_len
+            if isinstance(var.grid, CoordinateGrid) and not var.is_coord:
+                if var.vector_len is None:
+                    buff = tables.WaveformTable(size=n, wf_len=var.shape[0], dtype=dtype)
+                else:
+                    buff = tables.WaveformTable(size=n, values=tables.VectorOfVectors(shape_guess=(n, 0), dtype=dtype))
+            elif len(var.shape) == 0:
+                buff = tables.Array(shape=(n,), dtype=dtype)
+            elif var.vector_len is not None:
+                buff = tables.VectorOfVectors(shape_guess=(n, 0), dtype=dtype)
+            else:
+                buff = tables.ArrayOfEqualSizedArrays(shape=(n, *var.shape), dtype=dtype)
+
+        if varname in io_managers:
+            io_managers[varname].set_buffer(buff)
+            return buff
+
+        kind = kind_of(buff)
+        if kind in ("numpy", "tensor"):
+            man = NumpyIOManager(buff, var)
+        elif kind == "wftable":
+            man = WaveformIOManager(buff, var)
+        elif kind == "vov":
+            man = VectorOfVectorsIOManager(buff, var)
+        elif kind in ("array", "aoesa"):
+            man = ArrayIOManager(buff, var)
+        else:
+            raise ProcessingChainError("Could not link input buffer of unknown type", str(buff))
+        log.debug(f"added {'output' if output else 'input'} buffer: {man}")
+        io_managers[varname] = man
+        return buff
+
+    def link_input_buffer(self, varname, buff=None):
+        return self.link_io_buffer(varname, buff, output=False)
+
+    def link_output_buffer(self, varname, buff=None):
+        return self.link_io_buffer(varname, buff, output=True)
+
+    # -- processors ----------------------------------------------------------------
+    def add_processor(self, func, *args, signature=None, types=None, coord_grid=None) -> None:
+        """bind a processor to variables / constants (reference :635-663)"""
+        params = []
+        kw_params = {}
+        for param in args:
+            if isinstance(param, str):
+                param = self.get_variable(param)
+            if isinstance(param, MutableMapping):
+                kw_params.update(param)
+            else:
+                params.append(param)
+        if coord_grid is not None:
+            coord_grid = CoordinateGrid(coord_grid)
+        proc_man = ProcessorManager(self, func, params, kw_params, signature, types, coord_grid)
+        self._proc_managers.append(proc_man)
+        log.debug(f"added processor: {proc_man}")
+
+    # -- execution -----------------------------------------------------------------
+    def execute(self, start: int = 0, stop: int = None) -> None:
+        """run the chain over rows [start, stop) of the linked buffers, block by block"""
+        if stop is None:
+            stop = self._buffer_len
+        if self._fused is not None and self._fused.can_run(self):
+            self._fused.execute(self, start, stop)
+            return
+        with torch.cuda.device(self.device):
+            for i in range(start, stop, self._block_width):
+                try:
+                    self._execute_procs(i, min(i + self._block_width, stop))
+                except EndExecute:
+                    break
+            torch.cuda.current_stream(self.device).synchronize()
+
+    def __call__(self, tb_in, out=None):
+        """process a whole table (reference :675-716)"""
+        self._buffer_len = len(tb_in)
+        for varname in self._input_managers:
+            if varname not in tb_in:
+                raise ProcessingChainError(f"Require column {varname} in tb_in")
+            self.link_input_buffer(varname, tb_in[varname])
+        if out is None:
+            out = tables.Table({v: self.link_output_buffer(v) for v in self._output_managers}, size=len(tb_in))
+        else:
+            for varname in self._output_managers:
+                if varname not in out:
+                    raise ProcessingChainError(f"Require column {varname} in out")
+                self.link_output_buffer(varname, out[varname])
+        self.execute()
+        return out
+
+    def _execute_procs(self, begin: int, end: int) -> None:
+        """one block: copy in, launch every processor, copy out, raise recorded DSPFatal"""
+        for in_man in self._input_managers.values():
+            in_man.read(begin, end)
+        current = None
+        try:
+            for proc_man in self._proc_managers:
+                current = proc_man
+                proc_man.execute()
+        except DSPFatal as e:
+            e.processor = str(current)
+            e.wf_range = (begin, end)
+            raise e
+        self.stats["blocks"] += 1
+        self._raise_recorded_fatal(begin, end)
+        for out_man in self._output_managers.values():
+            out_man.write(begin, end)
+
+    def _new_fatal_slot(self, owner) -> torch.Tensor:
+        k = len(self._fatal_owner)
+        if k >= MAX_FATAL_SLOTS:
+            k = MAX_FATAL_SLOTS - 1
+        else:
+            self._fatal_owner.append(owner)
+        return self.fatal[k]
+
+    def _raise_recorded_fatal(self, begin, end) -> None:
+        n = max(1, len(self._fatal_owner))
+        rec = self.fatal[:n].cpu()  # one small synchronising read per block
+        hit = torch.nonzero(rec[:, 0])
+        if hit.numel():
+            k = int(hit[0])
+            code = int(rec[k, 0])
+            self.fatal.zero_()
+            e = DSPFatal(fatal_message(code))
+            e.code = code
+            e.wf_range = (begin, end)
+            if k < len(self._fatal_owner):
+                e.processor = str(self._fatal_owner[k])
+            raise e
+
+    def get_timing(self) -> dict[str, float]:
+        """cumulative host-side launch time per processor (reference :1188-1190); with
+        ``DSPEED_B200_TIMING=1`` launches are synchronised so this is device time"""
+        return {str(proc): proc.time_total for proc in self._proc_managers}
+
+    def __str__(self) -> str:
+        return ("Input variables:\n  " + "\n  ".join(str(m) for m in self._input_managers.values())
+                + "\nProcessors:\n  " + "\n  ".join(str(m) for m in self._proc_managers)
+                + "\nOutput variables:\n  " + "\n  ".join(str(m) for m in self._output_managers.values()))
+
+    # -- expression grammar (reference :718-1130) ------------------------------------
+    def get_variable(self, expr: str, get_names_only: bool = False, expr_only: bool = False) -> Any:
+        """Parse ``expr``: a variable name (created on first use), ``name(shape, dtype,
+        ...)`` declarations, arithmetic / comparison / ternary expressions (each emits a
+        processor), ``wf[a:b:c]`` views, ``round/floor/ceil/trunc/astype/where/isnan/
+        isfinite/len`` calls, unit names, ``np.pi``-style constants and ``kw=expr``."""
+        names: list[str] = []
+        try:
+            stmt = ast.parse(expr).body[0]
+            var = self._parse_expr(stmt.value, expr, get_names_only, names)
+        except ProcessingChainError:
+            raise
+        except Exception as e:
+            raise ProcessingChainError("Could not parse expression:\n  " + expr) from e
+        if get_names_only:
+            return names
+        if isinstance(stmt, ast.Expr):
+            return var
+        if isinstance(stmt, ast.Assign) and len(stmt.targets) == 1:
+            if expr_only:
+                raise ProcessingChainError("kwarg assignment is not allowed in this context\n  " + expr)
+            return {stmt.targets[0].id: var}
+        raise ProcessingChainError("Could not parse expression:\n  " + expr)
+
+    def _emit(self, func, params) -> None:
+        proc_man = ProcessorManager(self, func, params)
+        self._proc_managers.append(proc_man)
+        log.debug(f"added processor: {proc_man}")
+
+    def _parse_expr(self, node, expr: str, dry_run: bool, var_name_list: list[str]) -> Any:
+        if node is None:
+            return None
+
+        if isinstance(node, ast.List):
+            return np.array(ast.literal_eval(expr[node.col_offset : node.end_col_offset]))
+
+        if isinstance(node, ast.Constant):
+            return node.value
+
+        if isinstance(node, ast.Name):
+            if node.id in ureg:
+                return ureg(node.id)
+            var_name_list.append(node.id)
+            if dry_run:
+                return None
+            val = self._vars_dict.get(node.id, None)
+            if val is None:
+                val = self.add_variable(node.id)
+            return val
+
+        if isinstance(node, ast.BinOp):
+            lhs = self._parse_expr(node.left, expr, dry_run, var_name_list)
+            rhs = self._parse_expr(node.right, expr, dry_run, var_name_list)
+            if rhs is None or lhs is None:
+                return None
+            op, op_form = ast_ops_dict[type(node.op)]
+            lv, rv = isinstance(lhs, ProcChainVar), isinstance(rhs, ProcChainVar)
+            if not (lv or rv):
+                return _fold_constant(op, lhs, rhs)
+            name = "(" + op_form.format(str(lhs), str(rhs)) + ")"
+            if lv and rv:
+                if is_in_registry(lhs.unit) and is_in_registry(rhs.unit):
+                    unit = op(Quantity(1.0, as_unit(lhs.unit)), Quantity(1.0, as_unit(rhs.unit))).u
+                    if unit.dimensionless:
+                        unit = None
+                elif lhs.unit is not None and rhs.unit is not None:
+                    if type(node.op) in (ast.Mult, ast.Div, ast.FloorDiv):
+                        unit = op_form.format(str(lhs.unit), str(rhs.unit))
+                    else:
+                        unit = str(lhs.unit)
+                elif lhs.unit is not None:
+                    unit = lhs.unit
+                else:
+                    unit = rhs.unit
+                out = ProcChainVar(self, name, grid=None if lhs.is_coord and rhs.is_coord else auto,
+                                   is_coord=(False if lhs.is_coord is True and rhs.is_coord is True else auto),
+                                   unit=unit)
+            elif lv:
+                out = ProcChainVar(self, name, unit=lhs.unit, is_coord=lhs.is_coord)
+            else:
+                out = ProcChainVar(self, name, unit=rhs.unit, is_coord=rhs.is_coord)
+            self._emit(op, [lhs, rhs, out])
+            return out
+
+        if isinstance(node, ast.UnaryOp):
+            operand = self._parse_expr(node.operand, expr, dry_run, var_name_list)
+            if operand is None:
+                return None
+            op, op_form = ast_ops_dict[type(node.op)]
+            if isinstance(operand, ProcChainVar):
+                out = ProcChainVar(self, "(" + op_form.format(str(operand)) + ")", operand.shape, operand.dtype,
+                                   operand.grid, operand.unit, operand.is_coord)
+                self._emit(op, [operand, out])
+                return out
+            return op(operand)
+
+        if isinstance(node, ast.Compare):
+            lhs = self._parse_expr(node.left, expr, dry_run, var_name_list)
+            if len(node.comparators) != 1:
+                raise ProcessingChainError("Compound comparisons are not supported.")
+            rhs = self._parse_expr(node.comparators[0], expr, dry_run, var_name_list)
+            if rhs is None or lhs is None:
+                return None
+            op, op_form = ast_ops_dict[type(node.ops[0])]
+            if not (isinstance(lhs, ProcChainVar) or isinstance(rhs, ProcChainVar)):
+                return _fold_constant(op, lhs, rhs)
+            out = ProcChainVar(self, "(" + op_form.format(str(lhs), str(rhs)) + ")")
+            self._emit(op, [lhs, rhs, out])
+            return out
+
+        if isinstance(node, ast.Subscript):
+            return self._parse_subscript(node, expr, dry_run, var_name_list)
+
+        if isinstance(node, ast.IfExp):
+            condition = self._parse_expr(node.test, expr, dry_run, var_name_list)
+            a = self._parse_expr(node.body, expr, dry_run, var_name_list)
+            b = self._parse_expr(node.orelse, expr, dry_run, var_name_list)
+            return self._where(condition, a, b)
+
+        if isinstance(node, ast.Attribute):
+            module = expr[node.value.col_offset : node.value.end_col_offset]
+            if module in self.module_list:
+                attr = getattr(self.module_list[module], node.attr)
+                if not isinstance(attr, Real):
+                    raise ProcessingChainError(f"Attribute {node.attr} from {module} is not an int or float...")
+                return attr
+            val = self._parse_expr(node.value, expr, dry_run, var_name_list)
+            if val is None:
+                return None
+            return getattr(val, node.attr)
+
+        if isinstance(node, ast.Call):
+            func = self.func_list.get(node.func.id, None)
+            args = [self._parse_expr(arg, expr, dry_run, var_name_list) for arg in node.args]
+            kwargs = {kw.arg: self._parse_expr(kw.value, expr, dry_run, var_name_list) for kw in node.keywords}
+            if func is not None:
+                return func(self, *args, **kwargs) if not dry_run else None
+            if self._validate_name(node.func.id):
+                var_name = node.func.id
+                var_name_list.append(var_name)
+                if var_name in self._vars_dict:
+                    var = self._vars_dict[var_name]
+                    var.update_auto(*args, **kwargs)
+                    return var
+                if not dry_run:
+                    return self.add_variable(var_name, **{**_decl_args(args), **kwargs})
+                return None
+            raise ProcessingChainError(f"do not recognize call to {node.func.id}")
+
+        raise ProcessingChainError(f"cannot parse AST nodes of type {type(node).__name__}")
+
+    def _parse_subscript(self, node, expr, dry_run, var_name_list):
+        """``wf[i]`` / ``wf[a:b:c]``: views sharing the parent's buffer, with the grid
+        period scaled by the step and the offset shifted by the start (reference :947-1071)"""
+        val = self._parse_expr(node.value, expr, dry_run, var_name_list)
+        if val is None:
+            return None
+        if not isinstance(val, ProcChainVar) or not len(val.shape) > 0:
+            raise ProcessingChainError("Cannot apply subscript to", node.value)
+
+        def get_index(slice_value, var_len=None):
+            ret = self._parse_expr(slice_value, expr, dry_run, var_name_list)
+            if ret is None or isinstance(ret, ProcChainVar):
+                return ret
+            if isinstance(ret, Quantity):
+                ret = float(ret / val.period)
+            if isinstance(ret, Real):
+                round_ret = int(round(ret))
+                if abs(ret - round_ret) > 0.0001:
+                    log.warning(f"slice value is non-integer. Rounding to {round_ret}")
+                ret = round_ret
+            if ret < 0 and var_len is not None:
+                ret = self.get_variable(f"{var_len}{ret}")
+            return ret
+
+        if isinstance(node.slice, ast.Tuple):
+            raise ProcessingChainError("Tuple still isn't implemented...")
+
+        if not isinstance(node.slice, ast.Slice):
+            index = get_index(node.slice, val.vector_len)
+            if isinstance(index, int):
+                out_buf = val.buffer[..., index]
+                out_name = f"{str(val)}[{index}]"
+                out_grid = val.grid if val.is_coord else None
+            else:
+                out = ProcChainVar(self, name=f"{str(val)}[{index}]", shape=(), dtype=val.dtype,
+                                   grid=val.grid if val.is_coord else None, unit=val.unit, is_coord=val.is_coord)
+                default = np.nan if np.issubdtype(val.dtype, np.floating) else np.iinfo(val.dtype).max
+                self._emit(numpy_bridge.get_default, [val, index, default, out])
+                return out
+        else:
+            sl = slice(get_index(node.slice.lower), get_index(node.slice.upper), get_index(node.slice.step))
+            if any(isinstance(x, ProcChainVar) for x in (sl.start, sl.stop, sl.step)):
+                raise ProcessingChainError("Slice values must be constants")
+            out_buf = val.buffer[..., sl]
+            out_name = "{}[{}:{}{}]".format(str(val), "" if sl.start is None else str(sl.start),
+                                            "" if sl.stop is None else str(sl.stop),
+                                            "" if sl.step is None else ":" + str(sl.step))
+            if val.grid is None:
+                out_grid = None
+            else:
+                pd = val.period
+                if sl.step is not None:
+                    pd = pd * sl.step
+                off = val.offset
+                if sl.start is not None and sl.start > 0:
+                    start = sl.start * val.period
+                    if isinstance(off, ProcChainVar):
+                        new_off = ProcChainVar(self, name=f"({str(off)}+{str(start)})", is_coord=True)
+                        self._emit(np.add, [off, start, new_off])
+                        off = new_off
+                    else:
+                        off = off + start
+                out_grid = CoordinateGrid(pd, off)
+
+        out = ProcChainVar(self, out_name, shape=tuple(out_buf.shape[1:]), dtype=val.dtype, grid=out_grid,
+                           unit=val.unit, is_coord=val.is_coord)
+        out._buffer = [(out_buf, val._buffer[0][1])] if out.is_coord else out_buf
+        out.view_of = (val, node.slice)
+        return out
+
+    def _validate_name(self, name: str, raise_exception: bool = False) -> bool:
+        isgood = bool(re.match(r"\A\w+$", name)) and name not in self.func_list and name not in ureg \
+            and name not in self.module_list
+        if raise_exception and not isgood:
+            raise ProcessingChainError(f"{name} is not a valid variable name")
+        return isgood
+
+    # -- helper functions callable inside expressions (reference :1177-1482) -----------
+    def _length(self, var):
+        if var is None:
+            return None
+        if not isinstance(var, ProcChainVar):
+            raise ProcessingChainError(f"cannot call len() on {var}")
+        if var.vector_len is not None:
+            return var.vector_len
+        if not len(var.shape) == 1:
+            raise ProcessingChainError(f"{var} has wrong number of dims")
+        return var.shape[0]
+
+    def _round(self, var, to_nearest=1, dtype=None, mode="round"):
+        """round a value / a coordinate onto a grid (reference :1193-1266)"""
+        fun = getattr(numpy_bridge, f"{mode}_to_nearest", None)
+        if fun is None:
+            raise ProcessingChainError("Mode must be round, floor, ceil or trunc")
+        if var is None:
+            return None
+        to_nearest = from_foreign(to_nearest)
+        if not isinstance(var, ProcChainVar):
+            host = numpy_bridge.HOST_ROUNDERS[mode]
+            if isinstance(var, Quantity) and isinstance(to_nearest, Quantity):
+                return host(float(var / Quantity(1.0, to_nearest.u)), to_nearest.m) * Quantity(1.0, to_nearest.u)
+            if isinstance(var, Quantity):
+                var = float(var)
+            return host(var, to_nearest)
+        name = f"{mode}({var}, {to_nearest})"
+        dtype = np.dtype(dtype) if dtype is not None else var.dtype
+        if var.is_coord:
+            if isinstance(to_nearest, Real):
+                grid = CoordinateGrid(var.grid.period * to_nearest, var.grid.offset)
+            elif isinstance(to_nearest, (Unit, Quantity)):
+                grid = CoordinateGrid(to_nearest, var.grid.offset)
+            else:
+                grid = to_nearest
+            out = ProcChainVar(self, name, var.shape, dtype, grid, var.unit, var.is_coord)
+            conversion_manager = UnitConversionManager(var, grid, mode=mode, out_dtype=dtype)
+            out._buffer = conversion_manager.out_buffer
+            self._proc_managers.append(conversion_manager)
+            log.debug(f"added conversion: {conversion_manager}")
+        else:
+            out = ProcChainVar(self, name, var.shape, dtype, var.grid, var.unit, var.is_coord)
+            self.add_processor(fun, var, to_nearest, out)
+        return out
+
+    def _astype(self, var, dtype):
+        dtype = np.dtype(dtype)
+        if var is None:
+            return None
+        if not isinstance(var, ProcChainVar):
+            raise ProcessingChainError(f"cannot call astype() on {var}")
+        out = ProcChainVar(self, f"{var}.astype(`{dtype.char}`)", var.shape, dtype, var.grid, var.unit, var.is_coord)
+        self._emit(numpy_bridge.make_astype(var.dtype, dtype), [var, out])
+        return out
+
+    def _isnan(self, var):
+        if var is None:
+            return None
+        if not isinstance(var, ProcChainVar):
+            return np.isnan(var)
+        out = ProcChainVar(self, f"isnan({var})", var.shape, "bool", var.grid, var.unit, var.is_coord)
+        self._emit(np.isnan, [var, out])
+        return out
+
+    def _isfinite(self, var):
+        if var is None:
+            return None
+        if not isinstance(var, ProcChainVar):
+            return np.isfinite(var)
+        out = ProcChainVar(self, f"isfinite({var})", var.shape, "bool", var.grid, var.unit, var.is_coord)
+        self._emit(np.isfinite, [var, out])
+        return out
+
+    def _where(self, condition, a, b, dtype=auto):
+        """``where(cond, a, b)`` / ``a if cond else b`` with unit reconciliation
+        (reference :1345-1442)"""
+        if condition is None:
+            return None
+        if not (isinstance(condition, ProcChainVar) and condition.dtype == "?"):
+            raise ProcessingChainError(f"{condition} must be a boolean variable")
+        a, b = from_foreign(a), from_foreign(b)
+        name = f"where({condition}, {a}, {b})"
+        av, bv = isinstance(a, ProcChainVar), isinstance(b, ProcChainVar)
+        if av and bv:
+            if a.period != b.period:
+                raise ProcessingChainError(f"Cannot select between {a} and {b} with different periods")
+            if a.is_coord != b.is_coord:
+                raise ProcessingChainError(f"Cannot select between {a} and {b} with different is_coord")
+            is_coord = a.is_coord
+            if a.offset == b.offset:
+                grid = a.grid
+            else:
+                grid = CoordinateGrid(a.period, self._where(condition, a.offset, b.offset))
+            unit_a = as_unit(a.unit) if is_in_registry(a.unit) else a.unit
+            unit_b = as_unit(b.unit) if is_in_registry(b.unit) else b.unit
+            if unit_a == unit_b or not unit_b:
+                unit = unit_a
+            elif not unit_a:
+                unit = unit_b
+            else:
+                raise ProcessingChainError(f"{a} and {b} do not have compatible units")
+        elif av or bv:
+            var, const = (a, b) if av else (b, a)
+            grid = var.grid
+            is_coord = var.is_coord
+            if not var.unit:
+                unit = None
+            elif not isinstance(const, Quantity):
+                unit = var.unit
+            elif is_in_registry(var.unit):
+                unit = var.period if is_coord else Quantity(1, as_unit(var.unit))
+                if av:
+                    b = float(const / (1 * unit))
+                else:
+                    a = float(const / (1 * unit))
+            else:
+                raise ProcessingChainError(f"{a} and {b} do not have compatible units")
+        else:
+            grid = None
+            is_coord = False
+            if isinstance(a, Quantity) and isinstance(b, Quantity):
+                unit = a.u
+                b = float(b / Quantity(1.0, unit))
+                a = a.m
+            elif isinstance(a, Quantity):
+                unit, a = a.u, a.m
+            elif isinstance(b, Quantity):
+                unit, b = b.u, b.m
+            else:
+                unit = None
+        out = ProcChainVar(self, name, auto, dtype, grid, unit, is_coord)
+        self._emit(numpy_bridge.where, [condition, a, b, out])
+        return out
+
+    def _loadlh5(self, path_to_file, path_in_file):
+        try:
+            import lh5
+        except ImportError as e:
+            raise ProcessingChainError("loadlh5() needs the legend-lh5io package") from e
+        try:
+            loaded = lh5.read(path_in_file, path_to_file)
+            return loaded.value if hasattr(loaded, "value") else loaded.nda
+        except (ValueError, OSError):
+            raise ProcessingChainError(f"LH5 file not found: {path_to_file}")
+
+    func_list = {
+        "len": _length,
+        "isfinite": _isfinite,
+        "isnan": _isnan,
+        "round": partial(_round, mode="round"),
+        "floor": partial(_round, mode="floor"),
+        "ceil": partial(_round, mode="ceil"),
+        "trunc": partial(_round, mode="trunc"),
+        "astype": _astype,
+        "where": _where,
+        "loadlh5": _loadlh5,
+    }
+    module_list = {"np": np, "numpy": np}
+
+
+def _decl_args(args) -> dict:
+    """``name(shape, dtype, grid, unit, is_coord)``: positional declaration arguments follow
+    the ProcChainVar / update_auto order (the reference forwards them positionally to
+    add_variable, whose order differs -- reference :1117-1120); map them to keywords."""
+    return dict(zip(["shape", "dtype", "grid", "unit", "is_coord"], args))
+
+
+def _fold_constant(op, lhs, rhs):
+    """binary op on two constants, evaluated at build time (reference :839-845)"""
+    lhs, rhs = from_foreign(lhs), from_foreign(rhs)
+    if isinstance(lhs, (Quantity, Unit)) or isinstance(rhs, (Quantity, Unit)):
+        pyop = {np.add: lambda a, b: a + b, np.subtract: lambda a, b: a - b, np.multiply: lambda a, b: a * b,
+                np.divide: lambda a, b: a / b, np.floor_divide: lambda a, b: a // b,
+                np.equal: lambda a, b: a == b, np.not_equal: lambda a, b: not (a == b),
+                np.less: lambda a, b: a < b, np.less_equal: lambda a, b: a <= b,
+                np.greater: lambda a, b: a > b, np.greater_equal: lambda a, b: a >= b}[op]
+        ret = pyop(lhs, rhs)
+        if isinstance(ret, Unit):
+            ret = Quantity(1.0, ret)
+        if isinstance(ret, Quantity) and ret.u.dimensionless:
+            ret = float(ret)
+        return ret
+    return op(lhs, rhs)
+
+
+# ======================================================================================
+# processor binding
+# ======================================================================================
+class ProcessorManager:
+    """Freezes one processor call: picks the type loop, solves the gufunc dimensions,
+    deduces ``auto`` variables, converts unit-carrying scalars to samples and binds the
+    device buffers -- the launch descriptor of a block step (reference :1485-1803)."""
+
+    @dataclass
+    class DimInfo:
+        length: int
+        grid: Any
+
+    def __init__(self, proc_chain, func, params, kw_params=None, signature=None, types=None, grid=None) -> None:
+        assert isinstance(proc_chain, ProcessingChain) and callable(func) and isinstance(params, Collection)
+        kw_params = kw_params or {}
+        self.proc_chain = proc_chain
+        self.params = [from_foreign(p) for p in params]
+        self.kw_params = {k: from_foreign(v) for k, v in kw_params.items()}
+        self.args: list = []
+        self.kwargs: dict = {}
+        self.time_total = 0.0
+        self.n_calls = 0
+
+        # the device implementation behind this callable (raises if there is none)
+        self.host_func = func
+        self.processor = numpy_bridge.device_equivalent(func, signature)
+
+        self.signature = signature if signature is not None else getattr(self.processor, "signature", None)
+        if self.signature is None:
+            self.signature = ",".join(["()"] * self.processor.nin) + "->" + ",".join(["()"] * self.processor.nout)
+
+        if types is None:
+            types = list(getattr(self.processor, "types", None) or [])
+        if not types:
+            raise ProcessingChainError(f"could not find a type signature list for {func.__name__}. "
+                                       "Please supply a valid list of types.")
+        if isinstance(types, str) or not isinstance(types, Collection):
+            types = [types]
+        found_types = [t.replace("->", "") for t in types]
+
+        dims_list = re.findall(r"\((.*?)\)", self.signature)
+        all_params = list(it.chain(self.params, self.kw_params.values()))
+        if len(dims_list) != len(all_params):
+            raise ProcessingChainError(
+                f"expected {len(dims_list)} arguments from signature {self.signature}; found "
+                f"{len(all_params)}: ({', '.join(str(p) for p in all_params)})")
+
+        dims_dict: dict[str, ProcessorManager.DimInfo] = {}
+        outerdims: list[ProcessorManager.DimInfo] = []
+        bw = proc_chain._block_width
+
+        # pass 1: restrict the type loop and collect dimension lengths / grids
+        for ipar, (dims, param) in enumerate(zip(dims_list, all_params)):
+            if not isinstance(param, (ProcChainVar, np.ndarray)):
+                continue
+            if param.dtype is not auto:
+                ch = np.dtype(param.dtype).char
+                found_types = [t for t in found_types if np.can_cast(ch, t[ipar])]
+            if param.shape is auto:
+                continue
+            fun_dims = list(outerdims) + [d.strip() for d in dims.split(",") if d.strip()]
+            arr_dims = list(param.shape)
+            arr_grid = param.grid if (isinstance(param, ProcChainVar) and param.grid is not auto
+                                      and not param.is_coord) else None
+            if not grid:
+                grid = arr_grid
+            for i in range(max(len(fun_dims), len(arr_dims))):
+                fd = fun_dims[-i - 1] if i < len(fun_dims) else None
+                ad = arr_dims[-i - 1] if i < len(arr_dims) else (bw if i == len(arr_dims) else None)
+                if isinstance(fd, str):
+                    if fd in dims_dict:
+                        this = dims_dict[fd]
+                        if not ad or this.length != ad:
+                            raise ProcessingChainError(
+                                f"failed to broadcast array dimensions for {func.__name__}. Could not find "
+                                f"consistent value for dimension {fd}")
+                        if not this.grid:
+                            this.grid = arr_grid
+                    else:
+                        dims_dict[fd] = self.DimInfo(ad, arr_grid)
+                elif not fd:
+                    outerdims.insert(0, self.DimInfo(ad, arr_grid))
+                elif not ad:
+                    continue
+                elif fd.length != ad:
+                    if len(fun_dims) > len(arr_dims):
+                        arr_dims.insert(len(arr_dims) - i, 1)
+                    elif len(fun_dims) < len(arr_dims):
+                        outerdims.insert(len(fun_dims) - i, self.DimInfo(ad, arr_grid))
+                        fun_dims.insert(len(fun_dims) - i, ad)
+                    else:
+                        raise ProcessingChainError(
+                            f"failed to broadcast array dimensions for {func.__name__}. Input arrays do not "
+                            f"have consistent outer dimensions; found {tuple(arr_dims)} for {param}")
+                elif not fd.grid:
+                    outerdims[len(fun_dims) - 1 - i].grid = arr_grid
+                arr_grid = None  # only the innermost dimension carries a grid
+
+        if not found_types:
+            raise ProcessingChainError(
+                f"could not find a type signature matching the types of the variables given for {self} "
+                f"(types: {types})")
+        self.types = [np.dtype(t) for t in found_types[0]]
+
+        if not grid:
+            for param in all_params:
+                if isinstance(param, ProcChainVar) and param.is_coord is True:
+                    grid = param.grid
+                    break
+        self.grid = grid
+
+        # pass 2: deduce auto variables, convert scalars, bind buffers
+        named = it.chain(zip(it.repeat(None), self.params), self.kw_params.items())
+        for (arg_name, param), dims, dtype in zip(named, dims_list, self.types):
+            dim_list = list(outerdims)
+            for d in (x.strip() for x in dims.split(",")):
+                if not d:
+                    continue
+                if d not in dims_dict:
+                    if isinstance(param, np.ndarray):
+                        dims_dict[d] = self.DimInfo(len(param), None)
+                    else:
+                        raise ProcessingChainError(f"could not deduce dimension {d} for {param}")
+                dim_list.append(dims_dict[d])
+            shape = tuple(d.length for d in dim_list)
+            this_grid = dim_list[-1].grid if dim_list else None
+
+            if isinstance(param, ProcChainVar):
+                unit = None
+                is_coord = False
+                if param.is_coord is True and grid is not None:
+                    unit = str(grid.period.u)
+                    this_grid = grid
+                elif (is_in_registry(param.unit) and grid is not None
+                      and ureg.is_compatible_with(grid.period, param.unit)):
+                    is_coord = True
+                    this_grid = grid
+                param.update_auto(shape=shape, dtype=np.dtype(dtype), grid=this_grid, unit=unit, is_coord=is_coord)
+                buf = param.get_buffer(grid if param.is_coord else None)
+                arshape = list(buf.shape)
+                for idim in range(-1, -1 - len(shape), -1):
+                    if len(arshape) < -idim or arshape[idim] != shape[idim]:
+                        arshape.insert(len(arshape) + idim + 1, 1)
+                bound = buf.reshape(arshape) if list(buf.shape) != arshape else buf
+            elif isinstance(param, str):
+                bound = param
+                if np.issubdtype(dtype, np.integer):
+                    try:
+                        bound = np.frombuffer(param.encode("ascii"), dtype).reshape(shape)
+                    except ValueError:
+                        raise ProcessingChainError(
+                            f"could not convert string '{param}' into byte-array of type {dtype} and shape {shape}")
+                    if bound.size == 1:
+                        bound = int(bound.reshape(-1)[0])
+            elif isinstance(param, np.ndarray):
+                bound = torch.from_numpy(np.ascontiguousarray(param.astype(dtype))).to(proc_chain.device)
+            elif param is not None:
+                if isinstance(param, Unit):
+                    param = Quantity(1.0, param)
+                if isinstance(param, Quantity):
+                    if param.u.dimensionless:
+                        param = float(param)
+                    elif not isinstance(grid, CoordinateGrid):
+                        raise ProcessingChainError(
+                            f"could not find valid conversion for {param}; CoordinateGrid is {grid}")
+                    else:
+                        try:
+                            param = to_period_units(param, grid.period)
+                        except ValueError as e:
+                            raise ProcessingChainError(str(e)) from e
+                if np.issubdtype(dtype, np.integer):
+                    bound = dtype.type(np.round(param))
+                else:
+                    bound = dtype.type(param)
+            else:
+                bound = None
+
+            if arg_name is None:
+                self.args.append(bound)
+            else:
+                self.kwargs[arg_name] = bound
+
+        self._sync_timing = bool(int(__import__("os").environ.get("DSPEED_B200_TIMING", "0")))
+        self.fatal = proc_chain._new_fatal_slot(self)
+
+    def execute(self) -> None:
+        start = time.perf_counter()
+        self.processor(*self.args, fatal=self.fatal, **self.kwargs)
+        if self._sync_timing:
+            torch.cuda.current_stream(self.proc_chain.device).synchronize()
+        self.time_total += time.perf_counter() - start
+        self.n_calls += 1
+        self.proc_chain.stats["launches"] += getattr(self.processor, "launches_per_call", 1)
+
+    def __str__(self) -> str:
+        return (self.host_func.__name__ + "("
+                + ", ".join([str(p) for p in self.params] + [f"{k}={v}" for k, v in self.kw_params.items()]) + ")")
+
+
+class UnitConversionManager(ProcessorManager):
+    """Converts a coordinate variable between unit systems / grids:
+    ``(buf + offset_in) * ratio - offset_out`` in float64, optionally rounded
+    (reference :1806-1908 and processors/unit_conversion.py:16-78)."""
+
+    def __init__(self, var: ProcChainVar, unit, mode=None, out_dtype=None) -> None:
+        self.proc_chain = var.proc_chain
+        if mode not in (None, "round", "floor", "ceil", "trunc"):
+            raise ProcessingChainError("Mode must be round, floor, ceil or trunc")
+        self.mode = mode
+        self.host_func = numpy_bridge.convert
+        self.processor = numpy_bridge.convert
+
+        to_offset = 0
+        if isinstance(unit, CoordinateGrid):
+            to_offset = unit.get_offset()
+            unit = unit.period
+        if isinstance(var._buffer, list):
+            from_buffer, from_unit = var._buffer[0]
+        else:
+            from_buffer = var._buffer
+            from_unit = var.unit
+            if isinstance(from_unit, str) and from_unit in ureg:
+                from_unit = ureg.Quantity(from_unit)
+
+        self.params = [var]
+        self.kw_params = {"from": from_unit, "to": unit}
+
+        if isinstance(from_unit, CoordinateGrid):
+            ratio = from_unit.get_period(unit)
+            from_offset = from_unit.get_offset()
+        elif isinstance(from_unit, (Unit, Quantity)):
+            if isinstance(unit, str):
+                unit = ureg.Quantity(unit)
+            from_q = from_unit if isinstance(from_unit, Quantity) else Quantity(1.0, from_unit)
+            to_q = unit if isinstance(unit, Quantity) else Quantity(1.0, unit)
+            ratio = float(from_q / to_q)
+            from_offset = 0
+        else:
+            ratio = 1 / float(unit) if not isinstance(unit, Quantity) else 1.0 / unit.m
+            from_offset = 0
+
+        def expand(off):
+            if isinstance(off, torch.Tensor):
+                return off.reshape(off.shape[0], *[1] * (from_buffer.ndim - off.ndim))
+            return off
+
+        self.in_is_int = not np.issubdtype(var.dtype, np.floating)
+        odt = np.dtype(out_dtype) if out_dtype is not None else var.dtype
+        self.out_buffer = torch.zeros_like(from_buffer, dtype=_np2t(odt))
+        self.args = [from_buffer, expand(from_offset), expand(to_offset), ratio, self.out_buffer]
+        self.kwargs = {}
+        self.time_total = 0.0
+        self.n_calls = 0
+        self._sync_timing = False
+        self.fatal = self.proc_chain._new_fatal_slot(self)
+
+    def execute(self) -> None:
+        start = time.perf_counter()
+        numpy_bridge.convert(*self.args, mode=self.mode, int_check=self.in_is_int and self.mode is None,
+                             fatal=self.fatal)
+        self.time_total += time.perf_counter() - start
+        self.n_calls += 1
+        self.proc_chain.stats["launches"] += 1
+
+    def __str__(self) -> str:
+        return f"convert({self.params[0]}, from={self.kw_params['from']}, to={self.kw_params['to']})"
+
+
+# ======================================================================================
+# I/O managers: chunk column <-> device block buffer
+# ======================================================================================
+def _as_tensor(x) -> torch.Tensor:
+    """zero-copy torch view of a host numpy array / pass-through for tensors"""
+    if isinstance(x, torch.Tensor):
+        return x
+    return torch.from_numpy(x)
+
+
+class IOManager:
+    def _count(self, nbytes, out):
+        self.var.proc_chain.stats["d2h_bytes" if out else "h2d_bytes"] += int(nbytes)
+
+
+class NumpyIOManager(IOManager):
+    """plain numpy array or torch tensor column (reference :1942-1981)"""
+
+    def __init__(self, io_buf, var: ProcChainVar) -> None:
+        var.update_auto(dtype=tables.np_dtype_of(io_buf), shape=tuple(io_buf.shape[1:]))
+        self.var = var
+        self.raw_var = var.buffer
+        self.set_buffer(io_buf)
+
+    def set_buffer(self, io_buf) -> None:
+        if not isinstance(io_buf, (np.ndarray, torch.Tensor)):
+            raise ProcessingChainError(f"{self.var} must be set using a numpy array or a torch tensor")
+        if self.var.shape != tuple(io_buf.shape[1:]) or self.var.dtype != tables.np_dtype_of(io_buf):
+            raise ProcessingChainError(f"array<{tuple(io_buf.shape)}>{{{tables.np_dtype_of(io_buf)}}} "
+                                       f"is not compatible with variable {self.var}")
+        self.io_buf = io_buf
+        self.io_t = _as_tensor(io_buf)
+
+    def read(self, start: int, end: int) -> None:
+        if start >= self.io_t.shape[0]:
+            raise EndExecute
+        end = min(end, self.io_t.shape[0])
+        src = self.io_t[start:end]
+        self.raw_var[0 : end - start].copy_(src, non_blocking=True)
+        if not src.is_cuda:
+            self._count(src.numel() * src.element_size(), False)
+
+    def write(self, start: int, end: int) -> None:
+        dst = self.io_t[start:end]
+        dst.copy_(self.raw_var[0 : end - start] if not self.var.is_const else self.raw_var.expand(end - start, *self.var.shape),
+                  non_blocking=True)
+        if not dst.is_cuda:
+            self._count(dst.numel() * dst.element_size(), True)
+
+    def __str__(self) -> str:
+        return f"{self.var} linked to array(shape={tuple(self.io_buf.shape)}, dtype={tables.np_dtype_of(self.io_buf)})"
+
+
+def _resolve_io_unit(var: ProcChainVar, unit):
+    """unit system in which a column exchanges a variable (reference :1990-2011)"""
+    if isinstance(var.unit, (CoordinateGrid, Quantity, Unit)):
+        if isinstance(var.unit, CoordinateGrid):
+            var_u = var.unit.period.u
+        elif isinstance(var.unit, Quantity):
+            var_u = var.unit.u
+        else:
+            var_u = var.unit
+        if unit is None:
+            unit = var_u
+        elif ureg.is_compatible_with(var_u, unit):
+            unit = as_unit(unit)
+        else:
+            raise ProcessingChainError(f"array and variable {var} have incompatible units ({var_u} and {unit})")
+    elif isinstance(var.unit, str) and unit is None:
+        unit = var.unit
+    return unit
+
+
+class ArrayIOManager(IOManager):
+    """``Array`` / ``ArrayOfEqualSizedArrays`` column (reference :1984-2124)"""
+
+    def __init__(self, io_array, var: ProcChainVar) -> None:
+        unit = io_array.attrs.get("units", None)
+        var.update_auto(dtype=tables.np_dtype_of(io_array.nda), shape=tuple(io_array.nda.shape[1:]), unit=unit)
+        unit = _resolve_io_unit(var, unit)
+        self.var = var
+        self.raw_var = var.get_buffer(unit)
+        self.set_buffer(io_array)
+
+    def set_buffer(self, io_array) -> None:
+        if not hasattr(io_array, "nda"):
+            raise ProcessingChainError(f"{self.var} must be set using an Array")
+        if "units" not in io_array.attrs and self.var.unit is not None:
+            u = self.var.unit
+            io_array.attrs["units"] = str(u.u) if isinstance(u, Quantity) else str(u)
+        if (self.var.shape != tuple(io_array.nda.shape[1:])
+                or np.dtype(str(self.raw_var.dtype).replace("torch.", "")) != tables.np_dtype_of(io_array.nda)):
+            raise ProcessingChainError(f"LGDO object {io_array.form_datatype()} is incompatible with {self.var}")
+        self.io_array = io_array
+
+    def read(self, start: int, end: int) -> None:
+        n = len(self.io_array)
+        if start >= n:
+            raise EndExecute
+        end = min(end, n)
+        src = _as_tensor(self.io_array.nda)[start:end]
+        self.raw_var[0 : end - start].copy_(src, non_blocking=True)
+        if not src.is_cuda:
+            self._count(src.numel() * src.element_size(), False)
+
+    def write(self, start: int, end: int) -> None:
+        if len(self.io_array) < end:
+            self.io_array.resize(end)
+        dst = _as_tensor(self.io_array.nda)[start:end]
+        src = self.raw_var.expand(end - start, *self.raw_var.shape[1:]) if self.var.is_const \
+            else self.raw_var[0 : end - start]
+        dst.copy_(src, non_blocking=True)
+        if not dst.is_cuda:
+            self._count(dst.numel() * dst.element_size(), True)
+
+    def __str__(self) -> str:
+        return (f"{self.var} linked to Array(shape={tuple(self.io_array.nda.shape)}, "
+                f"dtype={tables.np_dtype_of(self.io_array.nda)}, attrs={self.io_array.attrs})")
+
+
+class VectorOfVectorsIOManager(IOManager):
+    """ragged column <-> NaN/zero padded block + length variable (reference :2127-2260).
+    The ragged <-> padded conversion is done on the host side of the copy."""
+
+    def __init__(self, io_vov, var: ProcChainVar) -> None:
+        if var.vector_len is None:
+            var.vector_len = ProcChainVar(var.proc_chain, f"len({var.name})", shape=(), dtype="uint32", grid=None,
+                                          unit=None)
+        if not np.issubdtype(var.vector_len.dtype, np.integer):
+            raise ProcessingChainError(f"{var.vector_len} must be an integer to act as a vector len")
+        self.unit = io_vov.attrs.get("units", None)
+        var.update_auto(dtype=io_vov.dtype, unit=self.unit)
+        self.unit = _resolve_io_unit(var, self.unit)
+        self.var = var
+        self.raw_var = None
+        self.len_var = var.vector_len.get_buffer()
+        self.set_buffer(io_vov)
+
+    def set_buffer(self, io_vov) -> None:
+        if "units" not in io_vov.attrs and self.var.unit is not None:
+            u = self.var.unit
+            io_vov.attrs["units"] = str(u.u) if isinstance(u, Quantity) else str(u)
+        if self.var.dtype != io_vov.dtype:
+            raise ProcessingChainError(f"VectorOfVectors of {io_vov.dtype} is incompatible with {self.var}")
+        self.io_vov = io_vov
+
+    def _ensure_raw(self, start, end):
+        if self.raw_var is None:
+            if self.var.shape is auto:
+                cl = np.asarray(self.io_vov.cumulative_length.nda)
+                lens = np.diff(np.concatenate([[0 if start == 0 else cl[start - 1]], cl[start:end]]))
+                self.var.update_auto(shape=2 * int(lens.max() if len(lens) else 1))
+                log.warning(f"No maximum length provided for VectorOfVectors {self.var}; using {self.var.shape}")
+            self.raw_var = self.var.get_buffer(self.unit)
+
+    def read(self, start: int, end: int) -> None:
+        n = len(self.io_vov)
+        if start >= n:
+            raise EndExecute
+        end = min(end, n)
+        self._ensure_raw(start, end)
+        cl = np.asarray(self.io_vov.cumulative_length.nda).astype(np.int64)
+        lo = np.concatenate([[0 if start == 0 else cl[start - 1]], cl[start : end - 1]])
+        lens = cl[start:end] - lo
+        width = self.raw_var.shape[1]
+        if len(lens) and lens.max() > width:
+            raise DSPFatal("VectorOfVectors entry has length larger than array variable length")
+        flat = np.asarray(self.io_vov.flattened_data.nda)
+        fill = 0 if np.issubdtype(self.var.dtype, np.integer) else np.nan
+        pad = np.full((end - start, width), fill, dtype=self.var.dtype)
+        mask = np.arange(width)[None, :] < lens[:, None]
+        pad[mask] = flat[int(lo[0]) if len(lo) else 0 : int(cl[end - 1]) if end > start else 0]
+        self.raw_var[: end - start].copy_(torch.from_numpy(pad))
+        self.len_var[: end - start].copy_(torch.from_numpy(lens.astype(np.uint32).astype(np.int64)).to(self.len_var.dtype))
+        self._count(pad.nbytes, False)
+
+    def write(self, start: int, end: int) -> None:
+        self._ensure_raw(start, end)
+        vals = self.raw_var[: end - start].cpu().numpy()
+        lens = self.len_var[: end - start].cpu().numpy().astype(np.int64)
+        if len(self.io_vov) < end:
+            self.io_vov.resize(end)
+        self.io_vov._set_vector_unsafe(start, vals, lens)
+        self._count(vals.nbytes, True)
+
+    def __str__(self) -> str:
+        return f"{self.var} linked to VectorOfVectors(vector_len={self.var.vector_len}, attrs={self.io_vov.attrs})"
+
+
+class WaveformIOManager(IOManager):
+    """``WaveformTable``: ``values`` block + per-event ``t0`` offset variable + ``dt``
+    period (reference :2263-2360)"""
+
+    def __init__(self, wf_table, variable: ProcChainVar) -> None:
+        dt_units = getattr(wf_table, "dt_units", None)
+        t0_units = getattr(wf_table, "t0_units", None)
+        if dt_units is None:
+            dt_units = t0_units
+        elif t0_units is None:
+            t0_units = dt_units
+        self.wf_var = variable
+        self.var = variable
+        if (self.wf_var.grid is auto and isinstance(dt_units, str) and dt_units in ureg
+                and isinstance(t0_units, str) and t0_units in ureg):
+            dt0 = float(np.asarray(_host_view(wf_table.dt.nda)[0:1])[0]) if len(wf_table.dt) else 1.0
+            self.wf_var.update_auto(
+                grid=CoordinateGrid(
+                    ureg.Quantity(dt0, dt_units),
+                    ProcChainVar(self.wf_var.proc_chain, self.wf_var.name + "_dt", shape=(),
+                                 dtype=tables.np_dtype_of(wf_table.t0.nda), grid=None, unit=dt_units, is_coord=True)),
+                is_coord=False)
+        else:
+            self.wf_var.update_auto(grid=None, is_coord=False)
+
+        values = tables.wf_values(wf_table)
+        if kind_of(values) == "vov":
+            self.val_ioman = VectorOfVectorsIOManager(values, self.wf_var)
+        else:
+            self.val_ioman = ArrayIOManager(values, self.wf_var)
+        if dt_units is None:
+            dt_units = self.wf_var.grid.unit_str()
+            t0_units = self.wf_var.grid.unit_str()
+        self.t0_var = self.wf_var.grid.get_offset(t0_units)
+        self.variable_t0 = isinstance(self.t0_var, torch.Tensor)
+        self.set_buffer(wf_table)
+
+    def set_buffer(self, wf_table) -> None:
+        if "units" not in wf_table.attrs and self.wf_var.unit is not None:
+            u = self.wf_var.unit
+            wf_table.attrs["units"] = str(u.u) if isinstance(u, Quantity) else str(u)
+        self.io_wf = wf_table
+        self.val_ioman.set_buffer(tables.wf_values(wf_table))
+        self._is_output_target = False
+
+    def prepare_output(self) -> None:
+        """stamp the grid onto an output table (period, constant offset, units)"""
+        if not self.variable_t0:
+            self.io_wf.t0.nda[...] = float(self.wf_var.offset / Quantity(1.0, self.wf_var.period.u))
+        dt_units = self.wf_var.period.u
+        self.io_wf.dt.nda[...] = self.wf_var.grid.get_period(Quantity(1.0, dt_units))
+        self.io_wf.dt_units = str(dt_units)
+        self.io_wf.t0_units = str(dt_units)
+
+    def read(self, start: int, end: int) -> None:
+        n = len(self.io_wf)
+        if start >= n:
+            raise EndExecute
+        end = min(end, n)
+        self.val_ioman.read(start, end)
+        if self.variable_t0:
+            src = _as_tensor(self.io_wf.t0.nda)[start:end]
+            self.t0_var[0 : end - start].copy_(src, non_blocking=True)
+
+    def write(self, start: int, end: int) -> None:
+        if len(self.io_wf) < end:
+            self.io_wf.resize(end)
+        if not self._is_output_target:
+            self.prepare_output()
+            self._is_output_target = True
+        self.val_ioman.write(start, end)
+        if self.variable_t0:
+            _as_tensor(self.io_wf.t0.nda)[start:end].copy_(self.t0_var[0 : end - start], non_blocking=True)
+
+    def __str__(self) -> str:
+        return f"{self.wf_var} linked to WaveformTable(values({self.val_ioman}))"
+
+
+def _host_view(x):
+    return x.detach().cpu().numpy() if isinstance(x, torch.Tensor) else np.asarray(x)
+
+
+# ======================================================================================
+# recipe compiler
+# ======================================================================================
+_MODULE_ALIASES = {
+    "dspeed.processors": "dspeed_b200.processors",
+    "pygama.dsp.processors": "dspeed_b200.processors",
+    "dspeed_b200.processors": "dspeed_b200.processors",
+}
+
+
+def _resolve_function(module_name: str, func_name: str):
+    """processor callable named by a recipe.  ``dspeed.processors.X`` resolves to the
+    CUDA processor of the same name; numpy / scipy functions are resolved as such and
+    mapped to a device implementation when bound (or rejected: no CPU fallback)."""
+    if module_name in _MODULE_ALIASES:
+        try:
+            return getattr(device_processors, func_name)
+        except AttributeError as e:
+            raise ProcessingChainError(str(e)) from e
+    module = importlib.import_module(module_name)
+    return getattr(module, func_name)
+
+
+def build_processing_chain(processors, tb_in=None, db_dict=None, outputs=None, block_width=None, device=None):
+    """Compile a JSON/YAML/dict recipe into a :class:`ProcessingChain`
+    (reference :2363-2872; same schema, same dependency resolution, same constant folding).
+
+    Returns ``(proc_chain, field_mask, tb_out)``."""
+    db_parser = re.compile(r"(?![^\w_.])db\.[\w_.]+")
+
+    if isinstance(processors, str):
+        with open(processors) as f:
+            from yaml import safe_load
+
+            processors = safe_load(f)
+    elif processors is None:
+        processors = {}
+    elif isinstance(processors, MutableMapping):
+        processors = deepcopy(processors)
+    else:
+        raise ValueError("processors must be a dict, json/yaml file, or None")
+
+    if outputs is None:
+        if "outputs" not in processors:
+            raise ValueError("outputs not provided")
+        outputs = processors["outputs"]
+    if "processors" in processors:
+        processors = processors["processors"]
+    processors = dict(processors)
+
+    buffer_len = len(tb_in) if tb_in is not None else 1
+    proc_chain = ProcessingChain(block_width, buffer_len, device=device)
+
+    def db_substitute(arg, node):
+        """replace ``db.a.b`` tokens by database values or the node's defaults"""
+        for db_var in db_parser.findall(arg):
+            try:
+                db_node = db_dict
+                for db_key in db_var[3:].split("."):
+                    db_node = db_node[db_key]
+            except (KeyError, TypeError):
+                try:
+                    db_node = node["defaults"][db_var]
+                except (KeyError, TypeError):
+                    raise ProcessingChainError(
+                        f"did not find {db_var} in database, and could not find default value.")
+            arg = db_node if arg == db_var else arg.replace(db_var, str(db_node))
+            if not isinstance(arg, str):
+                break
+        return arg
+
+    # ---- normalise every node into module / function / args, find prerequisites -------
+    multi_out_procs = {}
+    for key, node in processors.items():
+        keys = [k for k in re.split(",| ", key) if k != ""]
+        if len(keys) > 1:
+            for k in keys:
+                multi_out_procs[k] = key
+        if isinstance(node, str):
+            node = {"function": node}
+            processors[key] = node
+        if "function" not in node:
+            raise ProcessingChainError(f"no function given for parameter {key}")
+        function = node["function"]
+        f_parse = ast.parse(function, mode="eval").body
+        mod_err = f"Module specified twice for parameter {key}"
+        args_err = f"Cannot specify arguments if function is expr for parameter {key}"
+        seg = lambda n: function[n.col_offset : n.end_col_offset]  # noqa: E731
+        if isinstance(f_parse, ast.Name):
+            pass
+        elif isinstance(f_parse, ast.Attribute):
+            module = seg(f_parse.value)
+            if module in ProcessingChain.module_list and "args" not in node:
+                node["module"] = None
+                node["args"] = [function]
+            else:
+                node["function"] = f_parse.attr
+                if "module" in node:
+                    raise ProcessingChainError(mod_err)
+                node["module"] = module
+        elif isinstance(f_parse, ast.Call):
+            if "args" in node:
+                raise ProcessingChainError(args_err)
+            if isinstance(f_parse.func, ast.Name) and f_parse.func.id in ProcessingChain.func_list \
+                    and "module" not in node:
+                node["module"] = None
+                node["args"] = [function]
+            elif isinstance(f_parse.func, ast.Name):
+                node["function"] = f_parse.func.id
+                node["args"] = [seg(a) for a in f_parse.args + f_parse.keywords]
+            elif isinstance(f_parse.func, ast.Attribute):
+                node["function"] = f_parse.func.attr
+                if "module" in node:
+                    raise ProcessingChainError(mod_err)
+                node["module"] = seg(f_parse.func.value)
+                node["args"] = [seg(a) for a in f_parse.args + f_parse.keywords]
+        else:
+            if "args" in node:
+                raise ProcessingChainError(args_err)
+            if "module" in node:
+                raise ProcessingChainError(mod_err)
+            node["module"] = None
+            node["args"] = [function]
+        if "module" not in node:
+            raise ProcessingChainError(f"Could not find module for parameter {key}")
+        if "args" not in node:
+            raise ProcessingChainError(f"Could not find args for parameter {key}")
+
+        args = node["args"]
+        for i, arg in enumerate(args):
+            if isinstance(arg, str):
+                args[i] = db_substitute(arg, node)
+
+        if "prereqs" not in node:
+            prereqs = []
+            for arg in args:
+                if not isinstance(arg, str):
+                    continue
+                for prereq in proc_chain.get_variable(arg, True):
+                    if prereq not in prereqs and prereq not in keys:
+                        prereqs.append(prereq)
+            node["prereqs"] = prereqs
+        log.debug(f"prereqs for {key} are {node['prereqs']}")
+
+    processors.update(multi_out_procs)
+
+    # ---- dependency order from the requested outputs only ----------------------------
+    def resolve(par, resolved, leafs, unresolved=None):
+        unresolved = [] if unresolved is None else unresolved
+        if par in resolved:
+            return
+        if par in unresolved:
+            raise ProcessingChainError(f"Circular references detected for parameter '{par}'")
+        node = processors.get(par)
+        if node is None:
+            if par not in leafs:
+                leafs.append(par)
+            return
+        if isinstance(node, str):
+            resolve(node, resolved, leafs, unresolved)
+            return
+        unresolved.append(par)
+        for edge in node["prereqs"]:
+            resolve(edge, resolved, leafs, unresolved)
+        resolved.append(par)
+        unresolved.remove(par)
+
+    proc_par_list, input_par_list, copy_par_list, out_par_list = [], [], [], []
+    for out_par in outputs:
+        if out_par not in processors:
+            copy_par_list.append(out_par)
+        else:
+            resolve(out_par, proc_par_list, input_par_list)
+            out_par_list.append(out_par)
+
+    for input_par in input_par_list:
+        if tb_in is None or input_par not in tb_in:
+            log.warning(f"'{input_par}' not found in input files or dsp config.")
+        try:
+            proc_chain.link_input_buffer(input_par, tb_in[input_par])
+        except Exception as e:
+            raise ProcessingChainError(f"Exception raised while linking input buffer '{input_par}'.") from e
+
+    # ---- add the processors ------------------------------------------------------------
+    for proc_par in proc_par_list:
+        recipe = processors[proc_par]
+        try:
+            if recipe["module"] is None:
+                assert len(recipe["args"]) == 1
+                fun_var = proc_chain.get_variable(recipe["args"][0])
+                if isinstance(fun_var, ProcChainVar):
+                    new_var = proc_chain.add_variable(name=proc_par, dtype=fun_var.dtype, shape=fun_var.shape,
+                                                      grid=fun_var.grid, unit=fun_var.unit,
+                                                      is_coord=fun_var.is_coord)
+                    new_var._buffer = fun_var._buffer
+                    new_var.alias_of = fun_var
+                else:
+                    new_var = proc_chain.set_constant(varname=proc_par, val=fun_var)
+                continue
+
+            func = _resolve_function(recipe["module"], recipe["function"])
+            args = recipe["args"]
+            new_vars = [k for k in re.split(",| ", proc_par) if k != ""]
+
+            if "unit" in recipe:
+                for i, name in enumerate(new_vars):
+                    unit = recipe.get("unit", auto)
+                    if isinstance(unit, list):
+                        unit = unit[i]
+                    proc_chain.add_variable(name, unit=unit)
+
+            kwargs = dict(recipe.get("kwargs", {}))
+            kwargs.update({k: recipe[k] for k in ("signature", "types", "coord_grid") if k in recipe})
+
+            if "init_args" in recipe:
+                init_args, init_kwargs = [], {}
+                for arg in recipe["init_args"]:
+                    if not isinstance(arg, str):
+                        init_args.append(arg)
+                        continue
+                    arg = db_substitute(arg, recipe)
+                    if isinstance(arg, str):
+                        arg = proc_chain.get_variable(arg)
+                    if isinstance(arg, MutableMapping):
+                        init_kwargs.update(arg)
+                    else:
+                        init_args.append(arg)
+                func = func(*init_args, **init_kwargs)
+
+            params, kw_params, out_params = [], {}, []
+            is_const = True
+            for param in args:
+                if isinstance(param, str):
+                    param = proc_chain.get_variable(param)
+                if isinstance(param, MutableMapping):
+                    kw_params.update(param)
+                    param = list(param.values())[0]
+                elif isinstance(param, str):
+                    params.append(param)  # a string literal (e.g. the mode character 's')
+                else:
+                    params.append(param)
+                if isinstance(param, ProcChainVar):
+                    if param.name in new_vars:
+                        out_params.append(param)
+                    elif not param.is_const:
+                        is_const = False
+
+            if is_const:
+                # every input is a constant: run once now, outputs become constants
+                # (this is how cusp_kernel / zac_kernel / t0_kernel are made)
+                if out_params:
+                    for param in out_params:
+                        param.is_const = True
+                    proc_man = ProcessorManager(proc_chain, func, params, kw_params, kwargs.get("signature", None),
+                                                kwargs.get("types", None))
+                    if proc_chain.device.type != "meta":
+                        proc_man.execute()
+                        proc_chain._raise_recorded_fatal(0, 0)
+                else:
+                    const_val = func(*params, **kw_params)
+                    if len(new_vars) == 1:
+                        const_val = [const_val]
+                    for var, val in zip(new_vars, const_val):
+                        proc_chain.set_constant(var, val)
+            else:
+                coord_grid = kwargs.get("coord_grid", None)
+                proc_man = ProcessorManager(proc_chain, func, params, kw_params, kwargs.get("signature", None),
+                                            kwargs.get("types", None),
+                                            CoordinateGrid(coord_grid) if coord_grid is not None else None)
+                proc_chain._proc_managers.append(proc_man)
+                log.debug(f"added processor: {proc_man}")
+        except Exception as e:
+            raise ProcessingChainError("Exception raised while attempting to add processor:\n"
+                                       + json.dumps(recipe, indent=2, default=str)) from e
+
+    # ---- output table ------------------------------------------------------------------
+    tb_out = tables.Table(size=buffer_len)
+    for copy_par in copy_par_list:
+        if tb_in is None or copy_par not in tb_in:
+            log.warning(f"'{copy_par}' not found in input files or dsp . Building output without it!")
+            continue
+        try:
+            proc_chain.link_input_buffer(copy_par, tb_in[copy_par])
+            buf_out = proc_chain.link_output_buffer(copy_par)
+            buf_out.attrs.update(getattr(tb_in[copy_par], "attrs", {}))
+            buf_out.resize(len(tb_out))
+            tb_out.add_field(copy_par, buf_out)
+        except Exception as e:
+            raise ProcessingChainError(f"Exception raised while linking copy buffer '{copy_par}'.") from e
+
+    for out_par in out_par_list:
+        try:
+            buf_out = proc_chain.link_output_buffer(out_par)
+            recipe = processors[out_par]
+            if isinstance(recipe, str):
+                recipe = processors[recipe]
+            buf_out.attrs.update(recipe.get("lh5_attrs", {}))
+            if description := recipe.get("description"):
+                buf_out.attrs["description"] = description
+            buf_out.resize(len(tb_out))
+            tb_out.add_field(out_par, buf_out)
+        except Exception as e:
+            raise ProcessingChainError(f"Exception raised while linking output buffer {out_par}.") from e
+
+    field_mask = input_par_list + copy_par_list
+    proc_chain.recipe_info = {"proc_par_list": proc_par_list, "outputs": list(outputs)}
+    return (proc_chain, field_mask, tb_out)

