@@ -17,9 +17,14 @@
 
 namespace dspb {
 
-constexpr int NT = 256;          // threads per CTA for row-resident kernels
-constexpr int NW = NT / 32;      // warps per CTA
-constexpr int SCRATCH_BYTES = 1024;  // block-primitive scratch at the start of dynamic smem
+// Row-resident kernels are written for any 1-D CTA size that is a multiple of 32 (the
+// per-processor kernels launch 256 threads, the fused chain kernel 512): NT / NW read the
+// launch configuration.
+#define NT ((int)blockDim.x)
+#define NW ((int)(blockDim.x >> 5))
+constexpr int MAXW = 32;             // max warps per CTA
+constexpr int SCRATCH_BYTES = 2048;  // block-primitive scratch at the start of dynamic smem
+constexpr int DEFAULT_THREADS = 256;
 
 // Padded shared-memory index: one pad word per 32 elements.  With a thread-contiguous
 // chunk of C in {4,8,16,32} elements, lane l at step j touches bank (l*C + j + (l*C+j)/32) % 32,
@@ -49,8 +54,8 @@ struct Wave {
 };
 
 struct Scratch {
-  double d[NW * 4 + 4];
-  int i[NW * 4 + 4];
+  double d[MAXW * 4];
+  int i[MAXW * 4];
 };
 static_assert(sizeof(Scratch) <= SCRATCH_BYTES, "scratch too large");
 
@@ -73,7 +78,6 @@ __device__ __forceinline__ double block_excl_scan(double v, double& total, Scrat
   if (lane == 31) sc->d[w] = incl;
   __syncthreads();
   double woff = 0.0, tot = 0.0;
-#pragma unroll
   for (int k = 0; k < NW; k++) {
     double s = sc->d[k];
     if (k < w) woff += s;
@@ -96,7 +100,6 @@ __device__ __forceinline__ double block_excl_scan_rev(double v, double& total, S
   if (lane == 0) sc->d[w] = incl;
   __syncthreads();
   double woff = 0.0, tot = 0.0;
-#pragma unroll
   for (int k = 0; k < NW; k++) {
     double s = sc->d[k];
     if (k > w) woff += s;
@@ -113,7 +116,6 @@ __device__ __forceinline__ double block_sum(double v, Scratch* sc) {
   if (lane_id() == 0) sc->d[warp_id()] = v;
   __syncthreads();
   double tot = 0.0;
-#pragma unroll
   for (int k = 0; k < NW; k++) tot += sc->d[k];
   return tot;
 }
@@ -128,14 +130,13 @@ __device__ __forceinline__ void block_sum2(double& a, double& b, Scratch* sc) {
   __syncthreads();
   if (lane_id() == 0) {
     sc->d[warp_id()] = a;
-    sc->d[NW + warp_id()] = b;
+    sc->d[MAXW + warp_id()] = b;
   }
   __syncthreads();
   double ta = 0.0, tb = 0.0;
-#pragma unroll
   for (int k = 0; k < NW; k++) {
     ta += sc->d[k];
-    tb += sc->d[NW + k];
+    tb += sc->d[MAXW + k];
   }
   a = ta;
   b = tb;
@@ -151,7 +152,6 @@ __device__ __forceinline__ int block_min_int(int v, Scratch* sc) {
   if (lane_id() == 0) sc->i[warp_id()] = v;
   __syncthreads();
   int r = sc->i[0];
-#pragma unroll
   for (int k = 1; k < NW; k++) r = min(r, sc->i[k]);
   return r;
 }
@@ -162,7 +162,6 @@ __device__ __forceinline__ int block_max_int(int v, Scratch* sc) {
   if (lane_id() == 0) sc->i[warp_id()] = v;
   __syncthreads();
   int r = sc->i[0];
-#pragma unroll
   for (int k = 1; k < NW; k++) r = max(r, sc->i[k]);
   return r;
 }
@@ -182,20 +181,19 @@ __device__ __forceinline__ void block_argminmax(T& vmin, int& imin, T& vmax, int
   __syncthreads();
   if (lane_id() == 0) {
     sc->d[warp_id()] = (double)vmin;
-    sc->d[NW + warp_id()] = (double)vmax;
+    sc->d[MAXW + warp_id()] = (double)vmax;
     sc->i[warp_id()] = imin;
-    sc->i[NW + warp_id()] = imax;
+    sc->i[MAXW + warp_id()] = imax;
   }
   __syncthreads();
-  T bmin = (T)sc->d[0], bmax = (T)sc->d[NW];
-  int bimin = sc->i[0], bimax = sc->i[NW];
-#pragma unroll
+  T bmin = (T)sc->d[0], bmax = (T)sc->d[MAXW];
+  int bimin = sc->i[0], bimax = sc->i[MAXW];
   for (int k = 1; k < NW; k++) {
     T ov = (T)sc->d[k];
     int oi = sc->i[k];
     if (ov < bmin || (ov == bmin && oi < bimin)) { bmin = ov; bimin = oi; }
-    ov = (T)sc->d[NW + k];
-    oi = sc->i[NW + k];
+    ov = (T)sc->d[MAXW + k];
+    oi = sc->i[MAXW + k];
     if (ov > bmax || (ov == bmax && oi < bimax)) { bmax = ov; bimax = oi; }
   }
   vmin = bmin; imin = bimin; vmax = bmax; imax = bimax;

@@ -7,67 +7,15 @@
 // in float64 in a fixed order (deterministic).  float32 products are accumulated in
 // chunks of 64 taps that are flushed into float64 accumulators, so the error does not
 // grow with the kernel length (cusp/zac: 5792 taps).
-#include "common.cuh"
+#include "conv_ops.cuh"
 
 using namespace dspb;
 
 namespace {
 
 constexpr size_t MAX_SMEM = 227 * 1024;
-constexpr int R = 8;    // outputs per thread
-constexpr int CH = 64;  // taps per float32 accumulation chunk (multiple of 8)
-
 template <typename T>
-struct ConvPlan {
-  int n, m, p, off;  // out[k] = sum_j a[j] v[k + off - j]
-  int G, S, L;       // output groups, tap segments, taps per segment (multiple of 8)
-};
-
-template <typename T>
-__device__ __forceinline__ T lda(const T* a, int n, int idx) {
-  return (idx >= 0 && idx < n) ? a[sidx(idx)] : (T)0;
-}
-
-// accumulate taps [t_lo, t_hi) for outputs k0..k0+7 (kk0 = k0 + off)
-template <typename T>
-__device__ __forceinline__ void conv_group(const T* a, int n, const T* kv, int kk0, int t_lo, int t_hi,
-                                           double (&acc)[R]) {
-  for (int tb = t_lo; tb < t_hi; tb += CH) {
-    const int te = min(tb + CH, t_hi);
-    T f[R];
-#pragma unroll
-    for (int r = 0; r < R; r++) f[r] = (T)0;
-    int t = tb;
-    // window W[j] = a[kk0 - t - 7 + j], j = 0..14 ; output r at tap t+u reads W[r - u + 7]
-    T W[15];
-#pragma unroll
-    for (int j = 7; j < 15; j++) W[j] = lda<T>(a, n, kk0 - t - 7 + j);
-    for (; t + 8 <= te; t += 8) {
-#pragma unroll
-      for (int j = 0; j < 7; j++) W[j] = lda<T>(a, n, kk0 - t - 7 + j);
-#pragma unroll
-      for (int u = 0; u < 8; u++) {
-        const T kvv = kv[t + u];
-#pragma unroll
-        for (int r = 0; r < R; r++) f[r] = fma(W[r - u + 7], kvv, f[r]);
-      }
-      // next iteration (t+8): W'[j] = a[kk0 - t - 15 + j]; W'[8..14] = W[0..6]; W'[7] = a[kk0-t-8]
-#pragma unroll
-      for (int j = 14; j >= 8; j--) W[j] = W[j - 8];
-      W[7] = lda<T>(a, n, kk0 - t - 8);
-    }
-    for (; t < te; t++) {  // tail (< 8 taps)
-      const T kvv = kv[t];
-#pragma unroll
-      for (int r = 0; r < R; r++) f[r] = fma(lda<T>(a, n, kk0 + r - t), kvv, f[r]);
-    }
-#pragma unroll
-    for (int r = 0; r < R; r++) acc[r] += (double)f[r];
-  }
-}
-
-template <typename T>
-__global__ void __launch_bounds__(NT) k_convolve(Wave in, const T* __restrict__ kern, ConvPlan<T> pl, T* out,
+__global__ void __launch_bounds__(DEFAULT_THREADS) k_convolve(Wave in, const T* __restrict__ kern, ConvPlan<T> pl, T* out,
                                                  long long out_row_stride, long long n_rows) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* a = reinterpret_cast<T*>(smem_raw + SCRATCH_BYTES);
@@ -141,9 +89,9 @@ int launch_convolve(const void* w_in, int64_t rs, int32_t dt, int64_t n_rows, in
   ConvPlan<T> pl;
   pl.n = (int)n; pl.m = (int)m; pl.p = (int)p; pl.off = (int)off;
   pl.G = (int)((p + R - 1) / R);
-  if (pl.G >= NT) { pl.S = 1; pl.L = (int)m; }
+  if (pl.G >= DEFAULT_THREADS) { pl.S = 1; pl.L = (int)m; }
   else {
-    int S = NT / pl.G;
+    int S = DEFAULT_THREADS / pl.G;
     const int max_s = (int)((m + CH - 1) / CH);
     if (S > max_s) S = max_s;
     if (S < 1) S = 1;
@@ -161,7 +109,7 @@ int launch_convolve(const void* w_in, int64_t rs, int32_t dt, int64_t n_rows, in
   const int grid = (int)(n_rows < max_grid ? n_rows : max_grid);
   Wave in;
   in.ptr = w_in; in.row_stride = rs; in.dtype = dt;
-  kern<<<grid, NT, smem, (cudaStream_t)stream>>>(in, reinterpret_cast<const T*>(kernel), pl,
+  kern<<<grid, DEFAULT_THREADS, smem, (cudaStream_t)stream>>>(in, reinterpret_cast<const T*>(kernel), pl,
                                                  reinterpret_cast<T*>(w_out), out_rs, n_rows);
   e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -(int)e;

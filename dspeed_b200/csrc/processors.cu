@@ -14,7 +14,7 @@ namespace {
 constexpr size_t MAX_SMEM = 227 * 1024;
 
 template <typename T, class Body>
-__global__ void __launch_bounds__(NT) k_rows(const Body body, const long long n_rows) {
+__global__ void __launch_bounds__(DEFAULT_THREADS) k_rows(const Body body, const long long n_rows) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Scratch* sc = reinterpret_cast<Scratch*>(smem_raw);
   T* slots = reinterpret_cast<T*>(smem_raw + SCRATCH_BYTES);
@@ -36,7 +36,7 @@ int launch_rows(const Body& body, long long n_rows, int n_slots, long long max_l
   if (e != cudaSuccess) return -(int)e;
   const long long max_grid = 148LL * 16;
   const int grid = (int)(n_rows < max_grid ? n_rows : max_grid);
-  kern<<<grid, NT, smem, (cudaStream_t)stream>>>(body, n_rows);
+  kern<<<grid, DEFAULT_THREADS, smem, (cudaStream_t)stream>>>(body, n_rows);
   e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -(int)e;
 }
@@ -484,7 +484,7 @@ struct MultiLocalExtrema {
     // index lists (as floats; indices < 2^24) behind the row slot: L max, L min, R max, R min
     float* lst = reinterpret_cast<float*>(s + slot_words(n));
     float *l_max = lst, *l_min = lst + m, *r_max = lst + 2 * m, *r_min = lst + 3 * m;
-    int* cnt = sc->i + 2 * NW;  // 4 counters
+    int* cnt = sc->i + 2 * MAXW;  // 4 counters
     if (threadIdx.x < 4) cnt[threadIdx.x] = 0;
     __syncthreads();
     const bool do_left = (dir == (T)0) || (dir > (T)1);
@@ -697,7 +697,7 @@ int trap_static_check(int64_t n, int32_t rise, int32_t flat) {
     (void)fatal;                                                                                   \
     if (n <= 3) return DSPB_FATAL_DPZ_SHORT;                                                       \
     DoublePoleZero<T> b{WIN(w_in), (int)n, SC(t_tau1), SC(t_tau2), SC(frac), WOUT(w_out)};         \
-    return launch_rows<T>(b, n_rows, 2, n, stream, NW * sizeof(Aff2) + 16);                        \
+    return launch_rows<T>(b, n_rows, 2, n, stream, MAXW * sizeof(Aff2) + 16);                        \
   }                                                                                                \
   extern "C" int dspb_trap_filter##SFX(DSPB_WAVE_IN(w_in), int64_t n_rows, int64_t n,              \
                                        int32_t rise, int32_t flat, int32_t norm,                   \
@@ -850,7 +850,7 @@ int trap_static_check(int64_t n, int32_t rise, int32_t flat) {
     b.init_in = SC(init_in);                                                                       \
     b.init_out = SC(init_out);                                                                     \
     b.out = WOUT(w_out);                                                                           \
-    return launch_rows<T>(b, n_rows, 2, n, stream, NW * sizeof(Aff2) + 16);                        \
+    return launch_rows<T>(b, n_rows, 2, n, stream, MAXW * sizeof(Aff2) + 16);                        \
   }                                                                                                \
   extern "C" int dspb_cusp_filter##SFX(double sigma, double flat, double decay, void* kernel,      \
                                        int64_t length, void* stream) {                             \

@@ -488,6 +488,47 @@ __device__ __forceinline__ T op_interp_time_point_thresh(const T* in, int n, T t
   return nan_of<T>();
 }
 
+// cubic-spline mode of fixed_time_pickoff (fixed_time_pickoff.py:107-123), kept out of line:
+// it needs a small local window and is rarely used.
+template <typename T>
+__device__ __noinline__ T ftp_spline(const T* in, int n, int i_in, double t0, double t1) {
+  constexpr int HALO = 64;
+  // forward sweep needs u[i], w2f[i] for i in [i_in, top]; start HALO before that
+  const int top = min(n - 2, i_in + 1 + HALO);       // backward sweep starts here
+  const int first = max(1, i_in - HALO);
+  // forward coefficients w2f[i] = -0.5 / (0.5 w2f[i-1] + 2), w2f[0] = 0 (fixed point sqrt(3)-2)
+  double w2f = first == 1 ? 0.0 : -0.2679491924311227;
+  double u = 0.0;
+  // we need u[i], w2f[i] on [i_in, top] for the backward sweep: keep them in a small
+  // local window (top - i_in + 1 <= HALO + 2)
+  double uw[HALO + 3], cw[HALO + 3];
+  for (int k = 0; k < HALO + 3; k++) { uw[k] = 0.0; cw[k] = 0.0; }
+  for (int i = first; i <= min(top, n - 2); i++) {
+    const double p = 0.5 * w2f + 2.0;
+    w2f = -0.5 / p;
+    const double sec = ((double)in[sidx(i + 1)] - 2.0 * (double)in[sidx(i)]) + (double)in[sidx(i - 1)];
+    u = (3.0 * sec - 0.5 * u) / p;
+    if (i >= i_in) { uw[i - i_in] = u; cw[i - i_in] = w2f; }
+  }
+  // i_in == 0: u[0] = w2[0] = 0 in the reference
+  // backward: w2[i] = w2f[i] * w2[i+1] + u[i], from top down to i_in; w2[n-1] = 0
+  double w2n = 0.0;   // w2[i+1]
+  double w2_i = 0.0, w2_ip1 = 0.0;
+  for (int i = top; i >= i_in; i--) {
+    double v;
+    if (i == 0) v = 0.0 * w2n + 0.0;  // w2[0]*w2[1] + u[0] with w2[0] = u[0] = 0
+    else v = cw[i - i_in] * w2n + uw[i - i_in];
+    if (i == i_in + 1) w2_ip1 = v;
+    if (i == i_in) w2_i = v;
+    w2n = v;
+  }
+  if (i_in + 1 > top) w2_ip1 = 0.0;  // i_in + 1 == n - 1
+  const double a3 = t1 * t1 * t1, b3 = t0 * t0 * t0;
+  double r = t1 * (double)in[sidx(i_in)] + t0 * (double)in[sidx(i_in + 1)];
+  r += ((a3 - t1) * w2_i + (b3 - t0) * w2_ip1) / 6.0;
+  return (T)r;
+}
+
 // fixed_time_pickoff.py:12-125.  Executed by every thread redundantly (O(1) work; the
 // spline mode uses the exponentially decaying influence of far samples: the tridiagonal
 // recursions contract by 2-sqrt(3) = 0.268 per step, so a 64-sample halo reproduces the
@@ -518,43 +559,7 @@ __device__ __forceinline__ T op_fixed_time_pickoff(const T* in, int n, T t_in, i
       r += (b3 - b2) * m1;
       return (T)r;
     }
-    case 's': {
-      constexpr int HALO = 64;
-      // forward sweep needs u[i], w2f[i] for i in [i_in, top]; start HALO before that
-      const int top = min(n - 2, i_in + 1 + HALO);       // backward sweep starts here
-      const int first = max(1, i_in - HALO);
-      // forward coefficients w2f[i] = -0.5 / (0.5 w2f[i-1] + 2), w2f[0] = 0 (fixed point sqrt(3)-2)
-      double w2f = first == 1 ? 0.0 : -0.2679491924311227;
-      double u = 0.0;
-      // we need u[i], w2f[i] on [i_in, top] for the backward sweep: keep them in a small
-      // local window (top - i_in + 1 <= HALO + 2)
-      double uw[HALO + 3], cw[HALO + 3];
-      for (int k = 0; k < HALO + 3; k++) { uw[k] = 0.0; cw[k] = 0.0; }
-      for (int i = first; i <= min(top, n - 2); i++) {
-        const double p = 0.5 * w2f + 2.0;
-        w2f = -0.5 / p;
-        const double sec = ((double)in[sidx(i + 1)] - 2.0 * (double)in[sidx(i)]) + (double)in[sidx(i - 1)];
-        u = (3.0 * sec - 0.5 * u) / p;
-        if (i >= i_in) { uw[i - i_in] = u; cw[i - i_in] = w2f; }
-      }
-      // i_in == 0: u[0] = w2[0] = 0 in the reference
-      // backward: w2[i] = w2f[i] * w2[i+1] + u[i], from top down to i_in; w2[n-1] = 0
-      double w2n = 0.0;   // w2[i+1]
-      double w2_i = 0.0, w2_ip1 = 0.0;
-      for (int i = top; i >= i_in; i--) {
-        double v;
-        if (i == 0) v = 0.0 * w2n + 0.0;  // w2[0]*w2[1] + u[0] with w2[0] = u[0] = 0
-        else v = cw[i - i_in] * w2n + uw[i - i_in];
-        if (i == i_in + 1) w2_ip1 = v;
-        if (i == i_in) w2_i = v;
-        w2n = v;
-      }
-      if (i_in + 1 > top) w2_ip1 = 0.0;  // i_in + 1 == n - 1
-      const double a3 = t1 * t1 * t1, b3 = t0 * t0 * t0;
-      double r = t1 * (double)in[sidx(i_in)] + t0 * (double)in[sidx(i_in + 1)];
-      r += ((a3 - t1) * w2_i + (b3 - t0) * w2_ip1) / 6.0;
-      return (T)r;
-    }
+    case 's': return ftp_spline<T>(in, n, i_in, t0, t1);
   }
   fatal = DSPB_FATAL_INTERP_MODE;
   return nan_of<T>();

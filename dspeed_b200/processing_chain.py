@@ -30,6 +30,7 @@ import importlib
 import itertools as it
 import json
 import logging
+import os
 import re
 import time
 from collections.abc import Collection, MutableMapping
@@ -304,7 +305,9 @@ class ProcessingChain:
         self.fatal = torch.zeros((MAX_FATAL_SLOTS, 4), dtype=torch.int32, device=self.device)
         self._fatal_owner: list = []
         self._fused = None  # set by fusion.try_fuse()
-        self.stats = {"launches": 0, "blocks": 0, "h2d_bytes": 0, "d2h_bytes": 0}
+        #: launches = hand-written CUDA kernels launched; glue_ops = per-event scalar torch ops
+        self.stats = {"launches": 0, "glue_ops": 0, "blocks": 0, "h2d_bytes": 0, "d2h_bytes": 0}
+        self._event_timing = False
 
     # -- variables -----------------------------------------------------------------
     def add_variable(self, name, dtype=auto, shape=auto, grid=auto, unit=auto, is_coord=auto, period=None, offset=0,
@@ -484,9 +487,28 @@ class ProcessingChain:
             raise e
 
     def get_timing(self) -> dict[str, float]:
-        """cumulative host-side launch time per processor (reference :1188-1190); with
-        ``DSPEED_B200_TIMING=1`` launches are synchronised so this is device time"""
+        """cumulative time per processor in seconds (reference :1188-1190): device time
+        measured with CUDA events after :meth:`enable_event_timing`, else host launch time"""
+        if self._event_timing:
+            self._resolve_events()
+            return {str(proc): getattr(proc, "device_time", 0.0) for proc in self._proc_managers}
         return {str(proc): proc.time_total for proc in self._proc_managers}
+
+    def enable_event_timing(self, on: bool = True) -> None:
+        """bracket every processor launch with CUDA events on the launch stream"""
+        self._event_timing = on
+        self._pending_events = []
+        if on:
+            for proc in self._proc_managers:
+                proc.device_time = 0.0
+                proc.device_calls = 0
+
+    def _resolve_events(self) -> None:
+        torch.cuda.current_stream(self.device).synchronize()
+        for proc, e0, e1 in self._pending_events:
+            proc.device_time = getattr(proc, "device_time", 0.0) + e0.elapsed_time(e1) * 1e-3
+            proc.device_calls = getattr(proc, "device_calls", 0) + 1
+        self._pending_events = []
 
     def __str__(self) -> str:
         return ("Input variables:\n  " + "\n  ".join(str(m) for m in self._input_managers.values())
@@ -1090,17 +1112,28 @@ class ProcessorManager:
             else:
                 self.kwargs[arg_name] = bound
 
-        self._sync_timing = bool(int(__import__("os").environ.get("DSPEED_B200_TIMING", "0")))
+        self._sync_timing = bool(int(os.environ.get("DSPEED_B200_TIMING", "0")))
         self.fatal = proc_chain._new_fatal_slot(self)
 
     def execute(self) -> None:
         start = time.perf_counter()
-        self.processor(*self.args, fatal=self.fatal, **self.kwargs)
+        if self.proc_chain._event_timing:
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            self.processor(*self.args, fatal=self.fatal, **self.kwargs)
+            e1.record()
+            self.proc_chain._pending_events.append((self, e0, e1))
+        else:
+            self.processor(*self.args, fatal=self.fatal, **self.kwargs)
         if self._sync_timing:
             torch.cuda.current_stream(self.proc_chain.device).synchronize()
         self.time_total += time.perf_counter() - start
         self.n_calls += 1
-        self.proc_chain.stats["launches"] += getattr(self.processor, "launches_per_call", 1)
+        if getattr(self.processor, "native_kernel", False):
+            self.proc_chain.stats["launches"] += getattr(self.processor, "launches_per_call", 1)
+        else:
+            self.proc_chain.stats["glue_ops"] += 1
 
     def __str__(self) -> str:
         return (self.host_func.__name__ + "("
@@ -1170,7 +1203,7 @@ class UnitConversionManager(ProcessorManager):
                              fatal=self.fatal)
         self.time_total += time.perf_counter() - start
         self.n_calls += 1
-        self.proc_chain.stats["launches"] += 1
+        self.proc_chain.stats["glue_ops"] += 1
 
     def __str__(self) -> str:
         return f"convert({self.params[0]}, from={self.kw_params['from']}, to={self.kw_params['to']})"
@@ -1705,6 +1738,10 @@ def build_processing_chain(processors, tb_in=None, db_dict=None, outputs=None, b
                     if proc_chain.device.type != "meta":
                         proc_man.execute()
                         proc_chain._raise_recorded_fatal(0, 0)
+                    for param in out_params:
+                        # provenance of folded constants: lets the fusion compiler recognise
+                        # e.g. a cusp/zac kernel and verify an analytic model against it
+                        param.const_origin = (proc_man.processor.__name__, list(proc_man.args))
                 else:
                     const_val = func(*params, **kw_params)
                     if len(new_vars) == 1:
@@ -1753,4 +1790,8 @@ def build_processing_chain(processors, tb_in=None, db_dict=None, outputs=None, b
 
     field_mask = input_par_list + copy_par_list
     proc_chain.recipe_info = {"proc_par_list": proc_par_list, "outputs": list(outputs)}
+    if proc_chain.device.type == "cuda" and os.environ.get("DSPEED_B200_FUSE", "1") != "0":
+        from . import fusion
+
+        fusion.try_fuse(proc_chain)
     return (proc_chain, field_mask, tb_out)

@@ -158,6 +158,8 @@ class DeviceProcessor:
         self.nout = nout
         self.nin = signature.count("(") - nout if signature else None
         self.device_processor = True
+        self.native_kernel = True  # a hand-written CUDA kernel of this repository
+        self.launches_per_call = 1
 
     def __repr__(self):
         return f"<dspeed_b200 processor {self.__name__} {self.signature}>"

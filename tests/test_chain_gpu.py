@@ -103,6 +103,50 @@ def test_icpc_chain_matches_oracle(synth_batch):
     assert np.isnan(got["tp_0_est"]).sum() == np.isnan(o["tp_0_est"]).sum()
 
 
+def test_fused_icpc_chain_matches_oracle(synth_batch):
+    """the whole ICPC chain as ONE waveform-resident kernel launch per block"""
+    import yaml as _yaml
+
+    from dspeed_b200.build_dsp import build_dsp
+
+    vals, bl, o = synth_batch
+    out = build_dsp(raw_table(vals, bl), dsp_config=_yaml.safe_load(open(ICPC)), block_width=600)
+    fused = out.proc_chain._fused
+    assert fused is not None, getattr(out.proc_chain, "_not_fused_reason", None)
+    kinds = [c[0] for c in fused.conv_lowering]
+    assert kinds.count("seg") == 2 and kinds.count("runs") == 1, fused.conv_lowering
+    # 3 set-up launches (t0 / cusp / zac kernel synthesis, const-folded) + ceil(1536 / 600) block launches
+    assert out.proc_chain.stats["launches"] == 3 + 3
+    got = {k: np.asarray(out[k].nda) for k in out}
+    check_against(got, o, len(vals))
+
+
+@pytest.mark.parametrize("conv", ["direct", "auto"])
+def test_fused_equals_unfused(synth_batch, conv):
+    """same arithmetic routines on shared-memory resident data: the fused kernel must agree
+    with the per-processor kernels (bit for bit for everything that is not a convolution
+    with a different lowering)"""
+    vals, bl, _ = synth_batch
+    os.environ["DSPEED_B200_CONV"] = conv
+    try:
+        a = run_icpc(vals[:512], bl[:512], block_width=256, fuse=True)
+    finally:
+        os.environ.pop("DSPEED_B200_CONV", None)
+    b = run_icpc(vals[:512], bl[:512], block_width=256, fuse=False)
+    # The fused kernel runs 512 threads per waveform, the per-processor kernels 256: float64
+    # partial sums are grouped differently, so float outputs agree to rounding (1e-6), integer
+    # / index / extremum outputs exactly, threshold crossings except on marginal samples.
+    for k in a:
+        if k in EXACT:
+            assert np.array_equal(a[k], b[k], equal_nan=True), k
+        elif k.startswith("tp_"):
+            same = (a[k] == b[k]) | (np.isnan(a[k]) & np.isnan(b[k]))
+            assert same.mean() > 0.99, (k, same.mean())
+        else:
+            ok = (a["tp_0_est"] == b["tp_0_est"]) | (np.isnan(a["tp_0_est"]) & np.isnan(b["tp_0_est"]))
+            PT.assert_float_close(k, a[k], b[k], rtol=2e-6, mask=ok)
+
+
 def test_icpc_chain_matches_reference_golden():
     """10 hand-picked rows whose every intermediate was recorded from the reference's own
     numba/scipy processors (tests/golden/hpge_chain.npz)"""
