@@ -63,6 +63,9 @@ __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 __device__ __forceinline__ int warp_id() { return threadIdx.x >> 5; }
 
 // ---- block-wide primitives (all threads of the CTA must call) -------------------
+// Two-level: shuffles inside each warp, one shared-memory round trip for the (at most 32)
+// warp partials, then every warp combines the partials again with shuffles (lane k holds
+// the partial of warp k), so the cross-warp phase costs ~5 shuffle steps, not NW loads.
 
 // Exclusive prefix sum of one double per thread; returns the exclusive prefix,
 // writes the block total.
@@ -77,13 +80,15 @@ __device__ __forceinline__ double block_excl_scan(double v, double& total, Scrat
   __syncthreads();  // protect scratch reuse
   if (lane == 31) sc->d[w] = incl;
   __syncthreads();
-  double woff = 0.0, tot = 0.0;
-  for (int k = 0; k < NW; k++) {
-    double s = sc->d[k];
-    if (k < w) woff += s;
-    tot += s;
+  double part = lane < NW ? sc->d[lane] : 0.0;
+  double pin = part;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    double t = __shfl_up_sync(0xffffffffu, pin, o);
+    if (lane >= o) pin += t;
   }
-  total = tot;
+  total = __shfl_sync(0xffffffffu, pin, 31);
+  const double woff = __shfl_sync(0xffffffffu, pin - part, w);
   return woff + (incl - v);
 }
 
@@ -99,76 +104,67 @@ __device__ __forceinline__ double block_excl_scan_rev(double v, double& total, S
   __syncthreads();
   if (lane == 0) sc->d[w] = incl;
   __syncthreads();
-  double woff = 0.0, tot = 0.0;
-  for (int k = 0; k < NW; k++) {
-    double s = sc->d[k];
-    if (k > w) woff += s;
-    tot += s;
+  double part = lane < NW ? sc->d[lane] : 0.0;
+  double pin = part;  // suffix-inclusive over warps
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    double t = __shfl_down_sync(0xffffffffu, pin, o);
+    if (lane + o < 32) pin += t;
   }
-  total = tot;
+  total = __shfl_sync(0xffffffffu, pin, 0);
+  const double woff = __shfl_sync(0xffffffffu, pin - part, w);
   return woff + (incl - v);
 }
 
-__device__ __forceinline__ double block_sum(double v, Scratch* sc) {
+__device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ double block_sum(double v, Scratch* sc) {
+  v = warp_sum(v);
   __syncthreads();
   if (lane_id() == 0) sc->d[warp_id()] = v;
   __syncthreads();
-  double tot = 0.0;
-  for (int k = 0; k < NW; k++) tot += sc->d[k];
-  return tot;
+  return warp_sum(lane_id() < NW ? sc->d[lane_id()] : 0.0);
 }
 
 // two sums at once (saves barriers)
 __device__ __forceinline__ void block_sum2(double& a, double& b, Scratch* sc) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    a += __shfl_xor_sync(0xffffffffu, a, o);
-    b += __shfl_xor_sync(0xffffffffu, b, o);
-  }
+  a = warp_sum(a);
+  b = warp_sum(b);
   __syncthreads();
   if (lane_id() == 0) {
     sc->d[warp_id()] = a;
     sc->d[MAXW + warp_id()] = b;
   }
   __syncthreads();
-  double ta = 0.0, tb = 0.0;
-  for (int k = 0; k < NW; k++) {
-    ta += sc->d[k];
-    tb += sc->d[MAXW + k];
-  }
-  a = ta;
-  b = tb;
+  a = warp_sum(lane_id() < NW ? sc->d[lane_id()] : 0.0);
+  b = warp_sum(lane_id() < NW ? sc->d[MAXW + lane_id()] : 0.0);
 }
 
 __device__ __forceinline__ int block_or(int pred) { return __syncthreads_or(pred); }
 
 // Smallest int over the block (INT_MAX = none).
 __device__ __forceinline__ int block_min_int(int v, Scratch* sc) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+  v = __reduce_min_sync(0xffffffffu, v);
   __syncthreads();
   if (lane_id() == 0) sc->i[warp_id()] = v;
   __syncthreads();
-  int r = sc->i[0];
-  for (int k = 1; k < NW; k++) r = min(r, sc->i[k]);
-  return r;
+  return __reduce_min_sync(0xffffffffu, lane_id() < NW ? sc->i[lane_id()] : 0x7fffffff);
 }
 __device__ __forceinline__ int block_max_int(int v, Scratch* sc) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+  v = __reduce_max_sync(0xffffffffu, v);
   __syncthreads();
   if (lane_id() == 0) sc->i[warp_id()] = v;
   __syncthreads();
-  int r = sc->i[0];
-  for (int k = 1; k < NW; k++) r = max(r, sc->i[k]);
-  return r;
+  return __reduce_max_sync(0xffffffffu, lane_id() < NW ? sc->i[lane_id()] : (int)0x80000000);
 }
 
 // First-occurrence arg-min and arg-max (strict comparisons, as min_max.py:73-77).
 template <typename T>
-__device__ __forceinline__ void block_argminmax(T& vmin, int& imin, T& vmax, int& imax, Scratch* sc) {
+__device__ __forceinline__ void warp_argminmax(T& vmin, int& imin, T& vmax, int& imax) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     T ov = __shfl_xor_sync(0xffffffffu, vmin, o);
@@ -178,6 +174,10 @@ __device__ __forceinline__ void block_argminmax(T& vmin, int& imin, T& vmax, int
     oi = __shfl_xor_sync(0xffffffffu, imax, o);
     if (ov > vmax || (ov == vmax && oi < imax)) { vmax = ov; imax = oi; }
   }
+}
+template <typename T>
+__device__ __forceinline__ void block_argminmax(T& vmin, int& imin, T& vmax, int& imax, Scratch* sc) {
+  warp_argminmax<T>(vmin, imin, vmax, imax);
   __syncthreads();
   if (lane_id() == 0) {
     sc->d[warp_id()] = (double)vmin;
@@ -186,17 +186,13 @@ __device__ __forceinline__ void block_argminmax(T& vmin, int& imin, T& vmax, int
     sc->i[MAXW + warp_id()] = imax;
   }
   __syncthreads();
-  T bmin = (T)sc->d[0], bmax = (T)sc->d[MAXW];
-  int bimin = sc->i[0], bimax = sc->i[MAXW];
-  for (int k = 1; k < NW; k++) {
-    T ov = (T)sc->d[k];
-    int oi = sc->i[k];
-    if (ov < bmin || (ov == bmin && oi < bimin)) { bmin = ov; bimin = oi; }
-    ov = (T)sc->d[MAXW + k];
-    oi = sc->i[MAXW + k];
-    if (ov > bmax || (ov == bmax && oi < bimax)) { bmax = ov; bimax = oi; }
-  }
-  vmin = bmin; imin = bimin; vmax = bmax; imax = bimax;
+  // lanes >= NW replicate warp 0's partial (harmless for first-occurrence semantics)
+  const int k = lane_id() < NW ? lane_id() : 0;
+  vmin = (T)sc->d[k];
+  vmax = (T)sc->d[MAXW + k];
+  imin = sc->i[k];
+  imax = sc->i[MAXW + k];
+  warp_argminmax<T>(vmin, imin, vmax, imax);
 }
 
 // ---- row staging -----------------------------------------------------------------

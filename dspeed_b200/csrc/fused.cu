@@ -35,6 +35,8 @@ constexpr int MAX_PTRS = 64;
 constexpr int MAX_SREG = 128;
 constexpr int MAX_SLOTS = 8;
 constexpr int IARGS = 15;
+constexpr int MAX_PROG_SMEM = 160;    // instructions staged in shared memory (64 B each)
+constexpr int MAX_CONST_SMEM = 384;   // float64 constants staged in shared memory
 
 enum Op {
   OP_END = 0,
@@ -65,7 +67,9 @@ enum Op {
   OP_SC_UNARY = 25,
   OP_MIN_MAX_NORM = 26,
   OP_LSD = 27,
-  OP_MBT = 28
+  OP_MBT = 28,
+  OP_PREFIX = 29,
+  OP_PFIR = 30
 };
 
 struct Instr {
@@ -82,6 +86,7 @@ struct ChainParams {
   const Instr* prog;
   int n_instr;
   const double* consts;
+  int n_consts;
   int slot_words;  // floats per slot
   int n_slots;
   int* fatal;      // int32[n][4] table (may be null)
@@ -103,28 +108,6 @@ __device__ __forceinline__ double load_scalar_as_double(const void* p, long long
     case 6: return (double)reinterpret_cast<const long long*>(p)[idx];
   }
   return 0.0;
-}
-
-// forward cumulative sum written with an index shift: out[i - shift] = sum_{j<=i} d(j), i >= shift
-template <typename T, class D>
-__device__ __forceinline__ int cumsum_fwd_shift(D d, T* out, int n_total, int shift, Scratch* sc) {
-  int lo, hi;
-  chunk_range(n_total, lo, hi);
-  double loc = 0.0;
-  for (int i = lo; i < hi; i++) loc += d(i);
-  double tot;
-  double run = block_excl_scan(loc, tot, sc);
-  int bad = 0;
-  for (int i = lo; i < hi; i++) {
-    run += d(i);
-    if (i >= shift) {
-      T v = (T)run;
-      bad |= (v != v);
-      out[sidx(i - shift)] = v;
-    }
-  }
-  __syncthreads();
-  return bad;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -242,7 +225,35 @@ __device__ void op_conv_seg(const T* x, int N, T* out, double* tab, const double
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(FUSED_THREADS, 1)
+// out[i] = sum_s c_s * P[i + shift - t_s] with the (few) taps held in registers
+template <typename T, int MAXT>
+__device__ __forceinline__ int pfir_run(const double* __restrict__ Pq, const double* taps, int nt, int n, int shift,
+                                        int p, T* out) {
+  int tt[MAXT];
+  double cc[MAXT];
+#pragma unroll
+  for (int s = 0; s < MAXT; s++) {
+    tt[s] = s < nt ? shift - (int)taps[2 * s] : 0;
+    cc[s] = s < nt ? taps[2 * s + 1] : 0.0;
+  }
+  int bad = 0;
+  for (int i = threadIdx.x; i < p; i += NT) {
+    double v = 0.0;
+#pragma unroll
+    for (int s = 0; s < MAXT; s++) {
+      if (MAXT > 12 && s >= nt) break;
+      const int idx = min(i + tt[s], n - 1);
+      if (idx >= 0) v = fma(cc[s], Pq[sidx(idx)], v);
+    }
+    const T o = (T)v;
+    bad |= (o != o);
+    out[sidx(i)] = o;
+  }
+  return bad;
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
 k_chain(const ChainParams cp, const __grid_constant__ PtrTable pt, const long long n_rows) {
   using T = float;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -250,9 +261,20 @@ k_chain(const ChainParams cp, const __grid_constant__ PtrTable pt, const long lo
   double* sreg = reinterpret_cast<double*>(smem_raw + SCRATCH_BYTES);
   int* slot_nan = reinterpret_cast<int*>(sreg + MAX_SREG);
   Aff2* aff = reinterpret_cast<Aff2*>(slot_nan + 16);
-  T* slots = reinterpret_cast<T*>(aff + MAXW);
+  double* Ks = reinterpret_cast<double*>(aff + MAXW);
+  int4* prog_s = reinterpret_cast<int4*>(Ks + MAX_CONST_SMEM);
+  T* slots = reinterpret_cast<T*>(prog_s + 4 * MAX_PROG_SMEM);
   const int SW = cp.slot_words;
-  const double* K = cp.consts;
+  // stage the (small, read-only) program and constant pool once per CTA
+  const bool prog_in_smem = cp.n_instr <= MAX_PROG_SMEM;
+  const bool k_in_smem = cp.n_consts <= MAX_CONST_SMEM;
+  if (prog_in_smem)
+    for (int i = threadIdx.x; i < cp.n_instr * 4; i += NT) prog_s[i] = reinterpret_cast<const int4*>(cp.prog)[i];
+  if (k_in_smem)
+    for (int i = threadIdx.x; i < cp.n_consts; i += NT) Ks[i] = cp.consts[i];
+  __syncthreads();
+  const double* K = k_in_smem ? Ks : cp.consts;
+  const int4* prog = prog_in_smem ? prog_s : reinterpret_cast<const int4*>(cp.prog);
 
   auto slot = [&](int s) -> T* { return slots + (size_t)s * SW; };
   auto sget = [&](int kind, int idx) -> double { return kind == 0 ? sreg[idx] : K[idx]; };
@@ -262,9 +284,11 @@ k_chain(const ChainParams cp, const __grid_constant__ PtrTable pt, const long lo
     if (threadIdx.x < 16) slot_nan[threadIdx.x] = 0;
     __syncthreads();
     for (int pc = 0; pc < cp.n_instr; pc++) {
-      const Instr& I = cp.prog[pc];
-      const int* a = I.a;
-      switch (I.op) {
+      // one instruction = 4 x 128-bit loads into registers (no re-reads inside the op)
+      const int4 w0 = prog[4 * pc], w1 = prog[4 * pc + 1], w2 = prog[4 * pc + 2], w3 = prog[4 * pc + 3];
+      const int op = w0.x;
+      const int a[IARGS] = {w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w, w3.x, w3.y, w3.z, w3.w};
+      switch (op) {
         case OP_LOAD_WAVE: {  // a0 slot, a1 ptr, a2 n, a3 dtype
           Wave w;
           w.ptr = pt.p[a[1]]; w.row_stride = pt.s[a[1]]; w.dtype = a[3];
@@ -313,13 +337,6 @@ k_chain(const ChainParams cp, const __grid_constant__ PtrTable pt, const long lo
           __syncthreads();
           break;
         }
-        default: break;
-      }
-      // ---- ops on a (slot, off, n) input view: materialise a pointer with the offset folded
-      // in.  sidx() is not translation invariant, so views with off != 0 are handled by the
-      // routines through `in_off` (below) -- the compiler only emits off != 0 for ops that
-      // support it (reductions, searches, convolutions).
-      switch (I.op) {
         case OP_MIN_MAX: {  // a0 in, a1 off, a2 n, a3..a6 regs (tmin,tmax,vmin,vmax; -1 unused)
           const T* in = slot(a[0]);
           double r[4] = {CUDART_NAN, CUDART_NAN, CUDART_NAN, CUDART_NAN};
@@ -564,7 +581,7 @@ k_chain(const ChainParams cp, const __grid_constant__ PtrTable pt, const long lo
               }
               return v;
             };
-            cumsum_fwd_shift<T>(d, slot(a[3]), a[7] + a[4], a[7], sc);
+            cumsum_fwd<T>(d, [](double v) { return (T)v; }, slot(a[3]), a[7] + a[4], sc, a[7]);
           }
           if (threadIdx.x == 0) slot_nan[a[3]] = nanf;
           __syncthreads();
@@ -575,6 +592,48 @@ k_chain(const ChainParams cp, const __grid_constant__ PtrTable pt, const long lo
           const int p = a[2] - (int)K[a[5] + 3] + 1;
           if (nanf) { fill_slot_nan<T>(slot(a[3]), p); __syncthreads(); }
           else op_conv_seg<T>(slot(a[0]), a[2], slot(a[3]), reinterpret_cast<double*>(slot(a[8])), K + a[5], sc);
+          if (threadIdx.x == 0) slot_nan[a[3]] = nanf;
+          __syncthreads();
+          break;
+        }
+        case OP_PREFIX: {  // a0 in, a2 n, a3 first of two slots receiving the float64 inclusive prefix sums
+          // P[k] = sum_{j<=k} x[j] (float64, layout pidx): the common operand of every
+          // windowed / recursive filter of this waveform (trapezoids, run-structured kernels)
+          if (slot_nan[a[0]] == 0) {
+            const T* in = slot(a[0]);
+            double* Pq = reinterpret_cast<double*>(slot(a[3]));
+            const int n = a[2];
+            int lo, hi;
+            chunk_range(n, lo, hi);
+            double loc = 0.0;
+            for (int i = lo; i < hi; i++) loc += (double)in[sidx(i)];
+            double tot;
+            double run = block_excl_scan(loc, tot, sc);
+            for (int i = lo; i < hi; i++) {
+              run += (double)in[sidx(i)];
+              Pq[sidx(i)] = run;
+            }
+          }
+          __syncthreads();
+          break;
+        }
+        case OP_PFIR: {  // a0 src wave (NaN flag), a2 n, a3 out, a4 p, a5 consts idx (pairs t,c), a6 n_taps,
+                         // a7 shift, a8 prefix slots
+          // out[i] = sum_s c_s * P[i + shift - t_s]   (P[k<0] = 0, P[k>=n] = P[n-1])
+          const int nanf = slot_nan[a[0]] != 0;
+          T* out = slot(a[3]);
+          if (nanf) fill_slot_nan<T>(out, a[4]);
+          else {
+            const double* Pq = reinterpret_cast<const double*>(slot(a[8]));
+            const double* taps = K + a[5];
+            const int n = a[2], nt = a[6], shift = a[7], p = a[4];
+            int bad = 0;
+            if (nt <= 4) bad = pfir_run<T, 4>(Pq, taps, nt, n, shift, p, out);
+            else if (nt <= 12) bad = pfir_run<T, 12>(Pq, taps, nt, n, shift, p, out);
+            else bad = pfir_run<T, 32>(Pq, taps, nt, n, shift, p, out);
+            (void)bad;
+          }
+          __syncthreads();
           if (threadIdx.x == 0) slot_nan[a[3]] = nanf;
           __syncthreads();
           break;
@@ -669,10 +728,12 @@ struct dspb_chain {
   Instr* d_prog = nullptr;
   double* d_consts = nullptr;
   int n_instr = 0;
+  int n_consts = 0;
   int n_slots = 0;
   int slot_len = 0;
   size_t smem = 0;
   int num_sms = 148;
+  int threads = FUSED_THREADS;
 };
 
 extern "C" int dspb_chain_create(const int32_t* code, int64_t n_code, const double* consts, int64_t n_consts,
@@ -685,6 +746,7 @@ extern "C" int dspb_chain_create(const int32_t* code, int64_t n_code, const doub
   c->n_instr = code[2];
   if ((int64_t)c->n_instr * (1 + IARGS) + 3 != n_code || c->n_slots > MAX_SLOTS) { delete c; return DSPB_ERR_UNSUPPORTED; }
   c->smem = SCRATCH_BYTES + MAX_SREG * sizeof(double) + 16 * sizeof(int) + MAXW * sizeof(Aff2) +
+            MAX_CONST_SMEM * sizeof(double) + MAX_PROG_SMEM * sizeof(Instr) +
             (size_t)c->n_slots * slot_words_aligned(c->slot_len) * sizeof(float);
   if (c->smem > MAX_SMEM) { delete c; return DSPB_ERR_ROW_TOO_LONG; }
   std::vector<Instr> prog(c->n_instr);
@@ -695,10 +757,13 @@ extern "C" int dspb_chain_create(const int32_t* code, int64_t n_code, const doub
   }
   cudaError_t e = cudaMalloc(&c->d_prog, sizeof(Instr) * (size_t)c->n_instr);
   if (e == cudaSuccess) e = cudaMemcpy(c->d_prog, prog.data(), sizeof(Instr) * (size_t)c->n_instr, cudaMemcpyHostToDevice);
+  c->n_consts = (int)n_consts;
   const size_t nc = n_consts > 0 ? (size_t)n_consts : 1;
   if (e == cudaSuccess) e = cudaMalloc(&c->d_consts, sizeof(double) * nc);
   if (e == cudaSuccess && n_consts > 0) e = cudaMemcpy(c->d_consts, consts, sizeof(double) * nc, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem);
+  if (const char* t = getenv("DSPEED_B200_FUSED_THREADS")) c->threads = atoi(t) >= 1024 ? 1024 : FUSED_THREADS;
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_chain<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_chain<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem);
   int dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -720,12 +785,14 @@ extern "C" int dspb_chain_launch(dspb_chain* c, const void* const* ptrs, int64_t
   cp.prog = c->d_prog;
   cp.n_instr = c->n_instr;
   cp.consts = c->d_consts;
+  cp.n_consts = c->n_consts;
   cp.slot_words = slot_words_aligned(c->slot_len);
   cp.n_slots = c->n_slots;
   cp.fatal = fatal;
   cp.row0 = strides[n_ptrs];
   const int grid = (int)(n_rows < c->num_sms ? n_rows : c->num_sms);
-  k_chain<<<grid, FUSED_THREADS, c->smem, (cudaStream_t)stream>>>(cp, pt, n_rows);
+  if (c->threads == 1024) k_chain<1024><<<grid, 1024, c->smem, (cudaStream_t)stream>>>(cp, pt, n_rows);
+  else k_chain<512><<<grid, 512, c->smem, (cudaStream_t)stream>>>(cp, pt, n_rows);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -(int)e;
 }

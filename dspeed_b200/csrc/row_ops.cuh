@@ -23,20 +23,49 @@ namespace dspb {
 // accumulation is float64, `post` maps the float64 running sum to the stored value.
 // Returns (per thread) 1 if a NaN was stored.
 // ---------------------------------------------------------------------------------
+// When a thread's chunk has at most CUM_REG samples the per-sample terms are evaluated ONCE
+// and their running sums kept in registers across the block scan (single pass); longer
+// chunks fall back to evaluating d(j) twice.
+constexpr int CUM_REG = 16;
+
 template <typename T, class D, class Post>
-__device__ __forceinline__ int cumsum_fwd(D d, Post post, T* out, int n, Scratch* sc) {
+__device__ __forceinline__ int cumsum_fwd(D d, Post post, T* out, int n, Scratch* sc, int shift = 0) {
   int lo, hi;
   chunk_range(n, lo, hi);
-  double loc = 0.0;
-  for (int i = lo; i < hi; i++) loc += d(i);
-  double tot;
-  double run = block_excl_scan(loc, tot, sc);
+  const int c = (n + NT - 1) / NT;
   int bad = 0;
-  for (int i = lo; i < hi; i++) {
-    run += d(i);
-    T v = post(run);
-    bad |= (v != v);
-    out[sidx(i)] = v;
+  double tot;
+  if (c <= CUM_REG) {
+    double v[CUM_REG];
+    double run = 0.0;
+#pragma unroll
+    for (int k = 0; k < CUM_REG; k++) {
+      const int i = lo + k;
+      if (i < hi) run += d(i);
+      v[k] = run;
+    }
+    const double ex = block_excl_scan(run, tot, sc);
+#pragma unroll
+    for (int k = 0; k < CUM_REG; k++) {
+      const int i = lo + k;
+      if (i < hi && i >= shift) {
+        const T o = post(ex + v[k]);
+        bad |= (o != o);
+        out[sidx(i - shift)] = o;
+      }
+    }
+  } else {
+    double loc = 0.0;
+    for (int i = lo; i < hi; i++) loc += d(i);
+    double run = block_excl_scan(loc, tot, sc);
+    for (int i = lo; i < hi; i++) {
+      run += d(i);
+      if (i >= shift) {
+        const T o = post(run);
+        bad |= (o != o);
+        out[sidx(i - shift)] = o;
+      }
+    }
   }
   __syncthreads();
   return bad;
@@ -46,16 +75,38 @@ template <typename T, class D, class Post>
 __device__ __forceinline__ int cumsum_rev(D d, Post post, T* out, int n, Scratch* sc) {
   int lo, hi;
   chunk_range(n, lo, hi);
-  double loc = 0.0;
-  for (int i = hi - 1; i >= lo; i--) loc += d(i);
-  double tot;
-  double run = block_excl_scan_rev(loc, tot, sc);
+  const int c = (n + NT - 1) / NT;
   int bad = 0;
-  for (int i = hi - 1; i >= lo; i--) {
-    run += d(i);
-    T v = post(run);
-    bad |= (v != v);
-    out[sidx(i)] = v;
+  double tot;
+  if (c <= CUM_REG) {
+    double v[CUM_REG];
+    double run = 0.0;
+#pragma unroll
+    for (int k = 0; k < CUM_REG; k++) {
+      const int i = hi - 1 - k;
+      if (i >= lo) run += d(i);
+      v[k] = run;
+    }
+    const double ex = block_excl_scan_rev(run, tot, sc);
+#pragma unroll
+    for (int k = 0; k < CUM_REG; k++) {
+      const int i = hi - 1 - k;
+      if (i >= lo) {
+        const T o = post(ex + v[k]);
+        bad |= (o != o);
+        out[sidx(i)] = o;
+      }
+    }
+  } else {
+    double loc = 0.0;
+    for (int i = hi - 1; i >= lo; i--) loc += d(i);
+    double run = block_excl_scan_rev(loc, tot, sc);
+    for (int i = hi - 1; i >= lo; i--) {
+      run += d(i);
+      const T o = post(run);
+      bad |= (o != o);
+      out[sidx(i)] = o;
+    }
   }
   __syncthreads();
   return bad;
@@ -299,8 +350,8 @@ __device__ __forceinline__ int op_trap(const T* in, T* out, int n, int rise, int
     return v;
   };
   if (norm) {
-    const double r = (double)rise;
-    return cumsum_fwd<T>(d, [r](double s) { return (T)(s / r); }, out, n, sc);
+    const double ir = 1.0 / (double)rise;
+    return cumsum_fwd<T>(d, [ir](double s) { return (T)(s * ir); }, out, n, sc);
   }
   return cumsum_fwd<T>(d, [](double s) { return (T)s; }, out, n, sc);
 }
@@ -311,16 +362,14 @@ __device__ __forceinline__ int op_asym_trap(const T* in, T* out, int n, int rise
                                             Scratch* sc) {
   const int o1 = rise, o2 = rise + flat, o3 = rise + flat + fall;
   const double ir = 1.0 / (double)rise, ifl = 1.0 / (double)fall;
-  (void)ir; (void)ifl;
-  const double r = (double)rise, fl = (double)fall;
   auto d = [&](int i) -> double {
     double a = (double)in[sidx(i)];
     if (i >= o1) a -= (double)in[sidx(i - o1)];
-    double v = a / r;
+    double v = a * ir;
     if (i >= o2) {
       double b = (double)in[sidx(i - o2)];
       if (i >= o3) b -= (double)in[sidx(i - o3)];
-      v -= b / fl;
+      v -= b * ifl;
     }
     return v;
   };
@@ -353,11 +402,11 @@ __device__ __forceinline__ T op_trap_pickoff(const T* in, int n, int rise, int f
 template <typename T>
 __device__ __forceinline__ int op_mw_left(const T* in, T* out, int n, T length, Scratch* sc) {
   const int L = (int)length;
-  const double len = (double)length;
+  const double ilen = 1.0 / (double)length;
   auto d = [&](int i) -> double {
     if (i == 0) return (double)in[sidx(0)];
     const int j = i >= L ? i - L : 0;
-    return ((double)in[sidx(i)] - (double)in[sidx(j)]) / len;
+    return ((double)in[sidx(i)] - (double)in[sidx(j)]) * ilen;
   };
   return cumsum_fwd<T>(d, [](double s) { return (T)s; }, out, n, sc);
 }
@@ -366,11 +415,11 @@ __device__ __forceinline__ int op_mw_left(const T* in, T* out, int n, T length, 
 template <typename T>
 __device__ __forceinline__ int op_mw_right(const T* in, T* out, int n, T length, Scratch* sc) {
   const int L = (int)length;
-  const double len = (double)length;
+  const double ilen = 1.0 / (double)length;
   auto d = [&](int i) -> double {
     if (i == n - 1) return (double)in[sidx(n - 1)];
     const int j = i + L <= n - 1 ? i + L : n - 1;
-    return ((double)in[sidx(i)] - (double)in[sidx(j)]) / len;
+    return ((double)in[sidx(i)] - (double)in[sidx(j)]) * ilen;
   };
   return cumsum_rev<T>(d, [](double s) { return (T)s; }, out, n, sc);
 }

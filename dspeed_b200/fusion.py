@@ -37,14 +37,14 @@ IARGS = 15
 MAX_SREG = 128
 MAX_PTRS = 64
 MAX_SMEM = 227 * 1024
-FIXED_SMEM = 2048 + MAX_SREG * 8 + 16 * 4 + 32 * 48
+FIXED_SMEM = 2048 + MAX_SREG * 8 + 16 * 4 + 32 * 48 + 384 * 8 + 160 * 64
 FUSED_THREADS = 512
 R_OUT, CH = 8, 64
 
 (OP_END, OP_LOAD_WAVE, OP_LOAD_SCALAR, OP_STORE_SCALAR, OP_STORE_WAVE, OP_BL_SUB, OP_MIN_MAX, OP_LSF, OP_POLE_ZERO,
  OP_DPZ, OP_TRAP, OP_ASYM, OP_TRAP_PICKOFF, OP_MW, OP_AVG_CURRENT, OP_TPT, OP_ITPT, OP_FTP, OP_WINDOWER, OP_UPSAMPLER,
  OP_CONV_DIRECT, OP_CONV_RUNS, OP_CONV_SEG, OP_SC_BIN, OP_SC_CONVERT, OP_SC_UNARY, OP_MIN_MAX_NORM, OP_LSD,
- OP_MBT) = range(29)
+ OP_MBT, OP_PREFIX, OP_PFIR) = range(31)
 
 _DT = {torch.float32: 0, torch.float64: 1, torch.uint16: 2, torch.int16: 3, torch.int32: 4, torch.uint32: 5,
        torch.int64: 6}
@@ -58,8 +58,12 @@ def _slot_words(n: int) -> int:
     return (n + (n >> 5) + 1 + 3) & ~3
 
 
+_ALIAS: dict[int, int] = {}
+
+
 def _storage(t: torch.Tensor) -> int:
-    return t.untyped_storage().data_ptr()
+    st = t.untyped_storage().data_ptr()
+    return _ALIAS.get(st, st)
 
 
 class _Wave:
@@ -89,6 +93,10 @@ class FusedChain:
     def _compile(self, chain):
         managers = list(chain._proc_managers)
         self.n_managers = len(managers)
+        _ALIAS.clear()
+        self.prefix: dict[int, int] = {}      # wave storage -> first slot of its float64 prefix array
+        self.prefix_last: dict[int, int] = {}  # wave storage -> last manager index that wants the prefix
+        self.cse_skipped = 0
         self.code: list[list[int]] = []
         self.consts: list[float] = []
         self.ptrs: list = []          # ("in", manager, what) | ("buf", tensor) | ("const", tensor)
@@ -117,9 +125,38 @@ class FusedChain:
         for name, man in chain._input_managers.items():
             self._register_input(man)
 
+        # ---- pass 0: identical wave producers (same processor, same bound inputs) share one
+        # result, e.g. wf_etrap == wf_trap with the default database ------------------------------
+        seen = {}
+        self.skip = set()
+        for i, pm in enumerate(managers):
+            name = getattr(pm.processor, "__name__", "")
+            if not getattr(pm.processor, "native_kernel", False) or getattr(pm.processor, "nout", 1) != 1:
+                continue
+            out = pm.args[-1]
+            if not (isinstance(out, torch.Tensor) and out.ndim == 2 and out.storage_offset() == 0):
+                continue
+            key = [name]
+            for x in pm.args[:-1]:
+                if isinstance(x, torch.Tensor):
+                    key.append(("t", _storage(x), x.storage_offset(), tuple(x.shape), tuple(x.stride())))
+                else:
+                    key.append(("c", repr(x)))
+            key = tuple(key)
+            if key in seen and tuple(seen[key].shape) == tuple(out.shape):
+                _ALIAS[out.untyped_storage().data_ptr()] = _storage(seen[key])
+                self.skip.add(i)
+            else:
+                seen[key] = out
+
         # ---- pass 1: last use of every wave storage ------------------------------------------
         self._fatal_base = chain.fatal.data_ptr()
         for i, pm in enumerate(managers):
+            if i not in self.skip and getattr(pm.processor, "__name__", "") in (
+                    "trap_filter", "trap_norm", "asym_trap_filter", "convolve_wf", "fft_convolve_wf"):
+                x = pm.args[0]
+                if isinstance(x, torch.Tensor) and x.ndim == 2:
+                    self.prefix_last[_storage(x)] = i
             for a in pm.args:
                 if isinstance(a, torch.Tensor) and a.ndim >= 2 and _storage(a) not in self.const_storage:
                     w = self.waves.setdefault(_storage(a), _Wave(self._root_len(a)))
@@ -141,7 +178,10 @@ class FusedChain:
         for i, pm in enumerate(managers):
             self._cur = i
             self._fatal_idx = (pm.fatal.data_ptr() - self._fatal_base) // 16
-            self._lower(pm)
+            if i in self.skip:
+                self.cse_skipped += 1
+            else:
+                self._lower(pm)
             # outputs that are chain outputs are stored as soon as they are produced
             for a in self._outputs_of(pm):
                 if isinstance(a, torch.Tensor) and a.ndim >= 2 and _storage(a) in out_wave_storages \
@@ -245,18 +285,77 @@ class FusedChain:
 
     def _alloc_slot(self) -> int:
         if not self.free_slots:
+            self._evict_prefixes()
+        if not self.free_slots:
             raise NotFusable("not enough shared-memory slots for the live waveforms")
         s = self.free_slots.pop(0)
         self.slots_used = max(self.slots_used, s + 1)
         return s
 
+    def _free(self, *slots):
+        self.free_slots.extend(slots)
+        self.free_slots.sort()
+
+    def _evict_prefixes(self, keep=None):
+        """prefix arrays are caches: give their slot pairs back under pressure (they are
+        recomputed by a PREFIX instruction when the next consumer needs them)"""
+        for st in list(self.prefix):
+            if st != keep:
+                s0 = self.prefix.pop(st)
+                self._free(s0, s0 + 1)
+
+    def _prefix_of(self, t: torch.Tensor, slot_in: int, n: int):
+        """first slot of the float64 inclusive-prefix array of a whole waveform (two adjacent
+        slots), emitting the PREFIX instruction when it is not resident; None if there is no room"""
+        st = _storage(t)
+        if st in self.prefix:
+            return self.prefix[st]
+        if 8 * (n + (n >> 5) + 1) > 2 * _slot_words(self.slot_len) * 4:
+            return None
+
+        def find_pair():
+            for a in self.free_slots:
+                if a + 1 in self.free_slots:
+                    return a
+            return None
+
+        s0 = find_pair()
+        if s0 is None:
+            self._evict_prefixes()
+            s0 = find_pair()
+        if s0 is None or len(self.free_slots) < 3:  # keep one slot for the consumer's output
+            return None
+        self.free_slots.remove(s0)
+        self.free_slots.remove(s0 + 1)
+        self.slots_used = max(self.slots_used, s0 + 2)
+        self.prefix[st] = s0
+        self._emit(OP_PREFIX, slot_in, 0, n, s0)
+        return s0
+
+    def _pfir(self, t_in, s, n, so, p, taps, shift) -> bool:
+        """out[i] = sum_s c_s P[i + shift - t_s]; False when the prefix array cannot be resident"""
+        if len(taps) > 32:
+            return False
+        # the output slot must not be one of the prefix slots: allocate the prefix first
+        s0 = self._prefix_of(t_in, s, n)
+        if s0 is None or so in (s0, s0 + 1):
+            return False
+        pairs = []
+        for t, c in taps:
+            pairs += [float(t), float(c)]
+        self._emit(OP_PFIR, s, 0, n, so, p, self._const(*pairs), len(taps), shift, s0)
+        return True
+
     def _release_dead(self, i):
-        for w in self.waves.values():
+        for st, w in self.waves.items():
             if w.slot is not None and w.last_use <= i:
-                self.free_slots.append(w.slot)
-                self.free_slots.sort()
+                self._free(w.slot)
                 w.slot = None
                 w.dead = True
+        for st in list(self.prefix):
+            if self.prefix_last.get(st, -1) <= i:
+                s0 = self.prefix.pop(st)
+                self._free(s0, s0 + 1)
 
     def _wave_in(self, t: torch.Tensor, need_zero_offset=False):
         """(slot, offset, n) of an input waveform operand; loads chain inputs on first use"""
@@ -425,15 +524,28 @@ class FusedChain:
             rise, flat = int(a[1]), int(a[2])
             if rise < 0 or flat < 0 or 2 * rise + flat > n:
                 raise NotFusable("invalid trapezoid arguments (the per-processor path raises the DSPFatal)")
+            norm = name == "trap_norm"
+            if rise == 0 and norm:
+                raise NotFusable("trap_norm with rise == 0")
+            c = 1.0 / rise if norm else 1.0
+            s0 = self._prefix_of(a[0], s, n)   # before the output slot, so the pair stays adjacent
             so, _ = self._wave_out(a[3])
-            self._emit(OP_TRAP, s, 0, n, so, rise, flat, 1 if name == "trap_norm" else 0)
+            if s0 is None or not self._pfir(a[0], s, n, so, n, [(0, c), (rise, -c), (rise + flat, -c),
+                                                              (2 * rise + flat, c)], 0):
+                self._emit(OP_TRAP, s, 0, n, so, rise, flat, 1 if norm else 0)
         elif name == "asym_trap_filter":
             s, off, n = self._wave_in(a[0], True)
             rise, flat, fall = int(a[1]), int(a[2]), int(a[3])
             if min(rise, flat, fall) < 0 or rise + flat + fall > n:
                 raise NotFusable("invalid trapezoid arguments")
+            if rise == 0 or fall == 0:
+                raise NotFusable("asym_trap_filter with a zero-length side")
+            s0 = self._prefix_of(a[0], s, n)
             so, _ = self._wave_out(a[4])
-            self._emit(OP_ASYM, s, 0, n, so, rise, flat, fall)
+            if s0 is None or not self._pfir(a[0], s, n, so, n, [(0, 1.0 / rise), (rise, -1.0 / rise),
+                                                              (rise + flat, -1.0 / fall),
+                                                              (rise + flat + fall, 1.0 / fall)], 0):
+                self._emit(OP_ASYM, s, 0, n, so, rise, flat, fall)
         elif name == "trap_pickoff":
             s, off, n = self._wave_in(a[0], True)
             rise, flat = int(a[1]), int(a[2])
@@ -451,8 +563,7 @@ class FusedChain:
                 so, _ = self._wave_out(a[4])
                 tmp = self._alloc_slot()
                 self._emit(OP_MW, s, 0, n, so, tmp, self._const(length), 2, int(num), typ)
-                self.free_slots.append(tmp)
-                self.free_slots.sort()
+                self._free(tmp)
             else:
                 if not (0 <= length < n):
                     raise NotFusable("invalid moving-window arguments")
@@ -514,17 +625,23 @@ class FusedChain:
             raise NotFusable("invalid convolution arguments")
         p = {"f": n + m - 1, "v": n - m + 1, "s": n}[mode]
         coff = {"f": 0, "v": m - 1, "s": (m - 1) // 2}[mode]
-        so, p_out = self._wave_out(w_out)
-        if p_out != p:
-            raise NotFusable("convolution output length mismatch")
         if np.isnan(k).any():
             raise NotFusable("NaN in convolution kernel")
         choice = os.environ.get("DSPEED_B200_CONV", "auto")
+        dk0 = np.diff(np.concatenate([[0.0], k.astype(np.float64), [0.0]]))
+        runs_ok = choice in ("auto", "runs") and len(np.flatnonzero(dk0)) <= 24
+        s0 = self._prefix_of(w_in, s, n) if (runs_ok and off == 0) else None
+        so, p_out = self._wave_out(w_out)
+        if p_out != p:
+            raise NotFusable("convolution output length mismatch")
 
         # (1) run-structured kernels: sparse first difference -> FIR + cumulative sum (exact)
         dk = np.diff(np.concatenate([[0.0], k.astype(np.float64), [0.0]]))
         taps = np.flatnonzero(dk)
-        if choice in ("auto", "runs") and len(taps) <= 24:
+        if runs_ok and s0 is not None and self._pfir(w_in, s, n, so, p, [(int(t), float(dk[t])) for t in taps], coff):
+            self.conv_lowering = getattr(self, "conv_lowering", []) + [("runs", m, len(taps))]
+            return
+        if runs_ok:
             pairs = []
             for t in taps:
                 pairs += [float(t), float(dk[t])]
@@ -537,8 +654,7 @@ class FusedChain:
         if seg is not None and 13 * p * 8 <= _slot_words(self.slot_len) * 4:
             scratch = self._alloc_slot()
             self._emit(OP_CONV_SEG, s, 0, n, so, p, self._const(*seg), 0, 0, scratch)
-            self.free_slots.append(scratch)
-            self.free_slots.sort()
+            self._free(scratch)
             self.conv_lowering = getattr(self, "conv_lowering", []) + [("seg", m, "zac" if seg[9] else "cusp")]
             return
 
@@ -553,8 +669,7 @@ class FusedChain:
             scratch = self._alloc_slot()
         self._emit(OP_CONV_DIRECT, s, off, n, so, p, self._ptr(("const", kernel)), m, coff, scratch, S)
         if S > 1:
-            self.free_slots.append(scratch)
-            self.free_slots.sort()
+            self._free(scratch)
         self.conv_lowering = getattr(self, "conv_lowering", []) + [("direct", m, S)]
 
     def _seg_model(self, kernel_t, k):
@@ -605,7 +720,7 @@ class FusedChain:
         names = ["END", "LOAD_WAVE", "LOAD_SCALAR", "STORE_SCALAR", "STORE_WAVE", "BL_SUB", "MIN_MAX", "LSF", "POLE_ZERO",
                  "DPZ", "TRAP", "ASYM", "TRAP_PICKOFF", "MW", "AVG_CURRENT", "TPT", "ITPT", "FTP", "WINDOWER",
                  "UPSAMPLER", "CONV_DIRECT", "CONV_RUNS", "CONV_SEG", "SC_BIN", "SC_CONVERT", "SC_UNARY",
-                 "MIN_MAX_NORM", "LSD", "MBT"]
+                 "MIN_MAX_NORM", "LSD", "MBT", "PREFIX", "PFIR"]
         return "\n".join(f"{i:3d} {names[ins[0]]:13s} {ins[1:]}" for i, ins in enumerate(self.code))
 
     # ------------------------------------------------------------------------------------
@@ -614,38 +729,52 @@ class FusedChain:
     def can_run(self, chain) -> bool:
         return self.handle.value is not None and len(chain._proc_managers) == self.n_managers
 
-    def _pointer_table(self, begin, end):
-        """device pointers + row strides for rows [begin, end); device-resident input columns
-        are read in place, host columns go through the chain's block buffers"""
-        ptrs, strides = [], []
-        for key in self.ptrs:
-            kind = key[0]
-            if kind == "in":
-                man, what = key[1], key[2]
-                if what == "t0":
-                    src = man.io_wf.t0.nda
-                    buf = man.t0_var
-                else:
-                    src = man.io_array.nda if hasattr(man, "io_array") else man.io_buf
-                    buf = man.raw_var
-                if isinstance(src, torch.Tensor) and src.is_cuda and src.dtype == buf.dtype and \
-                        (src.ndim == 1 or src.stride(-1) == 1):
-                    view = src[begin:end]
-                    ptrs.append(view.data_ptr())
-                    strides.append(view.stride(0) if view.ndim >= 1 and view.shape[0] > 0 else 0)
-                else:
-                    n = end - begin
-                    t = src if isinstance(src, torch.Tensor) else torch.from_numpy(src)
-                    buf[:n].copy_(t[begin:end], non_blocking=True)
-                    if not t.is_cuda:
-                        self.chain.stats["h2d_bytes"] += n * buf[0].numel() * buf.element_size()
-                    ptrs.append(buf.data_ptr())
-                    strides.append(buf.stride(0))
-            else:
-                t = key[1]
-                ptrs.append(t.data_ptr())
-                strides.append(t.stride(0) if t.ndim >= 1 else 0)
-        return ptrs, strides
+    # -- input staging: host columns are copied into device staging buffers on a separate
+    # copy stream, double-buffered, so the H2D transfer of block k+1 overlaps the kernel of
+    # block k; device-resident columns are read in place (no copy at all) -------------------
+    def _input_sources(self):
+        """[(ptr-table index, source column, staging buffers[2] or None)]"""
+        if getattr(self, "_sources", None) is not None:
+            return self._sources
+        srcs = []
+        for idx, key in enumerate(self.ptrs):
+            if key[0] != "in":
+                continue
+            man, what = key[1], key[2]
+            buf = man.t0_var if what == "t0" else man.raw_var
+            srcs.append([idx, man, what, buf, [buf, None]])
+        self._sources = srcs
+        return srcs
+
+    @staticmethod
+    def _column(man, what):
+        if what == "t0":
+            return man.io_wf.t0.nda
+        return man.io_array.nda if hasattr(man, "io_array") else man.io_buf
+
+    def _stage_block(self, begin, end, stage, copy_stream):
+        """enqueue the H2D copies of rows [begin, end) into staging set `stage`; returns
+        {ptr index: (device pointer, row stride)}"""
+        res = {}
+        for src in self._input_sources():
+            idx, man, what, buf, staging = src
+            col = self._column(man, what)
+            if isinstance(col, torch.Tensor) and col.is_cuda and col.dtype == buf.dtype and \
+                    (col.ndim == 1 or col.stride(-1) == 1):
+                view = col[begin:end]
+                res[idx] = (view.data_ptr(), view.stride(0))
+                continue
+            if staging[stage] is None:
+                staging[stage] = torch.empty_like(buf)
+            dst = staging[stage]
+            t = col if isinstance(col, torch.Tensor) else torch.from_numpy(col)
+            n = end - begin
+            with torch.cuda.stream(copy_stream):
+                dst[:n].copy_(t[begin:end], non_blocking=True)
+            if not t.is_cuda:
+                self.chain.stats["h2d_bytes"] += n * dst[0].numel() * dst.element_size()
+            res[idx] = (dst.data_ptr(), dst.stride(0))
+        return res
 
     def execute(self, chain, start, stop):
         from . import processing_chain as pc
@@ -656,30 +785,60 @@ class FusedChain:
                    for m in chain._input_managers.values()) if chain._input_managers else stop
         stop = min(stop, n_in)
         bw = chain._block_width
+        blocks = [(b, min(b + bw, stop)) for b in range(start, stop, bw)]
+        if not blocks:
+            return
+        static = {}
+        for idx, key in enumerate(self.ptrs):
+            if key[0] != "in":
+                t = key[1]
+                static[idx] = (t.data_ptr(), t.stride(0) if t.ndim >= 1 else 0)
         with torch.cuda.device(chain.device):
-            stream = torch.cuda.current_stream(chain.device)
-            for begin in range(start, stop, bw):
-                end = min(begin + bw, stop)
-                ptrs, strides = self._pointer_table(begin, end)
-                n = len(ptrs)
+            compute = torch.cuda.current_stream(chain.device)
+            if getattr(self, "_copy_stream", None) is None:
+                self._copy_stream = torch.cuda.Stream(device=chain.device)
+                self._ev_copied = [torch.cuda.Event(), torch.cuda.Event()]
+                self._ev_free = [torch.cuda.Event(), torch.cuda.Event()]
+            cs = self._copy_stream
+            cs.wait_stream(compute)  # staging buffers may still be read by earlier work
+            staged = {}
+
+            def issue(k):
+                st = k % 2
+                if k >= 2:
+                    cs.wait_event(self._ev_free[st])  # the kernel that read this staging set is done
+                staged[k] = self._stage_block(blocks[k][0], blocks[k][1], st, cs)
+                self._ev_copied[st].record(cs)
+
+            issue(0)
+            for k, (begin, end) in enumerate(blocks):
+                if k + 1 < len(blocks):
+                    issue(k + 1)  # overlaps with the kernel of block k
+                compute.wait_event(self._ev_copied[k % 2])
+                table = dict(static)
+                table.update(staged.pop(k))
+                n = len(self.ptrs)
+                ptrs = [table[i][0] for i in range(n)]
+                strides = [table[i][1] for i in range(n)]
                 arr = (C.c_int64 * (2 * n + 1))(*ptrs, *strides, begin)
                 if chain._event_timing:
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     e0.record()
                 rc = lib.dspb_chain_launch(self.handle, C.cast(arr, C.c_void_p), C.c_int64(n), C.c_int64(end - begin),
-                                           C.c_void_p(chain.fatal.data_ptr()), C.c_void_p(stream.cuda_stream))
+                                           C.c_void_p(chain.fatal.data_ptr()), C.c_void_p(compute.cuda_stream))
                 if chain._event_timing:
                     e1.record()
                     self._events.append((e0, e1))
+                self._ev_free[k % 2].record(compute)
                 if rc:
                     raise RuntimeError(f"fused chain launch failed with {rc}")
                 self.rows_per_launch = max(self.rows_per_launch, end - begin)
                 chain.stats["launches"] += 1
                 chain.stats["blocks"] += 1
-                chain._raise_recorded_fatal(begin, end)
                 for out_man in chain._output_managers.values():
                     out_man.write(begin, end)
-            stream.synchronize()
+                chain._raise_recorded_fatal(begin, end)
+            compute.synchronize()
         if self._events:
             for e0, e1 in self._events:
                 self.device_time += e0.elapsed_time(e1) * 1e-3
