@@ -91,6 +91,7 @@ struct ChainParams {
   int n_slots;
   int* fatal;      // int32[n][4] table (may be null)
   long long row0;  // global index of the first row of this launch (for fatal records)
+  long long* prof; // optional [n_instr] cycle counters (CTA 0 only; profiling builds of a chain)
 };
 
 // slots are padded to a multiple of 4 words so that float64 scratch carved out of a slot
@@ -283,7 +284,13 @@ k_chain(const ChainParams cp, const __grid_constant__ PtrTable pt, const long lo
   for (long long row = blockIdx.x; row < n_rows; row += gridDim.x) {
     if (threadIdx.x < 16) slot_nan[threadIdx.x] = 0;
     __syncthreads();
+    long long t_prev = cp.prof ? clock64() : 0;
     for (int pc = 0; pc < cp.n_instr; pc++) {
+      if (cp.prof && pc > 0 && blockIdx.x == 0 && threadIdx.x == 0) {
+        const long long t_now = clock64();
+        cp.prof[pc - 1] += t_now - t_prev;
+        t_prev = t_now;
+      }
       // one instruction = 4 x 128-bit loads into registers (no re-reads inside the op)
       const int4 w0 = prog[4 * pc], w1 = prog[4 * pc + 1], w2 = prog[4 * pc + 2], w3 = prog[4 * pc + 3];
       const int op = w0.x;
@@ -718,6 +725,7 @@ k_chain(const ChainParams cp, const __grid_constant__ PtrTable pt, const long lo
         default: break;
       }
     }
+    if (cp.prof && cp.n_instr > 0 && blockIdx.x == 0 && threadIdx.x == 0) cp.prof[cp.n_instr - 1] += clock64() - t_prev;
     __syncthreads();
   }
 }
@@ -734,6 +742,7 @@ struct dspb_chain {
   size_t smem = 0;
   int num_sms = 148;
   int threads = FUSED_THREADS;
+  long long* d_prof = nullptr;  // per-instruction cycle counters (dspb_chain_profile)
 };
 
 extern "C" int dspb_chain_create(const int32_t* code, int64_t n_code, const double* consts, int64_t n_consts,
@@ -790,10 +799,30 @@ extern "C" int dspb_chain_launch(dspb_chain* c, const void* const* ptrs, int64_t
   cp.n_slots = c->n_slots;
   cp.fatal = fatal;
   cp.row0 = strides[n_ptrs];
+  cp.prof = c->d_prof;
   const int grid = (int)(n_rows < c->num_sms ? n_rows : c->num_sms);
   if (c->threads == 1024) k_chain<1024><<<grid, 1024, c->smem, (cudaStream_t)stream>>>(cp, pt, n_rows);
   else k_chain<512><<<grid, 512, c->smem, (cudaStream_t)stream>>>(cp, pt, n_rows);
   cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : -(int)e;
+}
+
+// Per-instruction cycle profile of CTA 0 (accumulated over its rows and over launches).
+// enable != 0 allocates/zeroes the counters; out (host, n_instr int64) receives them when non-null.
+extern "C" int dspb_chain_profile(dspb_chain* c, int enable, int64_t* out) {
+  if (!c) return DSPB_ERR_UNSUPPORTED;
+  cudaError_t e = cudaSuccess;
+  if (out && c->d_prof) {
+    e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpy(out, c->d_prof, sizeof(long long) * (size_t)c->n_instr, cudaMemcpyDeviceToHost);
+  }
+  if (enable) {
+    if (!c->d_prof && e == cudaSuccess) e = cudaMalloc(&c->d_prof, sizeof(long long) * (size_t)c->n_instr);
+    if (e == cudaSuccess) e = cudaMemset(c->d_prof, 0, sizeof(long long) * (size_t)c->n_instr);
+  } else if (c->d_prof) {
+    cudaFree(c->d_prof);
+    c->d_prof = nullptr;
+  }
   return e == cudaSuccess ? 0 : -(int)e;
 }
 
@@ -803,5 +832,6 @@ extern "C" void dspb_chain_destroy(dspb_chain* c) {
   if (!c) return;
   if (c->d_prog) cudaFree(c->d_prog);
   if (c->d_consts) cudaFree(c->d_consts);
+  if (c->d_prof) cudaFree(c->d_prof);
   delete c;
 }

@@ -61,8 +61,14 @@ def _slot_words(n: int) -> int:
 _ALIAS: dict[int, int] = {}
 
 
+def _storage_id(t: torch.Tensor) -> int:
+    """identity of the storage a tensor views (the StorageImpl address: also defined on the
+    "meta" device, where data pointers are all null, so programs can be planned without a GPU)"""
+    return t.untyped_storage()._cdata
+
+
 def _storage(t: torch.Tensor) -> int:
-    st = t.untyped_storage().data_ptr()
+    st = _storage_id(t)
     return _ALIAS.get(st, st)
 
 
@@ -144,13 +150,12 @@ class FusedChain:
                     key.append(("c", repr(x)))
             key = tuple(key)
             if key in seen and tuple(seen[key].shape) == tuple(out.shape):
-                _ALIAS[out.untyped_storage().data_ptr()] = _storage(seen[key])
+                _ALIAS[_storage_id(out)] = _storage(seen[key])
                 self.skip.add(i)
             else:
                 seen[key] = out
 
         # ---- pass 1: last use of every wave storage ------------------------------------------
-        self._fatal_base = chain.fatal.data_ptr()
         for i, pm in enumerate(managers):
             if i not in self.skip and getattr(pm.processor, "__name__", "") in (
                     "trap_filter", "trap_norm", "asym_trap_filter", "convolve_wf", "fft_convolve_wf"):
@@ -177,7 +182,7 @@ class FusedChain:
         # ---- pass 2: lower every manager ---------------------------------------------------------
         for i, pm in enumerate(managers):
             self._cur = i
-            self._fatal_idx = (pm.fatal.data_ptr() - self._fatal_base) // 16
+            self._fatal_idx = pm.fatal.storage_offset() // 4
             if i in self.skip:
                 self.cse_skipped += 1
             else:
@@ -864,3 +869,24 @@ def try_fuse(chain) -> bool:
         chain._fused = None
         chain._not_fused_reason = str(e)
         return False
+
+
+def profile_fused(chain, run, repeats: int = 1):
+    """Per-instruction SM-cycle profile of the fused program (CTA 0): calls ``run()``
+    `repeats` times with the counters enabled and returns [(cycles, share, text)] in
+    program order -- the device-side counterpart of the reference's per-processor timers
+    (processing_chain.py:1778-1781)."""
+    fc = chain._fused
+    if fc is None:
+        raise RuntimeError("chain is not fused")
+    lib = _lib.lib()
+    n = len(fc.code)
+    lib.dspb_chain_profile(fc.handle, 1, None)
+    for _ in range(repeats):
+        run()
+    out = (C.c_int64 * n)()
+    lib.dspb_chain_profile(fc.handle, 0, out)
+    cyc = np.array(out[:], dtype=np.float64)
+    tot = cyc.sum() or 1.0
+    text = fc.program_text.split("\n")
+    return [(cyc[i], cyc[i] / tot, text[i]) for i in range(n)]

@@ -204,6 +204,10 @@ int dspb_chain_create(const int32_t* code, int64_t n_code, const double* consts,
 int dspb_chain_launch(dspb_chain* chain, const void* const* ptrs, int64_t n_ptrs, int64_t n_rows,
                       int32_t* fatal, void* stream);
 int64_t dspb_chain_smem_bytes(const dspb_chain* chain);
+/* tracing (reference: the per-processor timers of processing_chain.py:1778-1781,1188-1190):
+ * per-instruction SM-cycle counters of CTA 0.  enable != 0 (re)starts counting; when `out`
+ * is non-NULL the n_instr counters accumulated so far are copied to it first. */
+int dspb_chain_profile(dspb_chain* chain, int enable, int64_t* out);
 void dspb_chain_destroy(dspb_chain* chain);
 
 #ifdef __cplusplus

@@ -33,3 +33,11 @@ for i in range(reps):
     torch.cuda.synchronize()
     dt = time.perf_counter() - t
     print(f"pass {i}: {dt * 1e3:.2f} ms  {n / dt / 1e6:.3f} M wf/s")
+if chain._fused is not None and os.environ.get("PROFILE_PROGRAM"):
+    from dspeed_b200 import fusion
+    prof = fusion.profile_fused(chain, lambda: chain(tb, out))
+    tot = sum(p[0] for p in prof)
+    rows_cta0 = -(-n // 148) if (bw or 16384) >= n else None
+    print(f"per-instruction cycles of CTA 0 (total {tot:.0f} cycles; smem {chain._fused.smem_bytes} B, slots {chain._fused.n_slots})")
+    for c, share, text in prof:
+        print(f"{c:12.0f} {100 * share:5.1f}%  {text}")
