@@ -16,7 +16,7 @@ CSRC = os.path.join(_HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 LIB_PATH = os.path.join(_HERE, "libdspeed_b200.so")
 SOURCES = ["processors.cu", "conv.cu", "fused.cu"]
-HEADERS = ["common.cuh", "row_ops.cuh"]
+HEADERS = ["common.cuh", "row_ops.cuh", "conv_ops.cuh", "conv_seg.cuh"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

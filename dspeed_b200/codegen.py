@@ -1,0 +1,1235 @@
+"""Chain code generator: turns a compiled :class:`ProcessingChain` into ONE specialised,
+straight-line CUDA kernel (sm_100a), compiles it with nvcc and launches it per block.
+
+The reference runs ~60 gufunc calls per 16-row block and writes every intermediate
+waveform to memory (processing_chain.py:1144-1163).  Here the frozen launch descriptors
+(``ProcessorManager.args``, reference :1493-1792) are lowered to a kernel in which
+
+* every thread owns a 16-sample chunk of the waveform and keeps it in registers from
+  one processor to the next (load -> min_max -> bl_subtract -> linear_slope_fit ->
+  pole_zero ... never leave the register file);
+* recursive filters (pole-zero, trapezoids, moving windows, run-structured convolution
+  kernels) are chunk-local running sums plus one block scan of the chunk totals;
+* block collectives are split into a *put* before and a *get* after a barrier, and all
+  independent collectives of consecutive processors share ONE barrier ("round");
+* per-event scalars are registers, scalar glue (``np.multiply``, unit conversion,
+  ``round``) is inline arithmetic;
+* parameters (tap positions, window lengths, slices) are literals, so all index
+  arithmetic folds at compile time.
+
+The device routines are hand-written (``csrc/chain_rt.cuh``, ``csrc/row_ops.cuh``); this
+module only sequences them.  Chains containing a processor without a specialised
+emitter stay on the interpreted program of :mod:`dspeed_b200.fusion`.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import hashlib
+import logging
+import math
+import os
+import subprocess
+import threading
+
+import numpy as np
+import torch
+
+from . import _lib, fusion, numpy_bridge
+from . import processors as P
+from .fusion import _DT, FusedChain, NotFusable, _storage, _storage_id
+
+log = logging.getLogger("dspeed")
+
+CHK = 16
+NT = 512
+MAX_SMEM = 227 * 1024
+CACHE_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_chains")
+_build_lock = threading.Lock()
+_loaded: dict[str, C.CDLL] = {}
+
+_CTYPE = {torch.float32: "float", torch.float64: "double", torch.uint16: "uint16_t", torch.int16: "int16_t",
+          torch.int32: "int32_t", torch.uint32: "uint32_t", torch.int64: "long long"}
+
+
+class NotSpecializable(NotFusable):
+    pass
+
+
+def _lit(v) -> str:
+    """C++ literal of a double (hex float: exact)"""
+    v = float(v)
+    if math.isnan(v):
+        return "CUDART_NAN"
+    if math.isinf(v):
+        return "CUDART_INF" if v > 0 else "(-CUDART_INF)"
+    return v.hex()
+
+
+def _flit(v) -> str:
+    """C++ literal of a float32 value"""
+    v = float(np.float32(v))
+    if math.isnan(v):
+        return "CUDART_NAN_F"
+    if math.isinf(v):
+        return "CUDART_INF_F" if v > 0 else "(-CUDART_INF_F)"
+    return v.hex() + "f"
+
+
+class Wave:
+    def __init__(self, wid, n):
+        self.id = wid
+        self.n = n               # root length
+        self.slot = None
+        self.reg = None          # name of the float[16] register chunk (own chunk), when live
+        self.nan = "0"           # uniform int expression: != 0 -> the whole wave is NaN
+        self.uses = []           # node indices reading it
+        self.producer = None
+        self.is_input = False
+        self.needs_slot = True
+        self.name = f"W{wid}"
+
+
+def host_kernel(origin, length):
+    """float32 kernel array of a const-folded generator (planning on the meta device only;
+    on a CUDA device the array computed by the device generator is used)"""
+    name, args = origin
+    f = np.float32
+    if name == "t0_filter":
+        rise, fall = (float(f(P._as_float(x))) for x in args[:2])
+        k = np.zeros(length, np.float64)
+        for i in range(int(rise)):
+            k[i] = 2 * (int(rise) - i) / (rise * (rise + 1))
+        k[int(rise):] = -1 / fall
+        return k.astype(f)
+    return None
+
+
+class SpecChain(FusedChain):
+    kernel_name = "k_chain_spec (specialised waveform-resident chain kernel)"
+
+    # ------------------------------------------------------------------------------------
+    # analysis
+    # ------------------------------------------------------------------------------------
+    def _compile(self, chain):
+        managers = list(chain._proc_managers)
+        self.n_managers = len(managers)
+        self.meta = chain.device.type == "meta"
+        fusion._ALIAS.clear()
+        self.cse_skipped = 0
+        self.ptrs = []
+        self.ptr_index = {}
+        self.waves: dict[int, Wave] = {}
+        self.svar: dict[int, str] = {}          # scalar storage -> C variable
+        self.const_storage = {}
+        self.input_wave = {}
+        self.input_scalar = {}
+        self.nodes = []
+        self.conv_lowering = []
+        self.prolog = []                         # input scalar loads
+        self._sources = None
+
+        all_vars = list(chain._vars_dict.values())
+        for pm in managers:
+            for prm in list(pm.params) + list(pm.kw_params.values()):
+                if hasattr(prm, "proc_chain") and prm not in all_vars:
+                    all_vars.append(prm)
+        self.var_of_storage = {}
+        for v in all_vars:
+            bufs = v._buffer if isinstance(v._buffer, list) else [(v._buffer, None)]
+            for b, _ in bufs:
+                if isinstance(b, torch.Tensor):
+                    self.var_of_storage.setdefault(_storage(b), v)
+                    if v.is_const:
+                        self.const_storage[_storage(b)] = b
+        for name, man in chain._input_managers.items():
+            self._register_input(man)
+
+        # identical wave producers share one result (wf_etrap == wf_trap with the default db)
+        seen = {}
+        self.skip = set()
+        for i, pm in enumerate(managers):
+            if not getattr(pm.processor, "native_kernel", False) or getattr(pm.processor, "nout", 1) != 1:
+                continue
+            out = pm.args[-1]
+            if not (isinstance(out, torch.Tensor) and out.ndim == 2 and out.storage_offset() == 0):
+                continue
+            key = [getattr(pm.processor, "__name__", "")]
+            for x in pm.args[:-1]:
+                if isinstance(x, torch.Tensor):
+                    key.append(("t", _storage(x), x.storage_offset(), tuple(x.shape), tuple(x.stride())))
+                else:
+                    key.append(("c", repr(x)))
+            key = tuple(key)
+            if key in seen and tuple(seen[key].shape) == tuple(out.shape):
+                fusion._ALIAS[_storage_id(out)] = _storage(seen[key])
+                self.skip.add(i)
+            else:
+                seen[key] = out
+
+        self.out_wave_storages = {}
+        self.out_scalars = []
+        for name, man in chain._output_managers.items():
+            rv = self._out_raw(man)
+            if rv.ndim >= 2:
+                self.out_wave_storages[_storage(rv)] = rv
+        # ---- nodes -------------------------------------------------------------------------
+        for i, pm in enumerate(managers):
+            self._cur = i
+            self._fatal_idx = pm.fatal.storage_offset() // 4
+            if i in self.skip:
+                self.cse_skipped += 1
+                continue
+            self._lower(pm)
+        # outputs
+        for name, man in chain._output_managers.items():
+            rv = self._out_raw(man)
+            st = _storage(rv)
+            if rv.ndim == 1:
+                if st in self.const_storage:
+                    continue
+                if st in self.input_scalar and st not in self.svar:
+                    self._sc(rv)
+                if st not in self.svar:
+                    raise NotSpecializable(f"output {name} is not produced by a specialisable processor")
+                if rv.dtype not in (torch.float32, torch.float64, torch.int32, torch.uint32):
+                    raise NotSpecializable(f"output dtype {rv.dtype}")
+                self.out_scalars.append((self.svar[st], self._ptr(("buf", rv)), _CTYPE[rv.dtype]))
+            else:
+                if st not in self.waves or self.waves[st].is_input:
+                    raise NotSpecializable("waveform pass-through outputs stay on the copy path")
+                self._node("store_wave", ins=[(self.waves[st], rv.storage_offset() % max(1, rv.stride(0)), rv.shape[1])],
+                           ptr=self._ptr(("buf", rv)))
+        if len(self.ptrs) > 64:
+            raise NotSpecializable("too many distinct device pointers")
+        self._schedule()
+        self._emit_kernel()
+        self._build()
+
+    # -- operands ----------------------------------------------------------------------------
+    def _node(self, kind, **kw):
+        nd = dict(kind=kind, idx=len(self.nodes), fatal=self._fatal_idx if hasattr(self, "_fatal_idx") else 0, **kw)
+        for w, _, _ in nd.get("ins", []):
+            w.uses.append(nd["idx"])
+        for w in nd.get("wouts", []):
+            w.producer = nd["idx"]
+        self.nodes.append(nd)
+        return nd
+
+    def _const_value(self, t: torch.Tensor):
+        var = self.var_of_storage.get(_storage(t))
+        hv = getattr(var, "host_value", None)
+        if hv is not None:
+            return np.asarray(hv).reshape(-1)
+        if self.meta:
+            origin = getattr(var, "const_origin", None)
+            if origin is not None:
+                k = host_kernel(origin, int(t.numel()))
+                if k is not None:
+                    return k
+            raise NotSpecializable("constant without a host value on the meta device")
+        return self.const_storage[_storage(t)].reshape(-1).detach().cpu().numpy()
+
+    def _sc(self, x):
+        """C expression (double) of a per-event scalar operand, and the names it depends on"""
+        if isinstance(x, torch.Tensor):
+            st = _storage(x)
+            if st in self.const_storage:
+                v = self._const_value(x)
+                if v.size != 1:
+                    raise NotSpecializable("non-scalar constant used as a scalar")
+                return _lit(v[0])
+            if x.numel() != x.shape[0]:
+                raise NotSpecializable("vector-valued per-event variable")
+            if st not in self.svar:
+                if st not in self.input_scalar:
+                    raise NotSpecializable("scalar operand read before it is produced")
+                man, what = self.input_scalar[st]
+                src = man.t0_var if what == "t0" else man.raw_var
+                if src.dtype not in _CTYPE:
+                    raise NotSpecializable(f"scalar input dtype {src.dtype}")
+                name = self._new_svar(st)
+                pi = self._ptr(("in", man, what))
+                self.prolog.append(f"const double {name} = (double)((const {_CTYPE[src.dtype]}*)A.p[{pi}])[row * A.s[{pi}]];")
+            return self.svar[st]
+        if x is None:
+            raise NotSpecializable("None argument")
+        return _lit(float(x))
+
+    def _new_svar(self, st):
+        name = f"s{len(self.svar)}"
+        self.svar[st] = name
+        return name
+
+    def _sout(self, t: torch.Tensor) -> str:
+        if not isinstance(t, torch.Tensor) or t.numel() != t.shape[0]:
+            raise NotSpecializable("scalar output must be a [block] tensor")
+        st = _storage(t)
+        if st in self.svar:
+            raise NotSpecializable("scalar variable written twice")
+        return self._new_svar(st)
+
+    def _win(self, t: torch.Tensor, need_zero_offset=False):
+        if t.ndim != 2 or (t.shape[-1] > 1 and t.stride(-1) != 1):
+            raise NotSpecializable("unsupported waveform view (stride)")
+        st = _storage(t)
+        w = self.waves.get(st)
+        if w is None:
+            if st not in self.input_wave:
+                raise NotSpecializable("waveform operand read before it is produced")
+            man, what = self.input_wave[st]
+            rv = man.raw_var
+            if rv.dtype not in _CTYPE:
+                raise NotSpecializable(f"input waveform dtype {rv.dtype}")
+            w = Wave(len(self.waves), int(rv.shape[1]))
+            w.is_input = True
+            self.waves[st] = w
+            self._node("load", wouts=[w], ptr=self._ptr(("in", man, what)), dtype=rv.dtype, n=int(rv.shape[1]))
+        off = t.storage_offset() % max(1, w.n) if t.storage_offset() else 0
+        if need_zero_offset and off != 0:
+            raise NotSpecializable("processor needs an unsliced waveform")
+        if w.n > CHK * NT:
+            raise NotSpecializable("waveform longer than 8192 samples")
+        return w, int(off), int(t.shape[1])
+
+    def _wout(self, t: torch.Tensor) -> Wave:
+        if t.ndim != 2 or t.storage_offset() != 0:
+            raise NotSpecializable("waveform outputs must be whole buffers")
+        st = _storage(t)
+        if st in self.waves:
+            raise NotSpecializable("waveform written twice")
+        n = int(t.shape[1])
+        if n > CHK * NT:
+            raise NotSpecializable("waveform longer than 8192 samples")
+        w = Wave(len(self.waves), n)
+        self.waves[st] = w
+        return w
+
+    # -- lowering: ProcessorManager -> node ----------------------------------------------------
+    def _lower(self, pm):
+        from . import processing_chain as pc
+
+        if isinstance(pm, pc.UnitConversionManager):
+            buf, off_in, off_out, ratio, out = pm.args
+            if buf.numel() != buf.shape[0] or out.dtype not in (torch.float32, torch.float64):
+                raise NotSpecializable("unit conversion of a non-scalar / integer variable")
+            if pm.in_is_int and pm.mode is None:
+                raise NotSpecializable("integer conversion check")
+            self._node("sc_convert", x=self._sc(buf), oi=self._sc(off_in), oo=self._sc(off_out), ratio=float(ratio),
+                       mode=pm.mode, f32=out.dtype == torch.float32, out=self._sout(out))
+            return
+        proc = pm.processor
+        name = proc.__name__
+        a = pm.args
+        f32 = not any(t.char == "d" for t in pm.types)
+        if isinstance(proc, numpy_bridge.ElementwiseOp):
+            if any(isinstance(x, torch.Tensor) and x.numel() != x.shape[0] and _storage(x) not in self.const_storage
+                   for x in a):
+                raise NotSpecializable(f"element-wise {name} on waveforms")
+            out = a[-1]
+            if out.dtype not in (torch.float32, torch.float64):
+                raise NotSpecializable(f"{name} with {out.dtype} output")
+            if name in ("add", "subtract", "multiply", "divide", "floor_divide"):
+                self._node("sc_bin", op=name, x=self._sc(a[0]), y=self._sc(a[1]), f32=out.dtype == torch.float32,
+                           out=self._sout(out))
+                return
+            if name == "negative":
+                self._node("sc_neg", x=self._sc(a[0]), out=self._sout(out))
+                return
+            raise NotSpecializable(f"element-wise {name}")
+        if not getattr(proc, "native_kernel", False):
+            raise NotSpecializable(f"helper processor {name}")
+        if not f32:
+            raise NotSpecializable(f"{name}: float64 type loop")
+
+        if name == "bl_subtract":
+            w, off, n = self._win(a[0], True)
+            if n != w.n:
+                raise NotSpecializable("bl_subtract on a slice")
+            self._node("bl_sub", ins=[(w, off, n)], b=self._sc(a[1]), wouts=[self._wout(a[2])])
+        elif name in ("min_max", "amax"):
+            w, off, n = self._win(a[0])
+            outs = [self._sout(x) for x in a[1:5]] if name == "min_max" else [None, None, None, self._sout(a[2])]
+            self._node("min_max", ins=[(w, off, n)], outs=outs)
+        elif name in ("linear_slope_fit", "mean_stdev"):
+            w, off, n = self._win(a[0])
+            outs = [self._sout(x) for x in a[1:]]
+            outs += [None] * (4 - len(outs))
+            self._node("lsf", ins=[(w, off, n)], outs=outs)
+        elif name == "pole_zero":
+            w, off, n = self._win(a[0], True)
+            if n != w.n:
+                raise NotSpecializable("pole_zero on a slice")
+            self._node("pole_zero", ins=[(w, off, n)], tau=self._sc(a[1]), wouts=[self._wout(a[2])])
+        elif name in ("trap_filter", "trap_norm"):
+            w, off, n = self._win(a[0], True)
+            rise, flat = int(a[1]), int(a[2])
+            if n != w.n or rise < 0 or flat < 0 or 2 * rise + flat > n or (rise == 0 and name == "trap_norm"):
+                raise NotSpecializable("trapezoid arguments (the interpreted path raises the DSPFatal)")
+            self._node("fir", ins=[(w, 0, n)], taps=[(0, 1.0), (rise, -1.0), (rise + flat, -1.0), (2 * rise + flat, 1.0)],
+                       scale=(1.0 / rise) if name == "trap_norm" else 1.0, p=n, extra=None, wouts=[self._wout(a[3])])
+        elif name == "asym_trap_filter":
+            w, off, n = self._win(a[0], True)
+            rise, flat, fall = int(a[1]), int(a[2]), int(a[3])
+            if n != w.n or min(rise, flat, fall) < 0 or rise + flat + fall > n or rise == 0 or fall == 0:
+                raise NotSpecializable("trapezoid arguments")
+            self._node("fir", ins=[(w, 0, n)], taps=[(0, 1.0 / rise), (rise, -1.0 / rise), (rise + flat, -1.0 / fall),
+                                                     (rise + flat + fall, 1.0 / fall)],
+                       scale=1.0, p=n, extra=None, wouts=[self._wout(a[4])])
+        elif name in ("moving_window_left", "moving_window_right", "moving_window_multi"):
+            w, off, n = self._win(a[0], True)
+            length = float(np.float32(a[1]))
+            if n != w.n or length != np.floor(length) or not (1 <= int(length) < n):
+                raise NotSpecializable("moving-window arguments")
+            if name == "moving_window_multi":
+                num, typ = float(np.float32(a[2])), int(a[3])
+                if num != np.floor(num) or num < 1 or typ not in (0, 1, 2):
+                    raise NotSpecializable("moving-window arguments")
+                dirs = [("r" if ((k & 1) and typ == 0) or typ == 2 else "l") for k in range(int(num))]
+                out = self._wout(a[4])
+            else:
+                dirs = ["l" if name.endswith("left") else "r"]
+                out = self._wout(a[2])
+            self._node("mw", ins=[(w, 0, n)], L=int(length), dirs=dirs, wouts=[out])
+        elif name == "avg_current":
+            w, off, n = self._win(a[0], True)
+            length = float(np.float32(a[1]))
+            out = self._wout(a[2])
+            if n != w.n or length != np.floor(length) or not (1 <= int(length) < n) or out.n != n - int(length):
+                raise NotSpecializable("avg_current arguments")
+            self._node("avg_current", ins=[(w, 0, n)], L=int(length), wouts=[out])
+        elif name == "time_point_thresh":
+            w, off, n = self._win(a[0], True)
+            if n != w.n:
+                raise NotSpecializable("time_point_thresh on a slice")
+            self._node("tpt", ins=[(w, 0, n)], thr=self._sc(a[1]), start=self._sc(a[2]), walk=self._sc(a[3]),
+                       out=self._sout(a[4]))
+        elif name == "fixed_time_pickoff":
+            w, off, n = self._win(a[0], True)
+            mode = P._as_int(a[2])
+            if n != w.n or chr(mode) == "s":
+                raise NotSpecializable("fixed_time_pickoff spline mode / slice")
+            self._node("ftp", ins=[(w, 0, n)], t=self._sc(a[1]), mode=mode, out=self._sout(a[3]))
+        elif name == "windower":
+            w, off, n = self._win(a[0], True)
+            out = self._wout(a[2])
+            if n != w.n or out.n >= n:
+                raise NotSpecializable("windower arguments")
+            self._node("windower", ins=[(w, 0, n)], t0=self._sc(a[1]), wouts=[out])
+        elif name == "upsampler":
+            w, off, n = self._win(a[0], True)
+            up = float(np.float32(a[1]))
+            if n != w.n or up != np.floor(up) or not up >= 1:
+                raise NotSpecializable("non-integer upsample factor")
+            self._node("upsampler", ins=[(w, 0, n)], up=int(up), wouts=[self._wout(a[2])])
+        elif name in ("convolve_wf", "fft_convolve_wf"):
+            self._lower_conv(pm)
+        else:
+            raise NotSpecializable(f"no specialised emitter for {name}")
+
+    def _lower_conv(self, pm):
+        w_in, kernel, mode, w_out = pm.args
+        if not isinstance(kernel, torch.Tensor) or _storage(kernel) not in self.const_storage:
+            raise NotSpecializable("convolution kernel is not a constant")
+        w, off, n = self._win(w_in)
+        if off != 0:
+            raise NotSpecializable("convolution of an offset slice")
+        m = int(kernel.numel())
+        mode = chr(P._as_int(mode))
+        if m > n or mode not in "fvs":
+            raise NotSpecializable("convolution arguments")
+        p = {"f": n + m - 1, "v": n - m + 1, "s": n}[mode]
+        coff = {"f": 0, "v": m - 1, "s": (m - 1) // 2}[mode]
+        var = self.var_of_storage.get(_storage(kernel))
+        origin = getattr(var, "const_origin", None)
+        # (1) cusp / zac kernels: weighted prefix sums (verified against the array on a real device)
+        if origin and origin[0] in ("cusp_filter", "zac_filter") and mode == "v":
+            if self.meta:   # plan only: no kernel array to verify the analytic model against
+                res = fusion.seg_params(origin, m)
+                seg = res[0] if res else None
+            else:
+                seg = self._seg_model(kernel, self._const_value(kernel).astype(np.float32))
+            if seg is not None and 13 * p * 8 <= 4 * (CHK * NT):
+                out = self._wout(w_out)
+                if out.n != p:
+                    raise NotSpecializable("convolution output length mismatch")
+                self._node("conv_seg", ins=[(w, 0, n)], seg=seg, p=p, wouts=[out])
+                self.conv_lowering.append(("seg", m, "zac" if seg[9] else "cusp"))
+                return
+        k = self._const_value(kernel).astype(np.float32)
+        if np.isnan(k).any():
+            raise NotSpecializable("NaN in convolution kernel")
+        # (2) run-structured kernels: sparse first difference -> sparse FIR + running sum
+        dk = np.diff(np.concatenate([[0.0], k.astype(np.float64), [0.0]]))
+        taps = np.flatnonzero(dk)
+        if len(taps) <= 24 and coff <= 1024 and p <= CHK * NT:
+            out = self._wout(w_out)
+            if out.n != p:
+                raise NotSpecializable("convolution output length mismatch")
+            extra = [float(x) for x in k[:coff]] if coff > 0 else None   # full[coff-1] = sum_j k[j] y[coff-1-j]
+            self._node("fir", ins=[(w, 0, n)], taps=[(int(t) - coff, float(dk[t])) for t in taps], scale=1.0, p=p,
+                       extra=extra, wouts=[out])
+            self.conv_lowering.append(("runs", m, len(taps)))
+            return
+        raise NotSpecializable("generic convolution kernel (direct lowering lives in the interpreted path)")
+
+    # ------------------------------------------------------------------------------------
+    # scheduling: hoist chunk-local reductions behind their producer, group FIRs
+    # ------------------------------------------------------------------------------------
+    def _schedule(self):
+        nodes = self.nodes
+        order = []
+        placed = set()
+        by_wave_reductions = {}
+        for nd in nodes:
+            if nd["kind"] in ("min_max", "lsf"):
+                by_wave_reductions.setdefault(nd["ins"][0][0].id, []).append(nd)
+
+        def place(nd):
+            if nd["idx"] in placed:
+                return
+            placed.add(nd["idx"])
+            order.append(nd)
+            for w in nd.get("wouts", []):
+                for r in by_wave_reductions.get(w.id, []):
+                    place(r)
+
+        for nd in nodes:
+            if nd["idx"] in placed:
+                continue
+            if nd["kind"] == "fir":
+                # all FIR-running-sum filters of the same input wave are evaluated together
+                w = nd["ins"][0][0]
+                group = [x for x in nodes if x["kind"] == "fir" and x["ins"][0][0] is w and x["idx"] not in placed]
+                for g in group:
+                    placed.add(g["idx"])
+                order.append(dict(kind="fir_group", idx=nd["idx"], members=group, ins=[nd["ins"][0]],
+                                  wouts=[g["wouts"][0] for g in group], fatal=nd["fatal"]))
+                for g in group:
+                    for r in by_wave_reductions.get(g["wouts"][0].id, []):
+                        place(r)
+                continue
+            place(nd)
+        self.order = order
+        # last use positions (in emission order) for slot liveness
+        pos = {}
+        for k, nd in enumerate(order):
+            members = nd["members"] if nd["kind"] == "fir_group" else [nd]
+            for m in members:
+                pos[m["idx"]] = k
+        for w in self.waves.values():
+            w.last = max([pos[u] for u in w.uses if u in pos] + [-1])
+            local = True
+            for u in w.uses:
+                nd = nodes[u]
+                if nd["kind"] == "store_wave":
+                    local &= nd["ins"][0][1] == 0
+                else:
+                    local &= nd["kind"] in ("min_max", "lsf", "bl_sub", "pole_zero")
+            first = pos.get(w.producer, 0) if w.producer is not None else 0
+            w.needs_slot = not (local and w.last - first <= 6)
+
+    # ------------------------------------------------------------------------------------
+    # emission
+    # ------------------------------------------------------------------------------------
+    def _emit_kernel(self):
+        self.L = []                 # body lines
+        self.pending = set()
+        self.dirty = set()
+        self.xread = set()
+        self.posts = []
+        self.post_dirty = []
+        self.nd_used = 0
+        self.ni_used = 0
+        self.free_slots = []
+        self.n_slots = 0
+        self.tmp = 0
+        self.live_regs = []
+        slot_len = max([w.n for w in self.waves.values()] + [CHK])
+        self.nchunks = (slot_len + CHK - 1) // CHK
+        self.psp = 4 * self.nchunks + 8
+        self.slot_words = 4 * self.psp
+        for k, nd in enumerate(self.order):
+            self.pos = k
+            self.L.append(f"// ---- [{k}] {self._describe_node(nd)}")
+            getattr(self, "_e_" + nd["kind"])(nd)
+            self.L.append("PROF_MARK(%d);" % k)
+            self._release(k)
+        self._close_round()
+        # scalar outputs
+        self.L.append("if (tid == 0) {")
+        for name, pi, ct in self.out_scalars:
+            self.L.append(f"  (({ct}*)A.p[{pi}])[row] = ({ct}){name};")
+        self.L.append("}")
+        self.L.append("PROF_MARK(%d);" % len(self.order))
+        fixed = 2048 + 8192 + 1024  # Scratch (old routines) + CScr + flags/aff2
+        self.smem_bytes = fixed + self.n_slots * self.slot_words * 4
+        if self.smem_bytes > MAX_SMEM:
+            raise NotSpecializable("not enough shared memory for the live waveforms")
+        self.program_text = "\n".join(f"{k:3d} {self._describe_node(nd)}" for k, nd in enumerate(self.order))
+        self.code = self.order  # (for len(code) users)
+
+    def _describe_node(self, nd):
+        if nd["kind"] == "fir_group":
+            return "fir_group " + " | ".join(f"{m['wouts'][0].name}<-{m['ins'][0][0].name} taps={len(m['taps'])}" for m in nd["members"])
+        ins = ",".join(f"{w.name}[{o}:{o + n}]" for w, o, n in nd.get("ins", []))
+        outs = ",".join(w.name for w in nd.get("wouts", []))
+        so = nd.get("out") or ",".join(str(x) for x in nd.get("outs", []) if x)
+        return f"{nd['kind']} {ins} -> {outs}{so}"
+
+    # -- round framework ---------------------------------------------------------------------
+    def _e(self, *lines):
+        self.L.extend(lines)
+
+    def _close_round(self):
+        if self.posts or self.nd_used or self.ni_used or self.pending:
+            self._e("__syncthreads();")
+            self._e(*self.posts)
+            self._e("par ^= 1;")
+        self.posts = []
+        self.pending.clear()
+        self.dirty.clear()
+        self.xread.clear()
+        self.dirty.update(self.post_dirty)   # chunks stored by the post-barrier code
+        self.post_dirty = []
+        self.nd_used = self.ni_used = 0
+
+    def _barrier(self):
+        if self.posts or self.nd_used or self.ni_used or self.pending:
+            self._close_round()
+        else:
+            self._e("__syncthreads();")
+            self.dirty.clear()
+            self.xread.clear()
+
+    def _need(self, *exprs):
+        """scalar expressions / wave names that must be available now"""
+        for e in exprs:
+            if e is not None and str(e) in self.pending:
+                self._close_round()
+                return
+
+    def _alloc_d(self, k):
+        if self.nd_used + k > 16:
+            self._close_round()
+        b = self.nd_used
+        self.nd_used += k
+        return b
+
+    def _alloc_i(self, k):
+        if self.ni_used + k > 8:
+            self._close_round()
+        b = self.ni_used
+        self.ni_used += k
+        return b
+
+    def _t(self, prefix="t"):
+        self.tmp += 1
+        return f"{prefix}{self.tmp}"
+
+    # -- slots and register chunks ---------------------------------------------------------
+    def _slot_alloc(self):
+        if self.free_slots:
+            s = self.free_slots.pop(0)
+        else:
+            s = self.n_slots
+            self.n_slots += 1
+        return s
+
+    def _release(self, k):
+        for w in self.waves.values():
+            if w.slot is not None and w.last <= k and not getattr(w, "released", False):
+                self.free_slots.append(w.slot)
+                self.free_slots.sort()
+                w.released = True
+
+    def _slot(self, w: Wave) -> str:
+        return f"SLOT({w.slot})"
+
+    def _give_slot(self, w: Wave, post=False):
+        if w.slot is None:
+            w.slot = self._slot_alloc()
+            # a pre-barrier store must not overtake other threads still reading the old tenant
+            if not post and w.slot in self.xread:
+                self._barrier()
+
+    def _chunk(self, w: Wave) -> str:
+        """register chunk (own 16 samples) of a wave"""
+        self._need(w.name)
+        if w.reg is not None:
+            return w.reg
+        if w.slot is None:
+            raise NotSpecializable("internal: wave has neither registers nor a slot")
+        r = self._t("r")
+        self._e(f"float {r}[16]; ld_chunk_n({self._slot(w)}, tid, {w.n}, {r});")
+        self._set_reg(w, r)
+        return r
+
+    def _set_reg(self, w: Wave, r: str):
+        w.reg = r
+        if w in self.live_regs:
+            self.live_regs.remove(w)
+        self.live_regs.append(w)
+        droppable = [x for x in self.live_regs if x.needs_slot]
+        while len(droppable) > 2:
+            x = droppable.pop(0)
+            x.reg = None
+            self.live_regs.remove(x)
+
+    def _store(self, w: Wave, r: str):
+        """own chunk -> slot (when other threads / later phases need the wave)"""
+        if w.needs_slot:
+            self._give_slot(w)
+            self._e(f"st_chunk_n({self._slot(w)}, tid, {w.n}, {r});")
+            self.dirty.add(w.slot)
+        self._set_reg(w, r)
+
+    def _post_store(self, w: Wave, r: str):
+        """like _store, but the chunk is produced by post-barrier code of the open round"""
+        if w.needs_slot:
+            self._give_slot(w, post=True)
+            self.posts.append(f"st_chunk_n({self._slot(w)}, tid, {w.n}, {r});")
+            self.post_dirty.append(w.slot)
+        self._set_reg(w, r)
+
+    def _visible(self, w: Wave):
+        """make the slot of `w` readable at other threads' positions"""
+        self._need(w.name)
+        if w.slot is None:
+            raise NotSpecializable("internal: cross-thread access to a register-only wave")
+        if w.slot in self.dirty:
+            self._barrier()
+        self.xread.add(w.slot)
+
+    # -- node emitters -----------------------------------------------------------------------
+    def _e_load(self, nd):
+        w = nd["wouts"][0]
+        r = self._t("r")
+        pi, n, dt = nd["ptr"], nd["n"], nd["dtype"]
+        ct = _CTYPE[dt]
+        self._e(f"float {r}[16];")
+        if dt == torch.uint16 and n % 16 == 0:
+            self._e(f"ldg_chunk_u16((const uint16_t*)A.p[{pi}] + row * A.s[{pi}], tid, {n}, {r});")
+            self.aligned_ptrs = getattr(self, "aligned_ptrs", []) + [pi]
+        else:
+            f = self._t("f")
+            self._e(f"int {f} = ldg_chunk_any<{ct}>((const {ct}*)A.p[{pi}] + row * A.s[{pi}], tid, {n}, {r});")
+            if dt in (torch.float32, torch.float64):
+                si = self._alloc_i(1)
+                nf = f"nan{w.name}"
+                self._e(f"put_imax(cs, par, {si}, {f}, lane, warp);")
+                self.posts.append(f"const int {nf} = get_imax(cs, par, {si}, lane);")
+                self.pending.add(nf)
+                w.nan = nf
+        self._store(w, r)
+
+    def _nan_guard(self, flags):
+        fl = [f for f in flags if f != "0"]
+        return " || ".join(f"({f})" for f in fl) if fl else None
+
+    def _e_min_max(self, nd):
+        w, off, n = nd["ins"][0]
+        outs = nd["outs"]
+        self._need(w.nan)
+        r = self._chunk(w)
+        need_min = outs[0] is not None or outs[2] is not None
+        need_max = outs[1] is not None or outs[3] is not None
+        m = self._t("mm")
+        self._e(f"const MinMax {m} = minmax_local({r}, 16 * tid, {off}, {off + n});")
+        g = self._nan_guard([w.nan])
+        if need_min:
+            si = self._alloc_i(2)
+            self._e(f"put_argmin(cs, par, {si}, {m}.vmin, {m}.imin, lane, warp);")
+            v, i = self._t("v"), self._t("i")
+            self.posts.append(f"float {v}; int {i}; get_argmin(cs, par, {si}, lane, {v}, {i});")
+            if outs[0]:
+                self.posts.append(f"const double {outs[0]} = {'(' + g + ') ? CUDART_NAN : ' if g else ''}(double){i};")
+            if outs[2]:
+                self.posts.append(f"const double {outs[2]} = {'(' + g + ') ? CUDART_NAN : ' if g else ''}(double){v};")
+        if need_max:
+            si = self._alloc_i(2)
+            self._e(f"put_argmax(cs, par, {si}, {m}.vmax, {m}.imax, lane, warp);")
+            v, i = self._t("v"), self._t("i")
+            self.posts.append(f"float {v}; int {i}; get_argmax(cs, par, {si}, lane, {v}, {i});")
+            if outs[1]:
+                self.posts.append(f"const double {outs[1]} = {'(' + g + ') ? CUDART_NAN : ' if g else ''}(double){i};")
+            if outs[3]:
+                self.posts.append(f"const double {outs[3]} = {'(' + g + ') ? CUDART_NAN : ' if g else ''}(double){v};")
+        self.pending.update(o for o in outs if o)
+
+    def _e_lsf(self, nd):
+        w, off, n = nd["ins"][0]
+        outs = nd["outs"]
+        self._need(w.nan)
+        r = self._chunk(w)
+        sd = self._alloc_d(3)
+        a, b, c = self._t("sy"), self._t("sxy"), self._t("syy")
+        self._e(f"double {a}, {b}, {c}; lsf_local({r}, 16 * tid, {off}, {off + n}, {a}, {b}, {c});",
+                f"put_sum(cs, par, {sd}, {a}, lane, warp); put_sum(cs, par, {sd + 1}, {b}, lane, warp); "
+                f"put_sum(cs, par, {sd + 2}, {c}, lane, warp);")
+        f = [self._t("f") for _ in range(4)]
+        g = self._nan_guard([w.nan])
+        post = (f"float {f[0]}, {f[1]}, {f[2]}, {f[3]}; lsf_finish({n}, get_sum(cs, par, {sd}, lane), "
+                f"get_sum(cs, par, {sd + 1}, lane), get_sum(cs, par, {sd + 2}, lane), {f[0]}, {f[1]}, {f[2]}, {f[3]});")
+        if g:
+            post += f" if ({g}) {{ {f[0]} = {f[1]} = {f[2]} = {f[3]} = CUDART_NAN_F; }}"
+        self.posts.append(post)
+        for k in range(4):
+            if outs[k]:
+                self.posts.append(f"const double {outs[k]} = (double){f[k]};")
+                self.pending.add(outs[k])
+
+    def _e_bl_sub(self, nd):
+        w, off, n = nd["ins"][0]
+        out = nd["wouts"][0]
+        self._need(nd["b"], w.nan)
+        r = self._chunk(w)
+        o = self._t("r")
+        b = self._t("b")
+        self._e(f"const float {b} = (float)({nd['b']});",
+                f"float {o}[16];",
+                f"_Pragma(\"unroll\") for (int j = 0; j < 16; j++) {o}[j] = {r}[j] - {b};")
+        flags = [w.nan] + ([f"({b} != {b})"] if not nd["b"].startswith(("0x", "-0x")) else [])
+        g = self._nan_guard(flags)
+        if g:
+            nf = f"nan{out.name}"
+            self._e(f"const int {nf} = {g};")
+            out.nan = nf
+        self._store(out, o)
+
+    def _e_pole_zero(self, nd):
+        w, off, n = nd["ins"][0]
+        out = nd["wouts"][0]
+        self._need(nd["tau"], w.nan)
+        r = self._chunk(w)
+        sd = self._alloc_d(1)
+        tot, incl, omc = self._t("tot"), self._t("incl"), self._t("omc")
+        self._e(f"const double {omc} = -expm1(-1.0 / (double)(float)({nd['tau']}));",
+                f"const double {tot} = chunk_sum_d({r});",
+                f"const double {incl} = put_scan(cs, par, {sd}, {tot}, lane, warp);")
+        o, dum = self._t("r"), self._t("tt")
+        self.posts.append(f"float {o}[16]; double {dum}; "
+                          f"pz_chunk({r}, get_excl(cs, par, {sd}, {incl}, {tot}, lane, warp, {dum}), {omc}, {o});")
+        const_tau = nd["tau"].startswith(("0x", "-0x"))
+        flags = [w.nan] + ([] if const_tau else [f"((float)({nd['tau']}) != (float)({nd['tau']}))"])
+        g = self._nan_guard(flags)
+        if g:
+            nf = f"nan{out.name}"
+            self.posts.append(f"const int {nf} = {g};")
+            out.nan = nf
+            self.pending.add(nf)
+        self.pending.add(out.name)
+        self._post_store(out, o)   # the output chunk exists after the barrier
+
+    def _e_fir_group(self, nd):
+        members = nd["members"]
+        w = nd["ins"][0][0]
+        n = nd["ins"][0][2]
+        self._need(w.nan)
+        own = self._chunk(w)          # own chunk in registers (tap offset 0)
+        if w.slot is None:
+            raise NotSpecializable("internal: FIR input without a slot")
+        self._visible(w)
+        # batches of at most 3 filters per round (register pressure)
+        for b0 in range(0, len(members), 3):
+            batch = members[b0:b0 + 3]
+            recs = []
+            for m in batch:
+                out = m["wouts"][0]
+                d, tot, incl = self._t("d"), self._t("tot"), self._t("incl")
+                self._e(f"float {d}[16];", f"_Pragma(\"unroll\") for (int j = 0; j < 16; j++) {d}[j] = 0.f;")
+                for (ts, c) in m["taps"]:
+                    if ts == 0:
+                        if c == 1.0:
+                            self._e(f"_Pragma(\"unroll\") for (int j = 0; j < 16; j++) {d}[j] += {own}[j];")
+                        else:
+                            self._e(f"_Pragma(\"unroll\") for (int j = 0; j < 16; j++) {d}[j] = fmaf({_flit(c)}, {own}[j], {d}[j]);")
+                    elif c == 1.0:
+                        self._e(f"fir_tap_add<{ts}>({self._slot(w)}, tid, {n}, {d});")
+                    elif c == -1.0:
+                        self._e(f"fir_tap_sub<{ts}>({self._slot(w)}, tid, {n}, {d});")
+                    else:
+                        self._e(f"fir_tap<{ts}>({self._slot(w)}, tid, {n}, {_flit(c)}, {d});")
+                sd = self._alloc_d(1)
+                self._e(f"const double {tot} = (double)cumsum_local({d});",
+                        f"const double {incl} = put_scan(cs, par, {sd}, {tot}, lane, warp);")
+                ex = None
+                if m["extra"]:
+                    kx = self._t("kx")
+                    ne = len(m["extra"])
+                    self.static_arrays = getattr(self, "static_arrays", [])
+                    self.static_arrays.append(f"__device__ const float {kx}[{ne}] = {{{', '.join(_flit(v) for v in m['extra'])}}};")
+                    sx = self._alloc_d(1)
+                    term = self._t("ex")
+                    self._e(f"double {term} = 0.0;",
+                            f"for (int q = tid; q < {ne}; q += 512) {term} += (double)({kx}[q] * at({self._slot(w)}, {ne - 1} - q));",
+                            f"put_sum(cs, par, {sx}, {term}, lane, warp);")
+                    ex = sx
+                recs.append((m, d, tot, incl, sd, ex))
+            for (m, d, tot, incl, sd, ex) in recs:
+                out = m["wouts"][0]
+                o, off, dum = self._t("r"), self._t("off"), self._t("tt")
+                sc = _flit(m["scale"])
+                extra = f" + get_sum(cs, par, {ex}, lane)" if ex is not None else ""
+                self.posts.append(
+                    f"double {dum}; const float {off} = (float)((get_excl(cs, par, {sd}, {incl}, {tot}, lane, warp, {dum}){extra}) * (double){sc});")
+                self.posts.append(f"float {o}[16]; _Pragma(\"unroll\") for (int j = 0; j < 16; j++) {o}[j] = fmaf({d}[j], {sc}, {off});")
+                out.nan = w.nan
+                self.pending.add(out.name)
+                self._post_store(out, o)
+            self._close_round()
+
+    def _e_tpt(self, nd):
+        w, off, n = nd["ins"][0]
+        self._need(nd["thr"], nd["start"], nd["walk"], w.nan)
+        self._visible(w)
+        self._close_round()
+        f = self._t("f")
+        g = self._nan_guard([w.nan])
+        call = (f"(double)tpt({self._slot(w)}, {n}, (float)({nd['thr']}), (float)({nd['start']}), (float)({nd['walk']}), "
+                f"{f}, cs, par, lane, warp)")
+        self._e(f"int {f} = 0;",
+                f"const double {nd['out']} = {'(' + g + ') ? CUDART_NAN : ' if g else ''}{call};",
+                f"if ({f} && tid == 0) raise_fatal(A.fatal ? A.fatal + 4 * {nd['fatal']} : nullptr, {f}, A.row0 + row);")
+
+    def _e_ftp(self, nd):
+        w, off, n = nd["ins"][0]
+        self._need(nd["t"], w.nan)
+        self._visible(w)
+        f = self._t("f")
+        g = self._nan_guard([w.nan])
+        call = f"(double)op_fixed_time_pickoff<float>({self._slot(w)}, {n}, (float)({nd['t']}), {nd['mode']}, {f})"
+        self._e(f"int {f} = 0;",
+                f"const double {nd['out']} = {'(' + g + ') ? CUDART_NAN : ' if g else ''}{call};",
+                f"if ({f} && tid == 0) raise_fatal(A.fatal ? A.fatal + 4 * {nd['fatal']} : nullptr, {f}, A.row0 + row);")
+
+    def _e_windower(self, nd):
+        # windower.py:12-54 : out[k] = in[t0 + k], NaN where the window leaves the waveform
+        w, off, n = nd["ins"][0]
+        out = nd["wouts"][0]
+        m = out.n
+        self._need(nd["t0"], w.nan)
+        self._visible(w)
+        o, pad, beg, tf = self._t("r"), self._t("pad"), self._t("beg"), self._t("tf")
+        si = self._alloc_i(1)
+        g = self._nan_guard([w.nan, f"({tf} != {tf})"])
+        self._e(f"float {o}[16]; int {pad} = 0;",
+                f"const float {tf} = (float)({nd['t0']});",
+                f"long long {beg} = ({tf} == {tf}) ? (long long){tf} : 0; if ({beg} > {n}) {beg} = {n};",
+                f"_Pragma(\"unroll\") for (int j = 0; j < 16; j++) {{ const long long q = {beg} + 16 * tid + j; float v = 0.f; "
+                f"if (16 * tid + j < {m}) {{ if (!({g}) && q >= 0 && q < {n}) v = at({self._slot(w)}, (int)q); "
+                f"else {{ {pad} = 1; v = CUDART_NAN_F; }} }} {o}[j] = v; }}",
+                f"put_imax(cs, par, {si}, {pad}, lane, warp);")
+        nf = f"nan{out.name}"
+        self.posts.append(f"const int {nf} = get_imax(cs, par, {si}, lane);")
+        self.pending.add(nf)
+        out.nan = nf
+        out.nan_elementwise = True
+        self._store(out, o)
+
+    def _e_avg_current(self, nd):
+        w, off, n = nd["ins"][0]
+        out = nd["wouts"][0]
+        L = nd["L"]
+        self._need(w.nan)
+        self._visible(w)
+        a = self._chunk(w)
+        b, o = self._t("r"), self._t("r")
+        self._e(f"float {b}[16]; ld_shift<{L}>({self._slot(w)}, tid, {n}, {b});",
+                f"float {o}[16]; _Pragma(\"unroll\") for (int j = 0; j < 16; j++) {o}[j] = ({b}[j] - {a}[j]) / {_flit(L)};")
+        out.nan = w.nan
+        self._store(out, o)
+
+    def _e_upsampler(self, nd):
+        # upsampler.py:14-49 with an integer factor: output t takes input floor((t + half) / up);
+        # outputs beyond the last input's span stay NaN
+        w, off, n = nd["ins"][0]
+        out = nd["wouts"][0]
+        up, m = nd["up"], out.n
+        half = up // 2
+        self._need(w.nan)
+        self._visible(w)
+        o = self._t("r")
+        holes = m > n * up - half
+        g = self._nan_guard([w.nan])
+        self._e(f"float {o}[16];",
+                f"_Pragma(\"unroll\") for (int j = 0; j < 16; j++) {{ const int t = 16 * tid + j; const int q = (t + {half}) / {up}; "
+                f"{o}[j] = t >= {m} ? 0.f : ((q < {n}{' && !(' + g + ')' if g else ''}) ? at({self._slot(w)}, q) : CUDART_NAN_F); }}")
+        if holes:
+            nf = f"nan{out.name}"
+            self._e(f"const int {nf} = 1;")
+            out.nan = nf
+        else:
+            out.nan = w.nan
+        out.nan_elementwise = True
+        self._store(out, o)
+
+    def _e_mw(self, nd):
+        # moving_windows.py:12-203 : successive boxcar means with edge-value padding, each one a
+        # chunk-local running sum of (x[i] - x[i -/+ L]) / L plus one block scan
+        w, off, n = nd["ins"][0]
+        out = nd["wouts"][0]
+        L = nd["L"]
+        il = _flit(1.0 / float(np.float32(L)))
+        dirs = nd["dirs"]
+        temps = []
+        src = w
+        for k, dr in enumerate(dirs):
+            last = k == len(dirs) - 1
+            if last:
+                dst = out
+            else:
+                if len(temps) < 2:
+                    tw = Wave(10000 + 10 * self.pos + k, n)
+                    tw.needs_slot = True
+                    tw.last = self.pos
+                    temps.append(tw)
+                dst = temps[k % 2]
+            self._need(src.nan)
+            self._visible(src)
+            x = self._chunk(src)
+            sh, d, tot, incl, e0, tt = (self._t(p) for p in ("r", "d", "tot", "incl", "e", "tt"))
+            sd = self._alloc_d(1)
+            sl = self._slot(src)
+            if dr == "l":
+                # out[0] = x[0]; out[i] = out[i-1] + (x[i] - x[max(i-L,0)]) / L
+                self._e(f"float {sh}[16]; ld_shift<{-L}>({sl}, tid, {n}, {sh}); const float {e0} = at({sl}, 0);",
+                        f"float {d}[16]; _Pragma(\"unroll\") for (int j = 0; j < 16; j++) {{ const int i = 16 * tid + j; "
+                        f"{d}[j] = i >= {n} ? 0.f : (i == 0 ? {e0} : ({x}[j] - (i >= {L} ? {sh}[j] : {e0})) * {il}); }}",
+                        f"const double {tot} = (double)cumsum_local({d});",
+                        f"const double {incl} = put_scan(cs, par, {sd}, {tot}, lane, warp);")
+                get = f"get_excl(cs, par, {sd}, {incl}, {tot}, lane, warp, {tt})"
+            else:
+                # mirror image: out[n-1] = x[n-1]; out[i] = out[i+1] + (x[i] - x[min(i+L,n-1)]) / L
+                self._e(f"float {sh}[16]; ld_shift<{L}>({sl}, tid, {n}, {sh}); const float {e0} = at({sl}, {n - 1});",
+                        f"float {d}[16]; _Pragma(\"unroll\") for (int j = 0; j < 16; j++) {{ const int i = 16 * tid + j; "
+                        f"{d}[j] = i >= {n} ? 0.f : (i == {n - 1} ? {e0} : ({x}[j] - (i + {L} <= {n - 1} ? {sh}[j] : {e0})) * {il}); }}",
+                        f"const double {tot} = (double)cumsum_local_rev({d});",
+                        f"const double {incl} = put_scan_rev(cs, par, {sd}, {tot}, lane, warp);")
+                get = f"get_excl_rev(cs, par, {sd}, {incl}, {tot}, lane, warp)"
+            o, offv = self._t("r"), self._t("off")
+            self.posts.append(f"double {tt} = 0.0; const float {offv} = (float){get}; (void){tt};")
+            self.posts.append(f"float {o}[16]; _Pragma(\"unroll\") for (int j = 0; j < 16; j++) {o}[j] = {d}[j] + {offv};")
+            dst.nan = src.nan
+            dst.reg = None
+            self.pending.add(dst.name)
+            self._post_store(dst, o)
+            self._close_round()
+            src = dst
+        for tw in temps:
+            if tw.slot is not None:
+                self.free_slots.append(tw.slot)
+                self.free_slots.sort()
+            if tw in self.live_regs:
+                self.live_regs.remove(tw)
+
+    def _e_conv_seg(self, nd):
+        w, off, n = nd["ins"][0]
+        out = nd["wouts"][0]
+        self._need(w.nan)
+        self._visible(w)
+        self._close_round()
+        scratch = self._slot_alloc()
+        if scratch in self.xread or scratch in self.dirty:
+            self._barrier()
+        self._give_slot(out)
+        seg = nd["seg"]
+        prm = self._t("prm")
+        self.static_arrays = getattr(self, "static_arrays", [])
+        self.static_arrays.append(f"__device__ const double {prm}[10] = {{{', '.join(_lit(v) for v in seg)}}};")
+        self._e(f"op_conv_seg<float>({self._slot(w)}, {n}, {self._slot(out)}, reinterpret_cast<double*>(SLOT({scratch})), {prm}, sc);")
+        self.free_slots.append(scratch)
+        self.free_slots.sort()
+        out.nan = w.nan
+        out.reg = None
+        self.dirty.discard(out.slot)
+
+    def _e_sc_bin(self, nd):
+        self._need(nd["x"], nd["y"])
+        op = {"add": "+", "subtract": "-", "multiply": "*", "divide": "/"}.get(nd["op"])
+        if nd["f32"]:
+            ex = f"(float)({nd['x']}) {op} (float)({nd['y']})" if op else f"floorf((float)({nd['x']}) / (float)({nd['y']}))"
+            self._e(f"const double {nd['out']} = (double)({ex});")
+        else:
+            ex = f"({nd['x']}) {op} ({nd['y']})" if op else f"floor(({nd['x']}) / ({nd['y']}))"
+            self._e(f"const double {nd['out']} = {ex};")
+
+    def _e_sc_neg(self, nd):
+        self._need(nd["x"])
+        self._e(f"const double {nd['out']} = -({nd['x']});")
+
+    def _e_sc_convert(self, nd):
+        self._need(nd["x"], nd["oi"], nd["oo"])
+        ex = f"(({nd['x']}) + ({nd['oi']})) * {_lit(nd['ratio'])} - ({nd['oo']})"
+        fn = {None: "", "round": "rint", "floor": "floor", "ceil": "ceil", "trunc": "trunc"}[nd["mode"]]
+        ex = f"{fn}({ex})"
+        if nd["f32"]:
+            ex = f"(double)(float)({ex})"
+        self._e(f"const double {nd['out']} = {ex};")
+
+    def _e_store_wave(self, nd):
+        w, off, n = nd["ins"][0]
+        pi = nd["ptr"]
+        self._need(w.nan)
+        g = self._nan_guard([w.nan])
+        dst = f"(float*)A.p[{pi}] + row * A.s[{pi}]"
+        if off == 0:
+            r = self._chunk(w)
+            body = f"stg_chunk({dst}, tid, {n}, {r});"
+        else:
+            self._visible(w)
+            body = f"for (int q = tid; q < {n}; q += 512) ({dst})[q] = at({self._slot(w)}, {off} + q);"
+        if g and not getattr(w, "nan_elementwise", False):
+            self._e(f"if ({g}) store_row_nan<float>({dst}, {n}); else {{ {body} }}")
+        else:
+            self._e(body)
+
+    # ------------------------------------------------------------------------------------
+    # source, build, launch
+    # ------------------------------------------------------------------------------------
+    def source(self) -> str:
+        np_ = max(1, len(self.ptrs))
+        body = "\n      ".join(self.prolog + self.L)
+        arrays = "\n".join(getattr(self, "static_arrays", []))
+        aligned = getattr(self, "aligned_ptrs", [])
+        align_check = "".join(f"  if (((uintptr_t)ptrs[{i}] & 15) || (strides[{i}] & 7)) return DSPB_ERR_UNSUPPORTED;\n" for i in aligned)
+        return f"""// generated by dspeed_b200/codegen.py -- do not edit
+#define DSPB_PSP {self.psp}
+#include "chain_rt.cuh"
+#include "conv_seg.cuh"
+using namespace dspb;
+using namespace crt;
+namespace {{
+constexpr int NP = {np_};
+constexpr int N_NODES = {len(self.order) + 1};
+struct Args {{
+  const void* p[NP];
+  long long s[NP];
+  long long n_rows, row0;
+  int* fatal;
+  long long* prof;
+}};
+{arrays}
+#define SLOT(k) (slots + (k) * {self.slot_words})
+#define PROF_MARK(k) if (A.prof && tid == 0 && (k) + 1 < 128) prof_ts[(k) + 1] = clock64();
+
+__global__ void __launch_bounds__(512, 1) k_chain_spec(const __grid_constant__ Args A) {{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Scratch* sc = reinterpret_cast<Scratch*>(smem_raw);
+  CScr* cs = reinterpret_cast<CScr*>(smem_raw + 2048);
+  float* slots = reinterpret_cast<float*>(smem_raw + 2048 + 8192 + 1024);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  long long* prof_ts = reinterpret_cast<long long*>(smem_raw + 2048 + 8192);
+  int par = 0;
+  for (long long row = blockIdx.x; row < A.n_rows; row += gridDim.x) {{
+    if (A.prof && tid == 0) prof_ts[0] = clock64();
+    {{
+      {body}
+    }}
+    __syncthreads();
+    if (A.prof && blockIdx.x == 0) {{  // per-node cycles of CTA 0 (tracing; off in production launches)
+      for (int k = tid; k < N_NODES && k + 1 < 128; k += 512) A.prof[k] += prof_ts[k + 1] - prof_ts[k];
+      __syncthreads();
+    }}
+  }}
+}}
+}}  // namespace
+
+extern "C" int chain_smem_bytes() {{ return {self.smem_bytes}; }}
+extern "C" int chain_n_nodes() {{ return N_NODES; }}
+extern "C" int chain_launch(const void* const* ptrs, long long n_ptrs, long long n_rows, int* fatal, long long* prof,
+                            int num_sms, void* stream) {{
+  if (n_ptrs != NP && !(n_ptrs == 0 && NP == 1)) return DSPB_ERR_UNSUPPORTED;
+  if (n_rows <= 0) return 0;
+  const long long* strides = reinterpret_cast<const long long*>(ptrs + n_ptrs);
+{align_check}  Args a;
+  for (int i = 0; i < n_ptrs; i++) {{ a.p[i] = ptrs[i]; a.s[i] = strides[i]; }}
+  a.n_rows = n_rows;
+  a.row0 = strides[n_ptrs];
+  a.fatal = fatal;
+  a.prof = prof;
+  static bool attr_set = false;
+  if (!attr_set) {{
+    cudaError_t e = cudaFuncSetAttribute(k_chain_spec, cudaFuncAttributeMaxDynamicSharedMemorySize, {self.smem_bytes});
+    if (e != cudaSuccess) return -(int)e;
+  }}
+  const int grid = (int)(n_rows < num_sms ? n_rows : num_sms);
+  k_chain_spec<<<grid, 512, {self.smem_bytes}, (cudaStream_t)stream>>>(a);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : -(int)e;
+}}
+"""
+
+    def _build(self):
+        src = self.source()
+        self.lib_path, self.src_path = build_source(src)
+        self.handle = C.c_void_p(1)  # marks "runnable" for can_run()
+        if self.meta:
+            return
+        self.lib = load_chain_lib(self.lib_path)
+        self.num_sms = torch.cuda.get_device_properties(self.chain.device).multi_processor_count
+        self.d_prof = None
+
+    def _launch(self, arr, n, n_rows, fatal_ptr, stream):
+        prof = C.c_void_p(self.d_prof.data_ptr()) if self.d_prof is not None else C.c_void_p(0)
+        return self.lib.chain_launch(C.cast(arr, C.c_void_p), C.c_int64(n), C.c_int64(n_rows), C.c_void_p(fatal_ptr), prof,
+                                     C.c_int(self.num_sms), C.c_void_p(stream))
+
+    def profile(self, run, repeats=1):
+        """per-node SM cycles of CTA 0 (see fusion.profile_fused)"""
+        n = len(self.order) + 1
+        self.d_prof = torch.zeros(n, dtype=torch.int64, device=self.chain.device)
+        for _ in range(repeats):
+            run()
+        torch.cuda.synchronize(self.chain.device)
+        cyc = self.d_prof.cpu().numpy().astype(np.float64)
+        self.d_prof = None
+        tot = cyc.sum() or 1.0
+        text = self.program_text.split("\n") + ["store scalars"]
+        return [(cyc[i], cyc[i] / tot, text[i]) for i in range(n)]
+
+    def __del__(self):
+        pass
+
+
+# ----------------------------------------------------------------------------------------
+# compile cache (in-tree: the built libraries travel with the repository snapshot)
+# ----------------------------------------------------------------------------------------
+def _headers_digest() -> str:
+    h = hashlib.sha1()
+    for f in ("common.cuh", "row_ops.cuh", "conv_ops.cuh", "chain_rt.cuh", "conv_seg.cuh"):
+        h.update(open(os.path.join(_lib.CSRC, f), "rb").read())
+    h.update(open(os.path.join(_lib.INCLUDE, "dspeed_b200.h"), "rb").read())
+    return h.hexdigest()
+
+
+def build_source(src: str, verbose=False):
+    """compile one generated kernel for sm_100a (cached by content hash)"""
+    tag = hashlib.sha1((src + _headers_digest()).encode()).hexdigest()[:16]
+    os.makedirs(CACHE_DIR, exist_ok=True)
+    so = os.path.join(CACHE_DIR, f"chain_{tag}.so")
+    cu = os.path.join(CACHE_DIR, f"chain_{tag}.cu")
+    with _build_lock:
+        if not os.path.exists(so):
+            with open(cu, "w") as f:
+                f.write(src)
+            tmp = so + f".tmp{os.getpid()}"
+            cmd = [_lib._nvcc(), *_lib.NVCC_FLAGS, "-I", _lib.INCLUDE, "-I", _lib.CSRC, "-o", tmp, cu]
+            env = dict(os.environ)
+            env.pop("CC", None)
+            env.pop("CXX", None)
+            log.info("compiling specialised chain kernel: " + " ".join(cmd))
+            try:
+                subprocess.run(cmd, env=env, check=True, capture_output=True, text=True)
+            except FileNotFoundError as e:
+                raise NotSpecializable(f"nvcc not available: {e}")
+            except subprocess.CalledProcessError as e:
+                raise RuntimeError(f"nvcc failed on {cu}:\n{e.stderr[-4000:]}")
+            os.replace(tmp, so)
+    return so, cu
+
+
+def load_chain_lib(path: str) -> C.CDLL:
+    if path not in _loaded:
+        _loaded[path] = C.CDLL(path)
+    return _loaded[path]

@@ -20,8 +20,14 @@ namespace dspb {
 // Row-resident kernels are written for any 1-D CTA size that is a multiple of 32 (the
 // per-processor kernels launch 256 threads, the fused chain kernel 512): NT / NW read the
 // launch configuration.
+#ifdef DSPB_PSP
+// specialised chain kernels (csrc/chain_rt.cuh) are always launched with 512 threads
+#define NT 512
+#define NW 16
+#else
 #define NT ((int)blockDim.x)
 #define NW ((int)(blockDim.x >> 5))
+#endif
 constexpr int MAXW = 32;             // max warps per CTA
 constexpr int SCRATCH_BYTES = 2048;  // block-primitive scratch at the start of dynamic smem
 constexpr int DEFAULT_THREADS = 256;
@@ -30,8 +36,19 @@ constexpr int DEFAULT_THREADS = 256;
 // chunk of C in {4,8,16,32} elements, lane l at step j touches bank (l*C + j + (l*C+j)/32) % 32,
 // which is a permutation of the 32 banks; unit-stride (thread-strided) access stays
 // conflict-free as well.
+#ifdef DSPB_PSP
+// "T4" layout of the specialised chain kernels: the waveform is cut into 16-sample chunks
+// (chunk c = samples [16c, 16c+16) belongs to thread c); float4 number p of every chunk
+// lives in plane p, planes are DSPB_PSP floats apart (= 4 * chunks + 8 pad words).  A thread
+// reads or writes its own chunk -- or the chunk a fixed number of samples away -- with four
+// or five conflict-free 128-bit accesses at immediate offsets; unit-stride access is
+// conflict-free as well thanks to the 8-word plane skew.
+__device__ __forceinline__ int sidx(int i) { return ((i >> 2) & 3) * DSPB_PSP + ((i >> 4) << 2) + (i & 3); }
+__host__ __device__ __forceinline__ int slot_words(int n) { return 4 * DSPB_PSP; }
+#else
 __device__ __forceinline__ int sidx(int i) { return i + (i >> 5); }
 __host__ __device__ __forceinline__ int slot_words(int n) { return n + (n >> 5) + 1; }
+#endif
 
 template <typename T> __device__ __forceinline__ T nan_of();
 template <> __device__ __forceinline__ float nan_of<float>() { return CUDART_NAN_F; }

@@ -54,6 +54,40 @@ class NotFusable(Exception):
     pass
 
 
+def seg_params(origin, L):
+    """(CONV_SEG parameters, float64 model of the kernel array, is_zac) of a cusp_filter /
+    zac_filter kernel of length L built from `origin` = (generator name, args); None when the
+    arguments are outside what the weighted-prefix-sum evaluation supports"""
+    f = np.float32
+    sigma, flat, decay = (float(f(P._as_float(x))) for x in origin[1][:3])
+    if sigma <= 0 or flat < 0 or decay <= 0 or flat != np.floor(flat):
+        return None
+    lt = int((L - flat) / 2)
+    fl = int(flat)
+    if lt < 2 or lt + fl + 1 >= L or L / sigma > 40.0:
+        return None
+    zac = origin[0] == "zac_filter"
+    i = np.arange(L, dtype=np.float64)
+    S = np.sinh(lt / sigma)
+    shape = np.zeros(L)
+    shape[:lt] = np.sinh(i[:lt] / sigma) / S
+    shape[lt : lt + fl + 1] = 1.0
+    shape[lt + fl + 1 :] = np.sinh((L - i[lt + fl + 1 :]) / sigma) / S
+    beta, h = 0.0, lt / 2.0
+    if zac:
+        par = np.zeros(L)
+        par[:lt] = (i[:lt] - h) ** 2 - h**2
+        par[lt + fl + 1 :] = (L - i[lt + fl + 1 :] - h) ** 2 - h**2
+        beta = -shape.sum() / par.sum()
+        shape = shape + beta * par
+    c = float(np.exp(-1.0 / decay))
+    model = shape.copy()
+    model[1:] -= c * shape[:-1]
+    prm = [sigma, float(lt), float(fl), float(L), c, 1.0 / (2.0 * S), float(shape[L - 1]), beta, h,
+           1.0 if zac else 0.0]
+    return prm, model, zac
+
+
 def _slot_words(n: int) -> int:
     return (n + (n >> 5) + 1 + 3) & ~3
 
@@ -685,32 +719,10 @@ class FusedChain:
         origin = getattr(var, "const_origin", None)
         if not origin or origin[0] not in ("cusp_filter", "zac_filter"):
             return None
-        f = np.float32
-        sigma, flat, decay = (float(f(P._as_float(x))) for x in origin[1][:3])
-        L = int(k.size)
-        if sigma <= 0 or flat < 0 or decay <= 0 or flat != np.floor(flat):
+        res = seg_params(origin, int(k.size))
+        if res is None:
             return None
-        lt = int((L - flat) / 2)
-        fl = int(flat)
-        if lt < 2 or lt + fl + 1 >= L or L / sigma > 40.0:
-            return None
-        zac = origin[0] == "zac_filter"
-        i = np.arange(L, dtype=np.float64)
-        S = np.sinh(lt / sigma)
-        shape = np.zeros(L)
-        shape[:lt] = np.sinh(i[:lt] / sigma) / S
-        shape[lt : lt + fl + 1] = 1.0
-        shape[lt + fl + 1 :] = np.sinh((L - i[lt + fl + 1 :]) / sigma) / S
-        beta, h = 0.0, lt / 2.0
-        if zac:
-            par = np.zeros(L)
-            par[:lt] = (i[:lt] - h) ** 2 - h**2
-            par[lt + fl + 1 :] = (L - i[lt + fl + 1 :] - h) ** 2 - h**2
-            beta = -shape.sum() / par.sum()
-            shape = shape + beta * par
-        c = float(np.exp(-1.0 / decay))
-        model = shape.copy()
-        model[1:] -= c * shape[:-1]
+        prm, model, zac = res
         # the reference rounds the shape to float32 before the differencing (cusp) or only the
         # final kernel (zac): allow exactly that much
         tol = 2.5e-7 if not zac else 4e-10 * max(1.0, float(np.abs(model).max()) / 1.7e-3)
@@ -718,8 +730,7 @@ class FusedChain:
         if not err <= tol:
             log.debug(f"cusp/zac model rejected: residual {err:.3e} > {tol:.1e}")
             return None
-        return [sigma, float(lt), float(fl), float(L), c, 1.0 / (2.0 * S), float(shape[L - 1]), beta, h,
-                1.0 if zac else 0.0]
+        return prm
 
     def _describe(self) -> str:
         names = ["END", "LOAD_WAVE", "LOAD_SCALAR", "STORE_SCALAR", "STORE_WAVE", "BL_SUB", "MIN_MAX", "LSF", "POLE_ZERO",
@@ -829,8 +840,7 @@ class FusedChain:
                 if chain._event_timing:
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     e0.record()
-                rc = lib.dspb_chain_launch(self.handle, C.cast(arr, C.c_void_p), C.c_int64(n), C.c_int64(end - begin),
-                                           C.c_void_p(chain.fatal.data_ptr()), C.c_void_p(compute.cuda_stream))
+                rc = self._launch(arr, n, end - begin, chain.fatal.data_ptr(), compute.cuda_stream)
                 if chain._event_timing:
                     e1.record()
                     self._events.append((e0, e1))
@@ -850,6 +860,10 @@ class FusedChain:
                 self.device_calls += 1
             self._events = []
 
+    def _launch(self, arr, n, n_rows, fatal_ptr, stream):
+        return _lib.lib().dspb_chain_launch(self.handle, C.cast(arr, C.c_void_p), C.c_int64(n), C.c_int64(n_rows),
+                                            C.c_void_p(fatal_ptr), C.c_void_p(stream))
+
     def __del__(self):
         try:
             if self.handle.value:
@@ -859,7 +873,19 @@ class FusedChain:
 
 
 def try_fuse(chain) -> bool:
-    """attach a fused program to the chain if every processor has a lowering"""
+    """attach a fused program to the chain if every processor has a lowering: the specialised
+    (generated, straight-line) kernel when every processor has an emitter, else the interpreted
+    program"""
+    if os.environ.get("DSPEED_B200_SPECIALIZE", "1") != "0":
+        from . import codegen
+
+        try:
+            chain._fused = codegen.SpecChain(chain)
+            log.debug(f"specialised chain kernel:\n{chain._fused.program_text}")
+            return True
+        except NotFusable as e:
+            log.info(f"chain not specialised ({e}); trying the interpreted program")
+            chain._not_specialised_reason = str(e)
     try:
         chain._fused = FusedChain(chain)
         log.debug(f"fused chain program:\n{chain._fused.program_text}")
@@ -879,6 +905,8 @@ def profile_fused(chain, run, repeats: int = 1):
     fc = chain._fused
     if fc is None:
         raise RuntimeError("chain is not fused")
+    if hasattr(fc, "profile"):
+        return fc.profile(run, repeats)
     lib = _lib.lib()
     n = len(fc.code)
     lib.dspb_chain_profile(fc.handle, 1, None)

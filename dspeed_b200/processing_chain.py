@@ -338,6 +338,7 @@ class ProcessingChain:
             val = val.detach().cpu().numpy()
         val = np.array(val, dtype=dtype)
         param.update_auto(shape=val.shape, dtype=val.dtype, unit=unit, is_coord=False)
+        param.host_value = np.ascontiguousarray(val).astype(param.dtype, casting="unsafe")  # for the chain compilers
         buf = param.get_buffer()
         buf.copy_(torch.from_numpy(np.ascontiguousarray(val).astype(param.dtype, casting="unsafe")).reshape(buf.shape))
         log.debug(f"set constant: {param.description()} = {val}")
