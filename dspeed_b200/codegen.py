@@ -87,6 +87,7 @@ class Wave:
         self.producer = None
         self.is_input = False
         self.needs_slot = True
+        self.scatter = False     # written at other threads' positions (needs a barrier before any read)
         self.name = f"W{wid}"
 
 
@@ -482,8 +483,32 @@ class SpecChain(FusedChain):
         placed = set()
         by_wave_reductions = {}
         for nd in nodes:
-            if nd["kind"] in ("min_max", "lsf"):
+            if nd["kind"] in ("min_max", "lsf") or (nd["kind"] == "ftp" and nd["t"].startswith(("0x", "-0x"))):
                 by_wave_reductions.setdefault(nd["ins"][0][0].id, []).append(nd)
+
+        segs_of_wave = {}
+        for nd in nodes:
+            if nd["kind"] == "conv_seg":
+                segs_of_wave.setdefault(nd["ins"][0][0].id, []).append(nd)
+
+        def place_seg(nd):
+            """cusp / zac convolutions with the same input and shared parameters are evaluated together"""
+            if nd["idx"] in placed:
+                return
+            key = (nd["ins"][0][0].id, nd["ins"][0][2], tuple(nd["seg"][:6]))
+            group = [x for x in nodes if x["kind"] == "conv_seg" and x["idx"] not in placed
+                     and (x["ins"][0][0].id, x["ins"][0][2], tuple(x["seg"][:6])) == key][:2]
+            if nd["ins"][0][2] >= CHK * NT:
+                placed.add(nd["idx"])
+                order.append(nd)
+                return
+            for g in group:
+                placed.add(g["idx"])
+            order.append(dict(kind="conv_seg_group", idx=nd["idx"], members=group, ins=[nd["ins"][0]],
+                              wouts=[g["wouts"][0] for g in group], fatal=nd["fatal"]))
+            for g in group:
+                for r in by_wave_reductions.get(g["wouts"][0].id, []):
+                    place(r)
 
         def place(nd):
             if nd["idx"] in placed:
@@ -493,9 +518,17 @@ class SpecChain(FusedChain):
             for w in nd.get("wouts", []):
                 for r in by_wave_reductions.get(w.id, []):
                     place(r)
+            # hoist the structure-aware convolutions of a fresh wave right behind it (its chunk is
+            # still in registers, and its slot can be recycled early)
+            for w in nd.get("wouts", []):
+                for sg in segs_of_wave.get(w.id, []):
+                    place_seg(sg)
 
         for nd in nodes:
             if nd["idx"] in placed:
+                continue
+            if nd["kind"] == "conv_seg":
+                place_seg(nd)
                 continue
             if nd["kind"] == "fir":
                 # all FIR-running-sum filters of the same input wave are evaluated together
@@ -514,7 +547,7 @@ class SpecChain(FusedChain):
         # last use positions (in emission order) for slot liveness
         pos = {}
         for k, nd in enumerate(order):
-            members = nd["members"] if nd["kind"] == "fir_group" else [nd]
+            members = nd["members"] if nd["kind"] in ("fir_group", "conv_seg_group") else [nd]
             for m in members:
                 pos[m["idx"]] = k
         for w in self.waves.values():
@@ -541,7 +574,7 @@ class SpecChain(FusedChain):
         self.post_dirty = []
         self.nd_used = 0
         self.ni_used = 0
-        self.free_slots = []
+        self.free_cols = []
         self.n_slots = 0
         self.tmp = 0
         self.live_regs = []
@@ -557,10 +590,9 @@ class SpecChain(FusedChain):
             self._release(k)
         self._close_round()
         # scalar outputs
-        self.L.append("if (tid == 0) {")
-        for name, pi, ct in self.out_scalars:
-            self.L.append(f"  (({ct}*)A.p[{pi}])[row] = ({ct}){name};")
-        self.L.append("}")
+        # output k is stored by one thread of warp k % 16 (parallel over warps)
+        for k, (name, pi, ct) in enumerate(self.out_scalars):
+            self.L.append(f"if (tid == {32 * (k % 16) + k // 16}) (({ct}*)A.p[{pi}])[row] = ({ct}){name};")
         self.L.append("PROF_MARK(%d);" % len(self.order))
         fixed = 2048 + 8192 + 1024  # Scratch (old routines) + CScr + flags/aff2
         self.smem_bytes = fixed + self.n_slots * self.slot_words * 4
@@ -570,6 +602,9 @@ class SpecChain(FusedChain):
         self.code = self.order  # (for len(code) users)
 
     def _describe_node(self, nd):
+        if nd["kind"] == "conv_seg_group":
+            return "conv_seg_group " + " | ".join(f"{m['wouts'][0].name}<-{m['ins'][0][0].name}[:{m['ins'][0][2]}] "
+                                                  f"{'zac' if m['seg'][9] else 'cusp'} L={int(m['seg'][3])}" for m in nd["members"])
         if nd["kind"] == "fir_group":
             return "fir_group " + " | ".join(f"{m['wouts'][0].name}<-{m['ins'][0][0].name} taps={len(m['taps'])}" for m in nd["members"])
         ins = ",".join(f"{w.name}[{o}:{o + n}]" for w, o, n in nd.get("ins", []))
@@ -628,29 +663,81 @@ class SpecChain(FusedChain):
         return f"{prefix}{self.tmp}"
 
     # -- slots and register chunks ---------------------------------------------------------
-    def _slot_alloc(self):
-        if self.free_slots:
-            s = self.free_slots.pop(0)
-        else:
-            s = self.n_slots
+    # A physical slot has `nchunks` chunk columns; a wave of n samples needs ceil(n / 16) of them,
+    # so several short waves (windowed leading edge, cusp / zac outputs ...) share one slot.
+    def _slot_alloc(self, ncols=None):
+        ncols = self.nchunks if ncols is None else min(self.nchunks, ncols)
+        best = None
+        for k, (slot, c0, c1) in enumerate(self.free_cols):
+            if c1 - c0 >= ncols and (best is None or (c1 - c0) < (self.free_cols[best][2] - self.free_cols[best][1])):
+                best = k
+        if best is None:
+            slot = self.n_slots
             self.n_slots += 1
-        return s
+            self.free_cols.append((slot, 0, self.nchunks))
+            best = len(self.free_cols) - 1
+        slot, c0, c1 = self.free_cols.pop(best)
+        if c1 - c0 > ncols:
+            self.free_cols.append((slot, c0 + ncols, c1))
+        return (slot, c0, ncols)
+
+    def _slot_alloc_adjacent(self, k):
+        """k whole physical slots that are adjacent in shared memory (large scratch tables)"""
+        full = sorted(sl for (sl, c0, c1) in self.free_cols if c0 == 0 and c1 == self.nchunks)
+        start = None
+        for a in full:
+            if all((a + d) in full for d in range(k)):
+                start = a
+                break
+        if start is None:
+            # extend at the end (re-using a free last slot when there is one)
+            start = self.n_slots
+            while start - 1 in full and self.n_slots - start < k:
+                start -= 1
+            for sid in range(self.n_slots, start + k):
+                self.free_cols.append((sid, 0, self.nchunks))
+            self.n_slots = max(self.n_slots, start + k)
+        res = []
+        for d in range(k):
+            self.free_cols.remove((start + d, 0, self.nchunks))
+            res.append((start + d, 0, self.nchunks))
+        return res
+
+    def _slot_free(self, sl):
+        slot, c0, nc = sl
+        self.free_cols.append((slot, c0, c0 + nc))
+        # merge adjacent free ranges of the same slot
+        self.free_cols.sort()
+        merged = []
+        for iv in self.free_cols:
+            if merged and merged[-1][0] == iv[0] and merged[-1][2] == iv[1]:
+                merged[-1] = (iv[0], merged[-1][1], iv[2])
+            else:
+                merged.append(iv)
+        self.free_cols = merged
 
     def _release(self, k):
         for w in self.waves.values():
             if w.slot is not None and w.last <= k and not getattr(w, "released", False):
-                self.free_slots.append(w.slot)
-                self.free_slots.sort()
+                self._slot_free(w.slot)
                 w.released = True
 
     def _slot(self, w: Wave) -> str:
-        return f"SLOT({w.slot})"
+        return self._slot_expr(w.slot)
+
+    def _zc(self, w: Wave) -> int:
+        """index (relative to the wave's slot pointer) of the always-zero pad column"""
+        return self.nchunks - w.slot[1]
+
+    @staticmethod
+    def _slot_expr(sl) -> str:
+        return f"SLOT({sl[0]})" if sl[1] == 0 else f"(SLOT({sl[0]}) + {4 * sl[1]})"
 
     def _give_slot(self, w: Wave, post=False):
         if w.slot is None:
-            w.slot = self._slot_alloc()
+            w.slot = self._slot_alloc((w.n + CHK - 1) // CHK)
             # a pre-barrier store must not overtake other threads still reading the old tenant
-            if not post and w.slot in self.xread:
+            if not post and w.slot[0] in self.xread:
                 self._barrier()
 
     def _chunk(self, w: Wave) -> str:
@@ -660,6 +747,8 @@ class SpecChain(FusedChain):
             return w.reg
         if w.slot is None:
             raise NotSpecializable("internal: wave has neither registers nor a slot")
+        if w.scatter and w.slot[0] in self.dirty:
+            self._barrier()
         r = self._t("r")
         self._e(f"float {r}[16]; ld_chunk_n({self._slot(w)}, tid, {w.n}, {r});")
         self._set_reg(w, r)
@@ -681,7 +770,7 @@ class SpecChain(FusedChain):
         if w.needs_slot:
             self._give_slot(w)
             self._e(f"st_chunk_n({self._slot(w)}, tid, {w.n}, {r});")
-            self.dirty.add(w.slot)
+            self.dirty.add(w.slot[0])
         self._set_reg(w, r)
 
     def _post_store(self, w: Wave, r: str):
@@ -689,7 +778,7 @@ class SpecChain(FusedChain):
         if w.needs_slot:
             self._give_slot(w, post=True)
             self.posts.append(f"st_chunk_n({self._slot(w)}, tid, {w.n}, {r});")
-            self.post_dirty.append(w.slot)
+            self.post_dirty.append(w.slot[0])
         self._set_reg(w, r)
 
     def _visible(self, w: Wave):
@@ -697,9 +786,9 @@ class SpecChain(FusedChain):
         self._need(w.name)
         if w.slot is None:
             raise NotSpecializable("internal: cross-thread access to a register-only wave")
-        if w.slot in self.dirty:
+        if w.slot[0] in self.dirty:
             self._barrier()
-        self.xread.add(w.slot)
+        self.xread.add(w.slot[0])
 
     # -- node emitters -----------------------------------------------------------------------
     def _e_load(self, nd):
@@ -838,18 +927,35 @@ class SpecChain(FusedChain):
                 out = m["wouts"][0]
                 d, tot, incl = self._t("d"), self._t("tot"), self._t("incl")
                 self._e(f"float {d}[16];", f"_Pragma(\"unroll\") for (int j = 0; j < 16; j++) {d}[j] = 0.f;")
-                for (ts, c) in m["taps"]:
+                taps = sorted(m["taps"])
+                k = 0
+                zc = self._zc(w)
+                while k < len(taps):
+                    ts, c = taps[k]
+                    run = 1
+                    # consecutive taps whose coefficients agree to float32 rounding of the kernel
+                    # (a linear ramp's first difference) are evaluated as one sliding window
+                    tol = 4e-7 * max(abs(x[1]) for x in taps)
+                    while (k + run < len(taps) and taps[k + run][0] == ts + run and abs(taps[k + run][1] - c) <= tol
+                           and run < 16):
+                        run += 1
+                    if run >= 3:
+                        cm = sum(x[1] for x in taps[k:k + run]) / run
+                        self._e(f"fir_run<{ts}, {run}>({self._slot(w)}, tid, {n}, {zc}, {_flit(cm)}, {d});")
+                        k += run
+                        continue
                     if ts == 0:
                         if c == 1.0:
                             self._e(f"_Pragma(\"unroll\") for (int j = 0; j < 16; j++) {d}[j] += {own}[j];")
                         else:
                             self._e(f"_Pragma(\"unroll\") for (int j = 0; j < 16; j++) {d}[j] = fmaf({_flit(c)}, {own}[j], {d}[j]);")
                     elif c == 1.0:
-                        self._e(f"fir_tap_add<{ts}>({self._slot(w)}, tid, {n}, {d});")
+                        self._e(f"fir_tap_add<{ts}>({self._slot(w)}, tid, {n}, {zc}, {d});")
                     elif c == -1.0:
-                        self._e(f"fir_tap_sub<{ts}>({self._slot(w)}, tid, {n}, {d});")
+                        self._e(f"fir_tap_sub<{ts}>({self._slot(w)}, tid, {n}, {zc}, {d});")
                     else:
-                        self._e(f"fir_tap<{ts}>({self._slot(w)}, tid, {n}, {_flit(c)}, {d});")
+                        self._e(f"fir_tap<{ts}>({self._slot(w)}, tid, {n}, {zc}, {_flit(c)}, {d});")
+                    k += 1
                 sd = self._alloc_d(1)
                 self._e(f"const double {tot} = (double)cumsum_local({d});",
                         f"const double {incl} = put_scan(cs, par, {sd}, {tot}, lane, warp);")
@@ -904,28 +1010,35 @@ class SpecChain(FusedChain):
                 f"if ({f} && tid == 0) raise_fatal(A.fatal ? A.fatal + 4 * {nd['fatal']} : nullptr, {f}, A.row0 + row);")
 
     def _e_windower(self, nd):
-        # windower.py:12-54 : out[k] = in[t0 + k], NaN where the window leaves the waveform
+        # windower.py:12-54 : out[k] = in[t0 + k], NaN where the window leaves the waveform; one
+        # sample per thread (the window start is data dependent)
         w, off, n = nd["ins"][0]
         out = nd["wouts"][0]
         m = out.n
+        mc = (m + CHK - 1) // CHK * CHK
         self._need(nd["t0"], w.nan)
         self._visible(w)
-        o, pad, beg, tf = self._t("r"), self._t("pad"), self._t("beg"), self._t("tf")
+        out.needs_slot = True
+        self._give_slot(out)
+        pad, beg, tf = self._t("pad"), self._t("beg"), self._t("tf")
         si = self._alloc_i(1)
         g = self._nan_guard([w.nan, f"({tf} != {tf})"])
-        self._e(f"float {o}[16]; int {pad} = 0;",
+        so = self._slot(out)
+        self._e(f"int {pad} = 0;",
                 f"const float {tf} = (float)({nd['t0']});",
-                f"long long {beg} = ({tf} == {tf}) ? (long long){tf} : 0; if ({beg} > {n}) {beg} = {n};",
-                f"_Pragma(\"unroll\") for (int j = 0; j < 16; j++) {{ const long long q = {beg} + 16 * tid + j; float v = 0.f; "
-                f"if (16 * tid + j < {m}) {{ if (!({g}) && q >= 0 && q < {n}) v = at({self._slot(w)}, (int)q); "
-                f"else {{ {pad} = 1; v = CUDART_NAN_F; }} }} {o}[j] = v; }}",
+                f"int {beg} = ({tf} == {tf}) ? (int)fminf(fmaxf({tf}, -1.0e9f), 1.0e9f) : 0; if ({beg} > {n}) {beg} = {n};",
+                f"for (int k = tid; k < {mc}; k += 512) {{ const int q = {beg} + k; float v = 0.f; "
+                f"if (k < {m}) {{ if (!({g}) && q >= 0 && q < {n}) v = at({self._slot(w)}, q); else {{ {pad} = 1; v = CUDART_NAN_F; }} }} "
+                f"{so}[sidx(k)] = v; }}",
                 f"put_imax(cs, par, {si}, {pad}, lane, warp);")
         nf = f"nan{out.name}"
         self.posts.append(f"const int {nf} = get_imax(cs, par, {si}, lane);")
         self.pending.add(nf)
         out.nan = nf
         out.nan_elementwise = True
-        self._store(out, o)
+        out.scatter = True
+        out.reg = None
+        self.dirty.add(out.slot[0])
 
     def _e_avg_current(self, nd):
         w, off, n = nd["ins"][0]
@@ -935,7 +1048,7 @@ class SpecChain(FusedChain):
         self._visible(w)
         a = self._chunk(w)
         b, o = self._t("r"), self._t("r")
-        self._e(f"float {b}[16]; ld_shift<{L}>({self._slot(w)}, tid, {n}, {b});",
+        self._e(f"float {b}[16]; ld_shift<{L}>({self._slot(w)}, tid, {n}, {self._zc(w)}, {b});",
                 f"float {o}[16]; _Pragma(\"unroll\") for (int j = 0; j < 16; j++) {o}[j] = ({b}[j] - {a}[j]) / {_flit(L)};")
         out.nan = w.nan
         self._store(out, o)
@@ -952,9 +1065,20 @@ class SpecChain(FusedChain):
         o = self._t("r")
         holes = m > n * up - half
         g = self._nan_guard([w.nan])
-        self._e(f"float {o}[16];",
-                f"_Pragma(\"unroll\") for (int j = 0; j < 16; j++) {{ const int t = 16 * tid + j; const int q = (t + {half}) / {up}; "
-                f"{o}[j] = t >= {m} ? 0.f : ((q < {n}{' && !(' + g + ')' if g else ''}) ? at({self._slot(w)}, q) : CUDART_NAN_F); }}")
+        ok = f"{' && !(' + g + ')' if g else ''}"
+        if up >= CHK and up % CHK == 0:
+            # a chunk of 16 outputs sees at most two inputs: q0 = floor((16 t + half) / up) and q0 + 1
+            q0, v0, v1, sw = self._t("q"), self._t("v"), self._t("v"), self._t("sw")
+            self._e(f"float {o}[16];",
+                    f"const int {q0} = (16 * tid + {half}) / {up};",
+                    f"const int {sw} = ({q0} + 1) * {up} - {half} - 16 * tid;   // first j that belongs to input q0 + 1",
+                    f"const float {v0} = ({q0} < {n}{ok}) ? at({self._slot(w)}, {q0}) : CUDART_NAN_F;",
+                    f"const float {v1} = ({q0} + 1 < {n}{ok}) ? at({self._slot(w)}, {q0} + 1) : CUDART_NAN_F;",
+                    f"_Pragma(\"unroll\") for (int j = 0; j < 16; j++) {o}[j] = 16 * tid + j >= {m} ? 0.f : (j < {sw} ? {v0} : {v1});")
+        else:
+            self._e(f"float {o}[16];",
+                    f"_Pragma(\"unroll\") for (int j = 0; j < 16; j++) {{ const int t = 16 * tid + j; const int q = (t + {half}) / {up}; "
+                    f"{o}[j] = t >= {m} ? 0.f : ((q < {n}{ok}) ? at({self._slot(w)}, q) : CUDART_NAN_F); }}")
         if holes:
             nf = f"nan{out.name}"
             self._e(f"const int {nf} = 1;")
@@ -993,7 +1117,7 @@ class SpecChain(FusedChain):
             sl = self._slot(src)
             if dr == "l":
                 # out[0] = x[0]; out[i] = out[i-1] + (x[i] - x[max(i-L,0)]) / L
-                self._e(f"float {sh}[16]; ld_shift<{-L}>({sl}, tid, {n}, {sh}); const float {e0} = at({sl}, 0);",
+                self._e(f"float {sh}[16]; ld_shift<{-L}>({sl}, tid, {n}, {self._zc(src)}, {sh}); const float {e0} = at({sl}, 0);",
                         f"float {d}[16]; _Pragma(\"unroll\") for (int j = 0; j < 16; j++) {{ const int i = 16 * tid + j; "
                         f"{d}[j] = i >= {n} ? 0.f : (i == 0 ? {e0} : ({x}[j] - (i >= {L} ? {sh}[j] : {e0})) * {il}); }}",
                         f"const double {tot} = (double)cumsum_local({d});",
@@ -1001,7 +1125,7 @@ class SpecChain(FusedChain):
                 get = f"get_excl(cs, par, {sd}, {incl}, {tot}, lane, warp, {tt})"
             else:
                 # mirror image: out[n-1] = x[n-1]; out[i] = out[i+1] + (x[i] - x[min(i+L,n-1)]) / L
-                self._e(f"float {sh}[16]; ld_shift<{L}>({sl}, tid, {n}, {sh}); const float {e0} = at({sl}, {n - 1});",
+                self._e(f"float {sh}[16]; ld_shift<{L}>({sl}, tid, {n}, {self._zc(src)}, {sh}); const float {e0} = at({sl}, {n - 1});",
                         f"float {d}[16]; _Pragma(\"unroll\") for (int j = 0; j < 16; j++) {{ const int i = 16 * tid + j; "
                         f"{d}[j] = i >= {n} ? 0.f : (i == {n - 1} ? {e0} : ({x}[j] - (i + {L} <= {n - 1} ? {sh}[j] : {e0})) * {il}); }}",
                         f"const double {tot} = (double)cumsum_local_rev({d});",
@@ -1018,8 +1142,7 @@ class SpecChain(FusedChain):
             src = dst
         for tw in temps:
             if tw.slot is not None:
-                self.free_slots.append(tw.slot)
-                self.free_slots.sort()
+                self._slot_free(tw.slot)
             if tw in self.live_regs:
                 self.live_regs.remove(tw)
 
@@ -1030,19 +1153,63 @@ class SpecChain(FusedChain):
         self._visible(w)
         self._close_round()
         scratch = self._slot_alloc()
-        if scratch in self.xread or scratch in self.dirty:
+        if scratch[0] in self.xread or scratch[0] in self.dirty:
             self._barrier()
         self._give_slot(out)
         seg = nd["seg"]
         prm = self._t("prm")
         self.static_arrays = getattr(self, "static_arrays", [])
         self.static_arrays.append(f"__device__ const double {prm}[10] = {{{', '.join(_lit(v) for v in seg)}}};")
-        self._e(f"op_conv_seg<float>({self._slot(w)}, {n}, {self._slot(out)}, reinterpret_cast<double*>(SLOT({scratch})), {prm}, sc);")
-        self.free_slots.append(scratch)
-        self.free_slots.sort()
+        self._e(f"op_conv_seg<float>({self._slot(w)}, {n}, {self._slot(out)}, reinterpret_cast<double*>(SLOT({scratch[0]})), {prm}, sc);")
+        self._slot_free(scratch)
         out.nan = w.nan
         out.reg = None
-        self.dirty.discard(out.slot)
+        self.dirty.discard(out.slot[0])
+
+    def _e_conv_seg_group(self, nd):
+        members = nd["members"]
+        w, off, n = nd["ins"][0]
+        self._need(w.nan)
+        x = self._chunk(w)
+        self._visible(w)
+        self._close_round()
+        two = len(members) == 2
+        seg = members[0]["seg"]
+        sigma, lt, fl, L, c, inv2S = seg[:6]
+        p = n - int(L) + 1
+        poly = any(m["seg"][7] != 0.0 for m in members)
+        nq = 5 if poly else 3
+        cw = (((p + CHK - 1) // CHK) + 1) | 1
+        need = nq * (4 * CHK * cw + NT) * 8
+        nsl = -(-need // (self.slot_words * 4))
+        scratch = self._slot_alloc_adjacent(nsl)
+        outs = []
+        for m in members:
+            out = m["wouts"][0]
+            self._give_slot(out, post=True)
+            outs.append(out)
+        busy = self.xread | self.dirty
+        if any(sl[0] in busy for sl in scratch) or any(o.slot[0] in busy for o in outs):
+            self._barrier()
+        so = [f"SegOut{{{_lit(m['seg'][6])}, {_lit(m['seg'][7])}, {_lit(m['seg'][8])}}}" for m in members]
+        if not two:
+            so.append(so[0])
+        pw = self._t("pw")
+        self.static_arrays = getattr(self, "static_arrays", [])
+        vals = [math.exp(o / sigma) for o in range(p)] + [math.exp(-o / sigma) for o in range(p)]
+        self.static_arrays.append(f"__device__ const double {pw}[{2 * p}] = {{{', '.join(_lit(v) for v in vals)}}};")
+        self._e(f"conv_seg_chunked<{'true' if poly else 'false'}, {'true' if two else 'false'}>({self._slot(w)}, {x}, {n}, "
+                f"{_lit(sigma)}, {int(lt)}, {int(fl)}, {int(L)}, {_lit(c)}, {_lit(inv2S)}, {_lit(math.exp(-1.0 / sigma))}, "
+                f"{_lit(math.exp(1.0 / sigma))}, {_lit(math.exp((L - 1) / sigma))}, {pw}, {so[0]}, {so[1]}, {self._slot(outs[0])}, {self._slot(outs[1 if two else 0])}, "
+                f"reinterpret_cast<double*>(SLOT({scratch[0][0]})), cs, par, tid, lane, warp);")
+        # the band table overwrote the (always-zero) pad columns of its slots
+        self._e(f"zero_pads(slots, {self.slot_words}, {self.nchunks}, {scratch[0][0]}, {scratch[-1][0] + 1}, tid);")
+        for sl in scratch:
+            self.dirty.add(sl[0])
+            self._slot_free(sl)
+        for out in outs:
+            out.nan = w.nan
+            out.reg = None
 
     def _e_sc_bin(self, nd):
         self._need(nd["x"], nd["y"])
@@ -1121,6 +1288,8 @@ __global__ void __launch_bounds__(512, 1) k_chain_spec(const __grid_constant__ A
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   long long* prof_ts = reinterpret_cast<long long*>(smem_raw + 2048 + 8192);
   int par = 0;
+  zero_pads(slots, {self.slot_words}, {self.nchunks}, 0, {self.n_slots}, tid);
+  __syncthreads();
   for (long long row = blockIdx.x; row < A.n_rows; row += gridDim.x) {{
     if (A.prof && tid == 0) prof_ts[0] = clock64();
     {{
@@ -1205,7 +1374,8 @@ def _headers_digest() -> str:
 
 def build_source(src: str, verbose=False):
     """compile one generated kernel for sm_100a (cached by content hash)"""
-    tag = hashlib.sha1((src + _headers_digest()).encode()).hexdigest()[:16]
+    extra = os.environ.get("DSPEED_B200_NVCC_EXTRA", "").split()   # experiments: -D switches of chain_rt.cuh
+    tag = hashlib.sha1((src + _headers_digest() + " ".join(extra)).encode()).hexdigest()[:16]
     os.makedirs(CACHE_DIR, exist_ok=True)
     so = os.path.join(CACHE_DIR, f"chain_{tag}.so")
     cu = os.path.join(CACHE_DIR, f"chain_{tag}.cu")
@@ -1214,7 +1384,7 @@ def build_source(src: str, verbose=False):
             with open(cu, "w") as f:
                 f.write(src)
             tmp = so + f".tmp{os.getpid()}"
-            cmd = [_lib._nvcc(), *_lib.NVCC_FLAGS, "-I", _lib.INCLUDE, "-I", _lib.CSRC, "-o", tmp, cu]
+            cmd = [_lib._nvcc(), *_lib.NVCC_FLAGS, *extra, "-I", _lib.INCLUDE, "-I", _lib.CSRC, "-o", tmp, cu]
             env = dict(os.environ)
             env.pop("CC", None)
             env.pop("CXX", None)

@@ -79,21 +79,35 @@ __device__ __forceinline__ void st_chunk_n(float* slot, int t, int n, const floa
 
 __host__ __device__ constexpr int floor_div16(int d) { return d >= 0 ? d / 16 : -((-d + 15) / 16); }
 
-// o[j] = x[16 t + j + D], zero outside [0, nceil) where nceil = n rounded up to whole chunks
-// (the tail of the last chunk holds zeros, see st_chunk_n).  D is a compile-time shift.
-template <int D>
-__device__ __forceinline__ void ld_shift(const float* slot, int t, int n, float (&o)[CHK]) {
+// o[m] = x[16 t + D + m] for m < CNT, zero outside [0, nceil) where nceil = n rounded up to whole
+// chunks (the tail of the last chunk holds zeros, see st_chunk_n).  D is a compile-time shift:
+// the vectors are read with 128-bit loads at immediate offsets.  Out-of-range chunks are
+// redirected to the always-zero pad column `zc` of the slot instead of being predicated.
+template <int D, int CNT>
+__device__ __forceinline__ void ld_span(const float* slot, int t, int n, int zc, float (&o)[CNT]) {
   constexpr int qd = floor_div16(D), rd = D - 16 * qd, a = rd >> 2, b = rd & 3;
-  constexpr int NV = b ? 5 : 4;
+  constexpr int NV = (b + CNT + 3) >> 2;
   float4 v[NV];
   const int nchunks = (n + CHK - 1) >> 4;
 #pragma unroll
   for (int u = 0; u < NV; u++) {
     const int vv = a + u, plane = vv & 3, c = t + qd + (vv >> 2);
-    v[u] = (c >= 0 && c < nchunks) ? ldv(slot, plane, c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    v[u] = ldv(slot, plane, ((unsigned)c < (unsigned)nchunks) ? c : zc);
   }
 #pragma unroll
-  for (int j = 0; j < CHK; j++) o[j] = comp(v[(j + b) >> 2], (j + b) & 3);
+  for (int m = 0; m < CNT; m++) o[m] = comp(v[(m + b) >> 2], (m + b) & 3);
+}
+template <int D>
+__device__ __forceinline__ void ld_shift(const float* slot, int t, int n, int zc, float (&o)[CHK]) {
+  ld_span<D, CHK>(slot, t, n, zc, o);
+}
+
+// the two pad columns at the end of every plane of slots [k0, k1) are kept zero
+__device__ __forceinline__ void zero_pads(float* slots, int slot_words, int nch, int k0, int k1, int tid) {
+  for (int q = tid; q < (k1 - k0) * 32; q += 512) {
+    const int k = k0 + (q >> 5), plane = (q >> 3) & 3, e = q & 7;
+    slots[k * slot_words + plane * DSPB_PSP + 4 * nch + e] = 0.f;
+  }
 }
 
 // raw waveform row from HBM: thread t reads its 16 samples (2 x 128-bit for uint16)
@@ -343,38 +357,69 @@ __device__ __forceinline__ float cumsum_local_rev(float (&d)[CHK]) {
 
 // d[j] += c * x[16 t + j - TS]   (one tap of a sparse FIR; zero outside the wave)
 template <int TS>
-__device__ __forceinline__ void fir_tap(const float* slot, int t, int n, float c, float (&d)[CHK]) {
+__device__ __forceinline__ void fir_tap(const float* slot, int t, int n, int zc, float c, float (&d)[CHK]) {
   float v[CHK];
-  ld_shift<-TS>(slot, t, n, v);
+  ld_shift<-TS>(slot, t, n, zc, v);
 #pragma unroll
   for (int j = 0; j < CHK; j++) d[j] = fmaf(c, v[j], d[j]);
 }
 template <int TS>
-__device__ __forceinline__ void fir_tap_add(const float* slot, int t, int n, float (&d)[CHK]) {
+__device__ __forceinline__ void fir_tap_add(const float* slot, int t, int n, int zc, float (&d)[CHK]) {
   float v[CHK];
-  ld_shift<-TS>(slot, t, n, v);
+  ld_shift<-TS>(slot, t, n, zc, v);
 #pragma unroll
   for (int j = 0; j < CHK; j++) d[j] += v[j];
 }
 template <int TS>
-__device__ __forceinline__ void fir_tap_sub(const float* slot, int t, int n, float (&d)[CHK]) {
+__device__ __forceinline__ void fir_tap_sub(const float* slot, int t, int n, int zc, float (&d)[CHK]) {
   float v[CHK];
-  ld_shift<-TS>(slot, t, n, v);
+  ld_shift<-TS>(slot, t, n, zc, v);
 #pragma unroll
   for (int j = 0; j < CHK; j++) d[j] -= v[j];
+}
+// LEN consecutive taps TS0 .. TS0+LEN-1 with one coefficient: d[j] += c * sum_s x[i - TS0 - s],
+// evaluated as a sliding window over one span of 16 + LEN - 1 samples
+template <int TS0, int LEN>
+__device__ __forceinline__ void fir_run(const float* slot, int t, int n, int zc, float c, float (&d)[CHK]) {
+  float v[CHK + LEN - 1];
+  ld_span<-(TS0 + LEN - 1), CHK + LEN - 1>(slot, t, n, zc, v);  // v[m] = x[16t + m - TS0 - LEN + 1]
+  float w = 0.f;
+#pragma unroll
+  for (int m = 0; m < LEN; m++) w += v[m];
+#pragma unroll
+  for (int j = 0; j < CHK; j++) {
+    d[j] = fmaf(c, w, d[j]);
+    if (j + 1 < CHK) w += v[j + LEN] - v[j];
+  }
 }
 
 // value of sample i of a slot (any thread)
 __device__ __forceinline__ float at(const float* slot, int i) { return slot[sidx(i)]; }
 
-// time_point_thresh.py:12-92 : block-wide search with ONE barrier per 512-sample window.
-// Thread (lane, warp) of window k looks at sample s -/+ (16 * lane + warp + 512 k): lanes of a
-// warp touch consecutive chunks at the same in-chunk offset (conflict-free in the T4 layout).
+// time_point_thresh.py:12-92.  The crossing usually lies within a few tens of samples of the
+// start, so every warp first walks (redundantly, no barrier) up to WARP_WINDOWS windows of 32
+// samples with a ballot; only a long walk falls back to block-wide 512-sample windows with one
+// barrier each.  All warps see the same data, so the control flow is uniform over the CTA.
+// In a block window thread (lane, warp) looks at sample s -/+ (16 * lane + warp): lanes touch
+// consecutive chunks at the same in-chunk offset (conflict-free in the T4 layout).
+constexpr int WARP_WINDOWS = 6;
 __device__ __forceinline__ int search_cross(const float* w, int n, float thr, int s, bool forward, int stop_back,
                                             CScr* cs, int& par, int lane, int warp) {
-  const int u = 16 * lane + warp;
   if (forward) {
-    for (int base = s; base < n - 1; base += 512) {
+    int base = s;
+#pragma unroll 1
+    for (int k = 0; k < WARP_WINDOWS && base < n - 1; k++, base += 32) {
+      const int i = base + lane;
+      bool hit = false;
+      if (i < n - 1) {
+        const float a = at(w, i), b = at(w, i + 1);
+        hit = (a <= thr && thr < b) || (a >= thr && thr > b);
+      }
+      const unsigned m = __ballot_sync(FULL, hit);
+      if (m) return base + __ffs(m) - 1;
+    }
+    const int u = 16 * lane + warp;
+    for (; base < n - 1; base += 512) {
       const int i = base + u;
       int hit = 0x7fffffff;
       if (i < n - 1) {
@@ -389,7 +434,20 @@ __device__ __forceinline__ int search_cross(const float* w, int n, float thr, in
     }
     return -1;
   }
-  for (int base = s; base >= stop_back; base -= 512) {
+  int base = s;
+#pragma unroll 1
+  for (int k = 0; k < WARP_WINDOWS && base >= stop_back; k++, base -= 32) {
+    const int i = base - lane;
+    bool hit = false;
+    if (i >= stop_back) {
+      const float a = at(w, i - 1), b = at(w, i);
+      hit = (a < thr && thr <= b) || (a > thr && thr >= b);
+    }
+    const unsigned m = __ballot_sync(FULL, hit);
+    if (m) return base - (__ffs(m) - 1);
+  }
+  const int u = 16 * lane + warp;
+  for (; base >= stop_back; base -= 512) {
     const int i = base - u;
     int hit = -1;
     if (i >= stop_back) {
@@ -415,6 +473,133 @@ __device__ __forceinline__ float tpt(const float* w, int n, float thr, float t_s
   if (s < 0 || s >= n) { fatal = DSPB_FATAL_TSTART_RANGE; return CUDART_NAN_F; }
   const int hit = search_cross(w, n, thr, (int)s, (long long)walk == 1, 1, cs, par, lane, warp);
   return hit < 0 ? CUDART_NAN_F : (float)hit;
+}
+
+// =========================================================================================
+// 'valid' convolution with cusp / zac kernels (energy_kernels.py:12-157), chunked form.
+//
+// Same mathematics as op_conv_seg (conv_seg.cuh): with z[j] = x[j] - c x[j-1] the kernel is
+// sinh ramps + flat top (+ beta * parabolas for zac), so every output is a combination of the
+// prefix sums  Em = sum e^{-j/s} z,  Ep = sum e^{+j/s} z,  P0 = sum z  (and M1 = sum jc z,
+// M2 = sum jc^2 z with jc = j - N/2 for the parabolas) at four window bounds
+//   hiA = L + o,  loA = L - lt + o,  loB = L - 1 - lt - fl + o,  loC = o      (o = output index).
+// Here: (1) one pass over the thread's chunk for the chunk sums and ONE scan round; (2) only
+// the threads whose chunk meets one of the four p-wide bands replay it (running sums only)
+// and deposit the prefix values at the band positions; (3) the p outputs are combined in
+// parallel, one thread each, with the powers q^o = e^{+-o/s} read from a table built by the
+// chain compiler.  Two kernels that share (sigma, lt, fl, L, c) -- the ICPC chain's cusp and
+// zac -- are evaluated together (TWO): sums, scan, replay and exponentials are shared.
+// tab: NQ * (4 * 16 * CW + 512) doubles of scratch (NQ = 5 with parabolas, else 3; CW = odd number of
+// chunk columns >= ceil(p / 16) + 1): entry (o % 16) * CW + o / 16 of a band, so that the lanes of a
+// warp (consecutive chunks, positions 16 apart) store to consecutive addresses.
+// pw: [2][p] doubles, pw[0][o] = e^{o/s}, pw[1][o] = e^{-o/s}.
+// Ends with a barrier; out* are complete slots.
+// =========================================================================================
+struct SegOut {
+  double kL, beta, h;  // k[L-1], parabola weight (0: cusp), parabola vertex
+};
+
+template <bool POLY, bool TWO>
+__device__ __forceinline__ void conv_seg_chunked(const float* X, const float (&x)[CHK], int N, double sigma, int lt,
+                                                 int fl, int L, double c, double inv2S, double qm, double qp,
+                                                 double eA, const double* __restrict__ pw, SegOut s0, SegOut s1, float* out0,
+                                                 float* out1, double* tab, CScr* cs, int& par, int tid, int lane,
+                                                 int warp) {
+  constexpr int NQ = POLY ? 5 : 3;
+  const int p = N - L + 1;
+  const int CW = (((p + CHK - 1) >> 4) + 1) | 1, PP = CHK * CW;
+  const int i0 = CHK * tid;
+  const double j0 = 0.5 * (double)N;
+  const float xm1 = (i0 > 0 && i0 < N) ? at(X, i0 - 1) : 0.f;
+  const int base[4] = {L, L - lt, L - 1 - lt - fl, 0};
+  // ---- pass 1: chunk sums; threads whose chunk meets a band also deposit the chunk-local
+  // running sums (sum over the chunk's elements before position j) at the band positions ----
+  double s[NQ];
+#pragma unroll
+  for (int q = 0; q < NQ; q++) s[q] = 0.0;
+  bool hit = false;
+#pragma unroll
+  for (int b = 0; b < 4; b++) hit |= (i0 + CHK - 1 >= base[b] && i0 <= base[b] + p - 1);
+  hit &= i0 <= N;
+  if (i0 < N || hit) {
+    const double wm0 = exp(-(double)i0 / sigma);
+    double wm = wm0, wp = 1.0 / wm0, jc = (double)i0 - j0;
+    float prev = xm1;
+#pragma unroll
+    for (int k = 0; k < CHK; k++) {
+      const int j = i0 + k;
+      if (hit && j <= N) {
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+          const int o = j - base[b];
+          if (o >= 0 && o < p) {
+#pragma unroll
+            for (int q = 0; q < NQ; q++) tab[(q * 4 + b) * PP + (o & 15) * CW + (o >> 4)] = s[q];
+          }
+        }
+      }
+      const double z = j < N ? fma(-c, (double)prev, (double)x[k]) : 0.0;
+      prev = x[k];
+      s[0] = fma(wm, z, s[0]);
+      s[1] = fma(wp, z, s[1]);
+      s[2] += z;
+      if (POLY) {
+        const double jz = jc * z;
+        s[3] += jz;
+        s[4] = fma(jc, jz, s[4]);
+        jc += 1.0;
+      }
+      wm *= qm;
+      wp *= qp;
+    }
+  }
+  double inc[NQ];
+#pragma unroll
+  for (int q = 0; q < NQ; q++) inc[q] = put_scan(cs, par, q, s[q], lane, warp);
+  __syncthreads();
+  // ---- pass 2: every thread publishes the prefix sums in front of its chunk ------------------
+  double* otab = tab + NQ * 4 * PP;
+  {
+    double tt;
+#pragma unroll
+    for (int q = 0; q < NQ; q++) otab[q * 512 + tid] = get_excl(cs, par, q, inc[q], s[q], lane, warp, tt);
+  }
+  par ^= 1;
+  __syncthreads();
+  // ---- pass 3: one thread per output ------------------------------------------------------------
+  const int pceil = (p + CHK - 1) & ~(CHK - 1);
+  const double eAm = 1.0 / eA;  // eA = e^{(L-1)/s}: e^{+-n/s} = eA^{+-1} * q^{+-o}
+  for (int o = tid; o < pceil; o += 512) {
+    float y0 = 0.f, y1 = 0.f;
+    if (o < p) {
+      const int ow[4] = {(base[0] + o) >> 4, (base[1] + o) >> 4, (base[2] + o) >> 4, (base[3] + o) >> 4};
+#define TB(q, b) (tab[((q)*4 + (b)) * PP + (o & 15) * CW + (o >> 4)] + otab[(q)*512 + ow[b]])
+      const double po = pw[o], mo = pw[p + o];
+      const double en = eA * po, enm = eAm * mo;      // e^{+-n/s}, n = L - 1 + o
+      const double eLn = qp * mo, eLnm = qm * po;     // e^{+-(L-n)/s} = e^{+-(1-o)/s}
+      const double yA = (en * (TB(0, 0) - TB(0, 1)) - enm * (TB(1, 0) - TB(1, 1))) * inv2S;
+      const double yB = TB(2, 1) - TB(2, 2);
+      const double yC = (eLn * (TB(1, 2) - TB(1, 3)) - eLnm * (TB(0, 2) - TB(0, 3))) * inv2S;
+      const double xm = o >= 1 ? (double)at(X, o - 1) : 0.0;
+      double ysh = yA + yB + yC;
+      double v0 = ysh + c * s0.kL * xm, v1 = ysh + c * s1.kL * xm;
+      if (POLY) {
+        const double n = (double)(L - 1 + o), nc = n - j0, a = ((double)L - n) + j0;
+        const double dPa = TB(2, 0) - TB(2, 1), dM1a = TB(3, 0) - TB(3, 1), dM2a = TB(4, 0) - TB(4, 1);
+        const double s2a = nc * nc * dPa - 2.0 * nc * dM1a + dM2a, s1a = nc * dPa - dM1a;
+        const double dPc = TB(2, 2) - TB(2, 3), dM1c = TB(3, 2) - TB(3, 3), dM2c = TB(4, 2) - TB(4, 3);
+        const double s2c = a * a * dPc + 2.0 * a * dM1c + dM2c, s1c = a * dPc + dM1c;
+        v0 += s0.beta * ((s2a - 2.0 * s0.h * s1a) + (s2c - 2.0 * s0.h * s1c));
+        v1 += s1.beta * ((s2a - 2.0 * s1.h * s1a) + (s2c - 2.0 * s1.h * s1c));
+      }
+#undef TB
+      y0 = (float)v0;
+      y1 = (float)v1;
+    }
+    out0[sidx(o)] = y0;
+    if (TWO) out1[sidx(o)] = y1;
+  }
+  __syncthreads();
 }
 
 }  // namespace crt
