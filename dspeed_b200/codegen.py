@@ -203,6 +203,14 @@ class SpecChain(FusedChain):
                            ptr=self._ptr(("buf", rv)))
         if len(self.ptrs) > 64:
             raise NotSpecializable("too many distinct device pointers")
+        self.used_scalars = {name for (name, _, _) in self.out_scalars}
+        for nd in self.nodes:
+            for key in ("x", "y", "thr", "start", "walk", "t", "t0", "b", "tau", "oi", "oo"):
+                if key in nd and isinstance(nd[key], str):
+                    self.used_scalars.add(nd[key])
+        self.out_of = {}
+        for k, (name, pi, ct) in enumerate(self.out_scalars):
+            self.out_of.setdefault(name, []).append((pi, ct, k))
         self._schedule()
         self._emit_kernel()
         self._build()
@@ -251,7 +259,7 @@ class SpecChain(FusedChain):
                     raise NotSpecializable(f"scalar input dtype {src.dtype}")
                 name = self._new_svar(st)
                 pi = self._ptr(("in", man, what))
-                self.prolog.append(f"const double {name} = (double)((const {_CTYPE[src.dtype]}*)A.p[{pi}])[row * A.s[{pi}]];")
+                self.prolog.append(f"{name} = (double)((const {_CTYPE[src.dtype]}*)A.p[{pi}])[row * A.s[{pi}]];")
             return self.svar[st]
         if x is None:
             raise NotSpecializable("None argument")
@@ -571,6 +579,11 @@ class SpecChain(FusedChain):
         self.dirty = set()
         self.xread = set()
         self.posts = []
+        self.posts0 = []            # post-barrier code that only the scalar warp (warp 0) executes
+        self.sdom = {}              # scalar variable -> "w0" (valid in warp 0 only); default: all threads
+        self.in_w0 = False
+        self.stored = set()
+        self.n_bcast = 0
         self.post_dirty = []
         self.nd_used = 0
         self.ni_used = 0
@@ -590,9 +603,11 @@ class SpecChain(FusedChain):
             self._release(k)
         self._close_round()
         # scalar outputs
-        # output k is stored by one thread of warp k % 16 (parallel over warps)
+        # scalar outputs not stored at their definition (pass-through input scalars)
         for k, (name, pi, ct) in enumerate(self.out_scalars):
-            self.L.append(f"if (tid == {32 * (k % 16) + k // 16}) (({ct}*)A.p[{pi}])[row] = ({ct}){name};")
+            if name not in self.stored:
+                self._e0(f"if (lane == {k % 32}) (({ct}*)A.p[{pi}])[row] = ({ct}){name};")
+        self._e()
         self.L.append("PROF_MARK(%d);" % len(self.order))
         fixed = 2048 + 8192 + 1024  # Scratch (old routines) + CScr + flags/aff2
         self.smem_bytes = fixed + self.n_slots * self.slot_words * 4
@@ -614,14 +629,32 @@ class SpecChain(FusedChain):
 
     # -- round framework ---------------------------------------------------------------------
     def _e(self, *lines):
+        """code executed by all threads"""
+        if self.in_w0:
+            self.L.append("}")
+            self.in_w0 = False
         self.L.extend(lines)
 
+    def _e0(self, *lines):
+        """code executed by the scalar warp only: per-event scalar work (threshold searches,
+        pick-offs, fit results, unit conversions) costs one warp's issue slots instead of sixteen"""
+        if not self.in_w0:
+            self.L.append("if (warp == 0) {")
+            self.in_w0 = True
+        self.L.extend(lines)
+
+    def _round_open(self):
+        return bool(self.posts or self.posts0 or self.nd_used or self.ni_used or self.pending)
+
     def _close_round(self):
-        if self.posts or self.nd_used or self.ni_used or self.pending:
+        if self._round_open():
             self._e("__syncthreads();")
             self._e(*self.posts)
+            if self.posts0:
+                self._e0(*self.posts0)   # reads the scratch of this round: before the parity flips
             self._e("par ^= 1;")
         self.posts = []
+        self.posts0 = []
         self.pending.clear()
         self.dirty.clear()
         self.xread.clear()
@@ -630,7 +663,7 @@ class SpecChain(FusedChain):
         self.nd_used = self.ni_used = 0
 
     def _barrier(self):
-        if self.posts or self.nd_used or self.ni_used or self.pending:
+        if self._round_open():
             self._close_round()
         else:
             self._e("__syncthreads();")
@@ -643,6 +676,35 @@ class SpecChain(FusedChain):
             if e is not None and str(e) in self.pending:
                 self._close_round()
                 return
+
+    def _is_w0(self, e):
+        return e is not None and self.sdom.get(str(e)) == "w0"
+
+    def _need_all(self, *exprs):
+        """scalars that every thread must hold: those living in the scalar warp are broadcast
+        through shared memory (one barrier for all of them)"""
+        self._need(*exprs)
+        names = sorted({str(e) for e in exprs if self._is_w0(e)})
+        if not names:
+            return
+        self._close_round()
+        for nme in names:
+            k = self.n_bcast % 16
+            self.n_bcast += 1
+            self._e0(f"if (lane == 0) bc[{k}] = {nme};")
+            self.posts.append(f"{nme} = bc[{k}];")
+            self.pending.add(nme)
+            self.sdom[nme] = "all"
+        self._close_round()
+
+    def _def0(self, name):
+        self.sdom[name] = "w0"
+
+    def _stores(self, name):
+        """statements (for the scalar warp) that write a just-defined scalar to its output columns:
+        results leave the register file as soon as they are final"""
+        self.stored.add(name)
+        return [f"if (lane == {k % 32}) (({ct}*)A.p[{pi}])[row] = ({ct}){name};" for (pi, ct, k) in self.out_of.get(name, [])]
 
     def _alloc_d(self, k):
         if self.nd_used + k > 16:
@@ -817,34 +879,41 @@ class SpecChain(FusedChain):
         return " || ".join(f"({f})" for f in fl) if fl else None
 
     def _e_min_max(self, nd):
+        # min_max.py:11-82 / numpy.amax: value via FMNMX, first-occurrence index via an equality pass;
+        # outputs nobody reads (and that are no chain outputs) are not computed at all
         w, off, n = nd["ins"][0]
-        outs = nd["outs"]
+        outs = [o if (o and o in self.used_scalars) else None for o in nd["outs"]]
         self._need(w.nan)
         r = self._chunk(w)
-        need_min = outs[0] is not None or outs[2] is not None
-        need_max = outs[1] is not None or outs[3] is not None
-        m = self._t("mm")
-        self._e(f"const MinMax {m} = minmax_local({r}, 16 * tid, {off}, {off + n});")
         g = self._nan_guard([w.nan])
-        if need_min:
-            si = self._alloc_i(2)
-            self._e(f"put_argmin(cs, par, {si}, {m}.vmin, {m}.imin, lane, warp);")
-            v, i = self._t("v"), self._t("i")
-            self.posts.append(f"float {v}; int {i}; get_argmin(cs, par, {si}, lane, {v}, {i});")
-            if outs[0]:
-                self.posts.append(f"const double {outs[0]} = {'(' + g + ') ? CUDART_NAN : ' if g else ''}(double){i};")
-            if outs[2]:
-                self.posts.append(f"const double {outs[2]} = {'(' + g + ') ? CUDART_NAN : ' if g else ''}(double){v};")
-        if need_max:
-            si = self._alloc_i(2)
-            self._e(f"put_argmax(cs, par, {si}, {m}.vmax, {m}.imax, lane, warp);")
-            v, i = self._t("v"), self._t("i")
-            self.posts.append(f"float {v}; int {i}; get_argmax(cs, par, {si}, lane, {v}, {i});")
-            if outs[1]:
-                self.posts.append(f"const double {outs[1]} = {'(' + g + ') ? CUDART_NAN : ' if g else ''}(double){i};")
-            if outs[3]:
-                self.posts.append(f"const double {outs[3]} = {'(' + g + ') ? CUDART_NAN : ' if g else ''}(double){v};")
-        self.pending.update(o for o in outs if o)
+        gq = f"({g}) ? CUDART_NAN : " if g else ""
+        full = "true" if (off == 0 and n >= w.n and w.n % CHK == 0 and w.n == CHK * NT) else "false"
+        for (it, iv, fn, put_a, get_a, put_v, get_v) in ((0, 2, "min", "put_argmin", "get_argmin", "put_fmin", "get_fmin"),
+                                                         (1, 3, "max", "put_argmax", "get_argmax", "put_fmax", "get_fmax")):
+            if outs[it] is None and outs[iv] is None:
+                continue
+            m = self._t("m")
+            self._e(f"const float {m} = {fn}_local<{full}>({r}, 16 * tid, {off}, {off + n});")
+            if outs[it] is not None:
+                si = self._alloc_i(2)
+                ix = self._t("ix")
+                # warp extreme first, then the first chunk position holding it (only lanes that tie search)
+                self._e(f"const int {ix} = first_eq_local<{full}>({r}, {m}, 16 * tid, {off}, {off + n});",
+                        f"{put_a}(cs, par, {si}, {m}, {ix}, lane, warp);")
+                v, i = self._t("v"), self._t("i")
+                self.posts0.append(f"float {v}; int {i}; {get_a}(cs, par, {si}, lane, {v}, {i});")
+                self.posts0.append(f"{outs[it]} = {gq}(double){i};")
+                if outs[iv]:
+                    self.posts0.append(f"{outs[iv]} = {gq}(double){v};")
+            else:
+                si = self._alloc_i(1)
+                self._e(f"{put_v}(cs, par, {si}, {m}, lane, warp);")
+                self.posts0.append(f"{outs[iv]} = {gq}(double){get_v}(cs, par, {si}, lane);")
+        for o in outs:
+            if o:
+                self.pending.add(o)
+                self._def0(o)
+                self.posts0.extend(self._stores(o))
 
     def _e_lsf(self, nd):
         w, off, n = nd["ins"][0]
@@ -862,16 +931,19 @@ class SpecChain(FusedChain):
                 f"get_sum(cs, par, {sd + 1}, lane), get_sum(cs, par, {sd + 2}, lane), {f[0]}, {f[1]}, {f[2]}, {f[3]});")
         if g:
             post += f" if ({g}) {{ {f[0]} = {f[1]} = {f[2]} = {f[3]} = CUDART_NAN_F; }}"
-        self.posts.append(post)
+        self.posts0.append(post)
         for k in range(4):
             if outs[k]:
-                self.posts.append(f"const double {outs[k]} = (double){f[k]};")
+                self.posts0.append(f"{outs[k]} = (double){f[k]};")
                 self.pending.add(outs[k])
+                self._def0(outs[k])
+                self.posts0.extend(self._stores(outs[k]))
 
     def _e_bl_sub(self, nd):
         w, off, n = nd["ins"][0]
         out = nd["wouts"][0]
-        self._need(nd["b"], w.nan)
+        self._need_all(nd["b"])
+        self._need(w.nan)
         r = self._chunk(w)
         o = self._t("r")
         b = self._t("b")
@@ -889,7 +961,8 @@ class SpecChain(FusedChain):
     def _e_pole_zero(self, nd):
         w, off, n = nd["ins"][0]
         out = nd["wouts"][0]
-        self._need(nd["tau"], w.nan)
+        self._need_all(nd["tau"])
+        self._need(w.nan)
         r = self._chunk(w)
         sd = self._alloc_d(1)
         tot, incl, omc = self._t("tot"), self._t("incl"), self._t("omc")
@@ -957,8 +1030,8 @@ class SpecChain(FusedChain):
                         self._e(f"fir_tap<{ts}>({self._slot(w)}, tid, {n}, {zc}, {_flit(c)}, {d});")
                     k += 1
                 sd = self._alloc_d(1)
-                self._e(f"const double {tot} = (double)cumsum_local({d});",
-                        f"const double {incl} = put_scan(cs, par, {sd}, {tot}, lane, warp);")
+                self._e(f"const float {tot} = cumsum_local({d});",
+                        f"const float {incl} = put_scan_f(cs, par, {sd}, {tot}, lane, warp);")
                 ex = None
                 if m["extra"]:
                     kx = self._t("kx")
@@ -978,7 +1051,7 @@ class SpecChain(FusedChain):
                 sc = _flit(m["scale"])
                 extra = f" + get_sum(cs, par, {ex}, lane)" if ex is not None else ""
                 self.posts.append(
-                    f"double {dum}; const float {off} = (float)((get_excl(cs, par, {sd}, {incl}, {tot}, lane, warp, {dum}){extra}) * (double){sc});")
+                    f"const float {off} = (float)((get_excl_f(cs, par, {sd}, {incl}, {tot}, lane, warp){extra}) * (double){sc});")
                 self.posts.append(f"float {o}[16]; _Pragma(\"unroll\") for (int j = 0; j < 16; j++) {o}[j] = fmaf({d}[j], {sc}, {off});")
                 out.nan = w.nan
                 self.pending.add(out.name)
@@ -989,14 +1062,15 @@ class SpecChain(FusedChain):
         w, off, n = nd["ins"][0]
         self._need(nd["thr"], nd["start"], nd["walk"], w.nan)
         self._visible(w)
-        self._close_round()
         f = self._t("f")
         g = self._nan_guard([w.nan])
-        call = (f"(double)tpt({self._slot(w)}, {n}, (float)({nd['thr']}), (float)({nd['start']}), (float)({nd['walk']}), "
-                f"{f}, cs, par, lane, warp)")
-        self._e(f"int {f} = 0;",
-                f"const double {nd['out']} = {'(' + g + ') ? CUDART_NAN : ' if g else ''}{call};",
-                f"if ({f} && tid == 0) raise_fatal(A.fatal ? A.fatal + 4 * {nd['fatal']} : nullptr, {f}, A.row0 + row);")
+        call = (f"(double)tpt_w({self._slot(w)}, {n}, (float)({nd['thr']}), (float)({nd['start']}), (float)({nd['walk']}), "
+                f"{f}, lane)")
+        self._e0(f"int {f} = 0;",
+                 f"{nd['out']} = {'(' + g + ') ? CUDART_NAN : ' if g else ''}{call};",
+                 f"if ({f} && lane == 0) raise_fatal(A.fatal ? A.fatal + 4 * {nd['fatal']} : nullptr, {f}, A.row0 + row);",
+                 *self._stores(nd["out"]))
+        self._def0(nd["out"])
 
     def _e_ftp(self, nd):
         w, off, n = nd["ins"][0]
@@ -1005,9 +1079,11 @@ class SpecChain(FusedChain):
         f = self._t("f")
         g = self._nan_guard([w.nan])
         call = f"(double)op_fixed_time_pickoff<float>({self._slot(w)}, {n}, (float)({nd['t']}), {nd['mode']}, {f})"
-        self._e(f"int {f} = 0;",
-                f"const double {nd['out']} = {'(' + g + ') ? CUDART_NAN : ' if g else ''}{call};",
-                f"if ({f} && tid == 0) raise_fatal(A.fatal ? A.fatal + 4 * {nd['fatal']} : nullptr, {f}, A.row0 + row);")
+        self._e0(f"int {f} = 0;",
+                 f"{nd['out']} = {'(' + g + ') ? CUDART_NAN : ' if g else ''}{call};",
+                 f"if ({f} && lane == 0) raise_fatal(A.fatal ? A.fatal + 4 * {nd['fatal']} : nullptr, {f}, A.row0 + row);",
+                 *self._stores(nd["out"]))
+        self._def0(nd["out"])
 
     def _e_windower(self, nd):
         # windower.py:12-54 : out[k] = in[t0 + k], NaN where the window leaves the waveform; one
@@ -1016,7 +1092,8 @@ class SpecChain(FusedChain):
         out = nd["wouts"][0]
         m = out.n
         mc = (m + CHK - 1) // CHK * CHK
-        self._need(nd["t0"], w.nan)
+        self._need_all(nd["t0"])
+        self._need(w.nan)
         self._visible(w)
         out.needs_slot = True
         self._give_slot(out)
@@ -1120,17 +1197,17 @@ class SpecChain(FusedChain):
                 self._e(f"float {sh}[16]; ld_shift<{-L}>({sl}, tid, {n}, {self._zc(src)}, {sh}); const float {e0} = at({sl}, 0);",
                         f"float {d}[16]; _Pragma(\"unroll\") for (int j = 0; j < 16; j++) {{ const int i = 16 * tid + j; "
                         f"{d}[j] = i >= {n} ? 0.f : (i == 0 ? {e0} : ({x}[j] - (i >= {L} ? {sh}[j] : {e0})) * {il}); }}",
-                        f"const double {tot} = (double)cumsum_local({d});",
-                        f"const double {incl} = put_scan(cs, par, {sd}, {tot}, lane, warp);")
-                get = f"get_excl(cs, par, {sd}, {incl}, {tot}, lane, warp, {tt})"
+                        f"const float {tot} = cumsum_local({d});",
+                        f"const float {incl} = put_scan_f(cs, par, {sd}, {tot}, lane, warp);")
+                get = f"get_excl_f(cs, par, {sd}, {incl}, {tot}, lane, warp)"
             else:
                 # mirror image: out[n-1] = x[n-1]; out[i] = out[i+1] + (x[i] - x[min(i+L,n-1)]) / L
                 self._e(f"float {sh}[16]; ld_shift<{L}>({sl}, tid, {n}, {self._zc(src)}, {sh}); const float {e0} = at({sl}, {n - 1});",
                         f"float {d}[16]; _Pragma(\"unroll\") for (int j = 0; j < 16; j++) {{ const int i = 16 * tid + j; "
                         f"{d}[j] = i >= {n} ? 0.f : (i == {n - 1} ? {e0} : ({x}[j] - (i + {L} <= {n - 1} ? {sh}[j] : {e0})) * {il}); }}",
-                        f"const double {tot} = (double)cumsum_local_rev({d});",
-                        f"const double {incl} = put_scan_rev(cs, par, {sd}, {tot}, lane, warp);")
-                get = f"get_excl_rev(cs, par, {sd}, {incl}, {tot}, lane, warp)"
+                        f"const float {tot} = cumsum_local_rev({d});",
+                        f"const float {incl} = put_scan_rev_f(cs, par, {sd}, {tot}, lane, warp);")
+                get = f"get_excl_rev_f(cs, par, {sd}, {incl}, {tot}, lane, warp)"
             o, offv = self._t("r"), self._t("off")
             self.posts.append(f"double {tt} = 0.0; const float {offv} = (float){get}; (void){tt};")
             self.posts.append(f"float {o}[16]; _Pragma(\"unroll\") for (int j = 0; j < 16; j++) {o}[j] = {d}[j] + {offv};")
@@ -1211,28 +1288,37 @@ class SpecChain(FusedChain):
             out.nan = w.nan
             out.reg = None
 
+    def _sc_emit(self, nd, expr, *operands):
+        """scalar glue runs where its operands live: in the scalar warp as soon as one of them does"""
+        self._need(*operands)
+        if any(self._is_w0(o) for o in operands):
+            self._e0(f"{nd['out']} = {expr};", *self._stores(nd["out"]))
+            self._def0(nd["out"])
+        else:
+            self._e(f"{nd['out']} = {expr};")
+            st = self._stores(nd["out"])
+            if st:
+                self._e0(*st)
+
     def _e_sc_bin(self, nd):
-        self._need(nd["x"], nd["y"])
         op = {"add": "+", "subtract": "-", "multiply": "*", "divide": "/"}.get(nd["op"])
         if nd["f32"]:
             ex = f"(float)({nd['x']}) {op} (float)({nd['y']})" if op else f"floorf((float)({nd['x']}) / (float)({nd['y']}))"
-            self._e(f"const double {nd['out']} = (double)({ex});")
+            ex = f"(double)({ex})"
         else:
             ex = f"({nd['x']}) {op} ({nd['y']})" if op else f"floor(({nd['x']}) / ({nd['y']}))"
-            self._e(f"const double {nd['out']} = {ex};")
+        self._sc_emit(nd, ex, nd["x"], nd["y"])
 
     def _e_sc_neg(self, nd):
-        self._need(nd["x"])
-        self._e(f"const double {nd['out']} = -({nd['x']});")
+        self._sc_emit(nd, f"-({nd['x']})", nd["x"])
 
     def _e_sc_convert(self, nd):
-        self._need(nd["x"], nd["oi"], nd["oo"])
         ex = f"(({nd['x']}) + ({nd['oi']})) * {_lit(nd['ratio'])} - ({nd['oo']})"
         fn = {None: "", "round": "rint", "floor": "floor", "ceil": "ceil", "trunc": "trunc"}[nd["mode"]]
         ex = f"{fn}({ex})"
         if nd["f32"]:
             ex = f"(double)(float)({ex})"
-        self._e(f"const double {nd['out']} = {ex};")
+        self._sc_emit(nd, ex, nd["x"], nd["oi"], nd["oo"])
 
     def _e_store_wave(self, nd):
         w, off, n = nd["ins"][0]
@@ -1257,6 +1343,8 @@ class SpecChain(FusedChain):
     def source(self) -> str:
         np_ = max(1, len(self.ptrs))
         body = "\n      ".join(self.prolog + self.L)
+        names = sorted(set(self.svar.values()), key=lambda x: int(x[1:]))
+        decl = ("double " + ", ".join(names) + ";") if names else ""
         arrays = "\n".join(getattr(self, "static_arrays", []))
         aligned = getattr(self, "aligned_ptrs", [])
         align_check = "".join(f"  if (((uintptr_t)ptrs[{i}] & 15) || (strides[{i}] & 7)) return DSPB_ERR_UNSUPPORTED;\n" for i in aligned)
@@ -1278,7 +1366,11 @@ struct Args {{
 }};
 {arrays}
 #define SLOT(k) (slots + (k) * {self.slot_words})
+#ifdef DSPB_PROFILE   // tracing build (SpecChain.profile): per-node SM-cycle stamps of CTA 0
 #define PROF_MARK(k) if (A.prof && tid == 0 && (k) + 1 < 128) prof_ts[(k) + 1] = clock64();
+#else
+#define PROF_MARK(k)
+#endif
 
 __global__ void __launch_bounds__(512, 1) k_chain_spec(const __grid_constant__ Args A) {{
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1287,19 +1379,26 @@ __global__ void __launch_bounds__(512, 1) k_chain_spec(const __grid_constant__ A
   float* slots = reinterpret_cast<float*>(smem_raw + 2048 + 8192 + 1024);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   long long* prof_ts = reinterpret_cast<long long*>(smem_raw + 2048 + 8192);
+  double* bc = reinterpret_cast<double*>(smem_raw + 2048 + 5120);   // scalar-warp -> all-threads broadcasts
+  (void)prof_ts;
   int par = 0;
   zero_pads(slots, {self.slot_words}, {self.nchunks}, 0, {self.n_slots}, tid);
   __syncthreads();
   for (long long row = blockIdx.x; row < A.n_rows; row += gridDim.x) {{
+#ifdef DSPB_PROFILE
     if (A.prof && tid == 0) prof_ts[0] = clock64();
+#endif
     {{
+      {decl}
       {body}
     }}
     __syncthreads();
-    if (A.prof && blockIdx.x == 0) {{  // per-node cycles of CTA 0 (tracing; off in production launches)
+#ifdef DSPB_PROFILE
+    if (A.prof && blockIdx.x == 0) {{
       for (int k = tid; k < N_NODES && k + 1 < 128; k += 512) A.prof[k] += prof_ts[k + 1] - prof_ts[k];
       __syncthreads();
     }}
+#endif
   }}
 }}
 }}  // namespace
@@ -1345,14 +1444,21 @@ extern "C" int chain_launch(const void* const* ptrs, long long n_ptrs, long long
                                      C.c_int(self.num_sms), C.c_void_p(stream))
 
     def profile(self, run, repeats=1):
-        """per-node SM cycles of CTA 0 (see fusion.profile_fused)"""
+        """per-node SM cycles of CTA 0 (see fusion.profile_fused); runs a tracing build of the kernel"""
         n = len(self.order) + 1
+        so, _ = build_source(self.source(), flags=("-DDSPB_PROFILE",))
+        prod_lib, self.lib = self.lib, load_chain_lib(so)
         self.d_prof = torch.zeros(n, dtype=torch.int64, device=self.chain.device)
-        for _ in range(repeats):
-            run()
-        torch.cuda.synchronize(self.chain.device)
-        cyc = self.d_prof.cpu().numpy().astype(np.float64)
-        self.d_prof = None
+        try:
+            run()   # warm-up of the tracing build
+            self.d_prof.zero_()
+            for _ in range(repeats):
+                run()
+            torch.cuda.synchronize(self.chain.device)
+            cyc = self.d_prof.cpu().numpy().astype(np.float64)
+        finally:
+            self.d_prof = None
+            self.lib = prod_lib
         tot = cyc.sum() or 1.0
         text = self.program_text.split("\n") + ["store scalars"]
         return [(cyc[i], cyc[i] / tot, text[i]) for i in range(n)]
@@ -1372,9 +1478,9 @@ def _headers_digest() -> str:
     return h.hexdigest()
 
 
-def build_source(src: str, verbose=False):
+def build_source(src: str, flags=()):
     """compile one generated kernel for sm_100a (cached by content hash)"""
-    extra = os.environ.get("DSPEED_B200_NVCC_EXTRA", "").split()   # experiments: -D switches of chain_rt.cuh
+    extra = list(flags) + os.environ.get("DSPEED_B200_NVCC_EXTRA", "").split()   # experiments: -D switches
     tag = hashlib.sha1((src + _headers_digest() + " ".join(extra)).encode()).hexdigest()[:16]
     os.makedirs(CACHE_DIR, exist_ok=True)
     so = os.path.join(CACHE_DIR, f"chain_{tag}.so")

@@ -71,6 +71,10 @@ __device__ __forceinline__ void st_chunk(float* slot, int t, const float (&v)[CH
 // shifted loads rely on); threads whose chunk starts beyond ceil16(n) do nothing
 __device__ __forceinline__ void st_chunk_n(float* slot, int t, int n, const float (&v)[CHK]) {
   if (CHK * t >= n + CHK - 1) return;
+  if ((n & (CHK - 1)) == 0) {  // whole chunks only (n is a literal at every call site)
+    st_chunk(slot, t, v);
+    return;
+  }
   float w[CHK];
 #pragma unroll
   for (int j = 0; j < CHK; j++) w[j] = (CHK * t + j < n) ? v[j] : 0.0f;
@@ -212,6 +216,57 @@ __device__ __forceinline__ double get_excl(const CScr* cs, int par, int slot, do
   total = __shfl_sync(FULL, pin, NWP - 1);
   return __shfl_sync(FULL, pin - part, warp) + (incl - v);
 }
+// float variants for running sums whose magnitude (< 2^24 times the output tolerance) allows it:
+// half the shuffles of the float64 scan
+__device__ __forceinline__ float wscan_incl_f(float v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const float t = __shfl_up_sync(FULL, v, o);
+    if (lane >= o) v += t;
+  }
+  return v;
+}
+__device__ __forceinline__ float wscan_incl_rev_f(float v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const float t = __shfl_down_sync(FULL, v, o);
+    if (lane + o < 32) v += t;
+  }
+  return v;
+}
+__device__ __forceinline__ float put_scan_f(CScr* cs, int par, int slot, float v, int lane, int warp) {
+  const float incl = wscan_incl_f(v, lane);
+  if (lane == 31) cs->d[par][slot][warp] = (double)incl;
+  return incl;
+}
+// exclusive prefix of this thread: float64 across the 16 warp totals, float inside the warp
+__device__ __forceinline__ double get_excl_f(const CScr* cs, int par, int slot, float incl, float v, int lane,
+                                             int warp) {
+  const double part = lane < NWP ? cs->d[par][slot][lane] : 0.0;
+  double pin = part;
+#pragma unroll
+  for (int o = 1; o < NWP; o <<= 1) {
+    const double t = __shfl_up_sync(FULL, pin, o);
+    if (lane >= o) pin += t;
+  }
+  return __shfl_sync(FULL, pin - part, warp) + (double)(incl - v);
+}
+__device__ __forceinline__ float put_scan_rev_f(CScr* cs, int par, int slot, float v, int lane, int warp) {
+  const float incl = wscan_incl_rev_f(v, lane);
+  if (lane == 0) cs->d[par][slot][warp] = (double)incl;
+  return incl;
+}
+__device__ __forceinline__ double get_excl_rev_f(const CScr* cs, int par, int slot, float incl, float v, int lane,
+                                                 int warp) {
+  const double part = lane < NWP ? cs->d[par][slot][lane] : 0.0;
+  double pin = part;
+#pragma unroll
+  for (int o = 1; o < NWP; o <<= 1) {
+    const double t = __shfl_down_sync(FULL, pin, o);
+    if (lane + o < NWP) pin += t;
+  }
+  return __shfl_sync(FULL, pin - part, warp) + (double)(incl - v);
+}
 // reverse (suffix) scan
 __device__ __forceinline__ double put_scan_rev(CScr* cs, int par, int slot, double v, int lane, int warp) {
   const double incl = wscan_incl_rev(v, lane);
@@ -289,6 +344,48 @@ __device__ __forceinline__ MinMax minmax_local(const float (&v)[CHK], int i0, in
     }
   }
   return m;
+}
+
+// value-only extrema (numpy.amax / unused index outputs): one FMNMX per sample
+template <bool FULL_RANGE>
+__device__ __forceinline__ float max_local(const float (&v)[CHK], int i0, int lo, int hi) {
+  float m = -CUDART_INF_F;
+#pragma unroll
+  for (int j = 0; j < CHK; j++)
+    if (FULL_RANGE || (i0 + j >= lo && i0 + j < hi)) m = fmaxf(m, v[j]);
+  return m;
+}
+template <bool FULL_RANGE>
+__device__ __forceinline__ float min_local(const float (&v)[CHK], int i0, int lo, int hi) {
+  float m = CUDART_INF_F;
+#pragma unroll
+  for (int j = 0; j < CHK; j++)
+    if (FULL_RANGE || (i0 + j >= lo && i0 + j < hi)) m = fminf(m, v[j]);
+  return m;
+}
+// first index (relative to lo) inside the chunk where v == m, or INT_MAX
+template <bool FULL_RANGE>
+__device__ __forceinline__ int first_eq_local(const float (&v)[CHK], float m, int i0, int lo, int hi) {
+  int idx = 0x7fffffff;
+#pragma unroll
+  for (int j = CHK - 1; j >= 0; j--)
+    if ((FULL_RANGE || (i0 + j >= lo && i0 + j < hi)) && v[j] == m) idx = i0 + j - lo;
+  return idx;
+}
+// value-only block max / min through the order-preserving key
+__device__ __forceinline__ void put_fmax(CScr* cs, int par, int slot, float v, int lane, int warp) {
+  const unsigned km = __reduce_max_sync(FULL, fkey(v));
+  if (lane == 0) cs->i[par][slot][warp] = (int)km;
+}
+__device__ __forceinline__ float get_fmax(const CScr* cs, int par, int slot, int lane) {
+  return fkey_inv(__reduce_max_sync(FULL, lane < NWP ? (unsigned)cs->i[par][slot][lane] : 0u));
+}
+__device__ __forceinline__ void put_fmin(CScr* cs, int par, int slot, float v, int lane, int warp) {
+  const unsigned km = __reduce_min_sync(FULL, fkey(v));
+  if (lane == 0) cs->i[par][slot][warp] = (int)km;
+}
+__device__ __forceinline__ float get_fmin(const CScr* cs, int par, int slot, int lane) {
+  return fkey_inv(__reduce_min_sync(FULL, lane < NWP ? (unsigned)cs->i[par][slot][lane] : 0xffffffffu));
 }
 
 // linear_slope_fit.py:11-90 : sums over [lo, hi), abscissa relative to lo
@@ -461,6 +558,85 @@ __device__ __forceinline__ int search_cross(const float* w, int n, float thr, in
     if (hit >= 0) return hit;
   }
   return -1;
+}
+
+// Warp-only search (scalar warp): windows of 32 samples, then 128 per step for long walks.
+__device__ __forceinline__ int search_cross_w(const float* w, int n, float thr, int s, bool forward, int stop_back,
+                                              int lane) {
+  if (forward) {
+    int base = s;
+#pragma unroll 1
+    for (int k = 0; k < WARP_WINDOWS && base < n - 1; k++, base += 32) {
+      const int i = base + lane;
+      bool hit = false;
+      if (i < n - 1) {
+        const float a = at(w, i), b = at(w, i + 1);
+        hit = (a <= thr && thr < b) || (a >= thr && thr > b);
+      }
+      const unsigned m = __ballot_sync(FULL, hit);
+      if (m) return base + __ffs(m) - 1;
+    }
+#pragma unroll 1
+    for (; base < n - 1; base += 128) {
+      unsigned m[4];
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const int i = base + 32 * q + lane;
+        bool hit = false;
+        if (i < n - 1) {
+          const float a = at(w, i), b = at(w, i + 1);
+          hit = (a <= thr && thr < b) || (a >= thr && thr > b);
+        }
+        m[q] = __ballot_sync(FULL, hit);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; q++)
+        if (m[q]) return base + 32 * q + __ffs(m[q]) - 1;
+    }
+    return -1;
+  }
+  int base = s;
+#pragma unroll 1
+  for (int k = 0; k < WARP_WINDOWS && base >= stop_back; k++, base -= 32) {
+    const int i = base - lane;
+    bool hit = false;
+    if (i >= stop_back) {
+      const float a = at(w, i - 1), b = at(w, i);
+      hit = (a < thr && thr <= b) || (a > thr && thr >= b);
+    }
+    const unsigned m = __ballot_sync(FULL, hit);
+    if (m) return base - (__ffs(m) - 1);
+  }
+#pragma unroll 1
+  for (; base >= stop_back; base -= 128) {
+    unsigned m[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const int i = base - 32 * q - lane;
+      bool hit = false;
+      if (i >= stop_back) {
+        const float a = at(w, i - 1), b = at(w, i);
+        hit = (a < thr && thr <= b) || (a > thr && thr >= b);
+      }
+      m[q] = __ballot_sync(FULL, hit);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+      if (m[q]) return base - 32 * q - (__ffs(m[q]) - 1);
+  }
+  return -1;
+}
+
+// time_point_thresh.py:12-92 evaluated by one warp
+__device__ __forceinline__ float tpt_w(const float* w, int n, float thr, float t_start, float walk, int& fatal,
+                                       int lane) {
+  fatal = 0;
+  if (thr != thr || t_start != t_start || walk != walk) return CUDART_NAN_F;
+  if (floorf(t_start) != t_start) { fatal = DSPB_FATAL_TSTART_NONINT; return CUDART_NAN_F; }
+  if (floorf(walk) != walk) { fatal = DSPB_FATAL_WALK_NONINT; return CUDART_NAN_F; }
+  if (!(t_start >= 0.f && t_start < (float)n)) { fatal = DSPB_FATAL_TSTART_RANGE; return CUDART_NAN_F; }
+  const int hit = search_cross_w(w, n, thr, (int)t_start, walk == 1.0f, 1, lane);
+  return hit < 0 ? CUDART_NAN_F : (float)hit;
 }
 
 __device__ __forceinline__ float tpt(const float* w, int n, float thr, float t_start, float walk, int& fatal,
