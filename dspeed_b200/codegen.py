@@ -122,6 +122,7 @@ class SpecChain(FusedChain):
         self.ptr_index = {}
         self.waves: dict[int, Wave] = {}
         self.svar: dict[int, str] = {}          # scalar storage -> C variable
+        self.stype: dict[str, str] = {}         # C variable -> "float" | "double"
         self.const_storage = {}
         self.input_wave = {}
         self.input_scalar = {}
@@ -257,18 +258,24 @@ class SpecChain(FusedChain):
                 src = man.t0_var if what == "t0" else man.raw_var
                 if src.dtype not in _CTYPE:
                     raise NotSpecializable(f"scalar input dtype {src.dtype}")
-                name = self._new_svar(st)
+                name = self._new_svar(st, src.dtype)
                 pi = self._ptr(("in", man, what))
-                self.prolog.append(f"{name} = (double)((const {_CTYPE[src.dtype]}*)A.p[{pi}])[row * A.s[{pi}]];")
+                self.prolog.append(self._asg(name, f"((const {_CTYPE[src.dtype]}*)A.p[{pi}])[row * A.s[{pi}]]"))
             return self.svar[st]
         if x is None:
             raise NotSpecializable("None argument")
         return _lit(float(x))
 
-    def _new_svar(self, st):
+    def _new_svar(self, st, dtype=None):
+        """per-event scalars are registers of the variable's own type: float32 values stay float
+        (no float64 round trips on the serial scalar path); everything else is carried as double"""
         name = f"s{len(self.svar)}"
         self.svar[st] = name
+        self.stype[name] = "float" if dtype == torch.float32 else "double"
         return name
+
+    def _asg(self, name, expr):
+        return f"{name} = ({self.stype[name]})({expr});"
 
     def _sout(self, t: torch.Tensor) -> str:
         if not isinstance(t, torch.Tensor) or t.numel() != t.shape[0]:
@@ -276,7 +283,7 @@ class SpecChain(FusedChain):
         st = _storage(t)
         if st in self.svar:
             raise NotSpecializable("scalar variable written twice")
-        return self._new_svar(st)
+        return self._new_svar(st, t.dtype)
 
     def _win(self, t: torch.Tensor, need_zero_offset=False):
         if t.ndim != 2 or (t.shape[-1] > 1 and t.stride(-1) != 1):
@@ -692,7 +699,7 @@ class SpecChain(FusedChain):
             k = self.n_bcast % 16
             self.n_bcast += 1
             self._e0(f"if (lane == 0) bc[{k}] = {nme};")
-            self.posts.append(f"{nme} = bc[{k}];")
+            self.posts.append(self._asg(nme, f"bc[{k}]"))
             self.pending.add(nme)
             self.sdom[nme] = "all"
         self._close_round()
@@ -886,7 +893,7 @@ class SpecChain(FusedChain):
         self._need(w.nan)
         r = self._chunk(w)
         g = self._nan_guard([w.nan])
-        gq = f"({g}) ? CUDART_NAN : " if g else ""
+        gq = f"({g}) ? CUDART_NAN_F : " if g else ""
         full = "true" if (off == 0 and n >= w.n and w.n % CHK == 0 and w.n == CHK * NT) else "false"
         for (it, iv, fn, put_a, get_a, put_v, get_v) in ((0, 2, "min", "put_argmin", "get_argmin", "put_fmin", "get_fmin"),
                                                          (1, 3, "max", "put_argmax", "get_argmax", "put_fmax", "get_fmax")):
@@ -902,13 +909,13 @@ class SpecChain(FusedChain):
                         f"{put_a}(cs, par, {si}, {m}, {ix}, lane, warp);")
                 v, i = self._t("v"), self._t("i")
                 self.posts0.append(f"float {v}; int {i}; {get_a}(cs, par, {si}, lane, {v}, {i});")
-                self.posts0.append(f"{outs[it]} = {gq}(double){i};")
+                self.posts0.append(self._asg(outs[it], f"{gq}(float){i}"))
                 if outs[iv]:
-                    self.posts0.append(f"{outs[iv]} = {gq}(double){v};")
+                    self.posts0.append(self._asg(outs[iv], f"{gq}{v}"))
             else:
                 si = self._alloc_i(1)
                 self._e(f"{put_v}(cs, par, {si}, {m}, lane, warp);")
-                self.posts0.append(f"{outs[iv]} = {gq}(double){get_v}(cs, par, {si}, lane);")
+                self.posts0.append(self._asg(outs[iv], f"{gq}{get_v}(cs, par, {si}, lane)"))
         for o in outs:
             if o:
                 self.pending.add(o)
@@ -934,7 +941,7 @@ class SpecChain(FusedChain):
         self.posts0.append(post)
         for k in range(4):
             if outs[k]:
-                self.posts0.append(f"{outs[k]} = (double){f[k]};")
+                self.posts0.append(self._asg(outs[k], f[k]))
                 self.pending.add(outs[k])
                 self._def0(outs[k])
                 self.posts0.extend(self._stores(outs[k]))
@@ -1000,35 +1007,59 @@ class SpecChain(FusedChain):
                 out = m["wouts"][0]
                 d, tot, incl = self._t("d"), self._t("tot"), self._t("incl")
                 self._e(f"float {d}[16];", f"_Pragma(\"unroll\") for (int j = 0; j < 16; j++) {d}[j] = 0.f;")
+                # Taps whose offsets lie within 16 samples of each other share ONE span load
+                # (16 + width samples, 128-bit loads): the filters are shared-memory-bandwidth
+                # bound, so a cluster costs (16 + width) / 4 loads instead of 5 per tap.  Inside a
+                # cluster, consecutive taps whose coefficients agree to float32 rounding of the
+                # kernel (a linear ramp's first difference) become one sliding-window sum.
                 taps = sorted(m["taps"])
-                k = 0
                 zc = self._zc(w)
+                tol = 4e-7 * max(abs(x[1]) for x in taps)
+                k = 0
                 while k < len(taps):
-                    ts, c = taps[k]
-                    run = 1
-                    # consecutive taps whose coefficients agree to float32 rounding of the kernel
-                    # (a linear ramp's first difference) are evaluated as one sliding window
-                    tol = 4e-7 * max(abs(x[1]) for x in taps)
-                    while (k + run < len(taps) and taps[k + run][0] == ts + run and abs(taps[k + run][1] - c) <= tol
-                           and run < 16):
-                        run += 1
-                    if run >= 3:
-                        cm = sum(x[1] for x in taps[k:k + run]) / run
-                        self._e(f"fir_run<{ts}, {run}>({self._slot(w)}, tid, {n}, {zc}, {_flit(cm)}, {d});")
-                        k += run
-                        continue
-                    if ts == 0:
+                    ts0 = taps[k][0]
+                    e = k
+                    while e + 1 < len(taps) and taps[e + 1][0] - ts0 <= 16:
+                        e += 1
+                    cluster = taps[k:e + 1]
+                    k = e + 1
+                    if len(cluster) == 1 and ts0 == 0:
+                        c = cluster[0][1]
                         if c == 1.0:
                             self._e(f"_Pragma(\"unroll\") for (int j = 0; j < 16; j++) {d}[j] += {own}[j];")
                         else:
                             self._e(f"_Pragma(\"unroll\") for (int j = 0; j < 16; j++) {d}[j] = fmaf({_flit(c)}, {own}[j], {d}[j]);")
-                    elif c == 1.0:
-                        self._e(f"fir_tap_add<{ts}>({self._slot(w)}, tid, {n}, {zc}, {d});")
-                    elif c == -1.0:
-                        self._e(f"fir_tap_sub<{ts}>({self._slot(w)}, tid, {n}, {zc}, {d});")
-                    else:
-                        self._e(f"fir_tap<{ts}>({self._slot(w)}, tid, {n}, {zc}, {_flit(c)}, {d});")
-                    k += 1
+                        continue
+                    width = cluster[-1][0] - ts0
+                    cnt = 16 + width
+                    v = self._t("v")
+                    # v[q] = x[16 t + q - (ts0 + width)]  ->  tap ts reads v[j + (ts0 + width - ts)]
+                    self._e(f"{{ float {v}[{cnt}]; ld_span<{-(ts0 + width)}, {cnt}>({self._slot(w)}, tid, {n}, {zc}, {v});")
+                    q = 0
+                    while q < len(cluster):
+                        ts, c = cluster[q]
+                        run = 1
+                        while (q + run < len(cluster) and cluster[q + run][0] == ts + run
+                               and abs(cluster[q + run][1] - c) <= tol):
+                            run += 1
+                        if run >= 3:
+                            cm = sum(x[1] for x in cluster[q:q + run]) / run
+                            lo = ts0 + width - (ts + run - 1)      # v index of the oldest sample of the window at j = 0
+                            ws = self._t("ws")
+                            self._e(f"  float {ws} = 0.f; _Pragma(\"unroll\") for (int u = 0; u < {run}; u++) {ws} += {v}[{lo} + u];",
+                                    f"  _Pragma(\"unroll\") for (int j = 0; j < 16; j++) {{ {d}[j] = fmaf({_flit(cm)}, {ws}, {d}[j]); "
+                                    f"if (j < 15) {ws} += {v}[{lo} + j + {run}] - {v}[{lo} + j]; }}")
+                            q += run
+                            continue
+                        off = ts0 + width - ts
+                        if c == 1.0:
+                            self._e(f"  _Pragma(\"unroll\") for (int j = 0; j < 16; j++) {d}[j] += {v}[j + {off}];")
+                        elif c == -1.0:
+                            self._e(f"  _Pragma(\"unroll\") for (int j = 0; j < 16; j++) {d}[j] -= {v}[j + {off}];")
+                        else:
+                            self._e(f"  _Pragma(\"unroll\") for (int j = 0; j < 16; j++) {d}[j] = fmaf({_flit(c)}, {v}[j + {off}], {d}[j]);")
+                        q += 1
+                    self._e("}")
                 sd = self._alloc_d(1)
                 self._e(f"const float {tot} = cumsum_local({d});",
                         f"const float {incl} = put_scan_f(cs, par, {sd}, {tot}, lane, warp);")
@@ -1064,10 +1095,10 @@ class SpecChain(FusedChain):
         self._visible(w)
         f = self._t("f")
         g = self._nan_guard([w.nan])
-        call = (f"(double)tpt_w({self._slot(w)}, {n}, (float)({nd['thr']}), (float)({nd['start']}), (float)({nd['walk']}), "
+        call = (f"tpt_w({self._slot(w)}, {n}, (float)({nd['thr']}), (float)({nd['start']}), (float)({nd['walk']}), "
                 f"{f}, lane)")
         self._e0(f"int {f} = 0;",
-                 f"{nd['out']} = {'(' + g + ') ? CUDART_NAN : ' if g else ''}{call};",
+                 self._asg(nd['out'], f"{'(' + g + ') ? CUDART_NAN_F : ' if g else ''}{call}"),
                  f"if ({f} && lane == 0) raise_fatal(A.fatal ? A.fatal + 4 * {nd['fatal']} : nullptr, {f}, A.row0 + row);",
                  *self._stores(nd["out"]))
         self._def0(nd["out"])
@@ -1078,9 +1109,9 @@ class SpecChain(FusedChain):
         self._visible(w)
         f = self._t("f")
         g = self._nan_guard([w.nan])
-        call = f"(double)op_fixed_time_pickoff<float>({self._slot(w)}, {n}, (float)({nd['t']}), {nd['mode']}, {f})"
+        call = f"op_fixed_time_pickoff<float>({self._slot(w)}, {n}, (float)({nd['t']}), {nd['mode']}, {f})"
         self._e0(f"int {f} = 0;",
-                 f"{nd['out']} = {'(' + g + ') ? CUDART_NAN : ' if g else ''}{call};",
+                 self._asg(nd['out'], f"{'(' + g + ') ? CUDART_NAN_F : ' if g else ''}{call}"),
                  f"if ({f} && lane == 0) raise_fatal(A.fatal ? A.fatal + 4 * {nd['fatal']} : nullptr, {f}, A.row0 + row);",
                  *self._stores(nd["out"]))
         self._def0(nd["out"])
@@ -1257,7 +1288,7 @@ class SpecChain(FusedChain):
         poly = any(m["seg"][7] != 0.0 for m in members)
         nq = 5 if poly else 3
         cw = (((p + CHK - 1) // CHK) + 1) | 1
-        need = nq * (4 * CHK * cw + NT) * 8
+        need = nq * (4 * CHK * cw + NT + 32) * 8
         nsl = -(-need // (self.slot_words * 4))
         scratch = self._slot_alloc_adjacent(nsl)
         outs = []
@@ -1292,10 +1323,10 @@ class SpecChain(FusedChain):
         """scalar glue runs where its operands live: in the scalar warp as soon as one of them does"""
         self._need(*operands)
         if any(self._is_w0(o) for o in operands):
-            self._e0(f"{nd['out']} = {expr};", *self._stores(nd["out"]))
+            self._e0(self._asg(nd['out'], expr), *self._stores(nd["out"]))
             self._def0(nd["out"])
         else:
-            self._e(f"{nd['out']} = {expr};")
+            self._e(self._asg(nd['out'], expr))
             st = self._stores(nd["out"])
             if st:
                 self._e0(*st)
@@ -1304,16 +1335,16 @@ class SpecChain(FusedChain):
         op = {"add": "+", "subtract": "-", "multiply": "*", "divide": "/"}.get(nd["op"])
         if nd["f32"]:
             ex = f"(float)({nd['x']}) {op} (float)({nd['y']})" if op else f"floorf((float)({nd['x']}) / (float)({nd['y']}))"
-            ex = f"(double)({ex})"
         else:
-            ex = f"({nd['x']}) {op} ({nd['y']})" if op else f"floor(({nd['x']}) / ({nd['y']}))"
+            ex = (f"(double)({nd['x']}) {op} (double)({nd['y']})" if op
+                  else f"floor((double)({nd['x']}) / (double)({nd['y']}))")
         self._sc_emit(nd, ex, nd["x"], nd["y"])
 
     def _e_sc_neg(self, nd):
         self._sc_emit(nd, f"-({nd['x']})", nd["x"])
 
     def _e_sc_convert(self, nd):
-        ex = f"(({nd['x']}) + ({nd['oi']})) * {_lit(nd['ratio'])} - ({nd['oo']})"
+        ex = f"((double)({nd['x']}) + (double)({nd['oi']})) * {_lit(nd['ratio'])} - (double)({nd['oo']})"
         fn = {None: "", "round": "rint", "floor": "floor", "ceil": "ceil", "trunc": "trunc"}[nd["mode"]]
         ex = f"{fn}({ex})"
         if nd["f32"]:
@@ -1344,7 +1375,8 @@ class SpecChain(FusedChain):
         np_ = max(1, len(self.ptrs))
         body = "\n      ".join(self.prolog + self.L)
         names = sorted(set(self.svar.values()), key=lambda x: int(x[1:]))
-        decl = ("double " + ", ".join(names) + ";") if names else ""
+        decl = " ".join(f"{ty} " + ", ".join(n for n in names if self.stype[n] == ty) + ";"
+                        for ty in ("float", "double") if any(self.stype[n] == ty for n in names))
         arrays = "\n".join(getattr(self, "static_arrays", []))
         aligned = getattr(self, "aligned_ptrs", [])
         align_check = "".join(f"  if (((uintptr_t)ptrs[{i}] & 15) || (strides[{i}] & 7)) return DSPB_ERR_UNSUPPORTED;\n" for i in aligned)

@@ -560,13 +560,72 @@ __device__ __forceinline__ int search_cross(const float* w, int n, float thr, in
   return -1;
 }
 
-// Warp-only search (scalar warp): windows of 32 samples, then 128 per step for long walks.
+// Warp-only search (scalar warp).  The scalar warp runs alone, so every instruction of this
+// routine is on the critical path (~5 cycles each): the common case -- a crossing within a few
+// tens of samples of the start -- is two plain 32-sample windows; only longer walks (a threshold
+// that is met by a noise excursion far away, or never) switch to 128-sample steps in which lane
+// l reads samples [b0 + 4l, b0 + 4l + 4) with ONE 128-bit load (conflict-free in the T4 layout)
+// and takes the neighbour sample of a pair from the adjacent lane by shuffle.
+__device__ __forceinline__ float4 ldq(const float* w, int i) {  // samples i .. i+3, i % 4 == 0
+  return *reinterpret_cast<const float4*>(w + sidx(i));
+}
+__device__ __noinline__ int search_cross_long(const float* w, int n, float thr, int s, bool forward, int stop_back,
+                                              int lane) {
+  const int nceil = (n + 15) & ~15;
+  if (forward) {
+#pragma unroll 1
+    for (int c0 = s & ~127; c0 < n - 1; c0 += 128) {
+      const int i0 = c0 + 4 * lane;
+      float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i0 < nceil) q = ldq(w, i0);
+      float nx = __shfl_down_sync(FULL, q.x, 1);
+      if (lane == 31) nx = (c0 + 128 < n) ? at(w, c0 + 128) : 0.f;
+      const float a[5] = {q.x, q.y, q.z, q.w, nx};
+      unsigned m = 0;
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const int i = i0 + k;
+        const bool hit = i >= s && i < n - 1 && ((a[k] <= thr && thr < a[k + 1]) || (a[k] >= thr && thr > a[k + 1]));
+        m |= hit ? (1u << k) : 0u;
+      }
+      const unsigned bal = __ballot_sync(FULL, m != 0);
+      if (bal) {
+        const int L = __ffs(bal) - 1;
+        return c0 + 4 * L + (__ffs(__shfl_sync(FULL, m, L)) - 1);
+      }
+    }
+    return -1;
+  }
+#pragma unroll 1
+  for (int c0 = s & ~127; c0 >= 0 && c0 + 127 >= stop_back; c0 -= 128) {
+    const int i0 = c0 + 4 * lane;
+    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i0 < nceil) q = ldq(w, i0);
+    float pv = __shfl_up_sync(FULL, q.w, 1);
+    if (lane == 0) pv = (c0 >= 1) ? at(w, c0 - 1) : 0.f;
+    const float a[5] = {pv, q.x, q.y, q.z, q.w};
+    unsigned m = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int i = i0 + k;
+      const bool hit = i <= s && i >= stop_back && i < n &&
+                       ((a[k] < thr && thr <= a[k + 1]) || (a[k] > thr && thr >= a[k + 1]));
+      m |= hit ? (1u << k) : 0u;
+    }
+    const unsigned bal = __ballot_sync(FULL, m != 0);
+    if (bal) {
+      const int L = 31 - __clz(bal);
+      return c0 + 4 * L + (31 - __clz(__shfl_sync(FULL, m, L)));
+    }
+  }
+  return -1;
+}
 __device__ __forceinline__ int search_cross_w(const float* w, int n, float thr, int s, bool forward, int stop_back,
                                               int lane) {
   if (forward) {
     int base = s;
 #pragma unroll 1
-    for (int k = 0; k < WARP_WINDOWS && base < n - 1; k++, base += 32) {
+    for (int k = 0; k < 2 && base < n - 1; k++, base += 32) {
       const int i = base + lane;
       bool hit = false;
       if (i < n - 1) {
@@ -576,28 +635,11 @@ __device__ __forceinline__ int search_cross_w(const float* w, int n, float thr, 
       const unsigned m = __ballot_sync(FULL, hit);
       if (m) return base + __ffs(m) - 1;
     }
-#pragma unroll 1
-    for (; base < n - 1; base += 128) {
-      unsigned m[4];
-#pragma unroll
-      for (int q = 0; q < 4; q++) {
-        const int i = base + 32 * q + lane;
-        bool hit = false;
-        if (i < n - 1) {
-          const float a = at(w, i), b = at(w, i + 1);
-          hit = (a <= thr && thr < b) || (a >= thr && thr > b);
-        }
-        m[q] = __ballot_sync(FULL, hit);
-      }
-#pragma unroll
-      for (int q = 0; q < 4; q++)
-        if (m[q]) return base + 32 * q + __ffs(m[q]) - 1;
-    }
-    return -1;
+    return base < n - 1 ? search_cross_long(w, n, thr, base, true, stop_back, lane) : -1;
   }
   int base = s;
 #pragma unroll 1
-  for (int k = 0; k < WARP_WINDOWS && base >= stop_back; k++, base -= 32) {
+  for (int k = 0; k < 2 && base >= stop_back; k++, base -= 32) {
     const int i = base - lane;
     bool hit = false;
     if (i >= stop_back) {
@@ -607,24 +649,7 @@ __device__ __forceinline__ int search_cross_w(const float* w, int n, float thr, 
     const unsigned m = __ballot_sync(FULL, hit);
     if (m) return base - (__ffs(m) - 1);
   }
-#pragma unroll 1
-  for (; base >= stop_back; base -= 128) {
-    unsigned m[4];
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-      const int i = base - 32 * q - lane;
-      bool hit = false;
-      if (i >= stop_back) {
-        const float a = at(w, i - 1), b = at(w, i);
-        hit = (a < thr && thr <= b) || (a > thr && thr >= b);
-      }
-      m[q] = __ballot_sync(FULL, hit);
-    }
-#pragma unroll
-    for (int q = 0; q < 4; q++)
-      if (m[q]) return base - 32 * q - (__ffs(m[q]) - 1);
-  }
-  return -1;
+  return base >= stop_back ? search_cross_long(w, n, thr, base, false, stop_back, lane) : -1;
 }
 
 // time_point_thresh.py:12-92 evaluated by one warp
@@ -665,7 +690,7 @@ __device__ __forceinline__ float tpt(const float* w, int n, float thr, float t_s
 // parallel, one thread each, with the powers q^o = e^{+-o/s} read from a table built by the
 // chain compiler.  Two kernels that share (sigma, lt, fl, L, c) -- the ICPC chain's cusp and
 // zac -- are evaluated together (TWO): sums, scan, replay and exponentials are shared.
-// tab: NQ * (4 * 16 * CW + 512) doubles of scratch (NQ = 5 with parabolas, else 3; CW = odd number of
+// tab: NQ * (4 * 16 * CW + 544) doubles of scratch (NQ = 5 with parabolas, else 3; CW = odd number of
 // chunk columns >= ceil(p / 16) + 1): entry (o % 16) * CW + o / 16 of a band, so that the lanes of a
 // warp (consecutive chunks, positions 16 apart) store to consecutive addresses.
 // pw: [2][p] doubles, pw[0][o] = e^{o/s}, pw[1][o] = e^{-o/s}.
@@ -729,18 +754,30 @@ __device__ __forceinline__ void conv_seg_chunked(const float* X, const float (&x
       wp *= qp;
     }
   }
-  double inc[NQ];
-#pragma unroll
-  for (int q = 0; q < NQ; q++) inc[q] = put_scan(cs, par, q, s[q], lane, warp);
-  __syncthreads();
-  // ---- pass 2: every thread publishes the prefix sums in front of its chunk ------------------
+  // ---- pass 2: exclusive scan of the chunk sums over the 512 threads, through shared memory:
+  // every thread deposits its NQ sums (one store each), warp q scans quantity q (lane l owns
+  // entries [16l, 16l+16), skewed by one word per 16 so that both access patterns are
+  // conflict-free), and pass 3 picks up the prefix in front of whatever chunk it needs.  Costs
+  // the block NQ stores per thread instead of NQ float64 shuffle scans per thread.
   double* otab = tab + NQ * 4 * PP;
-  {
-    double tt;
+  constexpr int OT = 512 + 32;
 #pragma unroll
-    for (int q = 0; q < NQ; q++) otab[q * 512 + tid] = get_excl(cs, par, q, inc[q], s[q], lane, warp, tt);
+  for (int q = 0; q < NQ; q++) otab[q * OT + tid + (tid >> 4)] = s[q];
+  __syncthreads();
+  if (warp < NQ) {
+    double* o = otab + warp * OT + 17 * lane;
+    double v[CHK];
+    double run = 0.0;
+#pragma unroll
+    for (int k = 0; k < CHK; k++) {
+      v[k] = run;       // exclusive inside the lane
+      run += o[k];
+    }
+    const double incl = wscan_incl(run, lane);
+    const double base_l = incl - run;
+#pragma unroll
+    for (int k = 0; k < CHK; k++) o[k] = v[k] + base_l;
   }
-  par ^= 1;
   __syncthreads();
   // ---- pass 3: one thread per output ------------------------------------------------------------
   const int pceil = (p + CHK - 1) & ~(CHK - 1);
@@ -749,7 +786,7 @@ __device__ __forceinline__ void conv_seg_chunked(const float* X, const float (&x
     float y0 = 0.f, y1 = 0.f;
     if (o < p) {
       const int ow[4] = {(base[0] + o) >> 4, (base[1] + o) >> 4, (base[2] + o) >> 4, (base[3] + o) >> 4};
-#define TB(q, b) (tab[((q)*4 + (b)) * PP + (o & 15) * CW + (o >> 4)] + otab[(q)*512 + ow[b]])
+#define TB(q, b) (tab[((q)*4 + (b)) * PP + (o & 15) * CW + (o >> 4)] + otab[(q)*OT + ow[b] + (ow[b] >> 4)])
       const double po = pw[o], mo = pw[p + o];
       const double en = eA * po, enm = eAm * mo;      // e^{+-n/s}, n = L - 1 + o
       const double eLn = qp * mo, eLnm = qm * po;     // e^{+-(L-n)/s} = e^{+-(1-o)/s}

@@ -41,3 +41,8 @@ if chain._fused is not None and os.environ.get("PROFILE_PROGRAM"):
     print(f"per-instruction cycles of CTA 0 (total {tot:.0f} cycles; smem {chain._fused.smem_bytes} B, slots {chain._fused.n_slots})")
     for c, share, text in prof:
         print(f"{c:12.0f} {100 * share:5.1f}%  {text}")
+if chain._fused is not None and os.environ.get("SAVE_KERNEL") and hasattr(chain._fused, "lib_path"):
+    import shutil
+    os.makedirs(os.path.join(REPO, "gpurun_out"), exist_ok=True)
+    shutil.copy(chain._fused.lib_path, os.path.join(REPO, "gpurun_out", "chain_spec.so"))
+    shutil.copy(chain._fused.src_path, os.path.join(REPO, "gpurun_out", "chain_spec.cu"))
