@@ -494,6 +494,22 @@ class SpecChain(FusedChain):
     # ------------------------------------------------------------------------------------
     def _schedule(self):
         nodes = self.nodes
+        # A windowed filter (trapezoid ...) whose output is only picked off at single positions is
+        # never materialised: the scalar warp evaluates it there from its input wave (window sums).
+        for nd in nodes:
+            if nd["kind"] != "fir" or nd["extra"] is not None:
+                continue
+            out = nd["wouts"][0]
+            users = [nodes[u] for u in out.uses]
+            taps = sorted(nd["taps"])
+            if (users and all(u["kind"] == "ftp" and chr(u["mode"]) in "infcl" for u in users)
+                    and abs(sum(c for _, c in taps)) < 1e-12 and taps[0][0] >= 0 and taps[-1][0] <= 2048):
+                nd["kind"] = "fir_lazy"
+                for u in users:
+                    u["lazy"] = nd
+                    u["ins"] = [nd["ins"][0]]
+                    nd["ins"][0][0].uses.append(u["idx"])
+                out.uses = []
         order = []
         placed = set()
         by_wave_reductions = {}
@@ -581,16 +597,18 @@ class SpecChain(FusedChain):
     # emission
     # ------------------------------------------------------------------------------------
     def _emit_kernel(self):
-        self.L = []                 # body lines
+        # Two instruction streams per row: the BLOCK stream (warps 0-15, everything that touches
+        # waveforms) and the SCALAR stream (warp 16: finishing of reductions, threshold searches,
+        # pick-offs, scalar glue, output stores).  They meet only through named-barrier events
+        # (B -> S: "partials / slots are ready", S -> B: "this scalar is ready") and at the row end,
+        # so the serial per-event scalar chain runs concurrently with the block work.
+        self.LB, self.LS = [], []
         self.pending = set()
         self.dirty = set()
         self.xread = set()
         self.posts = []
-        self.posts0 = []            # post-barrier code that only the scalar warp (warp 0) executes
-        self.sdom = {}              # scalar variable -> "w0" (valid in warp 0 only); default: all threads
-        self.in_w0 = False
+        self.sdom = {}              # scalar variable -> "s" (scalar warp only); default: both streams
         self.stored = set()
-        self.n_bcast = 0
         self.post_dirty = []
         self.nd_used = 0
         self.ni_used = 0
@@ -598,26 +616,42 @@ class SpecChain(FusedChain):
         self.n_slots = 0
         self.tmp = 0
         self.live_regs = []
+        self.n_mbd = 0              # mailbox entries (16 doubles / 16 ints each), unique per row
+        self.n_mbi = 0
+        self.n_bc = 0
+        self.s_dirty = False        # the block stream produced something the scalar warp will read
+        self.b2s_count = 0          # B -> S events since the last point where S provably caught up
+        self.s2b = {}               # scalar -> (event id, bc index) published by the scalar warp
+        self.s2b_ids = list(range(9, 15))
+        self.s_seq = 0              # number of scalar-stream nodes emitted
+        self.s_done = 0             # ... of which the block stream knows they are finished
+        self.flag_s = {}            # block-stream NaN flag -> its copy in the scalar stream
         slot_len = max([w.n for w in self.waves.values()] + [CHK])
         self.nchunks = (slot_len + CHK - 1) // CHK
         self.psp = 4 * self.nchunks + 8
         self.slot_words = 4 * self.psp
+        # scalars the block stream needs from the scalar warp
+        self.b_needed = set()
+        for nd in self.nodes:
+            for key in ("b", "tau", "t0"):
+                if key in nd and isinstance(nd[key], str) and not nd[key].startswith(("0x", "-0x", "CUDART")):
+                    self.b_needed.add(nd[key])
         for k, nd in enumerate(self.order):
             self.pos = k
-            self.L.append(f"// ---- [{k}] {self._describe_node(nd)}")
+            self.LB.append(f"// ---- [{k}] {self._describe_node(nd)}")
+            self.LS.append(f"// ---- [{k}] {self._describe_node(nd)}")
             getattr(self, "_e_" + nd["kind"])(nd)
-            self.L.append("PROF_MARK(%d);" % k)
+            self.LB.append("PROF_MARK(%d);" % k)
             self._release(k)
         self._close_round()
-        # scalar outputs
         # scalar outputs not stored at their definition (pass-through input scalars)
         for k, (name, pi, ct) in enumerate(self.out_scalars):
             if name not in self.stored:
-                self._e0(f"if (lane == {k % 32}) (({ct}*)A.p[{pi}])[row] = ({ct}){name};")
-        self._e()
-        self.L.append("PROF_MARK(%d);" % len(self.order))
-        fixed = 2048 + 8192 + 1024  # Scratch (old routines) + CScr + flags/aff2
-        self.smem_bytes = fixed + self.n_slots * self.slot_words * 4
+                self._es(f"if (lane == {k % 32}) (({ct}*)A.p[{pi}])[row] = ({ct}){name};")
+        self.LB.append("PROF_MARK(%d);" % len(self.order))
+        self.mb_bytes = (self.n_mbd * 16 * 8 + self.n_mbi * 16 * 4 + 15) & ~15
+        self.fixed_bytes = 2048 + 8192 + 1024 + self.mb_bytes   # Scratch + CScr/bc + prof stamps + mailbox
+        self.smem_bytes = self.fixed_bytes + self.n_slots * self.slot_words * 4
         if self.smem_bytes > MAX_SMEM:
             raise NotSpecializable("not enough shared memory for the live waveforms")
         self.program_text = "\n".join(f"{k:3d} {self._describe_node(nd)}" for k, nd in enumerate(self.order))
@@ -634,34 +668,24 @@ class SpecChain(FusedChain):
         so = nd.get("out") or ",".join(str(x) for x in nd.get("outs", []) if x)
         return f"{nd['kind']} {ins} -> {outs}{so}"
 
-    # -- round framework ---------------------------------------------------------------------
+    # -- stream / round framework -------------------------------------------------------------
     def _e(self, *lines):
-        """code executed by all threads"""
-        if self.in_w0:
-            self.L.append("}")
-            self.in_w0 = False
-        self.L.extend(lines)
+        """block stream"""
+        self.LB.extend(lines)
 
-    def _e0(self, *lines):
-        """code executed by the scalar warp only: per-event scalar work (threshold searches,
-        pick-offs, fit results, unit conversions) costs one warp's issue slots instead of sixteen"""
-        if not self.in_w0:
-            self.L.append("if (warp == 0) {")
-            self.in_w0 = True
-        self.L.extend(lines)
+    def _es(self, *lines):
+        """scalar stream"""
+        self.LS.extend(lines)
 
     def _round_open(self):
-        return bool(self.posts or self.posts0 or self.nd_used or self.ni_used or self.pending)
+        return bool(self.posts or self.nd_used or self.ni_used or self.pending)
 
     def _close_round(self):
         if self._round_open():
-            self._e("__syncthreads();")
+            self._e("BSYNC();")
             self._e(*self.posts)
-            if self.posts0:
-                self._e0(*self.posts0)   # reads the scratch of this round: before the parity flips
             self._e("par ^= 1;")
         self.posts = []
-        self.posts0 = []
         self.pending.clear()
         self.dirty.clear()
         self.xread.clear()
@@ -673,45 +697,104 @@ class SpecChain(FusedChain):
         if self._round_open():
             self._close_round()
         else:
-            self._e("__syncthreads();")
+            self._e("BSYNC();")
             self.dirty.clear()
             self.xread.clear()
 
     def _need(self, *exprs):
-        """scalar expressions / wave names that must be available now"""
+        """block-stream names (waves, flags) that must be defined now"""
         for e in exprs:
             if e is not None and str(e) in self.pending:
                 self._close_round()
                 return
 
-    def _is_w0(self, e):
-        return e is not None and self.sdom.get(str(e)) == "w0"
+    # ---- events -----------------------------------------------------------------------------
+    def _sync_s(self):
+        """the scalar warp is about to read something the block stream produced: one event
+        (bar.arrive by the 512 block threads, bar.sync by the scalar warp)"""
+        if not self.s_dirty:
+            return
+        self.s_dirty = False
+        if self.b2s_count >= 7:
+            # the 7 event barriers are all in flight: let the block stream wait for the scalar warp once
+            self._e("EV_WAIT(15);")
+            self._es("EV_WAIT(15);")
+            self.b2s_count = 0
+            self.s_done = self.s_seq
+            return
+        eid = 2 + self.b2s_count
+        self.b2s_count += 1
+        self._e(f"EV_ARRIVE({eid});")
+        self._es(f"EV_WAIT({eid});")
+
+    def _is_s(self, e):
+        return e is not None and self.sdom.get(str(e)) == "s"
+
+    def _def_s(self, name):
+        """`name` was just defined in the scalar stream; publish it when the block stream needs it"""
+        self.sdom[name] = "s"
+        if name in self.b_needed:
+            if not self.s2b_ids or self.n_bc >= 16:
+                raise NotSpecializable("too many scalars flow from the scalar warp to the block warps")
+            eid, k = self.s2b_ids.pop(0), self.n_bc
+            self.n_bc += 1
+            self._es(f"if (lane == 0) bc[{k}] = (double){name};", f"EV_ARRIVE({eid});")
+            self.s2b[name] = (eid, k, self.s_seq)
 
     def _need_all(self, *exprs):
-        """scalars that every thread must hold: those living in the scalar warp are broadcast
-        through shared memory (one barrier for all of them)"""
-        self._need(*exprs)
-        names = sorted({str(e) for e in exprs if self._is_w0(e)})
-        if not names:
-            return
-        self._close_round()
-        for nme in names:
-            k = self.n_bcast % 16
-            self.n_bcast += 1
-            self._e0(f"if (lane == 0) bc[{k}] = {nme};")
-            self.posts.append(self._asg(nme, f"bc[{k}]"))
-            self.pending.add(nme)
-            self.sdom[nme] = "all"
-        self._close_round()
+        """scalars the block stream must hold: wait for the scalar warp's event and fetch them"""
+        for e in exprs:
+            if self._is_s(e):
+                name = str(e)
+                if name not in self.s2b:
+                    raise NotSpecializable("internal: scalar not published to the block stream")
+                eid, k, seq = self.s2b.pop(name)
+                self._close_round()
+                self._e(f"EV_WAIT({eid});", self._asg(name, f"bc[{k}]"))
+                self.s2b_ids.append(eid)
+                self.s_done = max(self.s_done, seq)
+                self.sdom[name] = "both"
 
-    def _def0(self, name):
-        self.sdom[name] = "w0"
+    def _flag_s(self, flag):
+        """copy of a block-stream NaN flag in the scalar stream"""
+        if flag == "0":
+            return "0"
+        if flag not in self.flag_s:
+            self._need(flag)
+            k = self.n_mbi
+            self.n_mbi += 1
+            self._e(f"if (tid == 0) MBI({k})[0] = {flag};")
+            self.s_dirty = True
+            self._sync_s()
+            nm = flag + "_s"
+            self._es(f"const int {nm} = MBI({k})[0];")
+            self.flag_s[flag] = nm
+        return self.flag_s[flag]
+
+    def _s_wave(self, w: Wave):
+        """the scalar warp is about to read the slot of `w`"""
+        self._need(w.name)
+        if w.slot is None:
+            raise NotSpecializable("internal: scalar-warp access to a register-only wave")
+        self._sync_s()
+        self.s_seq += 1
+        w.s_last = self.s_seq
 
     def _stores(self, name):
-        """statements (for the scalar warp) that write a just-defined scalar to its output columns:
-        results leave the register file as soon as they are final"""
+        """statements (scalar warp) that write a just-defined scalar to its output columns: results
+        leave the register file as soon as they are final"""
         self.stored.add(name)
         return [f"if (lane == {k % 32}) (({ct}*)A.p[{pi}])[row] = ({ct}){name};" for (pi, ct, k) in self.out_of.get(name, [])]
+
+    def _mbd(self, k=1):
+        b = self.n_mbd
+        self.n_mbd += k
+        return b
+
+    def _mbi(self, k=1):
+        b = self.n_mbi
+        self.n_mbi += k
+        return b
 
     def _alloc_d(self, k):
         if self.nd_used + k > 16:
@@ -787,6 +870,8 @@ class SpecChain(FusedChain):
 
     def _release(self, k):
         for w in self.waves.values():
+            if getattr(w, "s_last", 0) > self.s_done:
+                continue   # the scalar warp may still be reading it (its slot is kept to the row end)
             if w.slot is not None and w.last <= k and not getattr(w, "released", False):
                 self._slot_free(w.slot)
                 w.released = True
@@ -840,6 +925,7 @@ class SpecChain(FusedChain):
             self._give_slot(w)
             self._e(f"st_chunk_n({self._slot(w)}, tid, {w.n}, {r});")
             self.dirty.add(w.slot[0])
+            self.s_dirty = True
         self._set_reg(w, r)
 
     def _post_store(self, w: Wave, r: str):
@@ -848,6 +934,7 @@ class SpecChain(FusedChain):
             self._give_slot(w, post=True)
             self.posts.append(f"st_chunk_n({self._slot(w)}, tid, {w.n}, {r});")
             self.post_dirty.append(w.slot[0])
+            self.s_dirty = True
         self._set_reg(w, r)
 
     def _visible(self, w: Wave):
@@ -875,8 +962,8 @@ class SpecChain(FusedChain):
             if dt in (torch.float32, torch.float64):
                 si = self._alloc_i(1)
                 nf = f"nan{w.name}"
-                self._e(f"put_imax(cs, par, {si}, {f}, lane, warp);")
-                self.posts.append(f"const int {nf} = get_imax(cs, par, {si}, lane);")
+                self._e(f"put_imax(CSI({si}), {f}, lane, warp);")
+                self.posts.append(f"const int {nf} = get_imax(CSI({si}), lane);")
                 self.pending.add(nf)
                 w.nan = nf
         self._store(w, r)
@@ -887,14 +974,16 @@ class SpecChain(FusedChain):
 
     def _e_min_max(self, nd):
         # min_max.py:11-82 / numpy.amax: value via FMNMX, first-occurrence index via an equality pass;
-        # outputs nobody reads (and that are no chain outputs) are not computed at all
+        # outputs nobody reads (and that are no chain outputs) are not computed at all.  The block
+        # warps deposit their partial results in the mailbox; the scalar warp combines them.
         w, off, n = nd["ins"][0]
         outs = [o if (o and o in self.used_scalars) else None for o in nd["outs"]]
+        if not any(outs):
+            return
         self._need(w.nan)
         r = self._chunk(w)
-        g = self._nan_guard([w.nan])
-        gq = f"({g}) ? CUDART_NAN_F : " if g else ""
         full = "true" if (off == 0 and n >= w.n and w.n % CHK == 0 and w.n == CHK * NT) else "false"
+        todo = []
         for (it, iv, fn, put_a, get_a, put_v, get_v) in ((0, 2, "min", "put_argmin", "get_argmin", "put_fmin", "get_fmin"),
                                                          (1, 3, "max", "put_argmax", "get_argmax", "put_fmax", "get_fmax")):
             if outs[it] is None and outs[iv] is None:
@@ -902,49 +991,57 @@ class SpecChain(FusedChain):
             m = self._t("m")
             self._e(f"const float {m} = {fn}_local<{full}>({r}, 16 * tid, {off}, {off + n});")
             if outs[it] is not None:
-                si = self._alloc_i(2)
+                mb = self._mbi(2)
                 ix = self._t("ix")
-                # warp extreme first, then the first chunk position holding it (only lanes that tie search)
                 self._e(f"const int {ix} = first_eq_local<{full}>({r}, {m}, 16 * tid, {off}, {off + n});",
-                        f"{put_a}(cs, par, {si}, {m}, {ix}, lane, warp);")
-                v, i = self._t("v"), self._t("i")
-                self.posts0.append(f"float {v}; int {i}; {get_a}(cs, par, {si}, lane, {v}, {i});")
-                self.posts0.append(self._asg(outs[it], f"{gq}(float){i}"))
-                if outs[iv]:
-                    self.posts0.append(self._asg(outs[iv], f"{gq}{v}"))
+                        f"{put_a}(MBI({mb}), {m}, {ix}, lane, warp);")
+                todo.append((it, iv, get_a, mb, True))
             else:
-                si = self._alloc_i(1)
-                self._e(f"{put_v}(cs, par, {si}, {m}, lane, warp);")
-                self.posts0.append(self._asg(outs[iv], f"{gq}{get_v}(cs, par, {si}, lane)"))
+                mb = self._mbi(1)
+                self._e(f"{put_v}(MBI({mb}), {m}, lane, warp);")
+                todo.append((it, iv, get_v, mb, False))
+        self.s_dirty = True
+        g = self._nan_guard([self._flag_s(w.nan)])
+        gq = f"({g}) ? CUDART_NAN_F : " if g else ""
+        self._sync_s()
+        self.s_seq += 1
+        for (it, iv, get, mb, with_idx) in todo:
+            if with_idx:
+                v, i = self._t("v"), self._t("i")
+                self._es(f"float {v}; int {i}; {get}(MBI({mb}), lane, {v}, {i});", self._asg(outs[it], f"{gq}(float){i}"))
+                if outs[iv]:
+                    self._es(self._asg(outs[iv], f"{gq}{v}"))
+            else:
+                self._es(self._asg(outs[iv], f"{gq}{get}(MBI({mb}), lane)"))
         for o in outs:
             if o:
-                self.pending.add(o)
-                self._def0(o)
-                self.posts0.extend(self._stores(o))
+                self._es(*self._stores(o))
+                self._def_s(o)
 
     def _e_lsf(self, nd):
         w, off, n = nd["ins"][0]
         outs = nd["outs"]
         self._need(w.nan)
         r = self._chunk(w)
-        sd = self._alloc_d(3)
+        mb = self._mbd(3)
         a, b, c = self._t("sy"), self._t("sxy"), self._t("syy")
         self._e(f"double {a}, {b}, {c}; lsf_local({r}, 16 * tid, {off}, {off + n}, {a}, {b}, {c});",
-                f"put_sum(cs, par, {sd}, {a}, lane, warp); put_sum(cs, par, {sd + 1}, {b}, lane, warp); "
-                f"put_sum(cs, par, {sd + 2}, {c}, lane, warp);")
+                f"put_sum(MBD({mb}), {a}, lane, warp); put_sum(MBD({mb + 1}), {b}, lane, warp); "
+                f"put_sum(MBD({mb + 2}), {c}, lane, warp);")
+        self.s_dirty = True
+        g = self._nan_guard([self._flag_s(w.nan)])
+        self._sync_s()
+        self.s_seq += 1
         f = [self._t("f") for _ in range(4)]
-        g = self._nan_guard([w.nan])
-        post = (f"float {f[0]}, {f[1]}, {f[2]}, {f[3]}; lsf_finish({n}, get_sum(cs, par, {sd}, lane), "
-                f"get_sum(cs, par, {sd + 1}, lane), get_sum(cs, par, {sd + 2}, lane), {f[0]}, {f[1]}, {f[2]}, {f[3]});")
+        post = (f"float {f[0]}, {f[1]}, {f[2]}, {f[3]}; lsf_finish({n}, get_sum(MBD({mb}), lane), "
+                f"get_sum(MBD({mb + 1}), lane), get_sum(MBD({mb + 2}), lane), {f[0]}, {f[1]}, {f[2]}, {f[3]});")
         if g:
             post += f" if ({g}) {{ {f[0]} = {f[1]} = {f[2]} = {f[3]} = CUDART_NAN_F; }}"
-        self.posts0.append(post)
+        self._es(post)
         for k in range(4):
             if outs[k]:
-                self.posts0.append(self._asg(outs[k], f[k]))
-                self.pending.add(outs[k])
-                self._def0(outs[k])
-                self.posts0.extend(self._stores(outs[k]))
+                self._es(self._asg(outs[k], f[k]), *self._stores(outs[k]))
+                self._def_s(outs[k])
 
     def _e_bl_sub(self, nd):
         w, off, n = nd["ins"][0]
@@ -975,10 +1072,10 @@ class SpecChain(FusedChain):
         tot, incl, omc = self._t("tot"), self._t("incl"), self._t("omc")
         self._e(f"const double {omc} = -expm1(-1.0 / (double)(float)({nd['tau']}));",
                 f"const double {tot} = chunk_sum_d({r});",
-                f"const double {incl} = put_scan(cs, par, {sd}, {tot}, lane, warp);")
+                f"const double {incl} = put_scan(CSD({sd}), {tot}, lane, warp);")
         o, dum = self._t("r"), self._t("tt")
         self.posts.append(f"float {o}[16]; double {dum}; "
-                          f"pz_chunk({r}, get_excl(cs, par, {sd}, {incl}, {tot}, lane, warp, {dum}), {omc}, {o});")
+                          f"pz_chunk({r}, get_excl(CSD({sd}), {incl}, {tot}, lane, warp, {dum}), {omc}, {o});")
         const_tau = nd["tau"].startswith(("0x", "-0x"))
         flags = [w.nan] + ([] if const_tau else [f"((float)({nd['tau']}) != (float)({nd['tau']}))"])
         g = self._nan_guard(flags)
@@ -1062,7 +1159,7 @@ class SpecChain(FusedChain):
                     self._e("}")
                 sd = self._alloc_d(1)
                 self._e(f"const float {tot} = cumsum_local({d});",
-                        f"const float {incl} = put_scan_f(cs, par, {sd}, {tot}, lane, warp);")
+                        f"const float {incl} = put_scan_f(CSD({sd}), {tot}, lane, warp);")
                 ex = None
                 if m["extra"]:
                     kx = self._t("kx")
@@ -1073,16 +1170,16 @@ class SpecChain(FusedChain):
                     term = self._t("ex")
                     self._e(f"double {term} = 0.0;",
                             f"for (int q = tid; q < {ne}; q += 512) {term} += (double)({kx}[q] * at({self._slot(w)}, {ne - 1} - q));",
-                            f"put_sum(cs, par, {sx}, {term}, lane, warp);")
+                            f"put_sum(CSD({sx}), {term}, lane, warp);")
                     ex = sx
                 recs.append((m, d, tot, incl, sd, ex))
             for (m, d, tot, incl, sd, ex) in recs:
                 out = m["wouts"][0]
                 o, off, dum = self._t("r"), self._t("off"), self._t("tt")
                 sc = _flit(m["scale"])
-                extra = f" + get_sum(cs, par, {ex}, lane)" if ex is not None else ""
+                extra = f" + get_sum(CSD({ex}), lane)" if ex is not None else ""
                 self.posts.append(
-                    f"const float {off} = (float)((get_excl_f(cs, par, {sd}, {incl}, {tot}, lane, warp){extra}) * (double){sc});")
+                    f"const float {off} = (float)((get_excl_f(CSD({sd}), {incl}, {tot}, lane, warp){extra}) * (double){sc});")
                 self.posts.append(f"float {o}[16]; _Pragma(\"unroll\") for (int j = 0; j < 16; j++) {o}[j] = fmaf({d}[j], {sc}, {off});")
                 out.nan = w.nan
                 self.pending.add(out.name)
@@ -1091,30 +1188,75 @@ class SpecChain(FusedChain):
 
     def _e_tpt(self, nd):
         w, off, n = nd["ins"][0]
-        self._need(nd["thr"], nd["start"], nd["walk"], w.nan)
-        self._visible(w)
+        self._s_wave(w)
         f = self._t("f")
-        g = self._nan_guard([w.nan])
+        g = self._nan_guard([self._flag_s(w.nan)])
         call = (f"tpt_w({self._slot(w)}, {n}, (float)({nd['thr']}), (float)({nd['start']}), (float)({nd['walk']}), "
                 f"{f}, lane)")
-        self._e0(f"int {f} = 0;",
+        self._es(f"int {f} = 0;",
                  self._asg(nd['out'], f"{'(' + g + ') ? CUDART_NAN_F : ' if g else ''}{call}"),
                  f"if ({f} && lane == 0) raise_fatal(A.fatal ? A.fatal + 4 * {nd['fatal']} : nullptr, {f}, A.row0 + row);",
                  *self._stores(nd["out"]))
-        self._def0(nd["out"])
+        self._def_s(nd["out"])
+
+    def _e_fir_lazy(self, nd):
+        pass   # evaluated at its pick-off positions (see _e_ftp)
+
+    def _e_ftp_lazy(self, nd):
+        fir = nd["lazy"]
+        w, off, n = nd["ins"][0]
+        self._s_wave(w)
+        g = self._nan_guard([self._flag_s(w.nan)])
+        taps = sorted(fir["taps"])
+        sc = _flit(fir["scale"])
+        t, i, v0, v1, res, f = (self._t(x) for x in ("t", "i", "v", "v", "res", "f"))
+        sl = self._slot(w)
+        # out[i] = scale * sum_k C_k * sum_{m in (i - t_{k+1}, i - t_k]} y[m],  C_k = c_0 + ... + c_k
+        terms, cum = [], 0.0
+        for k, (ts, c) in enumerate(taps):
+            cum += c
+            if abs(cum) > 1e-12 and k + 1 < len(taps):
+                terms.append(f"{_flit(cum)} * wrange_sum({sl}, {n}, {i} - {taps[k + 1][0]} + 1, {i} - {ts} + 1, lane)")
+        step = " + ".join(f"{_flit(c)} * at0({sl}, {n}, {i} + 1 - {ts})" for ts, c in taps)
+        mode = chr(nd["mode"])
+        if mode == "i":
+            frac = f"{f} = DSPB_FATAL_FTP_INT;"
+        elif mode == "f":
+            frac = f"{res} = {v0};"
+        else:
+            frac = f"const float {v1} = {v0} + {sc} * ({step}); "
+            if mode == "c":
+                frac += f"{res} = {v1};"
+            elif mode == "n":
+                frac += f"{res} = ({t} - (float){i} < 0.5f) ? {v0} : {v1};"
+            else:
+                frac += (f"const double t0_ = (double){t} - (double){i}; "
+                         f"{res} = (float)((1.0 - t0_) * (double){v0} + t0_ * (double){v1});")
+        self._es(f"int {f} = 0; float {res} = CUDART_NAN_F;",
+                 f"{{ const float {t} = (float)({nd['t']});",
+                 f"  if ({t} == {t} && {t} >= 0.f && {t} <= {float(n - 1)}f{' && !(' + g + ')' if g else ''}) {{",
+                 f"    const int {i} = (int){t};",
+                 f"    const float {v0} = {sc} * ({' + '.join(terms) if terms else '0.f'});",
+                 f"    if ((float){i} == {t}) {res} = {v0}; else {{ {frac} }}",
+                 "  } }",
+                 self._asg(nd['out'], res),
+                 f"if ({f} && lane == 0) raise_fatal(A.fatal ? A.fatal + 4 * {nd['fatal']} : nullptr, {f}, A.row0 + row);",
+                 *self._stores(nd["out"]))
+        self._def_s(nd["out"])
 
     def _e_ftp(self, nd):
+        if nd.get("lazy") is not None:
+            return self._e_ftp_lazy(nd)
         w, off, n = nd["ins"][0]
-        self._need(nd["t"], w.nan)
-        self._visible(w)
+        self._s_wave(w)
         f = self._t("f")
-        g = self._nan_guard([w.nan])
+        g = self._nan_guard([self._flag_s(w.nan)])
         call = f"op_fixed_time_pickoff<float>({self._slot(w)}, {n}, (float)({nd['t']}), {nd['mode']}, {f})"
-        self._e0(f"int {f} = 0;",
+        self._es(f"int {f} = 0;",
                  self._asg(nd['out'], f"{'(' + g + ') ? CUDART_NAN_F : ' if g else ''}{call}"),
                  f"if ({f} && lane == 0) raise_fatal(A.fatal ? A.fatal + 4 * {nd['fatal']} : nullptr, {f}, A.row0 + row);",
                  *self._stores(nd["out"]))
-        self._def0(nd["out"])
+        self._def_s(nd["out"])
 
     def _e_windower(self, nd):
         # windower.py:12-54 : out[k] = in[t0 + k], NaN where the window leaves the waveform; one
@@ -1138,15 +1280,16 @@ class SpecChain(FusedChain):
                 f"for (int k = tid; k < {mc}; k += 512) {{ const int q = {beg} + k; float v = 0.f; "
                 f"if (k < {m}) {{ if (!({g}) && q >= 0 && q < {n}) v = at({self._slot(w)}, q); else {{ {pad} = 1; v = CUDART_NAN_F; }} }} "
                 f"{so}[sidx(k)] = v; }}",
-                f"put_imax(cs, par, {si}, {pad}, lane, warp);")
+                f"put_imax(CSI({si}), {pad}, lane, warp);")
         nf = f"nan{out.name}"
-        self.posts.append(f"const int {nf} = get_imax(cs, par, {si}, lane);")
+        self.posts.append(f"const int {nf} = get_imax(CSI({si}), lane);")
         self.pending.add(nf)
         out.nan = nf
         out.nan_elementwise = True
         out.scatter = True
         out.reg = None
         self.dirty.add(out.slot[0])
+        self.s_dirty = True
 
     def _e_avg_current(self, nd):
         w, off, n = nd["ins"][0]
@@ -1229,16 +1372,16 @@ class SpecChain(FusedChain):
                         f"float {d}[16]; _Pragma(\"unroll\") for (int j = 0; j < 16; j++) {{ const int i = 16 * tid + j; "
                         f"{d}[j] = i >= {n} ? 0.f : (i == 0 ? {e0} : ({x}[j] - (i >= {L} ? {sh}[j] : {e0})) * {il}); }}",
                         f"const float {tot} = cumsum_local({d});",
-                        f"const float {incl} = put_scan_f(cs, par, {sd}, {tot}, lane, warp);")
-                get = f"get_excl_f(cs, par, {sd}, {incl}, {tot}, lane, warp)"
+                        f"const float {incl} = put_scan_f(CSD({sd}), {tot}, lane, warp);")
+                get = f"get_excl_f(CSD({sd}), {incl}, {tot}, lane, warp)"
             else:
                 # mirror image: out[n-1] = x[n-1]; out[i] = out[i+1] + (x[i] - x[min(i+L,n-1)]) / L
                 self._e(f"float {sh}[16]; ld_shift<{L}>({sl}, tid, {n}, {self._zc(src)}, {sh}); const float {e0} = at({sl}, {n - 1});",
                         f"float {d}[16]; _Pragma(\"unroll\") for (int j = 0; j < 16; j++) {{ const int i = 16 * tid + j; "
                         f"{d}[j] = i >= {n} ? 0.f : (i == {n - 1} ? {e0} : ({x}[j] - (i + {L} <= {n - 1} ? {sh}[j] : {e0})) * {il}); }}",
                         f"const float {tot} = cumsum_local_rev({d});",
-                        f"const float {incl} = put_scan_rev_f(cs, par, {sd}, {tot}, lane, warp);")
-                get = f"get_excl_rev_f(cs, par, {sd}, {incl}, {tot}, lane, warp)"
+                        f"const float {incl} = put_scan_rev_f(CSD({sd}), {tot}, lane, warp);")
+                get = f"get_excl_rev_f(CSD({sd}), {incl}, {tot}, lane, warp)"
             o, offv = self._t("r"), self._t("off")
             self.posts.append(f"double {tt} = 0.0; const float {offv} = (float){get}; (void){tt};")
             self.posts.append(f"float {o}[16]; _Pragma(\"unroll\") for (int j = 0; j < 16; j++) {o}[j] = {d}[j] + {offv};")
@@ -1255,6 +1398,7 @@ class SpecChain(FusedChain):
                 self.live_regs.remove(tw)
 
     def _e_conv_seg(self, nd):
+        raise NotSpecializable("cusp/zac convolution over a full-length waveform (interpreted path)")
         w, off, n = nd["ins"][0]
         out = nd["wouts"][0]
         self._need(w.nan)
@@ -1309,27 +1453,28 @@ class SpecChain(FusedChain):
         self._e(f"conv_seg_chunked<{'true' if poly else 'false'}, {'true' if two else 'false'}>({self._slot(w)}, {x}, {n}, "
                 f"{_lit(sigma)}, {int(lt)}, {int(fl)}, {int(L)}, {_lit(c)}, {_lit(inv2S)}, {_lit(math.exp(-1.0 / sigma))}, "
                 f"{_lit(math.exp(1.0 / sigma))}, {_lit(math.exp((L - 1) / sigma))}, {pw}, {so[0]}, {so[1]}, {self._slot(outs[0])}, {self._slot(outs[1 if two else 0])}, "
-                f"reinterpret_cast<double*>(SLOT({scratch[0][0]})), cs, par, tid, lane, warp);")
+                f"reinterpret_cast<double*>(SLOT({scratch[0][0]})), tid, lane, warp);")
         # the band table overwrote the (always-zero) pad columns of its slots
         self._e(f"zero_pads(slots, {self.slot_words}, {self.nchunks}, {scratch[0][0]}, {scratch[-1][0] + 1}, tid);")
         for sl in scratch:
             self.dirty.add(sl[0])
             self._slot_free(sl)
+        self.s_dirty = True
         for out in outs:
             out.nan = w.nan
             out.reg = None
 
     def _sc_emit(self, nd, expr, *operands):
-        """scalar glue runs where its operands live: in the scalar warp as soon as one of them does"""
-        self._need(*operands)
-        if any(self._is_w0(o) for o in operands):
-            self._e0(self._asg(nd['out'], expr), *self._stores(nd["out"]))
-            self._def0(nd["out"])
+        """scalar glue runs in the scalar stream; when none of its operands lives there (inputs,
+        constants) it is simply evaluated by both streams"""
+        out = nd["out"]
+        if any(self._is_s(o) for o in operands):
+            self.s_seq += 1
+            self._es(self._asg(out, expr), *self._stores(out))
+            self._def_s(out)
         else:
-            self._e(self._asg(nd['out'], expr))
-            st = self._stores(nd["out"])
-            if st:
-                self._e0(*st)
+            self._e(self._asg(out, expr))
+            self._es(self._asg(out, expr), *self._stores(out))
 
     def _e_sc_bin(self, nd):
         op = {"add": "+", "subtract": "-", "multiply": "*", "divide": "/"}.get(nd["op"])
@@ -1373,17 +1518,25 @@ class SpecChain(FusedChain):
     # ------------------------------------------------------------------------------------
     def source(self) -> str:
         np_ = max(1, len(self.ptrs))
-        body = "\n      ".join(self.prolog + self.L)
+        ind = "\n        "
+        body_b = ind.join(self.LB)
+        body_s = ind.join(self.LS)
+        prolog = "\n      ".join(self.prolog)
         names = sorted(set(self.svar.values()), key=lambda x: int(x[1:]))
         decl = " ".join(f"{ty} " + ", ".join(n for n in names if self.stype[n] == ty) + ";"
                         for ty in ("float", "double") if any(self.stype[n] == ty for n in names))
         arrays = "\n".join(getattr(self, "static_arrays", []))
         aligned = getattr(self, "aligned_ptrs", [])
         align_check = "".join(f"  if (((uintptr_t)ptrs[{i}] & 15) || (strides[{i}] & 7)) return DSPB_ERR_UNSUPPORTED;\n" for i in aligned)
+        mbd_off = 2048 + 8192 + 1024
+        mbi_off = mbd_off + self.n_mbd * 16 * 8
         return f"""// generated by dspeed_b200/codegen.py -- do not edit
 #define DSPB_PSP {self.psp}
+// the 16 block warps synchronise on named barrier 1; the scalar warp (warp 16) never joins it
+#define BSYNC() asm volatile("bar.sync 1, 512;" ::: "memory")
+#define EV_ARRIVE(id) asm volatile("bar.arrive %0, 544;" ::"r"(id) : "memory")
+#define EV_WAIT(id) asm volatile("bar.sync %0, 544;" ::"r"(id) : "memory")
 #include "chain_rt.cuh"
-#include "conv_seg.cuh"
 using namespace dspb;
 using namespace crt;
 namespace {{
@@ -1398,36 +1551,51 @@ struct Args {{
 }};
 {arrays}
 #define SLOT(k) (slots + (k) * {self.slot_words})
+#define CSD(k) (cs->d[par][k])
+#define CSI(k) (cs->i[par][k])
+#define MBD(k) (mbd + 16 * (k))
+#define MBI(k) (mbi + 16 * (k))
 #ifdef DSPB_PROFILE   // tracing build (SpecChain.profile): per-node SM-cycle stamps of CTA 0
 #define PROF_MARK(k) if (A.prof && tid == 0 && (k) + 1 < 128) prof_ts[(k) + 1] = clock64();
 #else
 #define PROF_MARK(k)
 #endif
 
-__global__ void __launch_bounds__(512, 1) k_chain_spec(const __grid_constant__ Args A) {{
+__global__ void __launch_bounds__(544, 1) k_chain_spec(const __grid_constant__ Args A) {{
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  Scratch* sc = reinterpret_cast<Scratch*>(smem_raw);
   CScr* cs = reinterpret_cast<CScr*>(smem_raw + 2048);
-  float* slots = reinterpret_cast<float*>(smem_raw + 2048 + 8192 + 1024);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double* bc = reinterpret_cast<double*>(smem_raw + 2048 + 5120);   // scalar warp -> block warps
   long long* prof_ts = reinterpret_cast<long long*>(smem_raw + 2048 + 8192);
-  double* bc = reinterpret_cast<double*>(smem_raw + 2048 + 5120);   // scalar-warp -> all-threads broadcasts
-  (void)prof_ts;
+  double* mbd = reinterpret_cast<double*>(smem_raw + {mbd_off});      // block warps -> scalar warp (partials)
+  int* mbi = reinterpret_cast<int*>(smem_raw + {mbi_off});
+  float* slots = reinterpret_cast<float*>(smem_raw + {self.fixed_bytes});
+  (void)prof_ts; (void)cs; (void)bc; (void)mbd; (void)mbi;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool scalar_warp = warp == 16;
   int par = 0;
-  zero_pads(slots, {self.slot_words}, {self.nchunks}, 0, {self.n_slots}, tid);
-  __syncthreads();
+  if (!scalar_warp) {{
+    zero_pads(slots, {self.slot_words}, {self.nchunks}, 0, {self.n_slots}, tid);
+    BSYNC();
+  }}
   for (long long row = blockIdx.x; row < A.n_rows; row += gridDim.x) {{
 #ifdef DSPB_PROFILE
     if (A.prof && tid == 0) prof_ts[0] = clock64();
 #endif
     {{
       {decl}
-      {body}
+      {prolog}
+      if (!scalar_warp) {{
+        // =============================== block stream (warps 0-15) ===============================
+        {body_b}
+      }} else {{
+        // =============================== scalar stream (warp 16) =================================
+        {body_s}
+      }}
     }}
-    __syncthreads();
+    __syncthreads();   // row end: both streams are done with the slots, the mailbox and bc[]
 #ifdef DSPB_PROFILE
     if (A.prof && blockIdx.x == 0) {{
-      for (int k = tid; k < N_NODES && k + 1 < 128; k += 512) A.prof[k] += prof_ts[k + 1] - prof_ts[k];
+      for (int k = tid; k < N_NODES && k + 1 < 128; k += 544) A.prof[k] += prof_ts[k + 1] - prof_ts[k];
       __syncthreads();
     }}
 #endif
@@ -1448,14 +1616,11 @@ extern "C" int chain_launch(const void* const* ptrs, long long n_ptrs, long long
   a.row0 = strides[n_ptrs];
   a.fatal = fatal;
   a.prof = prof;
-  static bool attr_set = false;
-  if (!attr_set) {{
-    cudaError_t e = cudaFuncSetAttribute(k_chain_spec, cudaFuncAttributeMaxDynamicSharedMemorySize, {self.smem_bytes});
-    if (e != cudaSuccess) return -(int)e;
-  }}
+  cudaError_t e = cudaFuncSetAttribute(k_chain_spec, cudaFuncAttributeMaxDynamicSharedMemorySize, {self.smem_bytes});
+  if (e != cudaSuccess) return -(int)e;
   const int grid = (int)(n_rows < num_sms ? n_rows : num_sms);
-  k_chain_spec<<<grid, 512, {self.smem_bytes}, (cudaStream_t)stream>>>(a);
-  cudaError_t e = cudaGetLastError();
+  k_chain_spec<<<grid, 544, {self.smem_bytes}, (cudaStream_t)stream>>>(a);
+  e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -(int)e;
 }}
 """
@@ -1504,7 +1669,7 @@ extern "C" int chain_launch(const void* const* ptrs, long long n_ptrs, long long
 # ----------------------------------------------------------------------------------------
 def _headers_digest() -> str:
     h = hashlib.sha1()
-    for f in ("common.cuh", "row_ops.cuh", "conv_ops.cuh", "chain_rt.cuh", "conv_seg.cuh"):
+    for f in ("common.cuh", "row_ops.cuh", "conv_ops.cuh", "chain_rt.cuh"):
         h.update(open(os.path.join(_lib.CSRC, f), "rb").read())
     h.update(open(os.path.join(_lib.INCLUDE, "dspeed_b200.h"), "rb").read())
     return h.hexdigest()

@@ -23,6 +23,12 @@
 #include "conv_ops.cuh"
 #include "row_ops.cuh"
 
+// Barrier of the 16 block warps.  Kernels that run a separate scalar warp define it as a named
+// barrier over the 512 block threads before including this header.
+#ifndef BSYNC
+#define BSYNC() __syncthreads()
+#endif
+
 namespace crt {
 using namespace dspb;
 
@@ -195,23 +201,23 @@ __device__ __forceinline__ float fkey_inv(unsigned k) {
 // block collectives, split into "put" (before the barrier) and "get" (after it)
 // ---------------------------------------------------------------------------------------
 // sum of one double per thread
-__device__ __forceinline__ void put_sum(CScr* cs, int par, int slot, double v, int lane, int warp) {
+__device__ __forceinline__ void put_sum(double* p, double v, int lane, int warp) {
   v = wsum(v);
-  if (lane == 0) cs->d[par][slot][warp] = v;
+  if (lane == 0) p[warp] = v;
 }
-__device__ __forceinline__ double get_sum(const CScr* cs, int par, int slot, int lane) {
-  return wsum(lane < NWP ? cs->d[par][slot][lane] : 0.0);
+__device__ __forceinline__ double get_sum(const double* p, int lane) {
+  return wsum(lane < NWP ? p[lane] : 0.0);
 }
 // exclusive forward scan of one double per thread; `incl` (this thread's inclusive warp
 // scan) must be kept by the caller for get_excl
-__device__ __forceinline__ double put_scan(CScr* cs, int par, int slot, double v, int lane, int warp) {
+__device__ __forceinline__ double put_scan(double* p, double v, int lane, int warp) {
   const double incl = wscan_incl(v, lane);
-  if (lane == 31) cs->d[par][slot][warp] = incl;
+  if (lane == 31) p[warp] = incl;
   return incl;
 }
-__device__ __forceinline__ double get_excl(const CScr* cs, int par, int slot, double incl, double v, int lane,
-                                           int warp, double& total) {
-  const double part = lane < NWP ? cs->d[par][slot][lane] : 0.0;
+__device__ __forceinline__ double get_excl(const double* p, double incl, double v, int lane, int warp,
+                                           double& total) {
+  const double part = lane < NWP ? p[lane] : 0.0;
   const double pin = wscan_incl(part, lane);
   total = __shfl_sync(FULL, pin, NWP - 1);
   return __shfl_sync(FULL, pin - part, warp) + (incl - v);
@@ -234,15 +240,14 @@ __device__ __forceinline__ float wscan_incl_rev_f(float v, int lane) {
   }
   return v;
 }
-__device__ __forceinline__ float put_scan_f(CScr* cs, int par, int slot, float v, int lane, int warp) {
+__device__ __forceinline__ float put_scan_f(double* p, float v, int lane, int warp) {
   const float incl = wscan_incl_f(v, lane);
-  if (lane == 31) cs->d[par][slot][warp] = (double)incl;
+  if (lane == 31) p[warp] = (double)incl;
   return incl;
 }
 // exclusive prefix of this thread: float64 across the 16 warp totals, float inside the warp
-__device__ __forceinline__ double get_excl_f(const CScr* cs, int par, int slot, float incl, float v, int lane,
-                                             int warp) {
-  const double part = lane < NWP ? cs->d[par][slot][lane] : 0.0;
+__device__ __forceinline__ double get_excl_f(const double* p, float incl, float v, int lane, int warp) {
+  const double part = lane < NWP ? p[lane] : 0.0;
   double pin = part;
 #pragma unroll
   for (int o = 1; o < NWP; o <<= 1) {
@@ -251,14 +256,13 @@ __device__ __forceinline__ double get_excl_f(const CScr* cs, int par, int slot, 
   }
   return __shfl_sync(FULL, pin - part, warp) + (double)(incl - v);
 }
-__device__ __forceinline__ float put_scan_rev_f(CScr* cs, int par, int slot, float v, int lane, int warp) {
+__device__ __forceinline__ float put_scan_rev_f(double* p, float v, int lane, int warp) {
   const float incl = wscan_incl_rev_f(v, lane);
-  if (lane == 0) cs->d[par][slot][warp] = (double)incl;
+  if (lane == 0) p[warp] = (double)incl;
   return incl;
 }
-__device__ __forceinline__ double get_excl_rev_f(const CScr* cs, int par, int slot, float incl, float v, int lane,
-                                                 int warp) {
-  const double part = lane < NWP ? cs->d[par][slot][lane] : 0.0;
+__device__ __forceinline__ double get_excl_rev_f(const double* p, float incl, float v, int lane, int warp) {
+  const double part = lane < NWP ? p[lane] : 0.0;
   double pin = part;
 #pragma unroll
   for (int o = 1; o < NWP; o <<= 1) {
@@ -268,59 +272,58 @@ __device__ __forceinline__ double get_excl_rev_f(const CScr* cs, int par, int sl
   return __shfl_sync(FULL, pin - part, warp) + (double)(incl - v);
 }
 // reverse (suffix) scan
-__device__ __forceinline__ double put_scan_rev(CScr* cs, int par, int slot, double v, int lane, int warp) {
+__device__ __forceinline__ double put_scan_rev(double* p, double v, int lane, int warp) {
   const double incl = wscan_incl_rev(v, lane);
-  if (lane == 0) cs->d[par][slot][warp] = incl;
+  if (lane == 0) p[warp] = incl;
   return incl;
 }
-__device__ __forceinline__ double get_excl_rev(const CScr* cs, int par, int slot, double incl, double v, int lane,
-                                               int warp) {
-  const double part = lane < NWP ? cs->d[par][slot][lane] : 0.0;
+__device__ __forceinline__ double get_excl_rev(const double* p, double incl, double v, int lane, int warp) {
+  const double part = lane < NWP ? p[lane] : 0.0;
   const double pin = wscan_incl_rev(part, lane);
   return __shfl_sync(FULL, pin - part, warp) + (incl - v);
 }
 
 // first-occurrence arg-max / arg-min of (value, index) pairs: two REDUX per level
-__device__ __forceinline__ void put_argmax(CScr* cs, int par, int slot, float v, int idx, int lane, int warp) {
+__device__ __forceinline__ void put_argmax(int* p, float v, int idx, int lane, int warp) {
   const unsigned k = fkey(v);
   const unsigned km = __reduce_max_sync(FULL, k);
   const int im = __reduce_min_sync(FULL, k == km ? idx : 0x7fffffff);
-  if (lane == 0) { cs->i[par][slot][warp] = (int)km; cs->i[par][slot + 1][warp] = im; }
+  if (lane == 0) { p[warp] = (int)km; p[NWP + warp] = im; }
 }
-__device__ __forceinline__ void get_argmax(const CScr* cs, int par, int slot, int lane, float& v, int& idx) {
-  const unsigned k = lane < NWP ? (unsigned)cs->i[par][slot][lane] : 0u;
-  const int ii = lane < NWP ? cs->i[par][slot + 1][lane] : 0x7fffffff;
+__device__ __forceinline__ void get_argmax(const int* p, int lane, float& v, int& idx) {
+  const unsigned k = lane < NWP ? (unsigned)p[lane] : 0u;
+  const int ii = lane < NWP ? p[NWP + lane] : 0x7fffffff;
   const unsigned km = __reduce_max_sync(FULL, k);
   idx = __reduce_min_sync(FULL, k == km ? ii : 0x7fffffff);
   v = fkey_inv(km);
 }
-__device__ __forceinline__ void put_argmin(CScr* cs, int par, int slot, float v, int idx, int lane, int warp) {
+__device__ __forceinline__ void put_argmin(int* p, float v, int idx, int lane, int warp) {
   const unsigned k = fkey(v);
   const unsigned km = __reduce_min_sync(FULL, k);
   const int im = __reduce_min_sync(FULL, k == km ? idx : 0x7fffffff);
-  if (lane == 0) { cs->i[par][slot][warp] = (int)km; cs->i[par][slot + 1][warp] = im; }
+  if (lane == 0) { p[warp] = (int)km; p[NWP + warp] = im; }
 }
-__device__ __forceinline__ void get_argmin(const CScr* cs, int par, int slot, int lane, float& v, int& idx) {
-  const unsigned k = lane < NWP ? (unsigned)cs->i[par][slot][lane] : 0xffffffffu;
-  const int ii = lane < NWP ? cs->i[par][slot + 1][lane] : 0x7fffffff;
+__device__ __forceinline__ void get_argmin(const int* p, int lane, float& v, int& idx) {
+  const unsigned k = lane < NWP ? (unsigned)p[lane] : 0xffffffffu;
+  const int ii = lane < NWP ? p[NWP + lane] : 0x7fffffff;
   const unsigned km = __reduce_min_sync(FULL, k);
   idx = __reduce_min_sync(FULL, k == km ? ii : 0x7fffffff);
   v = fkey_inv(km);
 }
 // max / min of one int per thread
-__device__ __forceinline__ void put_imax(CScr* cs, int par, int slot, int v, int lane, int warp) {
+__device__ __forceinline__ void put_imax(int* p, int v, int lane, int warp) {
   v = __reduce_max_sync(FULL, v);
-  if (lane == 0) cs->i[par][slot][warp] = v;
+  if (lane == 0) p[warp] = v;
 }
-__device__ __forceinline__ int get_imax(const CScr* cs, int par, int slot, int lane) {
-  return __reduce_max_sync(FULL, lane < NWP ? cs->i[par][slot][lane] : (int)0x80000000);
+__device__ __forceinline__ int get_imax(const int* p, int lane) {
+  return __reduce_max_sync(FULL, lane < NWP ? p[lane] : (int)0x80000000);
 }
-__device__ __forceinline__ void put_imin(CScr* cs, int par, int slot, int v, int lane, int warp) {
+__device__ __forceinline__ void put_imin(int* p, int v, int lane, int warp) {
   v = __reduce_min_sync(FULL, v);
-  if (lane == 0) cs->i[par][slot][warp] = v;
+  if (lane == 0) p[warp] = v;
 }
-__device__ __forceinline__ int get_imin(const CScr* cs, int par, int slot, int lane) {
-  return __reduce_min_sync(FULL, lane < NWP ? cs->i[par][slot][lane] : 0x7fffffff);
+__device__ __forceinline__ int get_imin(const int* p, int lane) {
+  return __reduce_min_sync(FULL, lane < NWP ? p[lane] : 0x7fffffff);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -373,19 +376,19 @@ __device__ __forceinline__ int first_eq_local(const float (&v)[CHK], float m, in
   return idx;
 }
 // value-only block max / min through the order-preserving key
-__device__ __forceinline__ void put_fmax(CScr* cs, int par, int slot, float v, int lane, int warp) {
+__device__ __forceinline__ void put_fmax(int* p, float v, int lane, int warp) {
   const unsigned km = __reduce_max_sync(FULL, fkey(v));
-  if (lane == 0) cs->i[par][slot][warp] = (int)km;
+  if (lane == 0) p[warp] = (int)km;
 }
-__device__ __forceinline__ float get_fmax(const CScr* cs, int par, int slot, int lane) {
-  return fkey_inv(__reduce_max_sync(FULL, lane < NWP ? (unsigned)cs->i[par][slot][lane] : 0u));
+__device__ __forceinline__ float get_fmax(const int* p, int lane) {
+  return fkey_inv(__reduce_max_sync(FULL, lane < NWP ? (unsigned)p[lane] : 0u));
 }
-__device__ __forceinline__ void put_fmin(CScr* cs, int par, int slot, float v, int lane, int warp) {
+__device__ __forceinline__ void put_fmin(int* p, float v, int lane, int warp) {
   const unsigned km = __reduce_min_sync(FULL, fkey(v));
-  if (lane == 0) cs->i[par][slot][warp] = (int)km;
+  if (lane == 0) p[warp] = (int)km;
 }
-__device__ __forceinline__ float get_fmin(const CScr* cs, int par, int slot, int lane) {
-  return fkey_inv(__reduce_min_sync(FULL, lane < NWP ? (unsigned)cs->i[par][slot][lane] : 0xffffffffu));
+__device__ __forceinline__ float get_fmin(const int* p, int lane) {
+  return fkey_inv(__reduce_min_sync(FULL, lane < NWP ? (unsigned)p[lane] : 0xffffffffu));
 }
 
 // linear_slope_fit.py:11-90 : sums over [lo, hi), abscissa relative to lo
@@ -493,73 +496,6 @@ __device__ __forceinline__ void fir_run(const float* slot, int t, int n, int zc,
 // value of sample i of a slot (any thread)
 __device__ __forceinline__ float at(const float* slot, int i) { return slot[sidx(i)]; }
 
-// time_point_thresh.py:12-92.  The crossing usually lies within a few tens of samples of the
-// start, so every warp first walks (redundantly, no barrier) up to WARP_WINDOWS windows of 32
-// samples with a ballot; only a long walk falls back to block-wide 512-sample windows with one
-// barrier each.  All warps see the same data, so the control flow is uniform over the CTA.
-// In a block window thread (lane, warp) looks at sample s -/+ (16 * lane + warp): lanes touch
-// consecutive chunks at the same in-chunk offset (conflict-free in the T4 layout).
-constexpr int WARP_WINDOWS = 6;
-__device__ __forceinline__ int search_cross(const float* w, int n, float thr, int s, bool forward, int stop_back,
-                                            CScr* cs, int& par, int lane, int warp) {
-  if (forward) {
-    int base = s;
-#pragma unroll 1
-    for (int k = 0; k < WARP_WINDOWS && base < n - 1; k++, base += 32) {
-      const int i = base + lane;
-      bool hit = false;
-      if (i < n - 1) {
-        const float a = at(w, i), b = at(w, i + 1);
-        hit = (a <= thr && thr < b) || (a >= thr && thr > b);
-      }
-      const unsigned m = __ballot_sync(FULL, hit);
-      if (m) return base + __ffs(m) - 1;
-    }
-    const int u = 16 * lane + warp;
-    for (; base < n - 1; base += 512) {
-      const int i = base + u;
-      int hit = 0x7fffffff;
-      if (i < n - 1) {
-        const float a = at(w, i), b = at(w, i + 1);
-        if ((a <= thr && thr < b) || (a >= thr && thr > b)) hit = i;
-      }
-      put_imin(cs, par, 0, hit, lane, warp);
-      __syncthreads();
-      hit = get_imin(cs, par, 0, lane);
-      par ^= 1;
-      if (hit != 0x7fffffff) return hit;
-    }
-    return -1;
-  }
-  int base = s;
-#pragma unroll 1
-  for (int k = 0; k < WARP_WINDOWS && base >= stop_back; k++, base -= 32) {
-    const int i = base - lane;
-    bool hit = false;
-    if (i >= stop_back) {
-      const float a = at(w, i - 1), b = at(w, i);
-      hit = (a < thr && thr <= b) || (a > thr && thr >= b);
-    }
-    const unsigned m = __ballot_sync(FULL, hit);
-    if (m) return base - (__ffs(m) - 1);
-  }
-  const int u = 16 * lane + warp;
-  for (; base >= stop_back; base -= 512) {
-    const int i = base - u;
-    int hit = -1;
-    if (i >= stop_back) {
-      const float a = at(w, i - 1), b = at(w, i);
-      if ((a < thr && thr <= b) || (a > thr && thr >= b)) hit = i;
-    }
-    put_imax(cs, par, 0, hit, lane, warp);
-    __syncthreads();
-    hit = get_imax(cs, par, 0, lane);
-    par ^= 1;
-    if (hit >= 0) return hit;
-  }
-  return -1;
-}
-
 // Warp-only search (scalar warp).  The scalar warp runs alone, so every instruction of this
 // routine is on the critical path (~5 cycles each): the common case -- a crossing within a few
 // tens of samples of the start -- is two plain 32-sample windows; only longer walks (a threshold
@@ -652,6 +588,19 @@ __device__ __forceinline__ int search_cross_w(const float* w, int n, float thr, 
   return base >= stop_back ? search_cross_long(w, n, thr, base, false, stop_back, lane) : -1;
 }
 
+// sum of w[a .. b) clipped to the wave, by one warp (lazy evaluation of a windowed filter at a
+// single position, e.g. a trapezoid that is only picked off at one time)
+__device__ __noinline__ float wrange_sum(const float* w, int n, int a, int b, int lane) {
+  a = max(a, 0);
+  b = min(b, n);
+  float acc = 0.f;
+  for (int m = a + lane; m < b; m += 32) acc += at(w, m);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
+  return acc;
+}
+__device__ __forceinline__ float at0(const float* w, int n, int i) { return (i >= 0 && i < n) ? at(w, i) : 0.f; }
+
 // time_point_thresh.py:12-92 evaluated by one warp
 __device__ __forceinline__ float tpt_w(const float* w, int n, float thr, float t_start, float walk, int& fatal,
                                        int lane) {
@@ -661,18 +610,6 @@ __device__ __forceinline__ float tpt_w(const float* w, int n, float thr, float t
   if (floorf(walk) != walk) { fatal = DSPB_FATAL_WALK_NONINT; return CUDART_NAN_F; }
   if (!(t_start >= 0.f && t_start < (float)n)) { fatal = DSPB_FATAL_TSTART_RANGE; return CUDART_NAN_F; }
   const int hit = search_cross_w(w, n, thr, (int)t_start, walk == 1.0f, 1, lane);
-  return hit < 0 ? CUDART_NAN_F : (float)hit;
-}
-
-__device__ __forceinline__ float tpt(const float* w, int n, float thr, float t_start, float walk, int& fatal,
-                                     CScr* cs, int& par, int lane, int warp) {
-  fatal = 0;
-  if (thr != thr || t_start != t_start || walk != walk) return CUDART_NAN_F;
-  if (floorf(t_start) != t_start) { fatal = DSPB_FATAL_TSTART_NONINT; return CUDART_NAN_F; }
-  if (floorf(walk) != walk) { fatal = DSPB_FATAL_WALK_NONINT; return CUDART_NAN_F; }
-  const long long s = (long long)t_start;
-  if (s < 0 || s >= n) { fatal = DSPB_FATAL_TSTART_RANGE; return CUDART_NAN_F; }
-  const int hit = search_cross(w, n, thr, (int)s, (long long)walk == 1, 1, cs, par, lane, warp);
   return hit < 0 ? CUDART_NAN_F : (float)hit;
 }
 
@@ -704,8 +641,7 @@ template <bool POLY, bool TWO>
 __device__ __forceinline__ void conv_seg_chunked(const float* X, const float (&x)[CHK], int N, double sigma, int lt,
                                                  int fl, int L, double c, double inv2S, double qm, double qp,
                                                  double eA, const double* __restrict__ pw, SegOut s0, SegOut s1, float* out0,
-                                                 float* out1, double* tab, CScr* cs, int& par, int tid, int lane,
-                                                 int warp) {
+                                                 float* out1, double* tab, int tid, int lane, int warp) {
   constexpr int NQ = POLY ? 5 : 3;
   const int p = N - L + 1;
   const int CW = (((p + CHK - 1) >> 4) + 1) | 1, PP = CHK * CW;
@@ -763,7 +699,7 @@ __device__ __forceinline__ void conv_seg_chunked(const float* X, const float (&x
   constexpr int OT = 512 + 32;
 #pragma unroll
   for (int q = 0; q < NQ; q++) otab[q * OT + tid + (tid >> 4)] = s[q];
-  __syncthreads();
+  BSYNC();
   if (warp < NQ) {
     double* o = otab + warp * OT + 17 * lane;
     double v[CHK];
@@ -778,7 +714,7 @@ __device__ __forceinline__ void conv_seg_chunked(const float* X, const float (&x
 #pragma unroll
     for (int k = 0; k < CHK; k++) o[k] = v[k] + base_l;
   }
-  __syncthreads();
+  BSYNC();
   // ---- pass 3: one thread per output ------------------------------------------------------------
   const int pceil = (p + CHK - 1) & ~(CHK - 1);
   const double eAm = 1.0 / eA;  // eA = e^{(L-1)/s}: e^{+-n/s} = eA^{+-1} * q^{+-o}
@@ -812,7 +748,7 @@ __device__ __forceinline__ void conv_seg_chunked(const float* X, const float (&x
     out0[sidx(o)] = y0;
     if (TWO) out1[sidx(o)] = y1;
   }
-  __syncthreads();
+  BSYNC();
 }
 
 }  // namespace crt
