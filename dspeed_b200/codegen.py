@@ -630,6 +630,13 @@ class SpecChain(FusedChain):
         self.nchunks = (slot_len + CHK - 1) // CHK
         self.psp = 4 * self.nchunks + 8
         self.slot_words = 4 * self.psp
+        # waves searched by the scalar warp carry a min/max summary (built when they are stored)
+        self.summ = {}
+        for nd in self.nodes:
+            if nd["kind"] == "tpt":
+                w = nd["ins"][0][0]
+                if w.id not in self.summ:
+                    self.summ[w.id] = len(self.summ)
         # scalars the block stream needs from the scalar warp
         self.b_needed = set()
         for nd in self.nodes:
@@ -642,6 +649,7 @@ class SpecChain(FusedChain):
             self.LS.append(f"// ---- [{k}] {self._describe_node(nd)}")
             getattr(self, "_e_" + nd["kind"])(nd)
             self.LB.append("PROF_MARK(%d);" % k)
+            self.LS.append("PROF_MARK_S(%d);" % k)
             self._release(k)
         self._close_round()
         # scalar outputs not stored at their definition (pass-through input scalars)
@@ -649,8 +657,10 @@ class SpecChain(FusedChain):
             if name not in self.stored:
                 self._es(f"if (lane == {k % 32}) (({ct}*)A.p[{pi}])[row] = ({ct}){name};")
         self.LB.append("PROF_MARK(%d);" % len(self.order))
+        self.LS.append("PROF_MARK_S(%d);" % len(self.order))
         self.mb_bytes = (self.n_mbd * 16 * 8 + self.n_mbi * 16 * 4 + 15) & ~15
-        self.fixed_bytes = 2048 + 8192 + 1024 + self.mb_bytes   # Scratch + CScr/bc + prof stamps + mailbox
+        self.mb_bytes += len(self.summ) * 4224   # sizeof(WaveSummary)
+        self.fixed_bytes = 2048 + 8192 + 2048 + self.mb_bytes   # Scratch + CScr/bc + prof stamps + mailbox
         self.smem_bytes = self.fixed_bytes + self.n_slots * self.slot_words * 4
         if self.smem_bytes > MAX_SMEM:
             raise NotSpecializable("not enough shared memory for the live waveforms")
@@ -924,6 +934,8 @@ class SpecChain(FusedChain):
         if w.needs_slot:
             self._give_slot(w)
             self._e(f"st_chunk_n({self._slot(w)}, tid, {w.n}, {r});")
+            if w.id in self.summ:
+                self._e(f"put_summary(SUMM({self.summ[w.id]}), {r}, {w.n}, tid, lane, warp);")
             self.dirty.add(w.slot[0])
             self.s_dirty = True
         self._set_reg(w, r)
@@ -933,6 +945,8 @@ class SpecChain(FusedChain):
         if w.needs_slot:
             self._give_slot(w, post=True)
             self.posts.append(f"st_chunk_n({self._slot(w)}, tid, {w.n}, {r});")
+            if w.id in self.summ:
+                self.posts.append(f"put_summary(SUMM({self.summ[w.id]}), {r}, {w.n}, tid, lane, warp);")
             self.post_dirty.append(w.slot[0])
             self.s_dirty = True
         self._set_reg(w, r)
@@ -1191,8 +1205,10 @@ class SpecChain(FusedChain):
         self._s_wave(w)
         f = self._t("f")
         g = self._nan_guard([self._flag_s(w.nan)])
-        call = (f"tpt_w({self._slot(w)}, {n}, (float)({nd['thr']}), (float)({nd['start']}), (float)({nd['walk']}), "
-                f"{f}, lane)")
+        if getattr(w, "scatter", False):
+            raise NotSpecializable("threshold search on a scattered waveform")
+        call = (f"tpt_w({self._slot(w)}, SUMM({self.summ[w.id]}), {n}, (float)({nd['thr']}), (float)({nd['start']}), "
+                f"(float)({nd['walk']}), {f}, lane)")
         self._es(f"int {f} = 0;",
                  self._asg(nd['out'], f"{'(' + g + ') ? CUDART_NAN_F : ' if g else ''}{call}"),
                  f"if ({f} && lane == 0) raise_fatal(A.fatal ? A.fatal + 4 * {nd['fatal']} : nullptr, {f}, A.row0 + row);",
@@ -1528,8 +1544,9 @@ class SpecChain(FusedChain):
         arrays = "\n".join(getattr(self, "static_arrays", []))
         aligned = getattr(self, "aligned_ptrs", [])
         align_check = "".join(f"  if (((uintptr_t)ptrs[{i}] & 15) || (strides[{i}] & 7)) return DSPB_ERR_UNSUPPORTED;\n" for i in aligned)
-        mbd_off = 2048 + 8192 + 1024
+        mbd_off = 2048 + 8192 + 2048
         mbi_off = mbd_off + self.n_mbd * 16 * 8
+        summ_off = (mbi_off + self.n_mbi * 16 * 4 + 15) & ~15
         return f"""// generated by dspeed_b200/codegen.py -- do not edit
 #define DSPB_PSP {self.psp}
 // the 16 block warps synchronise on named barrier 1; the scalar warp (warp 16) never joins it
@@ -1555,10 +1572,13 @@ struct Args {{
 #define CSI(k) (cs->i[par][k])
 #define MBD(k) (mbd + 16 * (k))
 #define MBI(k) (mbi + 16 * (k))
+#define SUMM(k) (summ + (k))
 #ifdef DSPB_PROFILE   // tracing build (SpecChain.profile): per-node SM-cycle stamps of CTA 0
 #define PROF_MARK(k) if (A.prof && tid == 0 && (k) + 1 < 128) prof_ts[(k) + 1] = clock64();
+#define PROF_MARK_S(k) if (A.prof && lane == 0 && (k) + 1 < 128) prof_ts[128 + (k) + 1] = clock64();
 #else
 #define PROF_MARK(k)
+#define PROF_MARK_S(k)
 #endif
 
 __global__ void __launch_bounds__(544, 1) k_chain_spec(const __grid_constant__ Args A) {{
@@ -1568,6 +1588,8 @@ __global__ void __launch_bounds__(544, 1) k_chain_spec(const __grid_constant__ A
   long long* prof_ts = reinterpret_cast<long long*>(smem_raw + 2048 + 8192);
   double* mbd = reinterpret_cast<double*>(smem_raw + {mbd_off});      // block warps -> scalar warp (partials)
   int* mbi = reinterpret_cast<int*>(smem_raw + {mbi_off});
+  WaveSummary* summ = reinterpret_cast<WaveSummary*>(smem_raw + {summ_off});
+  (void)summ;
   float* slots = reinterpret_cast<float*>(smem_raw + {self.fixed_bytes});
   (void)prof_ts; (void)cs; (void)bc; (void)mbd; (void)mbi;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1579,7 +1601,7 @@ __global__ void __launch_bounds__(544, 1) k_chain_spec(const __grid_constant__ A
   }}
   for (long long row = blockIdx.x; row < A.n_rows; row += gridDim.x) {{
 #ifdef DSPB_PROFILE
-    if (A.prof && tid == 0) prof_ts[0] = clock64();
+    if (A.prof && (tid == 0 || tid == 512)) prof_ts[tid == 0 ? 0 : 128] = clock64();
 #endif
     {{
       {decl}
@@ -1595,7 +1617,10 @@ __global__ void __launch_bounds__(544, 1) k_chain_spec(const __grid_constant__ A
     __syncthreads();   // row end: both streams are done with the slots, the mailbox and bc[]
 #ifdef DSPB_PROFILE
     if (A.prof && blockIdx.x == 0) {{
-      for (int k = tid; k < N_NODES && k + 1 < 128; k += 544) A.prof[k] += prof_ts[k + 1] - prof_ts[k];
+      for (int k = tid; k < N_NODES && k + 1 < 128; k += 544) {{
+        A.prof[k] += prof_ts[k + 1] - prof_ts[k];
+        A.prof[N_NODES + k] += prof_ts[128 + k + 1] - prof_ts[128 + k];
+      }}
       __syncthreads();
     }}
 #endif
@@ -1642,7 +1667,7 @@ extern "C" int chain_launch(const void* const* ptrs, long long n_ptrs, long long
 
     def profile(self, run, repeats=1):
         """per-node SM cycles of CTA 0 (see fusion.profile_fused); runs a tracing build of the kernel"""
-        n = len(self.order) + 1
+        n = 2 * (len(self.order) + 1)
         so, _ = build_source(self.source(), flags=("-DDSPB_PROFILE",))
         prod_lib, self.lib = self.lib, load_chain_lib(so)
         self.d_prof = torch.zeros(n, dtype=torch.int64, device=self.chain.device)
@@ -1658,6 +1683,7 @@ extern "C" int chain_launch(const void* const* ptrs, long long n_ptrs, long long
             self.lib = prod_lib
         tot = cyc.sum() or 1.0
         text = self.program_text.split("\n") + ["store scalars"]
+        text = ["B " + t for t in text] + ["S " + t for t in text]   # block stream, then scalar stream
         return [(cyc[i], cyc[i] / tot, text[i]) for i in range(n)]
 
     def __del__(self):

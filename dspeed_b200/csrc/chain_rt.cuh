@@ -496,72 +496,71 @@ __device__ __forceinline__ void fir_run(const float* slot, int t, int n, int zc,
 // value of sample i of a slot (any thread)
 __device__ __forceinline__ float at(const float* slot, int i) { return slot[sidx(i)]; }
 
-// Warp-only search (scalar warp).  The scalar warp runs alone, so every instruction of this
-// routine is on the critical path (~5 cycles each): the common case -- a crossing within a few
-// tens of samples of the start -- is two plain 32-sample windows; only longer walks (a threshold
-// that is met by a noise excursion far away, or never) switch to 128-sample steps in which lane
-// l reads samples [b0 + 4l, b0 + 4l + 4) with ONE 128-bit load (conflict-free in the T4 layout)
-// and takes the neighbour sample of a pair from the adjacent lane by shuffle.
-__device__ __forceinline__ float4 ldq(const float* w, int i) {  // samples i .. i+3, i % 4 == 0
-  return *reinterpret_cast<const float4*>(w + sidx(i));
+// ---------------------------------------------------------------------------------------
+// threshold search with a two-level summary (time_point_thresh.py:12-92)
+//
+// A waveform that is searched by the scalar warp carries a summary built by the block warps
+// when they store it: min / max of every 16-sample chunk (level 1, 512 entries) and of every
+// 512-sample stretch owned by one block warp (level 2, 16 entries).  A crossing of `thr`
+// between samples i-1 and i needs  min <= thr <= max  over the chunks that hold the pair, so
+// the search looks at level 2 (one ballot), then at the 32 chunks of the nearest candidate
+// stretch (one ballot), then checks the 16 samples of the nearest candidate chunk exactly --
+// three dependent steps whether the crossing is 5 or 5000 samples away.  Candidates are a
+// superset (equality cases, pairs across chunk borders), the final check is the reference's
+// exact condition, so the result is identical to the linear walk.
+// ---------------------------------------------------------------------------------------
+struct WaveSummary {
+  float mn1[512], mx1[512];  // per chunk
+  float mn2[16], mx2[16];    // per block warp (32 chunks)
+};
+
+// block side: called by every block thread with its own chunk in registers
+__device__ __forceinline__ void put_summary(WaveSummary* sm, const float (&v)[CHK], int n, int tid, int lane,
+                                            int warp) {
+  float mn = CUDART_INF_F, mx = -CUDART_INF_F;
+#pragma unroll
+  for (int j = 0; j < CHK; j++)
+    if (CHK * tid + j < n) { mn = fminf(mn, v[j]); mx = fmaxf(mx, v[j]); }
+  sm->mn1[tid] = mn;
+  sm->mx1[tid] = mx;
+  const unsigned kmn = __reduce_min_sync(FULL, fkey(mn)), kmx = __reduce_max_sync(FULL, fkey(mx));
+  if (lane == 0) { sm->mn2[warp] = fkey_inv(kmn); sm->mx2[warp] = fkey_inv(kmx); }
 }
-__device__ __noinline__ int search_cross_long(const float* w, int n, float thr, int s, bool forward, int stop_back,
-                                              int lane) {
-  const int nceil = (n + 15) & ~15;
-  if (forward) {
-#pragma unroll 1
-    for (int c0 = s & ~127; c0 < n - 1; c0 += 128) {
-      const int i0 = c0 + 4 * lane;
-      float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (i0 < nceil) q = ldq(w, i0);
-      float nx = __shfl_down_sync(FULL, q.x, 1);
-      if (lane == 31) nx = (c0 + 128 < n) ? at(w, c0 + 128) : 0.f;
-      const float a[5] = {q.x, q.y, q.z, q.w, nx};
-      unsigned m = 0;
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-        const int i = i0 + k;
-        const bool hit = i >= s && i < n - 1 && ((a[k] <= thr && thr < a[k + 1]) || (a[k] >= thr && thr > a[k + 1]));
-        m |= hit ? (1u << k) : 0u;
+
+// exact check of the pairs whose upper (backward) / lower (forward) sample lies in chunk c
+__device__ __forceinline__ int check_chunk(const float* w, int n, float thr, int c, int s, bool forward, int stop_back,
+                                           int lane) {
+  const int i = 16 * c + (lane & 15);
+  bool hit = false;
+  if (lane < 16) {
+    if (forward) {
+      if (i >= s && i < n - 1) {
+        const float a = at(w, i), b = at(w, i + 1);
+        hit = (a <= thr && thr < b) || (a >= thr && thr > b);
       }
-      const unsigned bal = __ballot_sync(FULL, m != 0);
-      if (bal) {
-        const int L = __ffs(bal) - 1;
-        return c0 + 4 * L + (__ffs(__shfl_sync(FULL, m, L)) - 1);
-      }
-    }
-    return -1;
-  }
-#pragma unroll 1
-  for (int c0 = s & ~127; c0 >= 0 && c0 + 127 >= stop_back; c0 -= 128) {
-    const int i0 = c0 + 4 * lane;
-    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (i0 < nceil) q = ldq(w, i0);
-    float pv = __shfl_up_sync(FULL, q.w, 1);
-    if (lane == 0) pv = (c0 >= 1) ? at(w, c0 - 1) : 0.f;
-    const float a[5] = {pv, q.x, q.y, q.z, q.w};
-    unsigned m = 0;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-      const int i = i0 + k;
-      const bool hit = i <= s && i >= stop_back && i < n &&
-                       ((a[k] < thr && thr <= a[k + 1]) || (a[k] > thr && thr >= a[k + 1]));
-      m |= hit ? (1u << k) : 0u;
-    }
-    const unsigned bal = __ballot_sync(FULL, m != 0);
-    if (bal) {
-      const int L = 31 - __clz(bal);
-      return c0 + 4 * L + (31 - __clz(__shfl_sync(FULL, m, L)));
+    } else if (i <= s && i >= stop_back && i < n) {
+      const float a = at(w, i - 1), b = at(w, i);
+      hit = (a < thr && thr <= b) || (a > thr && thr >= b);
     }
   }
-  return -1;
+  const unsigned m = __ballot_sync(FULL, hit);
+  if (!m) return -1;
+  return 16 * c + (forward ? __ffs(m) - 1 : 31 - __clz(m));
 }
-__device__ __forceinline__ int search_cross_w(const float* w, int n, float thr, int s, bool forward, int stop_back,
-                                              int lane) {
+
+__device__ __noinline__ int search_cross_far(const float* w, const WaveSummary* sm, int n, float thr, int s,
+                                             bool forward, int stop_back, int lane);
+
+// The common case -- the crossing lies within 32 samples of the start -- is one plain window
+// (the scalar warp runs alone: every instruction here is ~5 cycles of critical path); longer
+// walks go through the summary.
+__device__ __forceinline__ int search_cross_w(const float* w, const WaveSummary* sm, int n, float thr, int s,
+                                              bool forward, int stop_back, int lane) {
+  constexpr int NEAR = 3;  // plain 32-sample windows before the summary is consulted
   if (forward) {
     int base = s;
 #pragma unroll 1
-    for (int k = 0; k < 2 && base < n - 1; k++, base += 32) {
+    for (int k = 0; k < NEAR && base < n - 1; k++, base += 32) {
       const int i = base + lane;
       bool hit = false;
       if (i < n - 1) {
@@ -571,11 +570,11 @@ __device__ __forceinline__ int search_cross_w(const float* w, int n, float thr, 
       const unsigned m = __ballot_sync(FULL, hit);
       if (m) return base + __ffs(m) - 1;
     }
-    return base < n - 1 ? search_cross_long(w, n, thr, base, true, stop_back, lane) : -1;
+    return base < n - 1 ? search_cross_far(w, sm, n, thr, base, true, stop_back, lane) : -1;
   }
   int base = s;
 #pragma unroll 1
-  for (int k = 0; k < 2 && base >= stop_back; k++, base -= 32) {
+  for (int k = 0; k < NEAR && base >= stop_back; k++, base -= 32) {
     const int i = base - lane;
     bool hit = false;
     if (i >= stop_back) {
@@ -585,7 +584,45 @@ __device__ __forceinline__ int search_cross_w(const float* w, int n, float thr, 
     const unsigned m = __ballot_sync(FULL, hit);
     if (m) return base - (__ffs(m) - 1);
   }
-  return base >= stop_back ? search_cross_long(w, n, thr, base, false, stop_back, lane) : -1;
+  return base >= stop_back ? search_cross_far(w, sm, n, thr, base, false, stop_back, lane) : -1;
+}
+
+__device__ __noinline__ int search_cross_far(const float* w, const WaveSummary* sm, int n, float thr, int s,
+                                             bool forward, int stop_back, int lane) {
+  const int nch = (n + 15) >> 4;
+  const int cs = s >> 4;  // chunk of the start sample
+  // level 2: stretch g is a candidate if thr lies within [min, max] of stretches g-1 .. g+1 clipped
+  // (the neighbours cover pairs across stretch borders)
+  unsigned cand2;
+  {
+    const int g = lane & 15;
+    const float lo = fminf(sm->mn2[g], fminf(sm->mn2[max(g - 1, 0)], sm->mn2[min(g + 1, 15)]));
+    const float hi = fmaxf(sm->mx2[g], fmaxf(sm->mx2[max(g - 1, 0)], sm->mx2[min(g + 1, 15)]));
+    cand2 = __ballot_sync(FULL, lane < 16 && lo <= thr && thr <= hi);
+  }
+  const int gs = cs >> 5;
+  // stretches on the far side of the start are irrelevant
+  cand2 &= forward ? (0xffffffffu << gs) : (0xffffffffu >> (31 - gs));
+  while (cand2) {
+    const int g = forward ? __ffs(cand2) - 1 : 31 - __clz(cand2);
+    cand2 &= ~(1u << g);
+    // level 1: the 32 chunks of stretch g
+    const int c = 32 * g + lane;
+    bool cnd = false;
+    if (c < nch && (forward ? c >= cs : c <= cs)) {
+      const int cn = forward ? min(c + 1, nch - 1) : max(c - 1, 0);
+      const float lo = fminf(sm->mn1[c], sm->mn1[cn]), hi = fmaxf(sm->mx1[c], sm->mx1[cn]);
+      cnd = lo <= thr && thr <= hi;
+    }
+    unsigned cand1 = __ballot_sync(FULL, cnd);
+    while (cand1) {
+      const int l = forward ? __ffs(cand1) - 1 : 31 - __clz(cand1);
+      cand1 &= ~(1u << l);
+      const int r = check_chunk(w, n, thr, 32 * g + l, s, forward, stop_back, lane);
+      if (r >= 0) return r;
+    }
+  }
+  return -1;
 }
 
 // sum of w[a .. b) clipped to the wave, by one warp (lazy evaluation of a windowed filter at a
@@ -602,14 +639,14 @@ __device__ __noinline__ float wrange_sum(const float* w, int n, int a, int b, in
 __device__ __forceinline__ float at0(const float* w, int n, int i) { return (i >= 0 && i < n) ? at(w, i) : 0.f; }
 
 // time_point_thresh.py:12-92 evaluated by one warp
-__device__ __forceinline__ float tpt_w(const float* w, int n, float thr, float t_start, float walk, int& fatal,
-                                       int lane) {
+__device__ __forceinline__ float tpt_w(const float* w, const WaveSummary* sm, int n, float thr, float t_start,
+                                       float walk, int& fatal, int lane) {
   fatal = 0;
   if (thr != thr || t_start != t_start || walk != walk) return CUDART_NAN_F;
   if (floorf(t_start) != t_start) { fatal = DSPB_FATAL_TSTART_NONINT; return CUDART_NAN_F; }
   if (floorf(walk) != walk) { fatal = DSPB_FATAL_WALK_NONINT; return CUDART_NAN_F; }
   if (!(t_start >= 0.f && t_start < (float)n)) { fatal = DSPB_FATAL_TSTART_RANGE; return CUDART_NAN_F; }
-  const int hit = search_cross_w(w, n, thr, (int)t_start, walk == 1.0f, 1, lane);
+  const int hit = search_cross_w(w, sm, n, thr, (int)t_start, walk == 1.0f, 1, lane);
   return hit < 0 ? CUDART_NAN_F : (float)hit;
 }
 
