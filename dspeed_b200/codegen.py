@@ -1732,3 +1732,24 @@ def load_chain_lib(path: str) -> C.CDLL:
     if path not in _loaded:
         _loaded[path] = C.CDLL(path)
     return _loaded[path]
+
+
+def prebuild(config, wf_len=8192, with_baseline=True, dt_ns=16):
+    """Plan `config` on the meta device (no GPU needed) and compile its specialised kernel into the
+    in-tree cache, so that a GPU process that builds the same chain finds it ready
+    (``__graft_entry__.build`` does this for the shipped configurations)."""
+    from . import tables
+    from .processing_chain import build_processing_chain
+
+    n = 4
+    wf = tables.WaveformTable(size=n, t0=0, t0_units="ns", dt=dt_ns, dt_units="ns",
+                              values=np.zeros((n, wf_len), np.uint16))
+    cols = {"waveform": wf}
+    if with_baseline:
+        cols["baseline"] = tables.Array(np.zeros(n, np.uint16))
+    chain, _, _ = build_processing_chain(config, tables.Table(cols, size=n), block_width=16, device="meta")
+    try:
+        sc = SpecChain(chain)
+    except NotFusable as e:
+        return None, str(e)
+    return sc.lib_path, sc.program_text

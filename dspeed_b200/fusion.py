@@ -809,6 +809,28 @@ class FusedChain:
             if key[0] != "in":
                 t = key[1]
                 static[idx] = (t.data_ptr(), t.stride(0) if t.ndim >= 1 else 0)
+        # Output columns that already live on this device are written by the kernel in place (row
+        # `begin` of the column is row 0 of the launch); only host columns go through the block
+        # buffer and a D2H copy.
+        direct, copied = {}, []
+        for man in chain._output_managers.values():
+            try:
+                rv = self._out_raw(man)
+            except NotFusable:
+                copied.append(man)
+                continue
+            idx = self.ptr_index.get(("buf", _storage(rv), rv.storage_offset()))
+            col = None
+            if isinstance(man, pc.ArrayIOManager):
+                col = man.io_array.nda
+            elif isinstance(man, pc.NumpyIOManager):
+                col = man.io_buf
+            if (idx is not None and isinstance(col, torch.Tensor) and col.is_cuda and col.device == rv.device
+                    and col.dtype == rv.dtype and col.shape[0] >= stop and tuple(col.shape[1:]) == tuple(rv.shape[1:])
+                    and (col.ndim == 1 or col.stride(-1) == 1) and not getattr(man.var, "is_const", False)):
+                direct[idx] = col
+            else:
+                copied.append(man)
         with torch.cuda.device(chain.device):
             compute = torch.cuda.current_stream(chain.device)
             if getattr(self, "_copy_stream", None) is None:
@@ -833,6 +855,9 @@ class FusedChain:
                 compute.wait_event(self._ev_copied[k % 2])
                 table = dict(static)
                 table.update(staged.pop(k))
+                for idx, col in direct.items():
+                    view = col[begin:end]
+                    table[idx] = (view.data_ptr(), view.stride(0))
                 n = len(self.ptrs)
                 ptrs = [table[i][0] for i in range(n)]
                 strides = [table[i][1] for i in range(n)]
@@ -850,10 +875,12 @@ class FusedChain:
                 self.rows_per_launch = max(self.rows_per_launch, end - begin)
                 chain.stats["launches"] += 1
                 chain.stats["blocks"] += 1
-                for out_man in chain._output_managers.values():
+                for out_man in copied:
                     out_man.write(begin, end)
-                chain._raise_recorded_fatal(begin, end)
             compute.synchronize()
+            # data-dependent DSPFatal conditions are recorded on the device with their row: one
+            # check per call (the reference raises after the offending block, :1156-1159)
+            chain._raise_recorded_fatal(start, stop, block_width=bw)
         if self._events:
             for e0, e1 in self._events:
                 self.device_time += e0.elapsed_time(e1) * 1e-3

@@ -472,16 +472,20 @@ class ProcessingChain:
             self._fatal_owner.append(owner)
         return self.fatal[k]
 
-    def _raise_recorded_fatal(self, begin, end) -> None:
+    def _raise_recorded_fatal(self, begin, end, block_width=None) -> None:
         n = max(1, len(self._fatal_owner))
-        rec = self.fatal[:n].cpu()  # one small synchronising read per block
+        rec = self.fatal[:n].cpu()  # one small synchronising read
         hit = torch.nonzero(rec[:, 0])
         if hit.numel():
             k = int(hit[0])
             code = int(rec[k, 0])
+            row = (int(rec[k, 2]) << 31) | int(rec[k, 1])
             self.fatal.zero_()
             e = DSPFatal(fatal_message(code))
             e.code = code
+            if block_width:   # whole-call check: report the block that holds the recorded row
+                b0 = begin + (max(row - begin, 0) // block_width) * block_width
+                begin, end = b0, min(b0 + block_width, end)
             e.wf_range = (begin, end)
             if k < len(self._fatal_owner):
                 e.processor = str(self._fatal_owner[k])
