@@ -264,6 +264,22 @@ def run_b200(args, rank, world, local_rank):
             print(f"  {t / steps * 1e3:9.3f} ms/step {100 * t / tot_t:5.1f}%  {name}", file=sys.stderr)
     value = world * n * steps / t_dev
 
+    # ---- the one collective of the path: gather of the output tables (outside the hot path) -------
+    gather_ms = None
+    if world > 1:
+        from dspeed_b200 import parallel
+
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        g0.record()
+        full = parallel.gather_table(tb_out_dev, world * n, dst=0)
+        g1.record()
+        barrier()
+        gather_ms = max_over_ranks(g0.elapsed_time(g1))
+        if rank == 0:
+            assert len(full) == world * n
+        del full
+
     # ---- dominant kernel and its roofline ------------------------------------------------
     peak, peak_src = hbm_peak()
     fused = chain._fused is not None and chain._fused.can_run(chain)
@@ -342,6 +358,7 @@ def run_b200(args, rank, world, local_rank):
             "sharding": f"events x{world} (no collective on the hot path)",
             "l2_policy": "inputs (16 GB per step) are far larger than the 126 MB L2",
             "fused_kernel": bool(fused),
+            "output_gather_ms": gather_ms,
         },
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
         "output_checksum_trapEmax": checksum,
@@ -350,11 +367,14 @@ def run_b200(args, rank, world, local_rank):
 
 
 def _traffic_from_profile(kernel_name: str):
-    """per-launch DRAM bytes of the dominant kernel from the committed ncu capture, if any"""
+    """per-launch DRAM bytes (read + write) of the dominant kernel from the committed `ncu --set full`
+    capture (profiles/dominant_kernel_traffic.json), scaled to the rows of one bench launch"""
     p = os.path.join(REPO, "profiles", "dominant_kernel_traffic.json")
     try:
         d = json.load(open(p))
-        return d.get("dram_bytes_per_launch")
+        if d.get("kernel", "") not in kernel_name:
+            return None
+        return d["dram_bytes_per_row"] * 16384
     except Exception:
         return None
 
