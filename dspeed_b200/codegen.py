@@ -612,7 +612,6 @@ class SpecChain(FusedChain):
         self.post_dirty = []
         self.nd_used = 0
         self.ni_used = 0
-        self.free_cols = []
         self.n_slots = 0
         self.tmp = 0
         self.live_regs = []
@@ -622,7 +621,7 @@ class SpecChain(FusedChain):
         self.s_dirty = False        # the block stream produced something the scalar warp will read
         self.b2s_count = 0          # B -> S events since the last point where S provably caught up
         self.s2b = {}               # scalar -> (event id, bc index) published by the scalar warp
-        self.s2b_ids = list(range(9, 15))
+        self.s2b_ids = [12, 0]      # barrier ids for scalars published by the scalar warp
         self.s_seq = 0              # number of scalar-stream nodes emitted
         self.s_done = 0             # ... of which the block stream knows they are finished
         self.flag_s = {}            # block-stream NaN flag -> its copy in the scalar stream
@@ -630,6 +629,8 @@ class SpecChain(FusedChain):
         self.nchunks = (slot_len + CHK - 1) // CHK
         self.psp = 4 * self.nchunks + 8
         self.slot_words = 4 * self.psp
+        # waves the scalar warp reads (threshold searches, pick-offs)
+        self.s_read = {nd["ins"][0][0].id for nd in self.nodes if nd["kind"] in ("tpt", "ftp")}
         # waves searched by the scalar warp carry a min/max summary (built when they are stored)
         self.summ = {}
         for nd in self.nodes:
@@ -637,6 +638,14 @@ class SpecChain(FusedChain):
                 w = nd["ins"][0][0]
                 if w.id not in self.summ:
                     self.summ[w.id] = len(self.summ)
+        # fixed pool of physical slots: everything the 227 KB allow
+        self.MB_BUDGET = 4096       # mailbox bytes per row parity
+        fixed_est = 2048 + 8192 + 2048 + 2 * self.MB_BUDGET + len(self.summ) * 4224
+        total_slots = (MAX_SMEM - fixed_est) // (self.slot_words * 4)
+        if total_slots < 2:
+            raise NotSpecializable("waveforms too long for the shared-memory resident layout")
+        self.free_cols = [(k, 0, self.nchunks) for k in range(total_slots)]
+        self.total_slots = total_slots
         # scalars the block stream needs from the scalar warp
         self.b_needed = set()
         for nd in self.nodes:
@@ -659,13 +668,81 @@ class SpecChain(FusedChain):
         self.LB.append("PROF_MARK(%d);" % len(self.order))
         self.LS.append("PROF_MARK_S(%d);" % len(self.order))
         self.mb_bytes = (self.n_mbd * 16 * 8 + self.n_mbi * 16 * 4 + 15) & ~15
-        self.mb_bytes += len(self.summ) * 4224   # sizeof(WaveSummary)
-        self.fixed_bytes = 2048 + 8192 + 2048 + self.mb_bytes   # Scratch + CScr/bc + prof stamps + mailbox
+        if self.mb_bytes > self.MB_BUDGET:
+            raise NotSpecializable("too many reductions for the mailbox")
+        # Scratch + CScr/bc + prof stamps + mailbox (two row parities) + summaries
+        self.fixed_bytes = 2048 + 8192 + 2048 + 2 * self.MB_BUDGET + len(self.summ) * 4224
+        self.n_slots = self.total_slots
         self.smem_bytes = self.fixed_bytes + self.n_slots * self.slot_words * 4
+        self._pipeline_rows()
         if self.smem_bytes > MAX_SMEM:
             raise NotSpecializable("not enough shared memory for the live waveforms")
         self.program_text = "\n".join(f"{k:3d} {self._describe_node(nd)}" for k, nd in enumerate(self.order))
         self.code = self.order  # (for len(code) users)
+
+    def _pipeline_rows(self):
+        """Software pipelining across rows.  The block stream starts row r+1 while the scalar warp is
+        still finishing row r; mailbox / broadcast cells and the B -> S event barriers alternate with
+        the row parity, and two waits protect the shared-memory slots: before its first write to
+        the slot of the wave the scalar warp reads last, the block stream waits for "scalar warp done
+        with the previous row" (barrier 15); for the writes before that point (the head: raw-data
+        front end, scratch tables) it waits at the row start for a progress event (barrier 13) that
+        the scalar warp posts right after its last read of any slot the head overwrites."""
+        def overlap(a, b):
+            return a[0] == b[0] and a[1] < b[2] and b[1] < a[2]
+
+        reads = []          # (seq, region) of scalar-warp slot reads, in program order
+        for ln in self.LS:
+            if ln.startswith("//@R "):
+                sl, c0, c1, seq = (int(x) for x in ln.split()[1:5])
+                reads.append((seq, (sl, c0, c1)))
+        writes = []         # (LB index, region)
+        for k, ln in enumerate(self.LB):
+            if ln.startswith("//@W "):
+                sl, c0, c1 = (int(x) for x in ln.split()[1:4])
+                writes.append((k, (sl, c0, c1)))
+        # group the block stream's writes by node; need[k] = latest scalar-warp read (of the previous
+        # row) that node k's writes collide with
+        node_of, cur = {}, -1
+        starts = {}
+        for k, ln in enumerate(self.LB):
+            if ln.startswith("// ---- ["):
+                cur += 1
+                starts[cur] = k
+            node_of[k] = cur
+        need = {}
+        for k, reg in writes:
+            q = max([seq for seq, r in reads if overlap(reg, r)] + [0])
+            need[node_of[k]] = max(need.get(node_of[k], 0), q)
+        self.late_idx, self.progress_idx, self.progress_seq = None, None, 0
+        hot = sorted(nk for nk, q in need.items() if q > 0)
+        if hot:
+            first = hot[0]
+            self.progress_seq = need[first]          # early group: covered by the progress event
+            self.progress_idx = starts[first]
+            later = [nk for nk in hot if need[nk] > self.progress_seq]
+            if later:
+                self.late_idx = starts[later[0]]     # everything beyond waits for "scalar warp done"
+            last_seq = max(seq for seq, _ in reads)
+            if self.progress_seq >= last_seq:
+                # the first collision is already with the scalar warp's last read
+                self.late_idx, self.progress_idx, self.progress_seq = starts[first], None, 0
+        # scalar stream: progress event after node `progress_seq`, done event at the end
+        LS = list(self.LS)
+        if self.progress_seq:
+            k = next(i for i, ln in enumerate(LS) if ln.startswith("//@R ") and int(ln.split()[4]) == self.progress_seq)
+            nxt = next((i for i in range(k + 1, len(LS)) if LS[i].startswith("// ---- [")), len(LS))
+            LS.insert(nxt, "EV_ARRIVE(13);")
+        LS.append("EV_ARRIVE(15);")
+        self.LS = LS
+        LB = list(self.LB)
+        if self.late_idx is not None:
+            LB.insert(self.late_idx, "if (it > 0) EV_WAIT(15);   // the scalar warp is done with the previous row")
+        else:
+            LB.append("if (it > 0) EV_WAIT(15);")
+        if self.progress_seq:   # (inserted second: progress_idx < late_idx)
+            LB.insert(self.progress_idx, "if (it > 0) EV_WAIT(13);   // the scalar warp is past its reads of these slots")
+        self.LB = LB
 
     def _describe_node(self, nd):
         if nd["kind"] == "conv_seg_group":
@@ -725,17 +802,17 @@ class SpecChain(FusedChain):
         if not self.s_dirty:
             return
         self.s_dirty = False
-        if self.b2s_count >= 7:
-            # the 7 event barriers are all in flight: let the block stream wait for the scalar warp once
-            self._e("EV_WAIT(15);")
-            self._es("EV_WAIT(15);")
+        if self.b2s_count >= 5:
+            # the 5 event barriers of this row parity are in flight: let the two streams meet once
+            self._e("EV_WAIT(14);")
+            self._es("EV_WAIT(14);")
             self.b2s_count = 0
             self.s_done = self.s_seq
             return
-        eid = 2 + self.b2s_count
+        eid = self.b2s_count
         self.b2s_count += 1
-        self._e(f"EV_ARRIVE({eid});")
-        self._es(f"EV_WAIT({eid});")
+        self._e(f"EV_ARRIVE(EVB({eid}));")
+        self._es(f"EV_WAIT(EVB({eid}));")
 
     def _is_s(self, e):
         return e is not None and self.sdom.get(str(e)) == "s"
@@ -789,6 +866,11 @@ class SpecChain(FusedChain):
         self._sync_s()
         self.s_seq += 1
         w.s_last = self.s_seq
+        self._es(f"//@R {w.slot[0]} {w.slot[1]} {w.slot[1] + w.slot[2]} {self.s_seq}")
+
+    @staticmethod
+    def _wmark(sl):
+        return f"//@W {sl[0]} {sl[1]} {sl[1] + sl[2]}"
 
     def _stores(self, name):
         """statements (scalar warp) that write a just-defined scalar to its output columns: results
@@ -827,20 +909,22 @@ class SpecChain(FusedChain):
     # -- slots and register chunks ---------------------------------------------------------
     # A physical slot has `nchunks` chunk columns; a wave of n samples needs ceil(n / 16) of them,
     # so several short waves (windowed leading edge, cusp / zac outputs ...) share one slot.
-    def _slot_alloc(self, ncols=None):
+    def _slot_alloc(self, ncols=None, top=False):
+        """columns of a physical slot.  Waves the scalar warp reads (`top`) are taken from the
+        highest slots, everything else from the lowest: the head of the next row (its raw-data
+        front end and scratch tables) then never touches what the scalar warp is still reading"""
         ncols = self.nchunks if ncols is None else min(self.nchunks, ncols)
-        best = None
-        for k, (slot, c0, c1) in enumerate(self.free_cols):
-            if c1 - c0 >= ncols and (best is None or (c1 - c0) < (self.free_cols[best][2] - self.free_cols[best][1])):
-                best = k
-        if best is None:
-            slot = self.n_slots
-            self.n_slots += 1
-            self.free_cols.append((slot, 0, self.nchunks))
-            best = len(self.free_cols) - 1
-        slot, c0, c1 = self.free_cols.pop(best)
+        fits = [iv for iv in self.free_cols if iv[2] - iv[1] >= ncols]
+        if not fits:
+            raise NotSpecializable("not enough shared memory for the live waveforms")
+        if top:
+            slot, c0, c1 = max(fits, key=lambda iv: (iv[0], -(iv[2] - iv[1])))
+        else:
+            slot, c0, c1 = min(fits, key=lambda iv: (iv[2] - iv[1] if ncols < self.nchunks else 0, iv[0]))
+        self.free_cols.remove((slot, c0, c1))
         if c1 - c0 > ncols:
             self.free_cols.append((slot, c0 + ncols, c1))
+        self.n_slots = max(self.n_slots, slot + 1)
         return (slot, c0, ncols)
 
     def _slot_alloc_adjacent(self, k):
@@ -852,17 +936,12 @@ class SpecChain(FusedChain):
                 start = a
                 break
         if start is None:
-            # extend at the end (re-using a free last slot when there is one)
-            start = self.n_slots
-            while start - 1 in full and self.n_slots - start < k:
-                start -= 1
-            for sid in range(self.n_slots, start + k):
-                self.free_cols.append((sid, 0, self.nchunks))
-            self.n_slots = max(self.n_slots, start + k)
+            raise NotSpecializable("not enough shared memory for the scratch table")
         res = []
         for d in range(k):
             self.free_cols.remove((start + d, 0, self.nchunks))
             res.append((start + d, 0, self.nchunks))
+        self.n_slots = max(self.n_slots, start + k)
         return res
 
     def _slot_free(self, sl):
@@ -899,7 +978,7 @@ class SpecChain(FusedChain):
 
     def _give_slot(self, w: Wave, post=False):
         if w.slot is None:
-            w.slot = self._slot_alloc((w.n + CHK - 1) // CHK)
+            w.slot = self._slot_alloc((w.n + CHK - 1) // CHK, top=w.id in self.s_read)
             # a pre-barrier store must not overtake other threads still reading the old tenant
             if not post and w.slot[0] in self.xread:
                 self._barrier()
@@ -933,7 +1012,7 @@ class SpecChain(FusedChain):
         """own chunk -> slot (when other threads / later phases need the wave)"""
         if w.needs_slot:
             self._give_slot(w)
-            self._e(f"st_chunk_n({self._slot(w)}, tid, {w.n}, {r});")
+            self._e(self._wmark(w.slot), f"st_chunk_n({self._slot(w)}, tid, {w.n}, {r});")
             if w.id in self.summ:
                 self._e(f"put_summary(SUMM({self.summ[w.id]}), {r}, {w.n}, tid, lane, warp);")
             self.dirty.add(w.slot[0])
@@ -944,6 +1023,7 @@ class SpecChain(FusedChain):
         """like _store, but the chunk is produced by post-barrier code of the open round"""
         if w.needs_slot:
             self._give_slot(w, post=True)
+            self.posts.append(self._wmark(w.slot))
             self.posts.append(f"st_chunk_n({self._slot(w)}, tid, {w.n}, {r});")
             if w.id in self.summ:
                 self.posts.append(f"put_summary(SUMM({self.summ[w.id]}), {r}, {w.n}, tid, lane, warp);")
@@ -993,6 +1073,16 @@ class SpecChain(FusedChain):
         w, off, n = nd["ins"][0]
         outs = [o if (o and o in self.used_scalars) else None for o in nd["outs"]]
         if not any(outs):
+            return
+        if nd.get("from_conv"):
+            # the convolution already deposited the per-warp maxima in the mailbox
+            g = self._nan_guard([self._flag_s(w.nan)])
+            self.s_dirty = True
+            self._sync_s()
+            self.s_seq += 1
+            self._es(self._asg(outs[3], f"{'(' + g + ') ? CUDART_NAN_F : ' if g else ''}get_fmax(MBI({nd['from_conv'][1]}), lane)"),
+                     *self._stores(outs[3]))
+            self._def_s(outs[3])
             return
         self._need(w.nan)
         r = self._chunk(w)
@@ -1263,6 +1353,16 @@ class SpecChain(FusedChain):
     def _e_ftp(self, nd):
         if nd.get("lazy") is not None:
             return self._e_ftp_lazy(nd)
+        if nd.get("from_conv"):
+            w = nd["ins"][0][0]
+            g = self._nan_guard([self._flag_s(w.nan)])
+            self.s_dirty = True
+            self._sync_s()
+            self.s_seq += 1
+            self._es(self._asg(nd["out"], f"{'(' + g + ') ? CUDART_NAN_F : ' if g else ''}(float)MBD({nd['from_conv'][1]})[0]"),
+                     *self._stores(nd["out"]))
+            self._def_s(nd["out"])
+            return
         w, off, n = nd["ins"][0]
         self._s_wave(w)
         f = self._t("f")
@@ -1290,7 +1390,7 @@ class SpecChain(FusedChain):
         si = self._alloc_i(1)
         g = self._nan_guard([w.nan, f"({tf} != {tf})"])
         so = self._slot(out)
-        self._e(f"int {pad} = 0;",
+        self._e(self._wmark(out.slot), f"int {pad} = 0;",
                 f"const float {tf} = (float)({nd['t0']});",
                 f"int {beg} = ({tf} == {tf}) ? (int)fminf(fmaxf({tf}, -1.0e9f), 1.0e9f) : 0; if ({beg} > {n}) {beg} = {n};",
                 f"for (int k = tid; k < {mc}; k += 512) {{ const int q = {beg} + k; float v = 0.f; "
@@ -1434,6 +1534,28 @@ class SpecChain(FusedChain):
         out.reg = None
         self.dirty.discard(out.slot[0])
 
+    def _conv_sink_plan(self, m, p):
+        """(amax nodes, pick-off nodes) when the convolution output needs no slot, else None"""
+        out = m["wouts"][0]
+        amax, picks = [], []
+        for u in out.uses:
+            un = self.nodes[u]
+            if un["kind"] == "min_max":
+                used = [o if (o and o in self.used_scalars) else None for o in un["outs"]]
+                if any(used[:3]) or un["ins"][0][1] != 0 or un["ins"][0][2] != out.n:
+                    return None
+                amax.append(un)
+            elif un["kind"] == "ftp" and un["t"].startswith(("0x", "-0x")) and un.get("lazy") is None:
+                t = float.fromhex(un["t"])
+                if t != int(t) or not (0 <= t < p) or picks:
+                    return None
+                picks.append(un)
+            else:
+                return None
+        if p > NT:
+            return None
+        return amax, picks
+
     def _e_conv_seg_group(self, nd):
         members = nd["members"]
         w, off, n = nd["ins"][0]
@@ -1451,24 +1573,42 @@ class SpecChain(FusedChain):
         need = nq * (4 * CHK * cw + NT + 32) * 8
         nsl = -(-need // (self.slot_words * 4))
         scratch = self._slot_alloc_adjacent(nsl)
-        outs = []
+        outs, sinks = [], []
         for m in members:
             out = m["wouts"][0]
-            self._give_slot(out, post=True)
-            outs.append(out)
+            plan = self._conv_sink_plan(m, p)
+            if plan is None:
+                self._give_slot(out, post=True)
+                outs.append(out)
+                sinks.append(f"SegSink{{{self._slot(out)}, nullptr, nullptr, 0}}")
+                continue
+            amax, picks = plan
+            mb = self._mbi(1) if amax else None
+            pk = self._mbd(1) if picks else None
+            sinks.append(f"SegSink{{nullptr, {'MBI(%d)' % mb if amax else 'nullptr'}, "
+                         f"{'MBD(%d)' % pk if picks else 'nullptr'}, {int(float.fromhex(picks[0]['t'])) if picks else 0}}}")
+            for un in amax:
+                un["from_conv"] = ("max", mb)
+            for un in picks:
+                un["from_conv"] = ("pick", pk)
+            out.needs_slot = False
+            out.virtual = True
+        if not two:
+            sinks.append(sinks[0])
         busy = self.xread | self.dirty
         if any(sl[0] in busy for sl in scratch) or any(o.slot[0] in busy for o in outs):
             self._barrier()
         so = [f"SegOut{{{_lit(m['seg'][6])}, {_lit(m['seg'][7])}, {_lit(m['seg'][8])}}}" for m in members]
         if not two:
             so.append(so[0])
+        self._e(*[self._wmark(sl) for sl in scratch], *[self._wmark(o.slot) for o in outs])
         pw = self._t("pw")
         self.static_arrays = getattr(self, "static_arrays", [])
         vals = [math.exp(o / sigma) for o in range(p)] + [math.exp(-o / sigma) for o in range(p)]
         self.static_arrays.append(f"__device__ const double {pw}[{2 * p}] = {{{', '.join(_lit(v) for v in vals)}}};")
         self._e(f"conv_seg_chunked<{'true' if poly else 'false'}, {'true' if two else 'false'}>({self._slot(w)}, {x}, {n}, "
                 f"{_lit(sigma)}, {int(lt)}, {int(fl)}, {int(L)}, {_lit(c)}, {_lit(inv2S)}, {_lit(math.exp(-1.0 / sigma))}, "
-                f"{_lit(math.exp(1.0 / sigma))}, {_lit(math.exp((L - 1) / sigma))}, {pw}, {so[0]}, {so[1]}, {self._slot(outs[0])}, {self._slot(outs[1 if two else 0])}, "
+                f"{_lit(math.exp(1.0 / sigma))}, {_lit(math.exp((L - 1) / sigma))}, {pw}, {so[0]}, {so[1]}, {sinks[0]}, {sinks[1]}, "
                 f"reinterpret_cast<double*>(SLOT({scratch[0][0]})), tid, lane, warp);")
         # the band table overwrote the (always-zero) pad columns of its slots
         self._e(f"zero_pads(slots, {self.slot_words}, {self.nchunks}, {scratch[0][0]}, {scratch[-1][0] + 1}, tid);")
@@ -1476,9 +1616,9 @@ class SpecChain(FusedChain):
             self.dirty.add(sl[0])
             self._slot_free(sl)
         self.s_dirty = True
-        for out in outs:
-            out.nan = w.nan
-            out.reg = None
+        for m in members:
+            m["wouts"][0].nan = w.nan
+            m["wouts"][0].reg = None
 
     def _sc_emit(self, nd, expr, *operands):
         """scalar glue runs in the scalar stream; when none of its operands lives there (inputs,
@@ -1546,7 +1686,7 @@ class SpecChain(FusedChain):
         align_check = "".join(f"  if (((uintptr_t)ptrs[{i}] & 15) || (strides[{i}] & 7)) return DSPB_ERR_UNSUPPORTED;\n" for i in aligned)
         mbd_off = 2048 + 8192 + 2048
         mbi_off = mbd_off + self.n_mbd * 16 * 8
-        summ_off = (mbi_off + self.n_mbi * 16 * 4 + 15) & ~15
+        summ_off = mbd_off + 2 * self.MB_BUDGET
         return f"""// generated by dspeed_b200/codegen.py -- do not edit
 #define DSPB_PSP {self.psp}
 // the 16 block warps synchronise on named barrier 1; the scalar warp (warp 16) never joins it
@@ -1584,14 +1724,10 @@ struct Args {{
 __global__ void __launch_bounds__(544, 1) k_chain_spec(const __grid_constant__ Args A) {{
   extern __shared__ __align__(16) unsigned char smem_raw[];
   CScr* cs = reinterpret_cast<CScr*>(smem_raw + 2048);
-  double* bc = reinterpret_cast<double*>(smem_raw + 2048 + 5120);   // scalar warp -> block warps
   long long* prof_ts = reinterpret_cast<long long*>(smem_raw + 2048 + 8192);
-  double* mbd = reinterpret_cast<double*>(smem_raw + {mbd_off});      // block warps -> scalar warp (partials)
-  int* mbi = reinterpret_cast<int*>(smem_raw + {mbi_off});
   WaveSummary* summ = reinterpret_cast<WaveSummary*>(smem_raw + {summ_off});
-  (void)summ;
   float* slots = reinterpret_cast<float*>(smem_raw + {self.fixed_bytes});
-  (void)prof_ts; (void)cs; (void)bc; (void)mbd; (void)mbi;
+  (void)prof_ts; (void)cs; (void)summ;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool scalar_warp = warp == 16;
   int par = 0;
@@ -1599,10 +1735,19 @@ __global__ void __launch_bounds__(544, 1) k_chain_spec(const __grid_constant__ A
     zero_pads(slots, {self.slot_words}, {self.nchunks}, 0, {self.n_slots}, tid);
     BSYNC();
   }}
-  for (long long row = blockIdx.x; row < A.n_rows; row += gridDim.x) {{
+  int it = 0;
+  for (long long row = blockIdx.x; row < A.n_rows; row += gridDim.x, it++) {{
 #ifdef DSPB_PROFILE
     if (A.prof && (tid == 0 || tid == 512)) prof_ts[tid == 0 ? 0 : 128] = clock64();
 #endif
+    // cells that carry data between the two streams alternate with the row parity, so the block
+    // stream can run one row ahead of the scalar warp
+    const int rp = it & 1;
+    double* bc = reinterpret_cast<double*>(smem_raw + 2048 + 5120) + 16 * rp;        // scalar warp -> block warps
+    double* mbd = reinterpret_cast<double*>(smem_raw + {mbd_off} + {self.MB_BUDGET} * rp);  // block warps -> scalar warp
+    int* mbi = reinterpret_cast<int*>(smem_raw + {mbi_off} + {self.MB_BUDGET} * rp);
+    (void)bc; (void)mbd; (void)mbi;
+#define EVB(k) (2 + 5 * rp + (k))
     {{
       {decl}
       {prolog}
@@ -1614,8 +1759,9 @@ __global__ void __launch_bounds__(544, 1) k_chain_spec(const __grid_constant__ A
         {body_s}
       }}
     }}
-    __syncthreads();   // row end: both streams are done with the slots, the mailbox and bc[]
+#undef EVB
 #ifdef DSPB_PROFILE
+    __syncthreads();   // tracing build: rows do not overlap
     if (A.prof && blockIdx.x == 0) {{
       for (int k = tid; k < N_NODES && k + 1 < 128; k += 544) {{
         A.prof[k] += prof_ts[k + 1] - prof_ts[k];
@@ -1624,6 +1770,11 @@ __global__ void __launch_bounds__(544, 1) k_chain_spec(const __grid_constant__ A
       __syncthreads();
     }}
 #endif
+  }}
+  // consume the scalar warp's last "done" / "progress" events
+  if (!scalar_warp && it > 0) {{
+    EV_WAIT(15);
+    {"EV_WAIT(13);" if self.progress_seq else ""}
   }}
 }}
 }}  // namespace

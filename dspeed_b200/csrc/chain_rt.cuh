@@ -673,12 +673,22 @@ __device__ __forceinline__ float tpt_w(const float* w, const WaveSummary* sm, in
 struct SegOut {
   double kL, beta, h;  // k[L-1], parabola weight (0: cusp), parabola vertex
 };
+// Where an output of the convolution goes.  `slot` != null: the waveform is materialised.  When
+// its only consumers are numpy.amax and pick-offs at fixed integer positions (the ICPC chain's
+// cuspEmax / cuspEftp), the block warps hand the scalar warp the per-warp maxima (`mx`, 16 ints:
+// float keys) and the picked sample (`pick_dst[0]`) through the mailbox and no slot is needed.
+struct SegSink {
+  float* slot;
+  int* mx;
+  double* pick_dst;
+  int pick;
+};
 
 template <bool POLY, bool TWO>
 __device__ __forceinline__ void conv_seg_chunked(const float* X, const float (&x)[CHK], int N, double sigma, int lt,
                                                  int fl, int L, double c, double inv2S, double qm, double qp,
-                                                 double eA, const double* __restrict__ pw, SegOut s0, SegOut s1, float* out0,
-                                                 float* out1, double* tab, int tid, int lane, int warp) {
+                                                 double eA, const double* __restrict__ pw, SegOut s0, SegOut s1,
+                                                 SegSink k0, SegSink k1, double* tab, int tid, int lane, int warp) {
   constexpr int NQ = POLY ? 5 : 3;
   const int p = N - L + 1;
   const int CW = (((p + CHK - 1) >> 4) + 1) | 1, PP = CHK * CW;
@@ -755,6 +765,7 @@ __device__ __forceinline__ void conv_seg_chunked(const float* X, const float (&x
   // ---- pass 3: one thread per output ------------------------------------------------------------
   const int pceil = (p + CHK - 1) & ~(CHK - 1);
   const double eAm = 1.0 / eA;  // eA = e^{(L-1)/s}: e^{+-n/s} = eA^{+-1} * q^{+-o}
+  float mx0 = -CUDART_INF_F, mx1 = -CUDART_INF_F;
   for (int o = tid; o < pceil; o += 512) {
     float y0 = 0.f, y1 = 0.f;
     if (o < p) {
@@ -781,10 +792,16 @@ __device__ __forceinline__ void conv_seg_chunked(const float* X, const float (&x
 #undef TB
       y0 = (float)v0;
       y1 = (float)v1;
+      mx0 = fmaxf(mx0, y0);
+      mx1 = fmaxf(mx1, y1);
+      if (k0.pick_dst && o == k0.pick) k0.pick_dst[0] = (double)y0;
+      if (TWO && k1.pick_dst && o == k1.pick) k1.pick_dst[0] = (double)y1;
     }
-    out0[sidx(o)] = y0;
-    if (TWO) out1[sidx(o)] = y1;
+    if (k0.slot) k0.slot[sidx(o)] = y0;
+    if (TWO && k1.slot) k1.slot[sidx(o)] = y1;
   }
+  if (k0.mx) put_fmax(k0.mx, mx0, lane, warp);
+  if (TWO && k1.mx) put_fmax(k1.mx, mx1, lane, warp);
   BSYNC();
 }
 
