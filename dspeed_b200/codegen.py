@@ -1714,8 +1714,10 @@ struct Args {{
 #define MBI(k) (mbi + 16 * (k))
 #define SUMM(k) (summ + (k))
 #ifdef DSPB_PROFILE   // tracing build (SpecChain.profile): per-node SM-cycle stamps of CTA 0
-#define PROF_MARK(k) if (A.prof && tid == 0 && (k) + 1 < 128) prof_ts[(k) + 1] = clock64();
-#define PROF_MARK_S(k) if (A.prof && lane == 0 && (k) + 1 < 128) prof_ts[128 + (k) + 1] = clock64();
+// per-node SM cycles of both streams of CTA 0, accumulated in shared memory (time between consecutive
+// marks of a stream, waits included), flushed when the CTA exits; rows overlap as in production
+#define PROF_MARK(k) if (A.prof && tid == 0 && (k) < 128) {{ const long long t_ = clock64(); prof_ts[k] += t_ - prof_prev; prof_prev = t_; }}
+#define PROF_MARK_S(k) if (A.prof && lane == 0 && (k) < 128) {{ const long long t_ = clock64(); prof_ts[128 + (k)] += t_ - prof_prev; prof_prev = t_; }}
 #else
 #define PROF_MARK(k)
 #define PROF_MARK_S(k)
@@ -1736,10 +1738,12 @@ __global__ void __launch_bounds__(544, 1) k_chain_spec(const __grid_constant__ A
     BSYNC();
   }}
   int it = 0;
-  for (long long row = blockIdx.x; row < A.n_rows; row += gridDim.x, it++) {{
 #ifdef DSPB_PROFILE
-    if (A.prof && (tid == 0 || tid == 512)) prof_ts[tid == 0 ? 0 : 128] = clock64();
+  for (int k = tid; k < 256; k += 544) prof_ts[k] = 0;
+  __syncthreads();
+  long long prof_prev = clock64();
 #endif
+  for (long long row = blockIdx.x; row < A.n_rows; row += gridDim.x, it++) {{
     // cells that carry data between the two streams alternate with the row parity, so the block
     // stream can run one row ahead of the scalar warp
     const int rp = it & 1;
@@ -1760,22 +1764,20 @@ __global__ void __launch_bounds__(544, 1) k_chain_spec(const __grid_constant__ A
       }}
     }}
 #undef EVB
-#ifdef DSPB_PROFILE
-    __syncthreads();   // tracing build: rows do not overlap
-    if (A.prof && blockIdx.x == 0) {{
-      for (int k = tid; k < N_NODES && k + 1 < 128; k += 544) {{
-        A.prof[k] += prof_ts[k + 1] - prof_ts[k];
-        A.prof[N_NODES + k] += prof_ts[128 + k + 1] - prof_ts[128 + k];
-      }}
-      __syncthreads();
-    }}
-#endif
   }}
   // consume the scalar warp's last "done" / "progress" events
   if (!scalar_warp && it > 0) {{
     EV_WAIT(15);
     {"EV_WAIT(13);" if self.progress_seq else ""}
   }}
+#ifdef DSPB_PROFILE
+  __syncthreads();
+  if (A.prof && blockIdx.x == 0)
+    for (int k = tid; k < N_NODES && k < 128; k += 544) {{
+      A.prof[k] += prof_ts[k];
+      A.prof[N_NODES + k] += prof_ts[128 + k];
+    }}
+#endif
 }}
 }}  // namespace
 

@@ -616,10 +616,32 @@ __device__ __noinline__ int search_cross_far(const float* w, const WaveSummary* 
     }
     unsigned cand1 = __ballot_sync(FULL, cnd);
     while (cand1) {
-      const int l = forward ? __ffs(cand1) - 1 : 31 - __clz(cand1);
-      cand1 &= ~(1u << l);
-      const int r = check_chunk(w, n, thr, 32 * g + l, s, forward, stop_back, lane);
-      if (r >= 0) return r;
+      // the two nearest candidate chunks at once: lanes 0-15 check the nearer one, 16-31 the next
+      const int l0 = forward ? __ffs(cand1) - 1 : 31 - __clz(cand1);
+      cand1 &= ~(1u << l0);
+      int l1 = -1;
+      if (cand1) {
+        l1 = forward ? __ffs(cand1) - 1 : 31 - __clz(cand1);
+        cand1 &= ~(1u << l1);
+      }
+      const int cc = 32 * g + (lane < 16 ? l0 : l1);
+      const int i = 16 * cc + (lane & 15);
+      bool hit = false;
+      if (lane < 16 || l1 >= 0) {
+        if (forward) {
+          if (i >= s && i < n - 1) {
+            const float a = at(w, i), b = at(w, i + 1);
+            hit = (a <= thr && thr < b) || (a >= thr && thr > b);
+          }
+        } else if (i <= s && i >= stop_back && i < n) {
+          const float a = at(w, i - 1), b = at(w, i);
+          hit = (a < thr && thr <= b) || (a > thr && thr >= b);
+        }
+      }
+      const unsigned m = __ballot_sync(FULL, hit);
+      const unsigned m0 = m & 0xffffu, m1 = m >> 16;
+      if (m0) return 16 * (32 * g + l0) + (forward ? __ffs(m0) - 1 : 31 - __clz(m0));
+      if (m1) return 16 * (32 * g + l1) + (forward ? __ffs(m1) - 1 : 31 - __clz(m1));
     }
   }
   return -1;
@@ -631,7 +653,15 @@ __device__ __noinline__ float wrange_sum(const float* w, int n, int a, int b, in
   a = max(a, 0);
   b = min(b, n);
   float acc = 0.f;
-  for (int m = a + lane; m < b; m += 32) acc += at(w, m);
+  // 128 samples per step: lane l reads samples [g + 4l, g + 4l + 4) with one 128-bit load
+  for (int g = a & ~3; g < b; g += 128) {
+    const int i = g + 4 * lane;
+    if (i < b) {
+      const float4 q = *reinterpret_cast<const float4*>(w + sidx(i));
+      acc += (i >= a && i < b ? q.x : 0.f) + (i + 1 >= a && i + 1 < b ? q.y : 0.f) +
+             (i + 2 >= a && i + 2 < b ? q.z : 0.f) + (i + 3 >= a && i + 3 < b ? q.w : 0.f);
+    }
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
   return acc;
