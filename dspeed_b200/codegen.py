@@ -123,6 +123,7 @@ class SpecChain(FusedChain):
         self.waves: dict[int, Wave] = {}
         self.svar: dict[int, str] = {}          # scalar storage -> C variable
         self.stype: dict[str, str] = {}         # C variable -> "float" | "double"
+        self.never_nan: set[str] = set()        # scalars of integer input columns
         self.const_storage = {}
         self.input_wave = {}
         self.input_scalar = {}
@@ -259,6 +260,8 @@ class SpecChain(FusedChain):
                 if src.dtype not in _CTYPE:
                     raise NotSpecializable(f"scalar input dtype {src.dtype}")
                 name = self._new_svar(st, src.dtype)
+                if src.dtype not in (torch.float32, torch.float64):
+                    self.never_nan.add(name)
                 pi = self._ptr(("in", man, what))
                 self.prolog.append(self._asg(name, f"((const {_CTYPE[src.dtype]}*)A.p[{pi}])[row * A.s[{pi}]]"))
             return self.svar[st]
@@ -621,16 +624,31 @@ class SpecChain(FusedChain):
         self.s_dirty = False        # the block stream produced something the scalar warp will read
         self.b2s_count = 0          # B -> S events since the last point where S provably caught up
         self.s2b = {}               # scalar -> (event id, bc index) published by the scalar warp
-        self.s2b_ids = [12, 0]      # barrier ids for scalars published by the scalar warp
+        self.s2b_ids = [0]          # barrier id for a scalar published by the scalar warp
         self.s_seq = 0              # number of scalar-stream nodes emitted
         self.s_done = 0             # ... of which the block stream knows they are finished
         self.flag_s = {}            # block-stream NaN flag -> its copy in the scalar stream
+        self.s_deferred = []
         slot_len = max([w.n for w in self.waves.values()] + [CHK])
         self.nchunks = (slot_len + CHK - 1) // CHK
         self.psp = 4 * self.nchunks + 8
         self.slot_words = 4 * self.psp
-        # waves the scalar warp reads (threshold searches, pick-offs)
+        # waves the scalar warp reads (threshold searches, pick-offs); "late" ones are still read
+        # after the scalar warp has published the last scalar the block stream waits for
         self.s_read = {nd["ins"][0][0].id for nd in self.nodes if nd["kind"] in ("tpt", "ftp")}
+        pos_of = {nd["idx"]: k for k, nd in enumerate(self.order)}
+        for k, nd in enumerate(self.order):
+            for m in nd.get("members", []):
+                pos_of[m["idx"]] = k
+        b_need = set()
+        for nd in self.nodes:
+            for key in ("b", "tau", "t0"):
+                if key in nd and isinstance(nd[key], str):
+                    b_need.add(nd[key])
+        last_pub = max([pos_of.get(nd["idx"], -1) for nd in self.nodes
+                        if (nd.get("out") in b_need or any(o in b_need for o in nd.get("outs", []) if o))] + [-1])
+        self.s_late = {nd["ins"][0][0].id for nd in self.nodes
+                       if nd["kind"] in ("tpt", "ftp") and pos_of.get(nd["idx"], 0) > last_pub + 1}
         # waves searched by the scalar warp carry a min/max summary (built when they are stored)
         self.summ = {}
         for nd in self.nodes:
@@ -644,8 +662,11 @@ class SpecChain(FusedChain):
         total_slots = (MAX_SMEM - fixed_est) // (self.slot_words * 4)
         if total_slots < 2:
             raise NotSpecializable("waveforms too long for the shared-memory resident layout")
+        total_slots -= total_slots % 2       # two frames of the pool alternate with the row parity
         self.free_cols = [(k, 0, self.nchunks) for k in range(total_slots)]
         self.total_slots = total_slots
+        self.written_slots = set()
+        self.top_slots = set()
         # scalars the block stream needs from the scalar warp
         self.b_needed = set()
         for nd in self.nodes:
@@ -661,6 +682,7 @@ class SpecChain(FusedChain):
             self.LS.append("PROF_MARK_S(%d);" % k)
             self._release(k)
         self._close_round()
+        self._flush_s()
         # scalar outputs not stored at their definition (pass-through input scalars)
         for k, (name, pi, ct) in enumerate(self.out_scalars):
             if name not in self.stored:
@@ -686,7 +708,7 @@ class SpecChain(FusedChain):
         the row parity, and two waits protect the shared-memory slots: before its first write to
         the slot of the wave the scalar warp reads last, the block stream waits for "scalar warp done
         with the previous row" (barrier 15); for the writes before that point (the head: raw-data
-        front end, scratch tables) it waits at the row start for a progress event (barrier 13) that
+        front end, scratch tables) it waits for a progress event (barrier 14) that
         the scalar warp posts right after its last read of any slot the head overwrites."""
         def overlap(a, b):
             return a[0] == b[0] and a[1] < b[2] and b[1] < a[2]
@@ -696,11 +718,11 @@ class SpecChain(FusedChain):
             if ln.startswith("//@R "):
                 sl, c0, c1, seq = (int(x) for x in ln.split()[1:5])
                 reads.append((seq, (sl, c0, c1)))
-        writes = []         # (LB index, region)
+        writes = []         # (LB index, region as seen from the previous row's frame)
         for k, ln in enumerate(self.LB):
             if ln.startswith("//@W "):
                 sl, c0, c1 = (int(x) for x in ln.split()[1:4])
-                writes.append((k, (sl, c0, c1)))
+                writes.append((k, (self._rot(sl), c0, c1)))
         # group the block stream's writes by node; need[k] = latest scalar-warp read (of the previous
         # row) that node k's writes collide with
         node_of, cur = {}, -1
@@ -732,7 +754,7 @@ class SpecChain(FusedChain):
         if self.progress_seq:
             k = next(i for i, ln in enumerate(LS) if ln.startswith("//@R ") and int(ln.split()[4]) == self.progress_seq)
             nxt = next((i for i in range(k + 1, len(LS)) if LS[i].startswith("// ---- [")), len(LS))
-            LS.insert(nxt, "EV_ARRIVE(13);")
+            LS.insert(nxt, "EV_ARRIVE(14);")
         LS.append("EV_ARRIVE(15);")
         self.LS = LS
         LB = list(self.LB)
@@ -741,7 +763,7 @@ class SpecChain(FusedChain):
         else:
             LB.append("if (it > 0) EV_WAIT(15);")
         if self.progress_seq:   # (inserted second: progress_idx < late_idx)
-            LB.insert(self.progress_idx, "if (it > 0) EV_WAIT(13);   // the scalar warp is past its reads of these slots")
+            LB.insert(self.progress_idx, "if (it > 0) EV_WAIT(14);   // the scalar warp is past its reads of these slots")
         self.LB = LB
 
     def _describe_node(self, nd):
@@ -762,7 +784,19 @@ class SpecChain(FusedChain):
 
     def _es(self, *lines):
         """scalar stream"""
+        self._flush_s()
         self.LS.extend(lines)
+
+    def _es_later(self, *lines):
+        """scalar-stream code that only consumes mailbox partials: consecutive reductions are
+        collected and released behind ONE block -> scalar event"""
+        self.s_deferred.extend(lines)
+
+    def _flush_s(self):
+        if self.s_deferred:
+            d, self.s_deferred = self.s_deferred, []
+            self._sync_s()
+            self.LS.extend(d)
 
     def _round_open(self):
         return bool(self.posts or self.nd_used or self.ni_used or self.pending)
@@ -802,17 +836,12 @@ class SpecChain(FusedChain):
         if not self.s_dirty:
             return
         self.s_dirty = False
-        if self.b2s_count >= 5:
-            # the 5 event barriers of this row parity are in flight: let the two streams meet once
-            self._e("EV_WAIT(14);")
-            self._es("EV_WAIT(14);")
-            self.b2s_count = 0
-            self.s_done = self.s_seq
-            return
+        if self.b2s_count >= 6:
+            raise NotSpecializable("more block -> scalar events per row than named barriers")
         eid = self.b2s_count
         self.b2s_count += 1
         self._e(f"EV_ARRIVE(EVB({eid}));")
-        self._es(f"EV_WAIT(EVB({eid}));")
+        self.LS.append(f"EV_WAIT(EVB({eid}));")
 
     def _is_s(self, e):
         return e is not None and self.sdom.get(str(e)) == "s"
@@ -828,6 +857,16 @@ class SpecChain(FusedChain):
             self._es(f"if (lane == 0) bc[{k}] = (double){name};", f"EV_ARRIVE({eid});")
             self.s2b[name] = (eid, k, self.s_seq)
 
+    def _def_s_later(self, name):
+        self.sdom[name] = "s"
+        if name in self.b_needed:
+            if not self.s2b_ids or self.n_bc >= 16:
+                raise NotSpecializable("too many scalars flow from the scalar warp to the block warps")
+            eid, k = self.s2b_ids.pop(0), self.n_bc
+            self.n_bc += 1
+            self._es_later(f"if (lane == 0) bc[{k}] = (double){name};", f"EV_ARRIVE({eid});")
+            self.s2b[name] = (eid, k, self.s_seq)
+
     def _need_all(self, *exprs):
         """scalars the block stream must hold: wait for the scalar warp's event and fetch them"""
         for e in exprs:
@@ -836,6 +875,7 @@ class SpecChain(FusedChain):
                 if name not in self.s2b:
                     raise NotSpecializable("internal: scalar not published to the block stream")
                 eid, k, seq = self.s2b.pop(name)
+                self._flush_s()
                 self._close_round()
                 self._e(f"EV_WAIT({eid});", self._asg(name, f"bc[{k}]"))
                 self.s2b_ids.append(eid)
@@ -909,30 +949,44 @@ class SpecChain(FusedChain):
     # -- slots and register chunks ---------------------------------------------------------
     # A physical slot has `nchunks` chunk columns; a wave of n samples needs ceil(n / 16) of them,
     # so several short waves (windowed leading edge, cusp / zac outputs ...) share one slot.
-    def _slot_alloc(self, ncols=None, top=False):
-        """columns of a physical slot.  Waves the scalar warp reads (`top`) are taken from the
-        highest slots, everything else from the lowest: the head of the next row (its raw-data
-        front end and scratch tables) then never touches what the scalar warp is still reading"""
+    # Rows alternate between two frames of the slot pool: logical slot k is physical slot k in even
+    # rows and (k + T/2) % T in odd rows (T = pool size, even).  A full-size wave the scalar warp
+    # reads late is placed in a logical slot whose image in the other frame has not been written by
+    # the head of a row: then the head of row r+1 never touches what the scalar warp still reads
+    # of row r, and (by symmetry) neither does its own late-read wave.
+    def _rot(self, slot):
+        return (slot + self.total_slots // 2) % self.total_slots
+
+    def _slot_alloc(self, ncols=None, top=False, late=False):
         ncols = self.nchunks if ncols is None else min(self.nchunks, ncols)
         fits = [iv for iv in self.free_cols if iv[2] - iv[1] >= ncols]
         if not fits:
             raise NotSpecializable("not enough shared memory for the live waveforms")
         if top:
-            slot, c0, c1 = max(fits, key=lambda iv: (iv[0], -(iv[2] - iv[1])))
+            # 1st choice: the image in the other frame is untouched so far; 2nd: it at least does not
+            # hold a wave the scalar warp still reads late in the row
+            safe = ([iv for iv in fits if self._rot(iv[0]) not in self.written_slots]
+                    or [iv for iv in fits if self._rot(iv[0]) not in self.top_slots])
+            slot, c0, c1 = min(safe or fits, key=lambda iv: iv[0])
+            if late:
+                self.top_slots.add(slot)
         else:
             slot, c0, c1 = min(fits, key=lambda iv: (iv[2] - iv[1] if ncols < self.nchunks else 0, iv[0]))
         self.free_cols.remove((slot, c0, c1))
         if c1 - c0 > ncols:
             self.free_cols.append((slot, c0 + ncols, c1))
         self.n_slots = max(self.n_slots, slot + 1)
+        self.written_slots.add(slot)
         return (slot, c0, ncols)
 
     def _slot_alloc_adjacent(self, k):
-        """k whole physical slots that are adjacent in shared memory (large scratch tables)"""
+        """k whole physical slots that are adjacent in shared memory in BOTH row frames (large scratch
+        tables): inside one half of the pool"""
         full = sorted(sl for (sl, c0, c1) in self.free_cols if c0 == 0 and c1 == self.nchunks)
+        half = self.total_slots // 2
         start = None
         for a in full:
-            if all((a + d) in full for d in range(k)):
+            if all((a + d) in full for d in range(k)) and a // half == (a + k - 1) // half:
                 start = a
                 break
         if start is None:
@@ -941,6 +995,7 @@ class SpecChain(FusedChain):
         for d in range(k):
             self.free_cols.remove((start + d, 0, self.nchunks))
             res.append((start + d, 0, self.nchunks))
+            self.written_slots.add(start + d)
         self.n_slots = max(self.n_slots, start + k)
         return res
 
@@ -978,7 +1033,7 @@ class SpecChain(FusedChain):
 
     def _give_slot(self, w: Wave, post=False):
         if w.slot is None:
-            w.slot = self._slot_alloc((w.n + CHK - 1) // CHK, top=w.id in self.s_read)
+            w.slot = self._slot_alloc((w.n + CHK - 1) // CHK, top=w.id in self.s_read, late=w.id in self.s_late)
             # a pre-barrier store must not overtake other threads still reading the old tenant
             if not post and w.slot[0] in self.xread:
                 self._barrier()
@@ -1077,12 +1132,10 @@ class SpecChain(FusedChain):
         if nd.get("from_conv"):
             # the convolution already deposited the per-warp maxima in the mailbox
             g = self._nan_guard([self._flag_s(w.nan)])
-            self.s_dirty = True
-            self._sync_s()
             self.s_seq += 1
-            self._es(self._asg(outs[3], f"{'(' + g + ') ? CUDART_NAN_F : ' if g else ''}get_fmax(MBI({nd['from_conv'][1]}), lane)"),
-                     *self._stores(outs[3]))
-            self._def_s(outs[3])
+            self._es_later(self._asg(outs[3], f"{'(' + g + ') ? CUDART_NAN_F : ' if g else ''}get_fmax(MBI({nd['from_conv'][1]}), lane)"),
+                           *self._stores(outs[3]))
+            self._def_s_later(outs[3])
             return
         self._need(w.nan)
         r = self._chunk(w)
@@ -1104,23 +1157,22 @@ class SpecChain(FusedChain):
                 mb = self._mbi(1)
                 self._e(f"{put_v}(MBI({mb}), {m}, lane, warp);")
                 todo.append((it, iv, get_v, mb, False))
-        self.s_dirty = True
         g = self._nan_guard([self._flag_s(w.nan)])
         gq = f"({g}) ? CUDART_NAN_F : " if g else ""
-        self._sync_s()
+        self.s_dirty = True
         self.s_seq += 1
         for (it, iv, get, mb, with_idx) in todo:
             if with_idx:
                 v, i = self._t("v"), self._t("i")
-                self._es(f"float {v}; int {i}; {get}(MBI({mb}), lane, {v}, {i});", self._asg(outs[it], f"{gq}(float){i}"))
+                self._es_later(f"float {v}; int {i}; {get}(MBI({mb}), lane, {v}, {i});", self._asg(outs[it], f"{gq}(float){i}"))
                 if outs[iv]:
-                    self._es(self._asg(outs[iv], f"{gq}{v}"))
+                    self._es_later(self._asg(outs[iv], f"{gq}{v}"))
             else:
-                self._es(self._asg(outs[iv], f"{gq}{get}(MBI({mb}), lane)"))
+                self._es_later(self._asg(outs[iv], f"{gq}{get}(MBI({mb}), lane)"))
         for o in outs:
             if o:
-                self._es(*self._stores(o))
-                self._def_s(o)
+                self._es_later(*self._stores(o))
+                self._def_s_later(o)
 
     def _e_lsf(self, nd):
         w, off, n = nd["ins"][0]
@@ -1132,20 +1184,19 @@ class SpecChain(FusedChain):
         self._e(f"double {a}, {b}, {c}; lsf_local({r}, 16 * tid, {off}, {off + n}, {a}, {b}, {c});",
                 f"put_sum(MBD({mb}), {a}, lane, warp); put_sum(MBD({mb + 1}), {b}, lane, warp); "
                 f"put_sum(MBD({mb + 2}), {c}, lane, warp);")
-        self.s_dirty = True
         g = self._nan_guard([self._flag_s(w.nan)])
-        self._sync_s()
+        self.s_dirty = True
         self.s_seq += 1
         f = [self._t("f") for _ in range(4)]
         post = (f"float {f[0]}, {f[1]}, {f[2]}, {f[3]}; lsf_finish({n}, get_sum(MBD({mb}), lane), "
                 f"get_sum(MBD({mb + 1}), lane), get_sum(MBD({mb + 2}), lane), {f[0]}, {f[1]}, {f[2]}, {f[3]});")
         if g:
             post += f" if ({g}) {{ {f[0]} = {f[1]} = {f[2]} = {f[3]} = CUDART_NAN_F; }}"
-        self._es(post)
+        self._es_later(post)
         for k in range(4):
             if outs[k]:
-                self._es(self._asg(outs[k], f[k]), *self._stores(outs[k]))
-                self._def_s(outs[k])
+                self._es_later(self._asg(outs[k], f[k]), *self._stores(outs[k]))
+                self._def_s_later(outs[k])
 
     def _e_bl_sub(self, nd):
         w, off, n = nd["ins"][0]
@@ -1158,7 +1209,7 @@ class SpecChain(FusedChain):
         self._e(f"const float {b} = (float)({nd['b']});",
                 f"float {o}[16];",
                 f"_Pragma(\"unroll\") for (int j = 0; j < 16; j++) {o}[j] = {r}[j] - {b};")
-        flags = [w.nan] + ([f"({b} != {b})"] if not nd["b"].startswith(("0x", "-0x")) else [])
+        flags = [w.nan] + ([f"({b} != {b})"] if not (nd["b"].startswith(("0x", "-0x")) or nd["b"] in self.never_nan) else [])
         g = self._nan_guard(flags)
         if g:
             nf = f"nan{out.name}"
@@ -1356,12 +1407,10 @@ class SpecChain(FusedChain):
         if nd.get("from_conv"):
             w = nd["ins"][0][0]
             g = self._nan_guard([self._flag_s(w.nan)])
-            self.s_dirty = True
-            self._sync_s()
             self.s_seq += 1
-            self._es(self._asg(nd["out"], f"{'(' + g + ') ? CUDART_NAN_F : ' if g else ''}(float)MBD({nd['from_conv'][1]})[0]"),
-                     *self._stores(nd["out"]))
-            self._def_s(nd["out"])
+            self._es_later(self._asg(nd["out"], f"{'(' + g + ') ? CUDART_NAN_F : ' if g else ''}(float)MBD({nd['from_conv'][1]})[0]"),
+                           *self._stores(nd["out"]))
+            self._def_s_later(nd["out"])
             return
         w, off, n = nd["ins"][0]
         self._s_wave(w)
@@ -1611,7 +1660,7 @@ class SpecChain(FusedChain):
                 f"{_lit(math.exp(1.0 / sigma))}, {_lit(math.exp((L - 1) / sigma))}, {pw}, {so[0]}, {so[1]}, {sinks[0]}, {sinks[1]}, "
                 f"reinterpret_cast<double*>(SLOT({scratch[0][0]})), tid, lane, warp);")
         # the band table overwrote the (always-zero) pad columns of its slots
-        self._e(f"zero_pads(slots, {self.slot_words}, {self.nchunks}, {scratch[0][0]}, {scratch[-1][0] + 1}, tid);")
+        self._e(f"zero_pads(SLOT({scratch[0][0]}), {self.slot_words}, {self.nchunks}, 0, {len(scratch)}, tid);")
         for sl in scratch:
             self.dirty.add(sl[0])
             self._slot_free(sl)
@@ -1707,7 +1756,8 @@ struct Args {{
   long long* prof;
 }};
 {arrays}
-#define SLOT(k) (slots + (k) * {self.slot_words})
+// logical slot k of this row: physical slot k (even rows) or (k + {self.total_slots // 2}) % {self.total_slots} (odd rows)
+#define SLOT(k) (slots + (rp ? (((k) + {self.total_slots // 2}) % {self.total_slots}) * {self.slot_words} : (k) * {self.slot_words}))
 #define CSD(k) (cs->d[par][k])
 #define CSI(k) (cs->i[par][k])
 #define MBD(k) (mbd + 16 * (k))
@@ -1751,7 +1801,7 @@ __global__ void __launch_bounds__(544, 1) k_chain_spec(const __grid_constant__ A
     double* mbd = reinterpret_cast<double*>(smem_raw + {mbd_off} + {self.MB_BUDGET} * rp);  // block warps -> scalar warp
     int* mbi = reinterpret_cast<int*>(smem_raw + {mbi_off} + {self.MB_BUDGET} * rp);
     (void)bc; (void)mbd; (void)mbi;
-#define EVB(k) (2 + 5 * rp + (k))
+#define EVB(k) (2 + 6 * rp + (k))
     {{
       {decl}
       {prolog}
@@ -1768,7 +1818,7 @@ __global__ void __launch_bounds__(544, 1) k_chain_spec(const __grid_constant__ A
   // consume the scalar warp's last "done" / "progress" events
   if (!scalar_warp && it > 0) {{
     EV_WAIT(15);
-    {"EV_WAIT(13);" if self.progress_seq else ""}
+    {"EV_WAIT(14);" if self.progress_seq else ""}
   }}
 #ifdef DSPB_PROFILE
   __syncthreads();
