@@ -1102,7 +1102,18 @@ class SpecChain(FusedChain):
         pi, n, dt = nd["ptr"], nd["n"], nd["dtype"]
         ct = _CTYPE[dt]
         self._e(f"float {r}[16];")
-        if dt == torch.uint16 and n % 16 == 0:
+        if dt == torch.uint16 and n % 16 == 0 and not hasattr(self, "prefetch"):
+            # software prefetch: the raw chunk of the NEXT row is requested from HBM while this row is
+            # processed (two 128-bit loads per thread in flight for a whole row time)
+            self.prefetch = (pi, n)
+            self._e(f"if (16 * tid < {n}) {{ unpack_u16(pf0, {r}); unpack_u16(pf1, {r} + 8); }}",
+                    f"else {{ _Pragma(\"unroll\") for (int j = 0; j < 16; j++) {r}[j] = 0.f; }}",
+                    f"if (16 * tid < {n} && row + gridDim.x < A.n_rows) {{",
+                    f"  const uint16_t* g_ = (const uint16_t*)A.p[{pi}] + (row + gridDim.x) * A.s[{pi}] + 16 * tid;",
+                    "  pf0 = ldg_nc(g_); pf1 = ldg_nc(g_ + 8);",
+                    "}")
+            self.aligned_ptrs = getattr(self, "aligned_ptrs", []) + [pi]
+        elif dt == torch.uint16 and n % 16 == 0:
             self._e(f"ldg_chunk_u16((const uint16_t*)A.p[{pi}] + row * A.s[{pi}], tid, {n}, {r});")
             self.aligned_ptrs = getattr(self, "aligned_ptrs", []) + [pi]
         else:
@@ -1733,6 +1744,13 @@ class SpecChain(FusedChain):
         arrays = "\n".join(getattr(self, "static_arrays", []))
         aligned = getattr(self, "aligned_ptrs", [])
         align_check = "".join(f"  if (((uintptr_t)ptrs[{i}] & 15) || (strides[{i}] & 7)) return DSPB_ERR_UNSUPPORTED;\n" for i in aligned)
+        prefetch_init = ""
+        if hasattr(self, "prefetch"):
+            pi, n = self.prefetch
+            prefetch_init = (f"uint4 pf0 = make_uint4(0, 0, 0, 0), pf1 = pf0;   // raw chunk of the next row (prefetched)\n"
+                             f"  if (!scalar_warp && 16 * tid < {n} && blockIdx.x < A.n_rows) {{\n"
+                             f"    const uint16_t* g_ = (const uint16_t*)A.p[{pi}] + (long long)blockIdx.x * A.s[{pi}] + 16 * tid;\n"
+                             f"    pf0 = ldg_nc(g_); pf1 = ldg_nc(g_ + 8);\n  }}")
         mbd_off = 2048 + 8192 + 2048
         mbi_off = mbd_off + self.n_mbd * 16 * 8
         summ_off = mbd_off + 2 * self.MB_BUDGET
@@ -1788,6 +1806,7 @@ __global__ void __launch_bounds__(544, 1) k_chain_spec(const __grid_constant__ A
     BSYNC();
   }}
   int it = 0;
+  {prefetch_init}
 #ifdef DSPB_PROFILE
   for (int k = tid; k < 256; k += 544) prof_ts[k] = 0;
   __syncthreads();

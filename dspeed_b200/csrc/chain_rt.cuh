@@ -777,8 +777,10 @@ __device__ __forceinline__ void conv_seg_chunked(const float* X, const float (&x
 #pragma unroll
   for (int q = 0; q < NQ; q++) otab[q * OT + tid + (tid >> 4)] = s[q];
   BSYNC();
-  if (warp < NQ) {
-    double* o = otab + warp * OT + 17 * lane;
+  // (warps 1,2,3,5,6: the scalar warp shares scheduler partition 0 with warps 0,4,8,12)
+  const int sq = warp < 4 ? warp - 1 : (warp == 5 ? 3 : (warp == 6 ? 4 : -1));
+  if (sq >= 0 && sq < NQ) {
+    double* o = otab + sq * OT + 17 * lane;
     double v[CHK];
     double run = 0.0;
 #pragma unroll
