@@ -1,0 +1,73 @@
+"""Host-side checks of the chain code generator (no GPU): the ICPC recipe is planned on the
+"meta" device, and the generated kernel is inspected -- node order, shared-memory budget,
+the two instruction streams and their events -- and compiled for sm_100a."""
+
+import os
+import re
+import shutil
+
+import pytest
+import yaml
+
+from dspeed_b200 import codegen
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ICPC = os.path.join(REPO, "dspeed_b200", "configs", "hpge_icpc.yaml")
+
+
+@pytest.fixture(scope="module")
+def spec():
+    import numpy as np
+
+    from dspeed_b200 import tables
+    from dspeed_b200.processing_chain import build_processing_chain
+
+    n = 4
+    wf = tables.WaveformTable(size=n, t0=0, t0_units="ns", dt=16, dt_units="ns", values=np.zeros((n, 8192), np.uint16))
+    tb = tables.Table({"waveform": wf, "baseline": tables.Array(np.zeros(n, np.uint16))}, size=n)
+    chain, _, _ = build_processing_chain(yaml.safe_load(open(ICPC)), tb, block_width=16, device="meta")
+    build = codegen.SpecChain._build
+    codegen.SpecChain._build = lambda self: None     # plan only
+    try:
+        return codegen.SpecChain(chain)
+    finally:
+        codegen.SpecChain._build = build
+
+
+def test_icpc_program(spec):
+    kinds = [nd["kind"] for nd in spec.order]
+    # the raw row is loaded once; filters of one input are evaluated together; cusp + zac share
+    # one evaluation; the trapezoid that is only picked off is never materialised
+    assert kinds.count("load") == 1 and kinds.count("fir_group") == 1 and kinds.count("conv_seg_group") == 1
+    assert kinds.count("fir_lazy") == 1 and kinds.count("tpt") == 11
+    assert [c[0] for c in spec.conv_lowering] == ["runs", "seg", "seg"] and spec.cse_skipped == 1
+    # reductions follow their producer (they read the chunk from registers)
+    assert kinds[:4] == ["load", "min_max", "bl_sub", "lsf"]
+    assert spec.smem_bytes <= 227 * 1024 and spec.total_slots % 2 == 0
+    assert len(spec.out_scalars) == 34
+
+
+def test_streams_and_events(spec):
+    src = spec.source()
+    blk = src[src.index("block stream"):src.index("scalar stream")]
+    sca = src[src.index("scalar stream"):]
+    # threshold searches, pick-offs and output stores live in the scalar stream only
+    assert "tpt_w(" in sca and "tpt_w(" not in blk
+    assert "A.p[" in sca and "st_chunk_n" not in sca
+    # every block -> scalar event has exactly one arrive and one wait, in the same order
+    arr = re.findall(r"EV_ARRIVE\(EVB\((\d+)\)\)", blk)
+    wait = re.findall(r"EV_WAIT\(EVB\((\d+)\)\)", sca)
+    assert arr == wait and 1 <= len(arr) <= 6
+    # the scalar published to the block stream (tp_0_est -> windower) crosses once
+    assert blk.count("EV_WAIT(0);") == 1 and sca.count("EV_ARRIVE(0);") == 1
+    # cross-row pipelining: "done" event per row, consumed before the next row's first colliding write
+    assert sca.count("EV_ARRIVE(15);") == 1 and "if (it > 0) EV_WAIT(15);" in blk
+    # block-only barriers never involve the scalar warp
+    assert "__syncthreads()" not in blk
+
+
+@pytest.mark.skipif(shutil.which("nvcc") is None and not os.path.exists("/usr/local/cuda/bin/nvcc"), reason="nvcc not available")
+def test_generated_kernel_compiles_for_sm100a(spec):
+    so, cu = codegen.build_source(spec.source())
+    assert os.path.exists(so) and os.path.getsize(so) > 10000
+    assert "sm_100a" in " ".join(codegen._lib.NVCC_FLAGS)
