@@ -650,15 +650,18 @@ class SpecChain(FusedChain):
         self.s_late = {nd["ins"][0][0].id for nd in self.nodes
                        if nd["kind"] in ("tpt", "ftp") and pos_of.get(nd["idx"], 0) > last_pub + 1}
         # waves searched by the scalar warp carry a min/max summary (built when they are stored)
-        self.summ = {}
+        self.summ = {}          # wave id -> (first summary cell, one cell per row parity?)
+        self.n_summ = 0
         for nd in self.nodes:
             if nd["kind"] == "tpt":
                 w = nd["ins"][0][0]
                 if w.id not in self.summ:
-                    self.summ[w.id] = len(self.summ)
+                    par2 = w.id in self.s_late   # still searched while the block stream is in the next row
+                    self.summ[w.id] = (self.n_summ, par2)
+                    self.n_summ += 2 if par2 else 1
         # fixed pool of physical slots: everything the 227 KB allow
-        self.MB_BUDGET = 4096       # mailbox bytes per row parity
-        fixed_est = 2048 + 8192 + 2048 + 2 * self.MB_BUDGET + len(self.summ) * 4224
+        self.MB_BUDGET = 2048       # mailbox bytes per row parity
+        fixed_est = 2048 + 8192 + 2048 + 2 * self.MB_BUDGET + self.n_summ * 4224
         total_slots = (MAX_SMEM - fixed_est) // (self.slot_words * 4)
         if total_slots < 2:
             raise NotSpecializable("waveforms too long for the shared-memory resident layout")
@@ -693,7 +696,7 @@ class SpecChain(FusedChain):
         if self.mb_bytes > self.MB_BUDGET:
             raise NotSpecializable("too many reductions for the mailbox")
         # Scratch + CScr/bc + prof stamps + mailbox (two row parities) + summaries
-        self.fixed_bytes = 2048 + 8192 + 2048 + 2 * self.MB_BUDGET + len(self.summ) * 4224
+        self.fixed_bytes = 2048 + 8192 + 2048 + 2 * self.MB_BUDGET + self.n_summ * 4224
         self.n_slots = self.total_slots
         self.smem_bytes = self.fixed_bytes + self.n_slots * self.slot_words * 4
         self._pipeline_rows()
@@ -722,7 +725,7 @@ class SpecChain(FusedChain):
         for k, ln in enumerate(self.LB):
             if ln.startswith("//@W "):
                 sl, c0, c1 = (int(x) for x in ln.split()[1:4])
-                writes.append((k, (self._rot(sl), c0, c1)))
+                writes.append((k, (self._rot(sl) if sl < 1000 else sl, c0, c1)))
         # group the block stream's writes by node; need[k] = latest scalar-warp read (of the previous
         # row) that node k's writes collide with
         node_of, cur = {}, -1
@@ -912,6 +915,15 @@ class SpecChain(FusedChain):
     def _wmark(sl):
         return f"//@W {sl[0]} {sl[1]} {sl[1] + sl[2]}"
 
+    def _summ(self, w: Wave) -> str:
+        k, par2 = self.summ[w.id]
+        return f"SUMM({k} + rp)" if par2 else f"SUMM({k})"
+
+    def _summ_mark(self, w: Wave) -> str:
+        """summaries that exist once are part of the cross-row hazard analysis (pseudo slot 1000 + k)"""
+        k, par2 = self.summ[w.id]
+        return "//" if par2 else f"//@W {1000 + k} 0 1"
+
     def _stores(self, name):
         """statements (scalar warp) that write a just-defined scalar to its output columns: results
         leave the register file as soon as they are final"""
@@ -1069,7 +1081,7 @@ class SpecChain(FusedChain):
             self._give_slot(w)
             self._e(self._wmark(w.slot), f"st_chunk_n({self._slot(w)}, tid, {w.n}, {r});")
             if w.id in self.summ:
-                self._e(f"put_summary(SUMM({self.summ[w.id]}), {r}, {w.n}, tid, lane, warp);")
+                self._e(self._summ_mark(w), f"put_summary({self._summ(w)}, {r}, {w.n}, tid, lane, warp);")
             self.dirty.add(w.slot[0])
             self.s_dirty = True
         self._set_reg(w, r)
@@ -1081,7 +1093,8 @@ class SpecChain(FusedChain):
             self.posts.append(self._wmark(w.slot))
             self.posts.append(f"st_chunk_n({self._slot(w)}, tid, {w.n}, {r});")
             if w.id in self.summ:
-                self.posts.append(f"put_summary(SUMM({self.summ[w.id]}), {r}, {w.n}, tid, lane, warp);")
+                self.posts.append(self._summ_mark(w))
+                self.posts.append(f"put_summary({self._summ(w)}, {r}, {w.n}, tid, lane, warp);")
             self.post_dirty.append(w.slot[0])
             self.s_dirty = True
         self._set_reg(w, r)
@@ -1359,7 +1372,9 @@ class SpecChain(FusedChain):
         g = self._nan_guard([self._flag_s(w.nan)])
         if getattr(w, "scatter", False):
             raise NotSpecializable("threshold search on a scattered waveform")
-        call = (f"tpt_w({self._slot(w)}, SUMM({self.summ[w.id]}), {n}, (float)({nd['thr']}), (float)({nd['start']}), "
+        if not self.summ[w.id][1]:
+            self._es(f"//@R {1000 + self.summ[w.id][0]} 0 1 {self.s_seq}")
+        call = (f"tpt_w({self._slot(w)}, {self._summ(w)}, {n}, (float)({nd['thr']}), (float)({nd['start']}), "
                 f"(float)({nd['walk']}), {f}, lane)")
         self._es(f"int {f} = 0;",
                  self._asg(nd['out'], f"{'(' + g + ') ? CUDART_NAN_F : ' if g else ''}{call}"),

@@ -518,9 +518,14 @@ struct WaveSummary {
 __device__ __forceinline__ void put_summary(WaveSummary* sm, const float (&v)[CHK], int n, int tid, int lane,
                                             int warp) {
   float mn = CUDART_INF_F, mx = -CUDART_INF_F;
+  if (n == CHK * 512) {   // (n is a literal at every call site)
 #pragma unroll
-  for (int j = 0; j < CHK; j++)
-    if (CHK * tid + j < n) { mn = fminf(mn, v[j]); mx = fmaxf(mx, v[j]); }
+    for (int j = 0; j < CHK; j++) { mn = fminf(mn, v[j]); mx = fmaxf(mx, v[j]); }
+  } else {
+#pragma unroll
+    for (int j = 0; j < CHK; j++)
+      if (CHK * tid + j < n) { mn = fminf(mn, v[j]); mx = fmaxf(mx, v[j]); }
+  }
   sm->mn1[tid] = mn;
   sm->mx1[tid] = mx;
   const unsigned kmn = __reduce_min_sync(FULL, fkey(mn)), kmx = __reduce_max_sync(FULL, fkey(mx));
@@ -739,20 +744,8 @@ __device__ __forceinline__ void conv_seg_chunked(const float* X, const float (&x
     const double wm0 = exp(-(double)i0 / sigma);
     double wm = wm0, wp = 1.0 / wm0, jc = (double)i0 - j0;
     float prev = xm1;
-#pragma unroll
-    for (int k = 0; k < CHK; k++) {
-      const int j = i0 + k;
-      if (hit && j <= N) {
-#pragma unroll
-        for (int b = 0; b < 4; b++) {
-          const int o = j - base[b];
-          if (o >= 0 && o < p) {
-#pragma unroll
-            for (int q = 0; q < NQ; q++) tab[(q * 4 + b) * PP + (o & 15) * CW + (o >> 4)] = s[q];
-          }
-        }
-      }
-      const double z = j < N ? fma(-c, (double)prev, (double)x[k]) : 0.0;
+    auto step = [&](int k) {
+      const double z = i0 + k < N ? fma(-c, (double)prev, (double)x[k]) : 0.0;
       prev = x[k];
       s[0] = fma(wm, z, s[0]);
       s[1] = fma(wp, z, s[1]);
@@ -765,6 +758,30 @@ __device__ __forceinline__ void conv_seg_chunked(const float* X, const float (&x
       }
       wm *= qm;
       wp *= qp;
+    };
+    if (!hit) {
+      // the common case (3 of 4 warps): no band position in this chunk, sums only
+#pragma unroll
+      for (int k = 0; k < CHK; k++) step(k);
+    } else {
+      // o of the chunk's first position in every band; position j = i0 + k lies in band b iff
+      // 0 <= ob[b] + k < p (and j <= N)
+      const int ob[4] = {i0 - base[0], i0 - base[1], i0 - base[2], i0 - base[3]};
+#pragma unroll
+      for (int k = 0; k < CHK; k++) {
+        if (i0 + k <= N) {
+#pragma unroll
+          for (int b = 0; b < 4; b++) {
+            const int o = ob[b] + k;
+            if ((unsigned)o < (unsigned)p) {
+              double* t = tab + b * PP + (o & 15) * CW + (o >> 4);
+#pragma unroll
+              for (int q = 0; q < NQ; q++) t[q * 4 * PP] = s[q];
+            }
+          }
+        }
+        step(k);
+      }
     }
   }
   // ---- pass 2: exclusive scan of the chunk sums over the 512 threads, through shared memory:

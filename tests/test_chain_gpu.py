@@ -264,26 +264,27 @@ def test_specialised_kernel_is_deterministic_and_matches_interpreted(synth_batch
 
     from dspeed_b200 import synth
 
-    d = synth.hpge_waveforms(6000, seed=123, stress=True)
+    d = synth.hpge_waveforms(12000, seed=123, stress=True)   # ~80 rows per CTA: rows overlap all the time
     vals, bl = d["values"].numpy(), d["baseline"].numpy()
-    runs = [run_icpc(vals, bl, block_width=6000, device="cuda") for _ in range(3)]
+    runs = [run_icpc(vals, bl, block_width=12000, device="cuda") for _ in range(3)]
     for k in runs[0]:
         for r in runs[1:]:
             assert np.array_equal(runs[0][k], r[k], equal_nan=True), k
     os.environ["DSPEED_B200_SPECIALIZE"] = "0"
     try:
-        ref = run_icpc(vals, bl, block_width=6000, device="cuda")
+        ref = run_icpc(vals, bl, block_width=12000, device="cuda")
     finally:
         os.environ.pop("DSPEED_B200_SPECIALIZE", None)
     a = runs[0]
     t0_same = (a["tp_0_est"] == ref["tp_0_est"]) | (np.isnan(a["tp_0_est"]) & np.isnan(ref["tp_0_est"]))
-    assert t0_same.mean() > 0.995
+    assert t0_same.mean() > 0.9995
     for k in a:
         if k in EXACT:
             assert np.array_equal(a[k], ref[k], equal_nan=True), k
         elif k.startswith("tp_"):
+            # identical but for thresholds that differ in the last bit (tp_100: threshold = trapTmax)
             same = (a[k] == ref[k]) | (np.isnan(a[k]) & np.isnan(ref[k]))
-            assert same.mean() > 0.99, (k, same.mean())
+            assert same.mean() > 0.998, (k, same.mean())
         else:
             PT.assert_float_close(k, a[k], ref[k], rtol=5e-6, mask=t0_same)
     torch.cuda.synchronize()
