@@ -29,6 +29,7 @@ import hashlib
 import logging
 import math
 import os
+import re
 import subprocess
 import threading
 
@@ -629,6 +630,8 @@ class SpecChain(FusedChain):
         self.s_done = 0             # ... of which the block stream knows they are finished
         self.flag_s = {}            # block-stream NaN flag -> its copy in the scalar stream
         self.s_deferred = []
+        self.s_deferred_urgent = []
+        self._cur_def = []
         slot_len = max([w.n for w in self.waves.values()] + [CHK])
         self.nchunks = (slot_len + CHK - 1) // CHK
         self.psp = 4 * self.nchunks + 8
@@ -676,8 +679,15 @@ class SpecChain(FusedChain):
             for key in ("b", "tau", "t0"):
                 if key in nd and isinstance(nd[key], str) and not nd[key].startswith(("0x", "-0x", "CUDART")):
                     self.b_needed.add(nd[key])
+        self.urgent_names = set()
+        for nd in self.nodes:
+            if nd.get("out") in self.b_needed:
+                for key in ("thr", "start", "walk", "t", "x", "y", "oi", "oo"):
+                    if isinstance(nd.get(key), str) and not nd[key].startswith(("0x", "-0x", "CUDART")):
+                        self.urgent_names.add(nd[key])
         for k, nd in enumerate(self.order):
             self.pos = k
+            self._es_later_end()
             self.LB.append(f"// ---- [{k}] {self._describe_node(nd)}")
             self.LS.append(f"// ---- [{k}] {self._describe_node(nd)}")
             getattr(self, "_e_" + nd["kind"])(nd)
@@ -785,20 +795,33 @@ class SpecChain(FusedChain):
         """block stream"""
         self.LB.extend(lines)
 
-    def _es(self, *lines):
+    def _es(self, *lines, urgent=False):
         """scalar stream"""
-        self._flush_s()
+        self._flush_s(urgent)
         self.LS.extend(lines)
 
     def _es_later(self, *lines):
         """scalar-stream code that only consumes mailbox partials: consecutive reductions are
-        collected and released behind ONE block -> scalar event"""
-        self.s_deferred.extend(lines)
+        collected and released behind ONE block -> scalar event.  A node's block that feeds a scalar
+        the block stream waits for is released first (and alone, when the consumer is on that path)."""
+        self._cur_def.extend(lines)
 
-    def _flush_s(self):
-        if self.s_deferred:
-            d, self.s_deferred = self.s_deferred, []
+    def _es_later_end(self):
+        """end of a node: file its deferred block as urgent or not"""
+        if self._cur_def:
+            urgent = any(re.match(rf"\s*{n} = ", ln) for ln in self._cur_def for n in self.urgent_names)
+            (self.s_deferred_urgent if urgent else self.s_deferred).extend(self._cur_def)
+            self._cur_def = []
+
+    def _flush_s(self, urgent=False):
+        self._es_later_end()
+        if self.s_deferred_urgent or (self.s_deferred and not urgent):
             self._sync_s()
+        if self.s_deferred_urgent:
+            d, self.s_deferred_urgent = self.s_deferred_urgent, []
+            self.LS.extend(d)
+        if self.s_deferred and not urgent:
+            d, self.s_deferred = self.s_deferred, []
             self.LS.extend(d)
 
     def _round_open(self):
@@ -1379,7 +1402,7 @@ class SpecChain(FusedChain):
         self._es(f"int {f} = 0;",
                  self._asg(nd['out'], f"{'(' + g + ') ? CUDART_NAN_F : ' if g else ''}{call}"),
                  f"if ({f} && lane == 0) raise_fatal(A.fatal ? A.fatal + 4 * {nd['fatal']} : nullptr, {f}, A.row0 + row);",
-                 *self._stores(nd["out"]))
+                 *self._stores(nd["out"]), urgent=nd["out"] in self.b_needed)
         self._def_s(nd["out"])
 
     def _e_fir_lazy(self, nd):
