@@ -396,6 +396,12 @@ class SpecChain(FusedChain):
             self._node("fir", ins=[(w, 0, n)], taps=[(0, 1.0 / rise), (rise, -1.0 / rise), (rise + flat, -1.0 / fall),
                                                      (rise + flat + fall, 1.0 / fall)],
                        scale=1.0, p=n, extra=None, wouts=[self._wout(a[4])])
+        elif name == "trap_pickoff":
+            w, off, n = self._win(a[0], True)
+            rise, flat = int(a[1]), int(a[2])
+            if n != w.n or rise <= 0 or flat < 0 or 2 * rise + flat > n:
+                raise NotSpecializable("trapezoid arguments")
+            self._node("trap_pickoff", ins=[(w, 0, n)], rise=rise, flat=flat, t=self._sc(a[3]), out=self._sout(a[4]))
         elif name in ("moving_window_left", "moving_window_right", "moving_window_multi"):
             w, off, n = self._win(a[0], True)
             length = float(np.float32(a[1]))
@@ -638,7 +644,7 @@ class SpecChain(FusedChain):
         self.slot_words = 4 * self.psp
         # waves the scalar warp reads (threshold searches, pick-offs); "late" ones are still read
         # after the scalar warp has published the last scalar the block stream waits for
-        self.s_read = {nd["ins"][0][0].id for nd in self.nodes if nd["kind"] in ("tpt", "ftp")}
+        self.s_read = {nd["ins"][0][0].id for nd in self.nodes if nd["kind"] in ("tpt", "ftp", "trap_pickoff")}
         pos_of = {nd["idx"]: k for k, nd in enumerate(self.order)}
         for k, nd in enumerate(self.order):
             for m in nd.get("members", []):
@@ -651,7 +657,7 @@ class SpecChain(FusedChain):
         last_pub = max([pos_of.get(nd["idx"], -1) for nd in self.nodes
                         if (nd.get("out") in b_need or any(o in b_need for o in nd.get("outs", []) if o))] + [-1])
         self.s_late = {nd["ins"][0][0].id for nd in self.nodes
-                       if nd["kind"] in ("tpt", "ftp") and pos_of.get(nd["idx"], 0) > last_pub + 1}
+                       if nd["kind"] in ("tpt", "ftp", "trap_pickoff") and pos_of.get(nd["idx"], 0) > last_pub + 1}
         # waves searched by the scalar warp carry a min/max summary (built when they are stored)
         self.summ = {}          # wave id -> (first summary cell, one cell per row parity?)
         self.n_summ = 0
@@ -1403,6 +1409,29 @@ class SpecChain(FusedChain):
                  self._asg(nd['out'], f"{'(' + g + ') ? CUDART_NAN_F : ' if g else ''}{call}"),
                  f"if ({f} && lane == 0) raise_fatal(A.fatal ? A.fatal + 4 * {nd['fatal']} : nullptr, {f}, A.row0 + row);",
                  *self._stores(nd["out"]), urgent=nd["out"] in self.b_needed)
+        self._def_s(nd["out"])
+
+    def _e_trap_pickoff(self, nd):
+        # trap_filters.py:230-301 : the normalised trapezoid at ONE index from two window sums,
+        # evaluated by the scalar warp (NaN when the windows do not fit, fatal on a fractional index)
+        w, off, n = nd["ins"][0]
+        self._s_wave(w)
+        g = self._nan_guard([self._flag_s(w.nan)])
+        r_, fl = nd["rise"], nd["flat"]
+        t, st, res, f = (self._t(x) for x in ("t", "st", "res", "f"))
+        sl = self._slot(w)
+        self._es(f"int {f} = 0; float {res} = CUDART_NAN_F;",
+                 f"{{ const float {t} = (float)({nd['t']});",
+                 f"  if ({t} == {t}{' && !(' + g + ')' if g else ''}) {{",
+                 f"    if (floorf({t}) != {t}) {f} = DSPB_FATAL_PICKOFF_NONINT;",
+                 f"    else {{ const long long {st} = (long long)({t} + 1.0f);",
+                 f"      if ({st} <= {n} && {st} >= {2 * r_ + fl})",
+                 f"        {res} = (wrange_sum({sl}, {n}, (int){st} - {r_}, (int){st}, lane) - "
+                 f"wrange_sum({sl}, {n}, (int){st} - {2 * r_ + fl}, (int){st} - {r_ + fl}, lane)) / {float(r_)}f; }}",
+                 "  } }",
+                 self._asg(nd['out'], res),
+                 f"if ({f} && lane == 0) raise_fatal(A.fatal ? A.fatal + 4 * {nd['fatal']} : nullptr, {f}, A.row0 + row);",
+                 *self._stores(nd["out"]))
         self._def_s(nd["out"])
 
     def _e_fir_lazy(self, nd):

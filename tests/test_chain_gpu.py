@@ -113,6 +113,7 @@ def test_fused_icpc_chain_matches_oracle(synth_batch):
     out = build_dsp(raw_table(vals, bl), dsp_config=_yaml.safe_load(open(ICPC)), block_width=600)
     fused = out.proc_chain._fused
     assert fused is not None, getattr(out.proc_chain, "_not_fused_reason", None)
+    assert type(fused).__name__ == "SpecChain", getattr(out.proc_chain, "_not_specialised_reason", None)
     kinds = [c[0] for c in fused.conv_lowering]
     assert kinds.count("seg") == 2 and kinds.count("runs") == 1, fused.conv_lowering
     # 3 set-up launches (t0 / cusp / zac kernel synthesis, const-folded) + ceil(1536 / 600) block launches
@@ -207,6 +208,8 @@ def test_minimal_energy_chain():
     }
     wf = tables.WaveformTable(size=len(vals), t0=0, t0_units="ns", dt=16, dt_units="ns", values=vals)
     out = build_dsp(tables.Table({"waveform": wf}, size=len(vals)), dsp_config=cfg, block_width=256)
+    # specialised kernel: the baseline mean travels scalar warp -> block warps before bl_subtract
+    assert type(out.proc_chain._fused).__name__ == "SpecChain", getattr(out.proc_chain, "_not_specialised_reason", None)
     o = chains.minimal_chain(vals)
     # statistics of the *raw* waveform (values ~1.2e4, sigma 4): the reference's float32
     # Welford recursion drifts by ~1e-7 of the sample magnitude, i.e. 1e-3 on sigma
