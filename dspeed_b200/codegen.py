@@ -1305,10 +1305,12 @@ class SpecChain(FusedChain):
             raise NotSpecializable("internal: FIR input without a slot")
         self._visible(w)
         # batches of at most 3 filters per round (register pressure)
+        self._e("PROF_SUB_RESET();" if getattr(self, "_psub", False) else "PROF_SUB_BEGIN();")
+        self._psub = True
         for b0 in range(0, len(members), 3):
             batch = members[b0:b0 + 3]
             recs = []
-            for m in batch:
+            for mi, m in enumerate(batch):
                 out = m["wouts"][0]
                 d, tot, incl = self._t("d"), self._t("tot"), self._t("incl")
                 self._e(f"float {d}[16];", f"_Pragma(\"unroll\") for (int j = 0; j < 16; j++) {d}[j] = 0.f;")
@@ -1380,6 +1382,7 @@ class SpecChain(FusedChain):
                             f"for (int q = tid; q < {ne}; q += 512) {term} += (double)({kx}[q] * at({self._slot(w)}, {ne - 1} - q));",
                             f"put_sum(CSD({sx}), {term}, lane, warp);")
                     ex = sx
+                self._e(f"PROF_SUB({8 + b0 + mi});")
                 recs.append((m, d, tot, incl, sd, ex))
             for (m, d, tot, incl, sd, ex) in recs:
                 out = m["wouts"][0]
@@ -1823,6 +1826,7 @@ class SpecChain(FusedChain):
         summ_off = mbd_off + 2 * self.MB_BUDGET
         return f"""// generated by dspeed_b200/codegen.py -- do not edit
 #define DSPB_PSP {self.psp}
+#define DSPB_PROF_OFF (2048 + 8192)
 // the 16 block warps synchronise on named barrier 1; the scalar warp (warp 16) never joins it
 #define BSYNC() asm volatile("bar.sync 1, 512;" ::: "memory")
 #define EV_ARRIVE(id) asm volatile("bar.arrive %0, 544;" ::"r"(id) : "memory")
@@ -1912,6 +1916,7 @@ __global__ void __launch_bounds__(544, 1) k_chain_spec(const __grid_constant__ A
     for (int k = tid; k < N_NODES && k < 128; k += 544) {{
       A.prof[k] += prof_ts[k];
       A.prof[N_NODES + k] += prof_ts[128 + k];
+      if (k < 32) A.prof[2 * N_NODES + k] += prof_ts[96 + k];   // PROF_SUB stamps inside routines
     }}
 #endif
 }}
@@ -1959,7 +1964,7 @@ extern "C" int chain_launch(const void* const* ptrs, long long n_ptrs, long long
         n = 2 * (len(self.order) + 1)
         so, _ = build_source(self.source(), flags=("-DDSPB_PROFILE",))
         prod_lib, self.lib = self.lib, load_chain_lib(so)
-        self.d_prof = torch.zeros(n, dtype=torch.int64, device=self.chain.device)
+        self.d_prof = torch.zeros(n + 32, dtype=torch.int64, device=self.chain.device)
         try:
             run()   # warm-up of the tracing build
             self.d_prof.zero_()
@@ -1970,10 +1975,11 @@ extern "C" int chain_launch(const void* const* ptrs, long long n_ptrs, long long
         finally:
             self.d_prof = None
             self.lib = prod_lib
-        tot = cyc.sum() or 1.0
+        tot = cyc[:n].sum() or 1.0
         text = self.program_text.split("\n") + ["store scalars"]
         text = ["B " + t for t in text] + ["S " + t for t in text]   # block stream, then scalar stream
-        return [(cyc[i], cyc[i] / tot, text[i]) for i in range(n)]
+        text += [f"B sub-stamp {k}" for k in range(32)]              # PROF_SUB stamps (inside routines)
+        return [(cyc[i], cyc[i] / tot, text[i]) for i in range(n + 32) if i < n or cyc[i] > 0]
 
     def __del__(self):
         pass

@@ -23,6 +23,27 @@
 #include "conv_ops.cuh"
 #include "row_ops.cuh"
 
+// tracing build only: cycle stamps inside a routine (thread 0 of CTA 0), accumulated next to the per-node
+// stamps of the generated kernel (prof_ts[96 + k], offset DSPB_PROF_OFF of the dynamic shared memory)
+#if defined(DSPB_PROFILE) && defined(DSPB_PROF_OFF)
+#define PROF_SUB_BEGIN() long long psub_prev_ = clock64()
+#define PROF_SUB_RESET() psub_prev_ = clock64()
+#define PROF_SUB(k)                                                                        \
+  do {                                                                                     \
+    if (blockIdx.x == 0 && threadIdx.x == 0) {                                             \
+      extern __shared__ __align__(16) unsigned char psub_smem_[];                          \
+      long long* p_ = reinterpret_cast<long long*>(psub_smem_ + DSPB_PROF_OFF);            \
+      const long long t_ = clock64();                                                      \
+      p_[96 + (k)] += t_ - psub_prev_;                                                     \
+      psub_prev_ = t_;                                                                     \
+    }                                                                                      \
+  } while (0)
+#else
+#define PROF_SUB_BEGIN()
+#define PROF_SUB_RESET()
+#define PROF_SUB(k)
+#endif
+
 // Barrier of the 16 block warps.  Kernels that run a separate scalar warp define it as a named
 // barrier over the 512 block threads before including this header.
 #ifndef BSYNC
@@ -733,6 +754,7 @@ __device__ __forceinline__ void conv_seg_chunked(const float* X, const float (&x
   const int base[4] = {L, L - lt, L - 1 - lt - fl, 0};
   // ---- pass 1: chunk sums; threads whose chunk meets a band also deposit the chunk-local
   // running sums (sum over the chunk's elements before position j) at the band positions ----
+  PROF_SUB_BEGIN();
   double s[NQ];
 #pragma unroll
   for (int q = 0; q < NQ; q++) s[q] = 0.0;
@@ -789,11 +811,13 @@ __device__ __forceinline__ void conv_seg_chunked(const float* X, const float (&x
   // entries [16l, 16l+16), skewed by one word per 16 so that both access patterns are
   // conflict-free), and pass 3 picks up the prefix in front of whatever chunk it needs.  Costs
   // the block NQ stores per thread instead of NQ float64 shuffle scans per thread.
+  PROF_SUB(0);   // pass 1 (this thread)
   double* otab = tab + NQ * 4 * PP;
   constexpr int OT = 512 + 32;
 #pragma unroll
   for (int q = 0; q < NQ; q++) otab[q * OT + tid + (tid >> 4)] = s[q];
   BSYNC();
+  PROF_SUB(1);   // wait for the slowest pass-1 thread
   // (warps 1,2,3,5,6: the scalar warp shares scheduler partition 0 with warps 0,4,8,12)
   const int sq = warp < 4 ? warp - 1 : (warp == 5 ? 3 : (warp == 6 ? 4 : -1));
   if (sq >= 0 && sq < NQ) {
@@ -811,6 +835,7 @@ __device__ __forceinline__ void conv_seg_chunked(const float* X, const float (&x
     for (int k = 0; k < CHK; k++) o[k] = v[k] + base_l;
   }
   BSYNC();
+  PROF_SUB(2);   // pass 2 (scan warps)
   // ---- pass 3: one thread per output ------------------------------------------------------------
   const int pceil = (p + CHK - 1) & ~(CHK - 1);
   const double eAm = 1.0 / eA;  // eA = e^{(L-1)/s}: e^{+-n/s} = eA^{+-1} * q^{+-o}
@@ -849,9 +874,11 @@ __device__ __forceinline__ void conv_seg_chunked(const float* X, const float (&x
     if (k0.slot) k0.slot[sidx(o)] = y0;
     if (TWO && k1.slot) k1.slot[sidx(o)] = y1;
   }
+  PROF_SUB(3);   // pass 3 (this thread)
   if (k0.mx) put_fmax(k0.mx, mx0, lane, warp);
   if (TWO && k1.mx) put_fmax(k1.mx, mx1, lane, warp);
   BSYNC();
+  PROF_SUB(4);   // wait for the slowest pass-3 thread
 }
 
 }  // namespace crt

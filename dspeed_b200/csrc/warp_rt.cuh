@@ -1,0 +1,376 @@
+// dspeed_b200 -- device routines of the warp-per-row chain kernels (dspeed_b200/warpchain.py).
+//
+// Short waveforms (<= 2048 samples, the SiPM / LAr chains of BASELINE.json config 4): ONE WARP owns
+// one waveform.  Lane l holds samples [CH*l, CH*l + CH) in registers (CH = 8..64, a power of two),
+// recursive filters are lane-local running sums + one warp scan, halos travel by shuffles, and the
+// only shared memory is (a) the raw row of the NEXT waveform, staged with cp.async while this one is
+// processed, and (b) one float copy of the wave the peak finder walks.  No block-wide barrier
+// anywhere: warps run rows independently, 16 warps per SM.
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include "dspeed_b200.h"
+
+namespace wrt {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+// sample i of a wave slot: lane chunks are CH + 4 words apart (128-bit accesses of the 32 chunks
+// and unit-stride accesses inside a chunk are both conflict-free)
+template <int CH>
+__device__ __forceinline__ int widx(int i) {
+  return (i / CH) * (CH + 4) + (i % CH);
+}
+
+// ---------------------------------------------------------------------------------------
+// raw row staging: 16-byte cp.async pieces, chunk c of the row at byte c * (2 CH + 16)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem, const void* g) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// n % 8 == 0 and 16-byte aligned rows (checked by the launcher)
+template <int CH>
+__device__ __forceinline__ void stage_row_16(unsigned char* raw, const uint16_t* g, int n, int lane) {
+  constexpr int PPC = CH / 8;  // 16-byte pieces per chunk
+  const int np = n >> 3;
+  for (int q = lane; q < np; q += 32) cp_async16(raw + (q / PPC) * (2 * CH + 16) + (q % PPC) * 16, g + 8 * q);
+  cp_async_commit();
+}
+template <bool SIGNED>
+__device__ __forceinline__ float cvt16(unsigned h) {
+  return SIGNED ? (float)(short)(unsigned short)h : (float)h;
+}
+// own chunk of the staged row -> registers (positions >= n hold finite garbage, masked by the users)
+template <int CH, bool SIGNED>
+__device__ __forceinline__ void read_chunk_16(const unsigned char* raw, int lane, float (&x)[CH]) {
+  const uint4* p = reinterpret_cast<const uint4*>(raw + lane * (2 * CH + 16));
+#pragma unroll
+  for (int k = 0; k < CH / 8; k++) {
+    const uint4 q = p[k];
+    x[8 * k + 0] = cvt16<SIGNED>(q.x & 0xffffu); x[8 * k + 1] = cvt16<SIGNED>(q.x >> 16);
+    x[8 * k + 2] = cvt16<SIGNED>(q.y & 0xffffu); x[8 * k + 3] = cvt16<SIGNED>(q.y >> 16);
+    x[8 * k + 4] = cvt16<SIGNED>(q.z & 0xffffu); x[8 * k + 5] = cvt16<SIGNED>(q.z >> 16);
+    x[8 * k + 6] = cvt16<SIGNED>(q.w & 0xffffu); x[8 * k + 7] = cvt16<SIGNED>(q.w >> 16);
+  }
+}
+
+// own chunk <-> wave slot (128-bit, conflict-free)
+template <int CH>
+__device__ __forceinline__ void st_chunk(float* S, int lane, const float (&x)[CH]) {
+  float4* p = reinterpret_cast<float4*>(S + lane * (CH + 4));
+#pragma unroll
+  for (int k = 0; k < CH / 4; k++) p[k] = make_float4(x[4 * k], x[4 * k + 1], x[4 * k + 2], x[4 * k + 3]);
+}
+// own chunk -> a global row (waveform-valued outputs)
+template <int CH>
+__device__ __forceinline__ void stg_chunk(float* g, int lane, int n, const float (&x)[CH], bool nan) {
+#pragma unroll
+  for (int k = 0; k < CH / 4; k++) {
+    const int i = CH * lane + 4 * k;
+    if (i + 3 < n && ((reinterpret_cast<uintptr_t>(g) & 15) == 0)) {
+      reinterpret_cast<float4*>(g + i)[0] = nan ? make_float4(CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F)
+                                                : make_float4(x[4 * k], x[4 * k + 1], x[4 * k + 2], x[4 * k + 3]);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; e++)
+        if (i + e < n) g[i + e] = nan ? CUDART_NAN_F : x[4 * k + e];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// warp scans
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float wscan_excl_add(float v, int lane) {
+  float s = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const float t = __shfl_up_sync(FULL, s, d);
+    if (lane >= d) s += t;
+  }
+  const float e = __shfl_up_sync(FULL, s, 1);
+  return lane == 0 ? 0.f : e;
+}
+__device__ __forceinline__ float wscan_excl_add_rev(float v, int lane) {  // sum over the lanes ABOVE this one
+  float s = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const float t = __shfl_down_sync(FULL, s, d);
+    if (lane + d < 32) s += t;
+  }
+  const float e = __shfl_down_sync(FULL, s, 1);
+  return lane == 31 ? 0.f : e;
+}
+__device__ __forceinline__ float wscan_incl_max(float v, int lane) {
+  float s = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const float t = __shfl_up_sync(FULL, s, d);
+    if (lane >= d) s = fmaxf(s, t);
+  }
+  return s;
+}
+__device__ __forceinline__ int wscan_incl_add_i(int v, int lane) {
+  int s = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int t = __shfl_up_sync(FULL, s, d);
+    if (lane >= d) s += t;
+  }
+  return s;
+}
+
+// ---------------------------------------------------------------------------------------
+// bl_subtract.py:11-46
+// ---------------------------------------------------------------------------------------
+template <int CH>
+__device__ __forceinline__ void bl_sub(const float (&x)[CH], float b, float (&y)[CH]) {
+#pragma unroll
+  for (int j = 0; j < CH; j++) y[j] = x[j] - b;
+}
+
+// ---------------------------------------------------------------------------------------
+// moving_windows.py:12-114 : out[0] = x[0]; out[i] = out[i-1] + (x[i] - x[max(i-L, 0)]) / L and
+// its mirror image.  Lane-local running sum of the increments + one warp scan; the L samples of
+// the neighbouring chunk arrive by shuffles (L <= CH, compile time).
+// ---------------------------------------------------------------------------------------
+template <int CH, int L>
+__device__ __forceinline__ void mw_left(const float (&x)[CH], float (&y)[CH], int n, float il, int lane) {
+  static_assert(L >= 1 && L <= CH, "window longer than a lane chunk");
+  const float e0 = __shfl_sync(FULL, x[0], 0);
+  float h[L];
+#pragma unroll
+  for (int j = 0; j < L; j++) h[j] = __shfl_up_sync(FULL, x[CH - L + j], 1);
+  float run = 0.f;
+#pragma unroll
+  for (int j = 0; j < CH; j++) {
+    const int i = CH * lane + j;
+    const float prev = j >= L ? x[j >= L ? j - L : 0] : h[j < L ? j : 0];
+    float d = (x[j] - (i >= L ? prev : e0)) * il;
+    d = i == 0 ? e0 : d;
+    d = i >= n ? 0.f : d;
+    run += d;
+    y[j] = run;
+  }
+  const float off = wscan_excl_add(run, lane);
+#pragma unroll
+  for (int j = 0; j < CH; j++) y[j] += off;
+}
+template <int CH, int L, int N>
+__device__ __forceinline__ void mw_right(const float (&x)[CH], float (&y)[CH], float il, int lane) {
+  static_assert(L >= 1 && L <= CH, "window longer than a lane chunk");
+  constexpr int n = N;
+  const float e0 = __shfl_sync(FULL, x[(N - 1) % CH], (N - 1) / CH);
+  float h[L];
+#pragma unroll
+  for (int j = 0; j < L; j++) h[j] = __shfl_down_sync(FULL, x[j], 1);
+  float run = 0.f;
+#pragma unroll
+  for (int j = CH - 1; j >= 0; j--) {
+    const int i = CH * lane + j;
+    const float next = j + L < CH ? x[j + L < CH ? j + L : 0] : h[j + L >= CH ? j + L - CH : 0];
+    float d = (x[j] - (i + L <= n - 1 ? next : e0)) * il;
+    d = i == n - 1 ? e0 : d;
+    d = i >= n ? 0.f : d;
+    run += d;
+    y[j] = run;
+  }
+  const float off = wscan_excl_add_rev(run, lane);
+#pragma unroll
+  for (int j = 0; j < CH; j++) y[j] += off;
+}
+
+// avg_current (moving_windows.py:206-249): out[i] = (x[i + L] - x[i]) / L, n - L samples
+template <int CH, int L>
+__device__ __forceinline__ void avg_current(const float (&x)[CH], float (&y)[CH], float il, int lane) {
+  static_assert(L >= 1 && L <= CH, "window longer than a lane chunk");
+  float h[L];
+#pragma unroll
+  for (int j = 0; j < L; j++) h[j] = __shfl_down_sync(FULL, x[j], 1);
+#pragma unroll
+  for (int j = 0; j < CH; j++) {
+    const float next = j + L < CH ? x[j + L < CH ? j + L : 0] : h[j + L >= CH ? j + L - CH : 0];
+    y[j] = (next - x[j]) * il;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// min_max.py:11-82 over [lo, hi): first arg-min / arg-max and the values
+// ---------------------------------------------------------------------------------------
+template <int CH>
+__device__ __forceinline__ void min_max(const float (&x)[CH], int lo, int hi, int lane, float& t_min, float& t_max,
+                                        float& a_min, float& a_max) {
+  float vmin = CUDART_INF_F, vmax = -CUDART_INF_F;
+  int imin = 0x7fffffff, imax = 0x7fffffff;
+#pragma unroll
+  for (int j = 0; j < CH; j++) {
+    const int i = CH * lane + j;
+    const bool in = i >= lo && i < hi;
+    if (in && x[j] < vmin) { vmin = x[j]; imin = i; }
+    if (in && x[j] > vmax) { vmax = x[j]; imax = i; }
+  }
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) {
+    const float om = __shfl_xor_sync(FULL, vmin, d), oM = __shfl_xor_sync(FULL, vmax, d);
+    const int oi = __shfl_xor_sync(FULL, imin, d), oI = __shfl_xor_sync(FULL, imax, d);
+    if (om < vmin || (om == vmin && oi < imin)) { vmin = om; imin = oi; }
+    if (oM > vmax || (oM == vmax && oI < imax)) { vmax = oM; imax = oI; }
+  }
+  t_min = (float)(imin - lo); t_max = (float)(imax - lo); a_min = vmin; a_max = vmax;
+}
+
+// ---------------------------------------------------------------------------------------
+// get_multi_local_extrema.py:12-306 -- the peak-detection state machine, walked by the whole
+// warp.  The machine only changes state at an *event* (a sample that drops a_delta below the
+// running maximum, or rises a_delta above the running minimum), so the warp jumps from event to
+// event instead of visiting samples:
+//   * lane chunks carry (max, min) summaries; with the running extreme carried in by a prefix-max
+//     scan over the chunks, "no sample of this chunk can fire" is decided for 32 chunks at once
+//     (min < fl(max(carry, chunk max) - delta) is necessary for an event inside the chunk);
+//   * the first chunk that may fire is examined exactly, 32 samples at a time: prefix max over the
+//     lanes, the reference's float32 comparison v < fl(M - delta) per sample, ballot -> first event.
+// The find-min state is the find-max state on negated samples (negation is exact), the
+// right-to-left walk is the same walk on mirrored positions.  Extrema are recorded as bits of the
+// lane that owns the sample (bit k of lane l <-> sample CH*l + k), so merging the two search
+// directions (aggressive search = union) and sorting are free.
+// ---------------------------------------------------------------------------------------
+template <int CH>
+__device__ __forceinline__ void chunk_summary(const float (&x)[CH], int n, int lane, float& cmax, float& cmin) {
+  cmax = -CUDART_INF_F;
+  cmin = CUDART_INF_F;
+#pragma unroll
+  for (int j = 0; j < CH; j++) {
+    if (CH * lane + j < n) {
+      cmax = fmaxf(cmax, x[j]);
+      cmin = fminf(cmin, x[j]);
+    }
+  }
+}
+
+template <int CH, bool BWD>
+__device__ __forceinline__ void peak_walk(const float* S, int n, float d_max, float d_min, float a_max, float a_min, int m,
+                                       float cmax, float cmin, unsigned long long& bmax, unsigned long long& bmin,
+                                       int& n_found_max, int& n_found_min) {
+  constexpr int NTOT = 32 * CH;
+  constexpr int NW = (CH + 31) / 32;  // 32-sample windows per chunk
+  const int lane = threadIdx.x & 31;
+  // summaries in walk order
+  const float lmax = BWD ? __shfl_sync(FULL, cmax, 31 - lane) : cmax;
+  const float lmin = BWD ? __shfl_sync(FULL, cmin, 31 - lane) : cmin;
+  int p = BWD ? NTOT - n : 0;  // walk position; sample index = BWD ? NTOT - 1 - p : p
+  const int p_end = BWD ? NTOT : n;
+#define WRT_IDX(q) (BWD ? NTOT - 1 - (q) : (q))
+  bool mode_max = true;
+  int ei = WRT_IDX(p);
+  float ev = S[widx<CH>(ei)];
+  p += 1;
+  int cm = 0, cn = 0;
+  while (p < p_end) {
+    if ((mode_max ? cm : cn) >= m) break;  // the list is full: this state never fires again
+    const float sg = mode_max ? 1.f : -1.f;
+    const float dl = mode_max ? d_max : d_min;
+    const float ab = mode_max ? a_max : -a_min;
+    const int c = p / CH;
+    bool found = false;
+    // ---- exact examination of the rest of chunk c ------------------------------------------------
+    for (int w = (p - c * CH) >> 5; w < NW; w++) {
+      const int q0 = c * CH + w * 32;
+      const int q = q0 + lane;
+      const bool valid = q >= p && (w * 32 + lane) < CH && q < p_end;
+      const float v = valid ? sg * S[widx<CH>(WRT_IDX(q))] : -CUDART_INF_F;
+      const float pm = wscan_incl_max(v, lane);
+      const float M = fmaxf(ev, pm);
+      const bool cross = valid && (v < M - dl) && (M > ab);
+      const unsigned b = __ballot_sync(FULL, cross);
+      if (b) {
+        const int ls = __ffs(b) - 1;
+        const float Ms = __shfl_sync(FULL, M, ls);
+        if (Ms > ev) {  // the running extreme lies in this window: its first occurrence
+          const unsigned e = __ballot_sync(FULL, valid && v == Ms);
+          ei = WRT_IDX(q0 + __ffs(e) - 1);
+        }
+        if (lane == ei / CH) {
+          if (mode_max) bmax |= 1ull << (ei % CH);
+          else bmin |= 1ull << (ei % CH);
+        }
+        if (mode_max) cm++;
+        else cn++;
+        ev = -__shfl_sync(FULL, v, ls);  // the event sample starts the opposite search
+        ei = WRT_IDX(q0 + ls);
+        mode_max = !mode_max;
+        p = q0 + ls + 1;
+        found = true;
+        break;
+      }
+      const float wm = __shfl_sync(FULL, pm, 31);
+      if (wm > ev) {
+        const unsigned e = __ballot_sync(FULL, valid && v == wm);
+        ei = WRT_IDX(q0 + __ffs(e) - 1);
+        ev = wm;
+      }
+    }
+    if (found) continue;
+    // ---- next chunk that may fire (32 chunks at once) ---------------------------------------------
+    const float smx = mode_max ? lmax : -lmin;  // signed chunk max / min
+    const float smn = mode_max ? lmin : -lmax;
+    const float pmx = wscan_incl_max(lane > c ? smx : -CUDART_INF_F, lane);
+    const float ex = __shfl_up_sync(FULL, pmx, 1);
+    const float m_in = fmaxf(ev, lane == 0 ? -CUDART_INF_F : ex);  // running extreme on entry of chunk `lane`
+    const float m_full = fmaxf(m_in, smx);
+    const unsigned b = __ballot_sync(FULL, lane > c && (smn < m_full - dl) && (m_full > ab));
+    if (!b) break;
+    const int c2 = __ffs(b) - 1;
+    const float nev = __shfl_sync(FULL, m_in, c2);
+    if (nev > ev) {  // the extreme moved into one of the skipped chunks: first occurrence of it
+      const unsigned kb = __ballot_sync(FULL, lane > c && lane < c2 && smx == nev);
+      const int k = __ffs(kb) - 1;
+      for (int w = 0; w < NW; w++) {
+        const int q = k * CH + w * 32 + lane;
+        const bool valid = (w * 32 + lane) < CH && q < p_end && q >= (BWD ? NTOT - n : 0);
+        const float v = valid ? sg * S[widx<CH>(WRT_IDX(q))] : -CUDART_INF_F;
+        const unsigned e = __ballot_sync(FULL, valid && v == nev);
+        if (e) {
+          ei = WRT_IDX(k * CH + w * 32 + __ffs(e) - 1);
+          break;
+        }
+      }
+      ev = nev;
+    }
+    p = c2 * CH;
+  }
+#undef WRT_IDX
+  n_found_max = cm;
+  n_found_min = cn;
+}
+
+// extrema bit sets -> one list element per lane (NaN-padded, m <= 32), ascending or descending
+// positions; `buf`: 32 floats of shared memory of this warp.  Returns the number of entries.
+template <int CH>
+__device__ __forceinline__ int emit_list(unsigned long long bits, int m, bool descending, float* buf, int lane,
+                                         float& elem) {
+  const int cnt = __popcll(bits);
+  const int incl = wscan_incl_add_i(cnt, lane);
+  const int total = __shfl_sync(FULL, incl, 31);
+  int pos = incl - cnt;
+  buf[lane] = CUDART_NAN_F;
+  __syncwarp();
+  while (bits) {
+    const int k = __ffsll((long long)bits) - 1;
+    bits &= bits - 1;
+    const int o = descending ? total - 1 - pos : pos;
+    if (o >= 0 && o < m) buf[o] = (float)(CH * lane + k);
+    pos++;
+  }
+  __syncwarp();
+  elem = buf[lane];
+  __syncwarp();
+  return min(total, m);
+}
+
+}  // namespace wrt

@@ -904,8 +904,15 @@ def try_fuse(chain) -> bool:
     (generated, straight-line) kernel when every processor has an emitter, else the interpreted
     program"""
     if os.environ.get("DSPEED_B200_SPECIALIZE", "1") != "0":
-        from . import codegen
+        from . import codegen, warpchain
 
+        # short waveforms (<= 2048 samples): one warp per waveform, vector outputs supported
+        try:
+            chain._fused = warpchain.WarpChain(chain)
+            log.debug(f"warp-per-waveform chain kernel:\n{chain._fused.program_text}")
+            return True
+        except NotFusable as e:
+            chain._not_warp_reason = str(e)
         try:
             chain._fused = codegen.SpecChain(chain)
             log.debug(f"specialised chain kernel:\n{chain._fused.program_text}")

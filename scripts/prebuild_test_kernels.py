@@ -1,0 +1,18 @@
+"""Pre-compile (here, no GPU) the warp-tier kernels the GPU tests will ask for, so the GPU box finds them in the
+in-tree cache (dspeed_b200/_chains/) instead of spending box time in nvcc."""
+import os
+import sys
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+from dspeed_b200 import warpchain  # noqa: E402
+from tests.test_warpchain_gpu import _cfg  # noqa: E402
+
+jobs = [(2000, _cfg(s, 20, extra_outputs=("wf_mw", "a_mx", "t_mx", "a_mn", "t_mn"))) for s in (3, 0, 1)]
+kw = dict(d_max=9.0, d_min=4.0, a_max=-50.0, a_min=30.0, L=4, num=3, typ=0)
+jobs += [(n, _cfg(s, m, **kw)) for (n, m, s) in [(1000, 5, 3), (256, 3, 3), (2048, 32, 3), (512, 8, 1), (1024, 7, 0)]]
+jobs += [(2000, _cfg(3, 20, **k)) for k in (dict(d_max=0.0, d_min=0.0, a_max=-1e9, a_min=1e9),
+                                            dict(d_max=5.0, d_min=5.0, a_max=1e9, a_min=-1e9))]
+jobs += [(2000, _cfg(3, 20))]
+for n, cfg in jobs:
+    print(n, warpchain.prebuild(cfg, wf_len=n)[0])
