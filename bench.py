@@ -55,7 +55,8 @@ def parse_args():
     ap.add_argument("--rows", type=int, default=int(os.environ.get("DSPB_BENCH_ROWS", ROWS_PER_GPU)))
     ap.add_argument("--block-width", type=int, default=int(os.environ.get("DSPB_BENCH_BLOCK", 0)) or None)
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--cpu-rows", type=int, default=int(os.environ.get("DSPB_BENCH_CPU_ROWS", 4096)))
+    # bounded CPU sample: ~10-15 s of work on a 16-thread host at ~10 k wf/s (the chain is O(rows))
+    ap.add_argument("--cpu-rows", type=int, default=int(os.environ.get("DSPB_BENCH_CPU_ROWS", 98304)))
     return ap.parse_args()
 
 
@@ -78,7 +79,16 @@ def hbm_peak():
 # ----------------------------------------------------------------------------------------
 # CPU baseline: the oracle chain on the host cores
 # ----------------------------------------------------------------------------------------
-def cpu_chain_throughput(n_rows: int, repeats: int = 1):
+CPU_CHUNK = 8192   # rows per oracle call (the reference also walks its input in buffer_len chunks, build_dsp.py:399-407)
+
+
+def _cpu_pass(chains, vals, bl, consts, cores):
+    for lo in range(0, len(vals), CPU_CHUNK):
+        chains.icpc_chain(vals[lo:lo + CPU_CHUNK], bl[lo:lo + CPU_CHUNK], consts=consts, keep_waveforms=False,
+                          conv="library", threads=cores)
+
+
+def cpu_chain_throughput(n_rows: int, repeats: int = 1, vals=None, bl=None):
     """waveforms/s of the CPU oracle ICPC chain on `n_rows` synthetic waveforms using all
     host threads (OpenMP over rows, like LEGEND production parallelises over files)."""
     from dspeed_b200 import synth
@@ -86,14 +96,15 @@ def cpu_chain_throughput(n_rows: int, repeats: int = 1):
     from oracle import oracle as O
 
     cores = O.set_threads(os.cpu_count() or 1)
-    d = synth.hpge_waveforms(n_rows, seed=2026, stress=True)
-    vals, bl = d["values"].numpy(), d["baseline"].numpy()
+    if vals is None:
+        d = synth.hpge_waveforms(n_rows, seed=2026, stress=True)
+        vals, bl = d["values"].numpy(), d["baseline"].numpy()
     consts = chains.icpc_constants()
     chains.icpc_chain(vals[:64], bl[:64], consts=consts, keep_waveforms=False, conv="library", threads=cores)  # warm-up
     best = None
     for _ in range(max(1, repeats)):
         t = time.perf_counter()
-        chains.icpc_chain(vals, bl, consts=consts, keep_waveforms=False, conv="library", threads=cores)
+        _cpu_pass(chains, vals, bl, consts, cores)
         dt = time.perf_counter() - t
         best = dt if best is None else min(best, dt)
     return n_rows / best, cores, best
@@ -117,7 +128,7 @@ def run_reference(args, rank):
                           conv="library", threads=cores)
     t = time.perf_counter()
     for _ in range(steps):
-        chains.icpc_chain(vals, bl, consts=consts, keep_waveforms=False, conv="library", threads=cores)
+        _cpu_pass(chains, vals, bl, consts, cores)
     dt = (time.perf_counter() - t) / steps
     v = n / dt
     sample = (f"{n} synthetic 8192-sample waveforms per step (bounded sample of the 1M-row workload; "
@@ -300,7 +311,7 @@ def run_b200(args, rank, world, local_rank):
     achieved = algo / k_time / 1e9
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": _traffic_from_profile(dom_name), "kernel": dom_name, "kernel_share_of_step": share,
+        "traffic": _traffic_from_profile(dom_name, rows_per_launch), "kernel": dom_name, "kernel_share_of_step": share,
         "kernel_ms_per_launch": k_time * 1e3, "rows_per_launch": rows_per_launch,
         "algorithmic_bytes_per_waveform": ALGO_BYTES_PER_WF, "peak_source": peak_src,
         "chain_frac_of_hbm_roofline": (value / world) * ALGO_BYTES_PER_WF / 1e9 / peak,
@@ -336,9 +347,10 @@ def run_b200(args, rank, world, local_rank):
     # ---- CPU baseline (rank 0, single-GPU run only) --------------------------------------------
     cpu = None
     if rank == 0 and world == 1:
-        v, cores, secs = cpu_chain_throughput(args.cpu_rows)
+        m = min(args.cpu_rows, n)   # the first rows of the very batch the GPU processed
+        v, cores, secs = cpu_chain_throughput(m, vals=vals_d[:m].cpu().numpy(), bl=bl_d[:m].cpu().numpy())
         cpu = {"value": v, "unit": "waveforms/s", "cores": cores, "kind": "port",
-               "sample": f"{args.cpu_rows} of the same synthetic waveforms ({secs:.1f} s of CPU work), CPU oracle "
+               "sample": f"{m} of the same synthetic waveforms ({secs:.1f} s of CPU work), CPU oracle "
                          f"chain (C restatement of the reference's numba processors; convolutions through the "
                          f"reference's own numpy.convolve / scipy fftconvolve calls), {cores} threads"}
 
@@ -366,7 +378,7 @@ def run_b200(args, rank, world, local_rank):
     print(json.dumps(line), flush=True)
 
 
-def _traffic_from_profile(kernel_name: str):
+def _traffic_from_profile(kernel_name: str, rows_per_launch: int):
     """per-launch DRAM bytes (read + write) of the dominant kernel from the committed `ncu --set full`
     capture (profiles/dominant_kernel_traffic.json), scaled to the rows of one bench launch"""
     p = os.path.join(REPO, "profiles", "dominant_kernel_traffic.json")
@@ -374,7 +386,7 @@ def _traffic_from_profile(kernel_name: str):
         d = json.load(open(p))
         if d.get("kernel", "") not in kernel_name:
             return None
-        return d["dram_bytes_per_row"] * 16384
+        return d["dram_bytes_per_row"] * rows_per_launch
     except Exception:
         return None
 

@@ -240,29 +240,42 @@ __device__ __forceinline__ void min_max(const float (&x)[CH], int lo, int hi, in
 // lane that owns the sample (bit k of lane l <-> sample CH*l + k), so merging the two search
 // directions (aggressive search = union) and sorting are free.
 // ---------------------------------------------------------------------------------------
+// per-chunk summaries: extreme values, the largest fall (v[i] - v[j], i < j) and the largest rise
+// (v[j] - v[i], i < j) inside the chunk
+struct ChunkSumm {
+  float vmax, vmin, fall, rise;
+};
 template <int CH>
-__device__ __forceinline__ void chunk_summary(const float (&x)[CH], int n, int lane, float& cmax, float& cmin) {
-  cmax = -CUDART_INF_F;
-  cmin = CUDART_INF_F;
+__device__ __forceinline__ ChunkSumm chunk_summary(const float (&x)[CH], int n, int lane) {
+  ChunkSumm s{-CUDART_INF_F, CUDART_INF_F, 0.f, 0.f};
 #pragma unroll
   for (int j = 0; j < CH; j++) {
     if (CH * lane + j < n) {
-      cmax = fmaxf(cmax, x[j]);
-      cmin = fminf(cmin, x[j]);
+      s.vmax = fmaxf(s.vmax, x[j]);
+      s.vmin = fminf(s.vmin, x[j]);
+      s.fall = fmaxf(s.fall, s.vmax - x[j]);
+      s.rise = fmaxf(s.rise, x[j] - s.vmin);
     }
   }
+  return s;
 }
 
 template <int CH, bool BWD>
 __device__ __forceinline__ void peak_walk(const float* S, int n, float d_max, float d_min, float a_max, float a_min, int m,
-                                       float cmax, float cmin, unsigned long long& bmax, unsigned long long& bmin,
-                                       int& n_found_max, int& n_found_min) {
+                                            const ChunkSumm& cs, unsigned long long& bmax, unsigned long long& bmin,
+                                            int& n_found_max, int& n_found_min) {
   constexpr int NTOT = 32 * CH;
   constexpr int NW = (CH + 31) / 32;  // 32-sample windows per chunk
   const int lane = threadIdx.x & 31;
   // summaries in walk order
-  const float lmax = BWD ? __shfl_sync(FULL, cmax, 31 - lane) : cmax;
-  const float lmin = BWD ? __shfl_sync(FULL, cmin, 31 - lane) : cmin;
+  const float lmax = BWD ? __shfl_sync(FULL, cs.vmax, 31 - lane) : cs.vmax;
+  const float lmin = BWD ? __shfl_sync(FULL, cs.vmin, 31 - lane) : cs.vmin;
+  // the largest drop below a running maximum that starts INSIDE the chunk, in walk order (a fall of the
+  // samples when walking forward, a rise when walking backward), and the same for the find-min state
+  const float ldrop = BWD ? __shfl_sync(FULL, cs.rise, 31 - lane) : cs.fall;
+  const float lclimb = BWD ? __shfl_sync(FULL, cs.fall, 31 - lane) : cs.rise;
+  // float32 slack of "v < fl(M - delta)" against "fl(M - v) > delta" (only used to SKIP chunks)
+  const float slack = 0x1p-20f * (fabsf(lmax) + fabsf(lmin) + d_max + d_min);
   int p = BWD ? NTOT - n : 0;  // walk position; sample index = BWD ? NTOT - 1 - p : p
   const int p_end = BWD ? NTOT : n;
 #define WRT_IDX(q) (BWD ? NTOT - 1 - (q) : (q))
@@ -323,7 +336,10 @@ __device__ __forceinline__ void peak_walk(const float* S, int n, float d_max, fl
     const float ex = __shfl_up_sync(FULL, pmx, 1);
     const float m_in = fmaxf(ev, lane == 0 ? -CUDART_INF_F : ex);  // running extreme on entry of chunk `lane`
     const float m_full = fmaxf(m_in, smx);
-    const unsigned b = __ballot_sync(FULL, lane > c && (smn < m_full - dl) && (m_full > ab));
+    // an event inside chunk `lane` needs a sample below fl(carry - delta), or a drop of (almost) delta below a
+    // maximum of the chunk itself
+    const float drop = mode_max ? ldrop : lclimb;
+    const unsigned b = __ballot_sync(FULL, lane > c && (m_full > ab) && ((smn < m_in - dl) || (drop > dl - slack)));
     if (!b) break;
     const int c2 = __ffs(b) - 1;
     const float nev = __shfl_sync(FULL, m_in, c2);

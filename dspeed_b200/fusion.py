@@ -50,6 +50,10 @@ _DT = {torch.float32: 0, torch.float64: 1, torch.uint16: 2, torch.int16: 3, torc
        torch.int64: 6}
 
 
+#: rows per launch when all inputs and outputs are device-resident (nothing to stage)
+RESIDENT_ROWS_PER_LAUNCH = int(os.environ.get("DSPEED_B200_RESIDENT_ROWS", 1 << 22))
+
+
 class NotFusable(Exception):
     pass
 
@@ -768,6 +772,13 @@ class FusedChain:
             return man.io_wf.t0.nda
         return man.io_array.nda if hasattr(man, "io_array") else man.io_buf
 
+    def _resident(self, src) -> bool:
+        """is this input column consumed in place (already on the device, same dtype, unit stride)?"""
+        idx, man, what, buf, staging = src
+        col = self._column(man, what)
+        return bool(isinstance(col, torch.Tensor) and col.is_cuda and col.dtype == buf.dtype
+                    and (col.ndim == 1 or col.stride(-1) == 1))
+
     def _stage_block(self, begin, end, stage, copy_stream):
         """enqueue the H2D copies of rows [begin, end) into staging set `stage`; returns
         {ptr index: (device pointer, row stride)}"""
@@ -775,8 +786,7 @@ class FusedChain:
         for src in self._input_sources():
             idx, man, what, buf, staging = src
             col = self._column(man, what)
-            if isinstance(col, torch.Tensor) and col.is_cuda and col.dtype == buf.dtype and \
-                    (col.ndim == 1 or col.stride(-1) == 1):
+            if self._resident(src):
                 view = col[begin:end]
                 res[idx] = (view.data_ptr(), view.stride(0))
                 continue
@@ -801,8 +811,7 @@ class FusedChain:
                    for m in chain._input_managers.values()) if chain._input_managers else stop
         stop = min(stop, n_in)
         bw = chain._block_width
-        blocks = [(b, min(b + bw, stop)) for b in range(start, stop, bw)]
-        if not blocks:
+        if stop <= start:
             return
         static = {}
         for idx, key in enumerate(self.ptrs):
@@ -831,6 +840,14 @@ class FusedChain:
                 direct[idx] = col
             else:
                 copied.append(man)
+        # Blocks exist for the staging buffers (host columns in, block buffers out).  When every column the
+        # kernel touches already lives on the device, nothing is staged and the whole range is ONE launch
+        # (persistent CTAs stride over the rows): no per-block launch gaps or tails.
+        if not copied and all(self._resident(src) for src in self._input_sources()):
+            launch_rows = max(bw, RESIDENT_ROWS_PER_LAUNCH)
+        else:
+            launch_rows = bw
+        blocks = [(b, min(b + launch_rows, stop)) for b in range(start, stop, launch_rows)]
         with torch.cuda.device(chain.device):
             compute = torch.cuda.current_stream(chain.device)
             if getattr(self, "_copy_stream", None) is None:

@@ -349,19 +349,19 @@ class WarpChain(FusedChain):
                 raise NotSpecializable("vector variable written twice")
         sdir = int(sdir)
         self.uses_slot = True
-        cmx, cmn, bx, bn, c0, c1 = (self._t(p) for p in ("cmx", "cmn", "bx", "bn", "c", "c"))
+        cs, bx, bn, c0, c1 = (self._t(p) for p in ("cs", "bx", "bn", "c", "c"))
         vx, vn = self._t("v"), self._t("v")
         nx, nn = self._sout(nmax_t), self._sout(nmin_t)
         prm = f"{_flit(d_max)}, {_flit(d_min)}, {_flit(ab_max)}, {_flit(ab_min)}, {m}"
         self._e(f"st_chunk<CH>(S, lane, {w.reg});",
-                f"float {cmx}, {cmn}; chunk_summary<CH>({w.reg}, {n}, lane, {cmx}, {cmn});",
+                f"const ChunkSumm {cs} = chunk_summary<CH>({w.reg}, {n}, lane);",
                 "__syncwarp();",
                 f"unsigned long long {bx} = 0ull, {bn} = 0ull; int {c0} = 0, {c1} = 0; (void){c0}; (void){c1};",
                 f"if (!({w.nan})) {{")
         if sdir in (0, 3):
-            self._e(f"  peak_walk<CH, false>(S, {n}, {prm}, {cmx}, {cmn}, {bx}, {bn}, {c0}, {c1});")
+            self._e(f"  peak_walk<CH, false>(S, {n}, {prm}, {cs}, {bx}, {bn}, {c0}, {c1});")
         if sdir in (1, 3):
-            self._e(f"  peak_walk<CH, true>(S, {n}, {prm}, {cmx}, {cmn}, {bx}, {bn}, {c0}, {c1});")
+            self._e(f"  peak_walk<CH, true>(S, {n}, {prm}, {cs}, {bx}, {bn}, {c0}, {c1});")
         desc = "true" if sdir == 1 else "false"
         self._e("}",
                 f"float {vx}, {vn};",

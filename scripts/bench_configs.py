@@ -40,67 +40,80 @@ def chain_bench(name, cfg, tb, n, bytes_per_wf, out_cols):
                       "algorithmic_bytes_per_wf": bytes_per_wf, "frac_of_hbm_roofline": n / t * bytes_per_wf / 1e9 / PEAK}), flush=True)
 
 
-# ---- C1: minimal energy chain ---------------------------------------------------------------------
-n = 262144
-d = synth.hpge_waveforms(n, seed=5, device=dev)
-wf = tables.WaveformTable(size=n, t0=tables.Array(d["t0"], attrs={"units": "ns"}), dt=tables.Array(d["dt"], attrs={"units": "ns"}),
-                          values=d["values"])
-cfg1 = {
-    "outputs": ["bl_mean", "bl_std", "trapEmax", "tp_max", "trapEpick"],
-    "processors": {
-        "bl_mean, bl_std, bl_slope, bl_intercept": {
-            "function": "linear_slope_fit", "module": "dspeed.processors",
-            "args": ["waveform[0:750]", "bl_mean", "bl_std", "bl_slope", "bl_intercept"], "unit": ["ADC"] * 4},
-        "wf_blsub": "dspeed.processors.bl_subtract(waveform, bl_mean, wf_blsub(unit='ADC'))",
-        "wf_pz": {"function": "dspeed.processors.pole_zero(wf_blsub, db.pz.tau, wf_pz)", "unit": "ADC",
-                  "defaults": {"db.pz.tau": "27460.5"}},
-        "wf_trap": {"function": "dspeed.processors.trap_norm(wf_pz, 10*us, 3.008*us, wf_trap)", "unit": "ADC"},
-        "tmn, tp_max, emn, trapEmax": {"function": "dspeed.processors.min_max(wf_trap, tmn, tp_max, emn, trapEmax)",
-                                       "unit": ["ns", "ns", "ADC", "ADC"]},
-        "trapEpick": {"function": "dspeed.processors.trap_pickoff(wf_pz, 10*us, 3.008*us, tp_max, trapEpick)", "unit": "ADC"},
-    },
-}
-chain_bench("C1 minimal energy chain (lsf + bl_subtract + pole_zero + trap_norm + min_max + trap_pickoff), L=8192",
-            cfg1, tables.Table({"waveform": wf}, size=n), n, 8192 * 2 + 2 + 4 * 5, cfg1["outputs"])
-del d, wf
-torch.cuda.empty_cache()
+SEL = os.environ.get("DSPB_CONFIGS", "C1,C4,C5").split(",")   # e.g. DSPB_CONFIGS=C4
 
-# ---- C4: SiPM chain ---------------------------------------------------------------------------------
-n = 1 << 20
-d = synth.sipm_waveforms(n, seed=9, device=dev)
-wf = tables.WaveformTable(size=n, t0=0, t0_units="ns", dt=16, dt_units="ns", values=d["values"])
-cfg4 = {
-    "outputs": ["vt_max", "vt_min", "n_max", "n_min"],
-    "processors": {
-        "wf_blsub": "dspeed.processors.bl_subtract(waveform, baseline, wf_blsub(unit='ADC'))",
-        "wf_mw": {"function": "dspeed.processors.moving_window_multi(wf_blsub, 8, 2, 0, wf_mw)", "unit": "ADC"},
-        "vt_max, vt_min, n_max, n_min": {
-            "function": "get_multi_local_extrema", "module": "dspeed.processors",
-            "args": ["wf_mw", 12.0, 6.0, 3, 15.0, 1000.0, "vt_max(20, 'f')", "vt_min(20, 'f')", "n_max", "n_min"],
-            "unit": ["ns", "ns", "none", "none"]},
-    },
-}
-tb = tables.Table({"waveform": wf, "baseline": tables.Array(d["baseline"])}, size=n)
-chain, _, tb_out = build_processing_chain(cfg4, tb, device=dev)
-t = timed(lambda: chain(tb, tb_out), reps=2, warm=3)
-L = d["values"].shape[1]
-b4 = L * 2 + 2 + 4 * 40 + 8
-print(json.dumps({"config": f"C4 SiPM chain (bl_subtract + moving_window_multi + get_multi_local_extrema), L={L}, host output table",
-                  "rows": n, "waveforms_per_s": n / t, "ms": t * 1e3,
-                  "tier": type(chain._fused).__name__ if chain._fused is not None else "per-processor kernels",
-                  "algorithmic_bytes_per_wf": b4, "frac_of_hbm_roofline": n / t * b4 / 1e9 / PEAK}), flush=True)
-del d, wf, tb, chain
-torch.cuda.empty_cache()
+if "C1" in SEL:
+    # ---- C1: minimal energy chain ---------------------------------------------------------------------
+    n = 262144
+    d = synth.hpge_waveforms(n, seed=5, device=dev)
+    wf = tables.WaveformTable(size=n, t0=tables.Array(d["t0"], attrs={"units": "ns"}), dt=tables.Array(d["dt"], attrs={"units": "ns"}),
+                              values=d["values"])
+    cfg1 = {
+        "outputs": ["bl_mean", "bl_std", "trapEmax", "tp_max", "trapEpick"],
+        "processors": {
+            "bl_mean, bl_std, bl_slope, bl_intercept": {
+                "function": "linear_slope_fit", "module": "dspeed.processors",
+                "args": ["waveform[0:750]", "bl_mean", "bl_std", "bl_slope", "bl_intercept"], "unit": ["ADC"] * 4},
+            "wf_blsub": "dspeed.processors.bl_subtract(waveform, bl_mean, wf_blsub(unit='ADC'))",
+            "wf_pz": {"function": "dspeed.processors.pole_zero(wf_blsub, db.pz.tau, wf_pz)", "unit": "ADC",
+                      "defaults": {"db.pz.tau": "27460.5"}},
+            "wf_trap": {"function": "dspeed.processors.trap_norm(wf_pz, 10*us, 3.008*us, wf_trap)", "unit": "ADC"},
+            "tmn, tp_max, emn, trapEmax": {"function": "dspeed.processors.min_max(wf_trap, tmn, tp_max, emn, trapEmax)",
+                                           "unit": ["ns", "ns", "ADC", "ADC"]},
+            "trapEpick": {"function": "dspeed.processors.trap_pickoff(wf_pz, 10*us, 3.008*us, tp_max, trapEpick)", "unit": "ADC"},
+        },
+    }
+    chain_bench("C1 minimal energy chain (lsf + bl_subtract + pole_zero + trap_norm + min_max + trap_pickoff), L=8192",
+                cfg1, tables.Table({"waveform": wf}, size=n), n, 8192 * 2 + 2 + 4 * 5, cfg1["outputs"])
+    del d, wf
+    torch.cuda.empty_cache()
 
-# ---- C5: long-kernel 'valid' convolution sweep (direct SMEM-tiled kernel) ------------------------------------
-n = 65536
-d = synth.hpge_waveforms(n, seed=11, device=dev)
-x = (d["values"].to(torch.float32) - d["baseline"].to(torch.float32)[:, None]).contiguous()
-rng = np.random.default_rng(0)
-for K in (256, 512, 1024, 2048, 4096):
-    k = torch.from_numpy(rng.standard_normal(K).astype(np.float32)).to(dev)
-    out = torch.empty((n, 8192 - K + 1), dtype=torch.float32, device=dev)
-    t = timed(lambda: P.convolve_wf(x, k, np.int8(ord("v")), out), reps=2, warm=3)
-    flops = 2.0 * K * (8192 - K + 1)
-    print(json.dumps({"config": f"C5 convolve_wf 'valid', generic kernel K={K}, L=8192 (direct, SMEM-tiled, fp32 FMA + fp64 chunk sums)",
-                      "rows": n, "waveforms_per_s": n / t, "ms": t * 1e3, "useful_TFLOP_per_s": flops * n / t / 1e12}), flush=True)
+if "C4" in SEL:
+    # ---- C4: SiPM chain ---------------------------------------------------------------------------------
+    n = int(os.environ.get("DSPB_C4_ROWS", 1 << 22))   # BASELINE.json config 4: 4 M short waveforms
+    d = synth.sipm_waveforms(n, seed=9, device=dev)
+    wf = tables.WaveformTable(size=n, t0=tables.Array(torch.zeros(n, dtype=torch.float64, device=dev), attrs={"units": "ns"}),
+                              dt=tables.Array(torch.full((n,), 16.0, dtype=torch.float64, device=dev), attrs={"units": "ns"}),
+                              values=d["values"])
+    cfg4 = {
+        "outputs": ["vt_max", "vt_min", "n_max", "n_min"],
+        "processors": {
+            "wf_blsub": "dspeed.processors.bl_subtract(waveform, baseline, wf_blsub(unit='ADC'))",
+            "wf_mw": {"function": "dspeed.processors.moving_window_multi(wf_blsub, 8, 2, 0, wf_mw)", "unit": "ADC"},
+            "vt_max, vt_min, n_max, n_min": {
+                "function": "get_multi_local_extrema", "module": "dspeed.processors",
+                "args": ["wf_mw", 12.0, 6.0, 3, 15.0, 1000.0, "vt_max(20, 'f')", "vt_min(20, 'f')", "n_max", "n_min"],
+                "unit": ["ns", "ns", "none", "none"]},
+        },
+    }
+    tb = tables.Table({"waveform": wf, "baseline": tables.Array(d["baseline"])}, size=n)
+    chain, _, tb_out = build_processing_chain(cfg4, tb, device=dev, block_width=int(os.environ.get("DSPB_C4_BLOCK", 0)) or None)
+    # device-resident output columns (written in place by the kernel), like the ICPC bench
+    out4 = tables.Table({k: type(v)(torch.empty(tuple(v.nda.shape), dtype=getattr(torch, str(v.nda.dtype)), device=dev),
+                                    attrs=dict(v.attrs)) for k, v in tb_out.items()}, size=n)
+    t = timed(lambda: chain(tb, out4), reps=3, warm=3)
+    L = d["values"].shape[1]
+    b4 = L * 2 + 2 + 4 * 40 + 8
+    print(json.dumps({"config": f"C4 SiPM chain (bl_subtract + moving_window_multi + get_multi_local_extrema), L={L}, device-resident in/out",
+                      "rows": n, "block_width": chain._block_width, "waveforms_per_s": n / t, "ms": t * 1e3,
+                      "tier": type(chain._fused).__name__ if chain._fused is not None else "per-processor kernels",
+                      "algorithmic_bytes_per_wf": b4, "achieved_GBps": n / t * b4 / 1e9,
+                      "frac_of_hbm_roofline": n / t * b4 / 1e9 / PEAK}), flush=True)
+    del out4
+    del d, wf, tb, chain
+    torch.cuda.empty_cache()
+
+if "C5" in SEL:
+    # ---- C5: long-kernel 'valid' convolution sweep (direct SMEM-tiled kernel) ------------------------------------
+    n = 65536
+    d = synth.hpge_waveforms(n, seed=11, device=dev)
+    x = (d["values"].to(torch.float32) - d["baseline"].to(torch.float32)[:, None]).contiguous()
+    rng = np.random.default_rng(0)
+    for K in (256, 512, 1024, 2048, 4096):
+        k = torch.from_numpy(rng.standard_normal(K).astype(np.float32)).to(dev)
+        out = torch.empty((n, 8192 - K + 1), dtype=torch.float32, device=dev)
+        t = timed(lambda: P.convolve_wf(x, k, np.int8(ord("v")), out), reps=2, warm=3)
+        flops = 2.0 * K * (8192 - K + 1)
+        print(json.dumps({"config": f"C5 convolve_wf 'valid', generic kernel K={K}, L=8192 (direct, SMEM-tiled, fp32 FMA + fp64 chunk sums)",
+                          "rows": n, "waveforms_per_s": n / t, "ms": t * 1e3, "useful_TFLOP_per_s": flops * n / t / 1e12}), flush=True)
+
