@@ -1736,10 +1736,28 @@ class SpecChain(FusedChain):
         self.static_arrays = getattr(self, "static_arrays", [])
         vals = [math.exp(o / sigma) for o in range(p)] + [math.exp(-o / sigma) for o in range(p)]
         self.static_arrays.append(f"__device__ const double {pw}[{2 * p}] = {{{', '.join(_lit(v) for v in vals)}}};")
-        self._e(f"conv_seg_chunked<{'true' if poly else 'false'}, {'true' if two else 'false'}>({self._slot(w)}, {x}, {n}, "
-                f"{_lit(sigma)}, {int(lt)}, {int(fl)}, {int(L)}, {_lit(c)}, {_lit(inv2S)}, {_lit(math.exp(-1.0 / sigma))}, "
-                f"{_lit(math.exp(1.0 / sigma))}, {_lit(math.exp((L - 1) / sigma))}, {pw}, {so[0]}, {so[1]}, {sinks[0]}, {sinks[1]}, "
-                f"reinterpret_cast<double*>(SLOT({scratch[0][0]})), tid, lane, warp);")
+        # pass-1 variant: when the threads beyond the end of the input can take all (band, chunk) pairs, the chunk
+        # sums are float32 inside a chunk / float64 across chunks and the band deposits move to those helper threads
+        nch = -(-n // CHK)
+        hb = -(-nch // 32) * 32
+        bases = [int(L), int(L - lt), int(L - 1 - lt - fl), 0]
+        pairs = sum(((bb + p - 1) >> 4) - (bb >> 4) + 1 for bb in bases)
+        helpers = os.environ.get("DSPEED_B200_CONV_HELPERS", "1") != "0" and pairs <= NT - hb and 16.0 * nch / sigma < 600.0
+        tmpl = f"{'true' if poly else 'false'}, {'true' if two else 'false'}"
+        args_a = (f"{self._slot(w)}, {x}, {n}, {_lit(sigma)}, {int(lt)}, {int(fl)}, {int(L)}, {_lit(c)}, {_lit(inv2S)}, "
+                  f"{_lit(math.exp(-1.0 / sigma))}, {_lit(math.exp(1.0 / sigma))}, {_lit(math.exp((L - 1) / sigma))}, {pw}")
+        args_b = (f"{so[0]}, {so[1]}, {sinks[0]}, {sinks[1]}, reinterpret_cast<double*>(SLOT({scratch[0][0]})), "
+                  f"tid, lane, warp);")
+        if helpers:
+            pwc, wm, wp = self._t("pwc"), self._t("wm"), self._t("wp")
+            tab = [math.exp(-16.0 * t / sigma) if t <= nch else 0.0 for t in range(NT)] + \
+                  [math.exp(16.0 * t / sigma) if t <= nch else 0.0 for t in range(NT)]
+            self.static_arrays.append(f"__device__ const double {pwc}[{2 * NT}] = {{{', '.join(_lit(v) for v in tab)}}};")
+            self._e(f"const float {wm}[16] = {{{', '.join(_flit(math.exp(-k / sigma)) for k in range(16))}}};",
+                    f"const float {wp}[16] = {{{', '.join(_flit(math.exp(k / sigma)) for k in range(16))}}};",
+                    f"conv_seg_chunked_h<{tmpl}, {hb}, {NT}>({args_a}, {pwc}, {wm}, {wp}, {args_b}")
+        else:
+            self._e(f"conv_seg_chunked<{tmpl}>({args_a}, {args_b}")
         # the band table overwrote the (always-zero) pad columns of its slots
         self._e(f"zero_pads(SLOT({scratch[0][0]}), {self.slot_words}, {self.nchunks}, 0, {len(scratch)}, tid);")
         for sl in scratch:

@@ -26,11 +26,14 @@
 // tracing build only: cycle stamps inside a routine (thread 0 of CTA 0), accumulated next to the per-node
 // stamps of the generated kernel (prof_ts[96 + k], offset DSPB_PROF_OFF of the dynamic shared memory)
 #if defined(DSPB_PROFILE) && defined(DSPB_PROF_OFF)
+#ifndef DSPB_PROF_TID
+#define DSPB_PROF_TID 0   // the observing thread of CTA 0 (-DDSPB_PROF_TID=n: another warp's view)
+#endif
 #define PROF_SUB_BEGIN() long long psub_prev_ = clock64()
 #define PROF_SUB_RESET() psub_prev_ = clock64()
 #define PROF_SUB(k)                                                                        \
   do {                                                                                     \
-    if (blockIdx.x == 0 && threadIdx.x == 0) {                                             \
+    if (blockIdx.x == 0 && threadIdx.x == DSPB_PROF_TID) {                                 \
       extern __shared__ __align__(16) unsigned char psub_smem_[];                          \
       long long* p_ = reinterpret_cast<long long*>(psub_smem_ + DSPB_PROF_OFF);            \
       const long long t_ = clock64();                                                      \
@@ -740,6 +743,95 @@ struct SegSink {
   int pick;
 };
 
+// passes 2 and 3 of the chunked cusp / zac convolution (shared by both pass-1 variants): `s` = this
+// thread's chunk sums, the band table `tab` holds the chunk-local running sums at the band positions
+template <bool POLY, bool TWO>
+__device__ __forceinline__ void conv_seg_finish(const float* X, int N, int lt, int fl, int L, double c, double inv2S,
+                                                double qm, double qp, double eA, const double* __restrict__ pw,
+                                                SegOut s0, SegOut s1, SegSink k0, SegSink k1, double* tab,
+                                                const double (&s)[POLY ? 5 : 3], int tid, int lane, int warp) {
+  constexpr int NQ = POLY ? 5 : 3;
+  const int p = N - L + 1;
+  // operands of pass 3 that come from global memory: requested now, consumed two barriers later
+  const double po_pf = tid < p ? pw[tid] : 0.0, mo_pf = tid < p ? pw[p + tid] : 0.0;
+  const int CW = (((p + CHK - 1) >> 4) + 1) | 1, PP = CHK * CW;
+  const double j0 = 0.5 * (double)N;
+  const int base[4] = {L, L - lt, L - 1 - lt - fl, 0};
+  PROF_SUB_BEGIN();
+  // ---- pass 2: exclusive scan of the chunk sums over the 512 threads, through shared memory:
+  // every thread deposits its NQ sums (one store each), warp q scans quantity q (lane l owns
+  // entries [16l, 16l+16), skewed by one word per 16 so that both access patterns are
+  // conflict-free), and pass 3 picks up the prefix in front of whatever chunk it needs.  Costs
+  // the block NQ stores per thread instead of NQ float64 shuffle scans per thread.
+  double* otab = tab + NQ * 4 * PP;
+  constexpr int OT = 512 + 32;
+#pragma unroll
+  for (int q = 0; q < NQ; q++) otab[q * OT + tid + (tid >> 4)] = s[q];
+  BSYNC();
+  PROF_SUB(1);   // wait for the slowest pass-1 thread
+  // (warps 1,2,3,5,6: the scalar warp shares scheduler partition 0 with warps 0,4,8,12)
+  const int sq = warp < 4 ? warp - 1 : (warp == 5 ? 3 : (warp == 6 ? 4 : -1));
+  if (sq >= 0 && sq < NQ) {
+    double* o = otab + sq * OT + 17 * lane;
+    double v[CHK];
+    double run = 0.0;
+#pragma unroll
+    for (int k = 0; k < CHK; k++) {
+      v[k] = run;       // exclusive inside the lane
+      run += o[k];
+    }
+    const double incl = wscan_incl(run, lane);
+    const double base_l = incl - run;
+#pragma unroll
+    for (int k = 0; k < CHK; k++) o[k] = v[k] + base_l;
+  }
+  BSYNC();
+  PROF_SUB(2);   // pass 2 (scan warps)
+  // ---- pass 3: one thread per output ------------------------------------------------------------
+  const int pceil = (p + CHK - 1) & ~(CHK - 1);
+  const double eAm = 1.0 / eA;  // eA = e^{(L-1)/s}: e^{+-n/s} = eA^{+-1} * q^{+-o}
+  float mx0 = -CUDART_INF_F, mx1 = -CUDART_INF_F;
+  for (int o = tid; o < pceil; o += 512) {
+    float y0 = 0.f, y1 = 0.f;
+    if (o < p) {
+      const int ow[4] = {(base[0] + o) >> 4, (base[1] + o) >> 4, (base[2] + o) >> 4, (base[3] + o) >> 4};
+#define TB(q, b) (tab[((q)*4 + (b)) * PP + (o & 15) * CW + (o >> 4)] + otab[(q)*OT + ow[b] + (ow[b] >> 4)])
+      const double po = o == tid ? po_pf : pw[o], mo = o == tid ? mo_pf : pw[p + o];
+      const double en = eA * po, enm = eAm * mo;      // e^{+-n/s}, n = L - 1 + o
+      const double eLn = qp * mo, eLnm = qm * po;     // e^{+-(L-n)/s} = e^{+-(1-o)/s}
+      const double yA = (en * (TB(0, 0) - TB(0, 1)) - enm * (TB(1, 0) - TB(1, 1))) * inv2S;
+      const double yB = TB(2, 1) - TB(2, 2);
+      const double yC = (eLn * (TB(1, 2) - TB(1, 3)) - eLnm * (TB(0, 2) - TB(0, 3))) * inv2S;
+      const double xm = o >= 1 ? (double)at(X, o - 1) : 0.0;
+      double ysh = yA + yB + yC;
+      double v0 = ysh + c * s0.kL * xm, v1 = ysh + c * s1.kL * xm;
+      if (POLY) {
+        const double n = (double)(L - 1 + o), nc = n - j0, a = ((double)L - n) + j0;
+        const double dPa = TB(2, 0) - TB(2, 1), dM1a = TB(3, 0) - TB(3, 1), dM2a = TB(4, 0) - TB(4, 1);
+        const double s2a = nc * nc * dPa - 2.0 * nc * dM1a + dM2a, s1a = nc * dPa - dM1a;
+        const double dPc = TB(2, 2) - TB(2, 3), dM1c = TB(3, 2) - TB(3, 3), dM2c = TB(4, 2) - TB(4, 3);
+        const double s2c = a * a * dPc + 2.0 * a * dM1c + dM2c, s1c = a * dPc + dM1c;
+        v0 += s0.beta * ((s2a - 2.0 * s0.h * s1a) + (s2c - 2.0 * s0.h * s1c));
+        v1 += s1.beta * ((s2a - 2.0 * s1.h * s1a) + (s2c - 2.0 * s1.h * s1c));
+      }
+#undef TB
+      y0 = (float)v0;
+      y1 = (float)v1;
+      mx0 = fmaxf(mx0, y0);
+      mx1 = fmaxf(mx1, y1);
+      if (k0.pick_dst && o == k0.pick) k0.pick_dst[0] = (double)y0;
+      if (TWO && k1.pick_dst && o == k1.pick) k1.pick_dst[0] = (double)y1;
+    }
+    if (k0.slot) k0.slot[sidx(o)] = y0;
+    if (TWO && k1.slot) k1.slot[sidx(o)] = y1;
+  }
+  PROF_SUB(3);   // pass 3 (this thread)
+  if (k0.mx) put_fmax(k0.mx, mx0, lane, warp);
+  if (TWO && k1.mx) put_fmax(k1.mx, mx1, lane, warp);
+  BSYNC();
+  PROF_SUB(4);   // wait for the slowest pass-3 thread
+}
+
 template <bool POLY, bool TWO>
 __device__ __forceinline__ void conv_seg_chunked(const float* X, const float (&x)[CHK], int N, double sigma, int lt,
                                                  int fl, int L, double c, double inv2S, double qm, double qp,
@@ -806,79 +898,118 @@ __device__ __forceinline__ void conv_seg_chunked(const float* X, const float (&x
       }
     }
   }
-  // ---- pass 2: exclusive scan of the chunk sums over the 512 threads, through shared memory:
-  // every thread deposits its NQ sums (one store each), warp q scans quantity q (lane l owns
-  // entries [16l, 16l+16), skewed by one word per 16 so that both access patterns are
-  // conflict-free), and pass 3 picks up the prefix in front of whatever chunk it needs.  Costs
-  // the block NQ stores per thread instead of NQ float64 shuffle scans per thread.
   PROF_SUB(0);   // pass 1 (this thread)
-  double* otab = tab + NQ * 4 * PP;
-  constexpr int OT = 512 + 32;
+  conv_seg_finish<POLY, TWO>(X, N, lt, fl, L, c, inv2S, qm, qp, eA, pw, s0, s1, k0, k1, tab, s, tid, lane, warp);
+}
+
+// ---------------------------------------------------------------------------------------
+// Pass 1 with helper threads.  The chunk sums are float32 inside a 16-sample chunk (weights relative
+// to the chunk start, compile-time tables `wm` / `wp`; z = (x[k] - x[k-1]) + (1 - c) x[k-1] keeps the
+// pole-zero difference exact) and float64 across chunks (`pwc[t]` = e^{-16 t / sigma}, `pwc[NPW + t]`
+// its inverse).  Owner threads never deposit: the (band, chunk) pairs that need the running sums at
+// every position are handed to the threads beyond the end of the input (tid >= HB, idle otherwise),
+// which re-read the chunk from shared memory -- the 4 warps that used to be the critical path
+// (16 x 4 predicated bands x 5 stores) are gone and the work is spread over all 16 warps.
+// ---------------------------------------------------------------------------------------
+template <bool POLY, bool TWO, int HB, int NPW>
+__device__ __forceinline__ void conv_seg_chunked_h(const float* X, const float (&x)[CHK], int N, double sigma, int lt,
+                                                   int fl, int L, double c, double inv2S, double qm, double qp,
+                                                   double eA, const double* __restrict__ pw,
+                                                   const double* __restrict__ pwc, const float (&wm)[CHK],
+                                                   const float (&wp)[CHK], SegOut s0, SegOut s1, SegSink k0,
+                                                   SegSink k1, double* tab, int tid, int lane, int warp) {
+  constexpr int NQ = POLY ? 5 : 3;
+  const int p = N - L + 1;
+  const int CW = (((p + CHK - 1) >> 4) + 1) | 1, PP = CHK * CW;
+  const double j0 = 0.5 * (double)N;
+  const float omc = (float)(1.0 - c);
+  const int base[4] = {L, L - lt, L - 1 - lt - fl, 0};
+  (void)sigma;
+  PROF_SUB_BEGIN();
+  double s[NQ];
 #pragma unroll
-  for (int q = 0; q < NQ; q++) otab[q * OT + tid + (tid >> 4)] = s[q];
-  BSYNC();
-  PROF_SUB(1);   // wait for the slowest pass-1 thread
-  // (warps 1,2,3,5,6: the scalar warp shares scheduler partition 0 with warps 0,4,8,12)
-  const int sq = warp < 4 ? warp - 1 : (warp == 5 ? 3 : (warp == 6 ? 4 : -1));
-  if (sq >= 0 && sq < NQ) {
-    double* o = otab + sq * OT + 17 * lane;
-    double v[CHK];
-    double run = 0.0;
+  for (int q = 0; q < NQ; q++) s[q] = 0.0;
+  if (tid < HB) {
+    // ---- owner threads: chunk sums of the own chunk (registers) ------------------------------------
+    const int i0 = CHK * tid;
+    if (i0 < N) {
+      float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f, r4 = 0.f;
+      float prev = i0 > 0 ? at(X, i0 - 1) : 0.f;
+      const bool whole = i0 + CHK <= N;
 #pragma unroll
-    for (int k = 0; k < CHK; k++) {
-      v[k] = run;       // exclusive inside the lane
-      run += o[k];
-    }
-    const double incl = wscan_incl(run, lane);
-    const double base_l = incl - run;
-#pragma unroll
-    for (int k = 0; k < CHK; k++) o[k] = v[k] + base_l;
-  }
-  BSYNC();
-  PROF_SUB(2);   // pass 2 (scan warps)
-  // ---- pass 3: one thread per output ------------------------------------------------------------
-  const int pceil = (p + CHK - 1) & ~(CHK - 1);
-  const double eAm = 1.0 / eA;  // eA = e^{(L-1)/s}: e^{+-n/s} = eA^{+-1} * q^{+-o}
-  float mx0 = -CUDART_INF_F, mx1 = -CUDART_INF_F;
-  for (int o = tid; o < pceil; o += 512) {
-    float y0 = 0.f, y1 = 0.f;
-    if (o < p) {
-      const int ow[4] = {(base[0] + o) >> 4, (base[1] + o) >> 4, (base[2] + o) >> 4, (base[3] + o) >> 4};
-#define TB(q, b) (tab[((q)*4 + (b)) * PP + (o & 15) * CW + (o >> 4)] + otab[(q)*OT + ow[b] + (ow[b] >> 4)])
-      const double po = pw[o], mo = pw[p + o];
-      const double en = eA * po, enm = eAm * mo;      // e^{+-n/s}, n = L - 1 + o
-      const double eLn = qp * mo, eLnm = qm * po;     // e^{+-(L-n)/s} = e^{+-(1-o)/s}
-      const double yA = (en * (TB(0, 0) - TB(0, 1)) - enm * (TB(1, 0) - TB(1, 1))) * inv2S;
-      const double yB = TB(2, 1) - TB(2, 2);
-      const double yC = (eLn * (TB(1, 2) - TB(1, 3)) - eLnm * (TB(0, 2) - TB(0, 3))) * inv2S;
-      const double xm = o >= 1 ? (double)at(X, o - 1) : 0.0;
-      double ysh = yA + yB + yC;
-      double v0 = ysh + c * s0.kL * xm, v1 = ysh + c * s1.kL * xm;
-      if (POLY) {
-        const double n = (double)(L - 1 + o), nc = n - j0, a = ((double)L - n) + j0;
-        const double dPa = TB(2, 0) - TB(2, 1), dM1a = TB(3, 0) - TB(3, 1), dM2a = TB(4, 0) - TB(4, 1);
-        const double s2a = nc * nc * dPa - 2.0 * nc * dM1a + dM2a, s1a = nc * dPa - dM1a;
-        const double dPc = TB(2, 2) - TB(2, 3), dM1c = TB(3, 2) - TB(3, 3), dM2c = TB(4, 2) - TB(4, 3);
-        const double s2c = a * a * dPc + 2.0 * a * dM1c + dM2c, s1c = a * dPc + dM1c;
-        v0 += s0.beta * ((s2a - 2.0 * s0.h * s1a) + (s2c - 2.0 * s0.h * s1c));
-        v1 += s1.beta * ((s2a - 2.0 * s1.h * s1a) + (s2c - 2.0 * s1.h * s1c));
+      for (int k = 0; k < CHK; k++) {
+        float z = (x[k] - prev) + omc * prev;
+        if (!whole) z = i0 + k < N ? z : 0.f;
+        prev = x[k];
+        r0 = fmaf(wm[k], z, r0);
+        r1 = fmaf(wp[k], z, r1);
+        r2 += z;
+        if (POLY) {
+          r3 = fmaf((float)k, z, r3);
+          r4 = fmaf((float)(k * k), z, r4);
+        }
       }
-#undef TB
-      y0 = (float)v0;
-      y1 = (float)v1;
-      mx0 = fmaxf(mx0, y0);
-      mx1 = fmaxf(mx1, y1);
-      if (k0.pick_dst && o == k0.pick) k0.pick_dst[0] = (double)y0;
-      if (TWO && k1.pick_dst && o == k1.pick) k1.pick_dst[0] = (double)y1;
+      const double jc0 = (double)i0 - j0;
+      s[0] = pwc[tid] * (double)r0;
+      s[1] = pwc[NPW + tid] * (double)r1;
+      s[2] = (double)r2;
+      if (POLY) {
+        s[3] = fma(jc0, s[2], (double)r3);
+        s[4] = fma(jc0 * jc0, s[2], fma(2.0 * jc0, (double)r3, (double)r4));
+      }
     }
-    if (k0.slot) k0.slot[sidx(o)] = y0;
-    if (TWO && k1.slot) k1.slot[sidx(o)] = y1;
+  } else {
+    // ---- helper threads: one (band, chunk) pair each -------------------------------------------------
+    int h = tid - HB, b = -1, ch = 0, bbase = 0;
+#pragma unroll
+    for (int bb = 0; bb < 4; bb++) {
+      const int c_lo = base[bb] >> 4, cnt = ((base[bb] + p - 1) >> 4) - c_lo + 1;
+      if (b < 0) {
+        if (h < cnt) { b = bb; ch = c_lo + h; bbase = base[bb]; }
+        else h -= cnt;
+      }
+    }
+    if (b >= 0 && CHK * ch <= N) {
+      const int i0 = CHK * ch;
+      float xs[CHK];
+      ld_chunk(X, ch, xs);
+      float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f, r4 = 0.f;
+      float prev = i0 > 0 ? at(X, i0 - 1) : 0.f;
+      const double w0 = pwc[ch], w0i = pwc[NPW + ch];
+      const double jc0 = (double)i0 - j0, jc02 = jc0 * jc0, jc2 = 2.0 * jc0;
+      const int ob = i0 - bbase;
+      double* tb = tab + b * PP;
+#pragma unroll
+      for (int k = 0; k < CHK; k++) {
+        // Branch-free deposit: positions outside the band write to a column of the band table that no
+        // band position uses (CW - 1 > (p - 1) / 16), so the 16 positions form ONE basic block and the
+        // conversions / FP64 products / stores of consecutive positions overlap.
+        const int o = ob + k;
+        const bool dep = (unsigned)o < (unsigned)p && i0 + k <= N;
+        double* t = tb + (dep ? (o & 15) * CW + (o >> 4) : CW - 1);
+        const double d2 = (double)r2, d3 = (double)r3;
+        t[0] = w0 * (double)r0;
+        t[4 * PP] = w0i * (double)r1;
+        t[2 * 4 * PP] = d2;
+        if (POLY) {
+          t[3 * 4 * PP] = fma(jc0, d2, d3);
+          t[4 * 4 * PP] = fma(jc02, d2, fma(jc2, d3, (double)r4));
+        }
+        float z = (xs[k] - prev) + omc * prev;
+        z = i0 + k < N ? z : 0.f;
+        prev = xs[k];
+        r0 = fmaf(wm[k], z, r0);
+        r1 = fmaf(wp[k], z, r1);
+        r2 += z;
+        if (POLY) {
+          r3 = fmaf((float)k, z, r3);
+          r4 = fmaf((float)(k * k), z, r4);
+        }
+      }
+    }
   }
-  PROF_SUB(3);   // pass 3 (this thread)
-  if (k0.mx) put_fmax(k0.mx, mx0, lane, warp);
-  if (TWO && k1.mx) put_fmax(k1.mx, mx1, lane, warp);
-  BSYNC();
-  PROF_SUB(4);   // wait for the slowest pass-3 thread
+  PROF_SUB(0);   // pass 1 (this thread)
+  conv_seg_finish<POLY, TWO>(X, N, lt, fl, L, c, inv2S, qm, qp, eA, pw, s0, s1, k0, k1, tab, s, tid, lane, warp);
 }
 
 }  // namespace crt
