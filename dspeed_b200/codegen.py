@@ -584,6 +584,37 @@ class SpecChain(FusedChain):
                         place(r)
                 continue
             place(nd)
+        # Fill the block stream's wait for a scalar of the scalar stream.  A windower needs its start
+        # sample from a threshold search (scalar warp, latency bound): the block warps would idle at that
+        # point.  A fit / extremum reduction whose results only the scalar stream (outputs) consumes, and
+        # whose input wave is still in its slot at that point anyway, is evaluated there instead of right
+        # behind its producer (the chunk is re-read from the slot: 4 shared-memory loads per thread).
+        if os.environ.get("DSPEED_B200_FILL_WAIT", "1") != "0":
+            keys = ("x", "y", "thr", "start", "walk", "t", "t0", "b", "tau", "oi", "oo")
+            wpos = next((k for k, nd in enumerate(order) if nd["kind"] == "windower" and not str(nd["t0"]).startswith(("0x", "-0x"))),
+                        None)
+            if wpos is not None:
+                wave_last = {}
+                for k, nd in enumerate(order):
+                    for m in (nd["members"] if nd["kind"] in ("fir_group", "conv_seg_group") else [nd]):
+                        for (w, _, _) in m.get("ins", []):
+                            wave_last[w.id] = k
+                best = None
+                for k, nd in enumerate(order[:wpos]):
+                    if nd["kind"] != "lsf":
+                        continue
+                    w, off, n = nd["ins"][0]
+                    outs = {o for o in nd["outs"] if o}
+                    used_between = any(isinstance(x.get(key), str) and x[key] in outs for x in order[k + 1:wpos + 1] for key in keys)
+                    if used_between or wave_last.get(w.id, -1) < wpos or w.is_input:
+                        continue
+                    if best is None or n > best[1]:
+                        best = (k, n)
+                if best is not None:
+                    nd = order.pop(best[0])
+                    order.insert(wpos - 1, nd)     # wpos shifted by one after the pop
+                    w = nd["ins"][0][0]
+                    w.force_slot = True
         self.order = order
         # last use positions (in emission order) for slot liveness
         pos = {}
@@ -601,7 +632,7 @@ class SpecChain(FusedChain):
                 else:
                     local &= nd["kind"] in ("min_max", "lsf", "bl_sub", "pole_zero")
             first = pos.get(w.producer, 0) if w.producer is not None else 0
-            w.needs_slot = not (local and w.last - first <= 6)
+            w.needs_slot = not (local and w.last - first <= 6) or getattr(w, "force_slot", False)
 
     # ------------------------------------------------------------------------------------
     # emission
@@ -2008,7 +2039,7 @@ extern "C" int chain_launch(const void* const* ptrs, long long n_ptrs, long long
 # ----------------------------------------------------------------------------------------
 def _headers_digest() -> str:
     h = hashlib.sha1()
-    for f in ("common.cuh", "row_ops.cuh", "conv_ops.cuh", "chain_rt.cuh"):
+    for f in ("common.cuh", "row_ops.cuh", "conv_ops.cuh", "chain_rt.cuh", "warp_rt.cuh"):
         h.update(open(os.path.join(_lib.CSRC, f), "rb").read())
     h.update(open(os.path.join(_lib.INCLUDE, "dspeed_b200.h"), "rb").read())
     return h.hexdigest()

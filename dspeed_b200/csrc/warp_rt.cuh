@@ -108,12 +108,11 @@ __device__ __forceinline__ float wscan_excl_add_rev(float v, int lane) {  // sum
   return lane == 31 ? 0.f : e;
 }
 __device__ __forceinline__ float wscan_incl_max(float v, int lane) {
+  // shfl.up hands lanes below `d` their own value back and max is idempotent: no lane predicate
   float s = v;
+  (void)lane;
 #pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const float t = __shfl_up_sync(FULL, s, d);
-    if (lane >= d) s = fmaxf(s, t);
-  }
+  for (int d = 1; d < 32; d <<= 1) s = fmaxf(s, __shfl_up_sync(FULL, s, d));
   return s;
 }
 __device__ __forceinline__ int wscan_incl_add_i(int v, int lane) {
@@ -148,15 +147,25 @@ __device__ __forceinline__ void mw_left(const float (&x)[CH], float (&y)[CH], in
 #pragma unroll
   for (int j = 0; j < L; j++) h[j] = __shfl_up_sync(FULL, x[CH - L + j], 1);
   float run = 0.f;
+  if (lane > 0 && CH * (lane + 1) <= n) {
+    // interior lanes: no edge cases
 #pragma unroll
-  for (int j = 0; j < CH; j++) {
-    const int i = CH * lane + j;
-    const float prev = j >= L ? x[j >= L ? j - L : 0] : h[j < L ? j : 0];
-    float d = (x[j] - (i >= L ? prev : e0)) * il;
-    d = i == 0 ? e0 : d;
-    d = i >= n ? 0.f : d;
-    run += d;
-    y[j] = run;
+    for (int j = 0; j < CH; j++) {
+      const float prev = j >= L ? x[j >= L ? j - L : 0] : h[j < L ? j : 0];
+      run += (x[j] - prev) * il;
+      y[j] = run;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < CH; j++) {
+      const int i = CH * lane + j;
+      const float prev = j >= L ? x[j >= L ? j - L : 0] : h[j < L ? j : 0];
+      float d = (x[j] - (i >= L ? prev : e0)) * il;
+      d = i == 0 ? e0 : d;
+      d = i >= n ? 0.f : d;
+      run += d;
+      y[j] = run;
+    }
   }
   const float off = wscan_excl_add(run, lane);
 #pragma unroll
@@ -171,15 +180,25 @@ __device__ __forceinline__ void mw_right(const float (&x)[CH], float (&y)[CH], f
 #pragma unroll
   for (int j = 0; j < L; j++) h[j] = __shfl_down_sync(FULL, x[j], 1);
   float run = 0.f;
+  if (CH * (lane + 1) + L <= n) {
+    // interior lanes: no edge cases
 #pragma unroll
-  for (int j = CH - 1; j >= 0; j--) {
-    const int i = CH * lane + j;
-    const float next = j + L < CH ? x[j + L < CH ? j + L : 0] : h[j + L >= CH ? j + L - CH : 0];
-    float d = (x[j] - (i + L <= n - 1 ? next : e0)) * il;
-    d = i == n - 1 ? e0 : d;
-    d = i >= n ? 0.f : d;
-    run += d;
-    y[j] = run;
+    for (int j = CH - 1; j >= 0; j--) {
+      const float next = j + L < CH ? x[j + L < CH ? j + L : 0] : h[j + L >= CH ? j + L - CH : 0];
+      run += (x[j] - next) * il;
+      y[j] = run;
+    }
+  } else {
+#pragma unroll
+    for (int j = CH - 1; j >= 0; j--) {
+      const int i = CH * lane + j;
+      const float next = j + L < CH ? x[j + L < CH ? j + L : 0] : h[j + L >= CH ? j + L - CH : 0];
+      float d = (x[j] - (i + L <= n - 1 ? next : e0)) * il;
+      d = i == n - 1 ? e0 : d;
+      d = i >= n ? 0.f : d;
+      run += d;
+      y[j] = run;
+    }
   }
   const float off = wscan_excl_add_rev(run, lane);
 #pragma unroll
@@ -248,6 +267,16 @@ struct ChunkSumm {
 template <int CH>
 __device__ __forceinline__ ChunkSumm chunk_summary(const float (&x)[CH], int n, int lane) {
   ChunkSumm s{-CUDART_INF_F, CUDART_INF_F, 0.f, 0.f};
+  if (CH * (lane + 1) <= n) {
+#pragma unroll
+    for (int j = 0; j < CH; j++) {
+      s.vmax = fmaxf(s.vmax, x[j]);
+      s.vmin = fminf(s.vmin, x[j]);
+      s.fall = fmaxf(s.fall, s.vmax - x[j]);
+      s.rise = fmaxf(s.rise, x[j] - s.vmin);
+    }
+    return s;
+  }
 #pragma unroll
   for (int j = 0; j < CH; j++) {
     if (CH * lane + j < n) {

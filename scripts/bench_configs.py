@@ -75,17 +75,9 @@ if "C4" in SEL:
     wf = tables.WaveformTable(size=n, t0=tables.Array(torch.zeros(n, dtype=torch.float64, device=dev), attrs={"units": "ns"}),
                               dt=tables.Array(torch.full((n,), 16.0, dtype=torch.float64, device=dev), attrs={"units": "ns"}),
                               values=d["values"])
-    cfg4 = {
-        "outputs": ["vt_max", "vt_min", "n_max", "n_min"],
-        "processors": {
-            "wf_blsub": "dspeed.processors.bl_subtract(waveform, baseline, wf_blsub(unit='ADC'))",
-            "wf_mw": {"function": "dspeed.processors.moving_window_multi(wf_blsub, 8, 2, 0, wf_mw)", "unit": "ADC"},
-            "vt_max, vt_min, n_max, n_min": {
-                "function": "get_multi_local_extrema", "module": "dspeed.processors",
-                "args": ["wf_mw", 12.0, 6.0, 3, 15.0, 1000.0, "vt_max(20, 'f')", "vt_min(20, 'f')", "n_max", "n_min"],
-                "unit": ["ns", "ns", "none", "none"]},
-        },
-    }
+    import yaml
+
+    cfg4 = yaml.safe_load(open(os.path.join(REPO, "dspeed_b200", "configs", "sipm_peaks.yaml")))
     tb = tables.Table({"waveform": wf, "baseline": tables.Array(d["baseline"])}, size=n)
     chain, _, tb_out = build_processing_chain(cfg4, tb, device=dev, block_width=int(os.environ.get("DSPB_C4_BLOCK", 0)) or None)
     # device-resident output columns (written in place by the kernel), like the ICPC bench
