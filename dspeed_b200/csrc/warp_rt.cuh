@@ -135,72 +135,66 @@ __device__ __forceinline__ void bl_sub(const float (&x)[CH], float b, float (&y)
 }
 
 // ---------------------------------------------------------------------------------------
+// Invariant of every wave in registers: positions >= n repeat sample n - 1 ("right-edge extended").
+// It costs one pass when a wave is created with a new length and makes the window filters and the
+// chunk summaries branch-free (the reference's edge padding x[min(i + L, n - 1)] comes for free).
+// ---------------------------------------------------------------------------------------
+template <int CH, int N>
+__device__ __forceinline__ void edge_extend(float (&x)[CH], int lane) {
+  if (N >= 32 * CH) return;
+  constexpr int LAST = (N - 1) / CH, JL = (N - 1) % CH;   // lane / register of sample N - 1
+  const float e = __shfl_sync(FULL, x[JL], LAST);
+  const bool above = lane > LAST, from = lane >= LAST;    // one select per register, no branch
+#pragma unroll
+  for (int j = 0; j < CH; j++) x[j] = (j > JL ? from : above) ? e : x[j];
+}
+
+// ---------------------------------------------------------------------------------------
 // moving_windows.py:12-114 : out[0] = x[0]; out[i] = out[i-1] + (x[i] - x[max(i-L, 0)]) / L and
 // its mirror image.  Lane-local running sum of the increments + one warp scan; the L samples of
-// the neighbouring chunk arrive by shuffles (L <= CH, compile time).
+// the neighbouring chunk arrive by shuffles (L <= CH, compile time).  Lane 0 sees x[0] in its left
+// halo and the right halo is the edge extension, so no position is special.
 // ---------------------------------------------------------------------------------------
-template <int CH, int L>
-__device__ __forceinline__ void mw_left(const float (&x)[CH], float (&y)[CH], int n, float il, int lane) {
+template <int CH, int L, int N>
+__device__ __forceinline__ void mw_left(const float (&x)[CH], float (&y)[CH], float il, int lane) {
   static_assert(L >= 1 && L <= CH, "window longer than a lane chunk");
   const float e0 = __shfl_sync(FULL, x[0], 0);
   float h[L];
 #pragma unroll
-  for (int j = 0; j < L; j++) h[j] = __shfl_up_sync(FULL, x[CH - L + j], 1);
-  float run = 0.f;
-  if (lane > 0 && CH * (lane + 1) <= n) {
-    // interior lanes: no edge cases
-#pragma unroll
-    for (int j = 0; j < CH; j++) {
-      const float prev = j >= L ? x[j >= L ? j - L : 0] : h[j < L ? j : 0];
-      run += (x[j] - prev) * il;
-      y[j] = run;
-    }
-  } else {
-#pragma unroll
-    for (int j = 0; j < CH; j++) {
-      const int i = CH * lane + j;
-      const float prev = j >= L ? x[j >= L ? j - L : 0] : h[j < L ? j : 0];
-      float d = (x[j] - (i >= L ? prev : e0)) * il;
-      d = i == 0 ? e0 : d;
-      d = i >= n ? 0.f : d;
-      run += d;
-      y[j] = run;
-    }
+  for (int j = 0; j < L; j++) {
+    const float t = __shfl_up_sync(FULL, x[CH - L + j], 1);
+    h[j] = lane == 0 ? e0 : t;
   }
-  const float off = wscan_excl_add(run, lane);
+  float run = 0.f;
+#pragma unroll
+  for (int j = 0; j < CH; j++) {
+    const float prev = j >= L ? x[j >= L ? j - L : 0] : h[j < L ? j : 0];
+    run += (x[j] - prev) * il;
+    y[j] = run;
+  }
+  const float off = wscan_excl_add(run, lane) + e0;
 #pragma unroll
   for (int j = 0; j < CH; j++) y[j] += off;
+  edge_extend<CH, N>(y, lane);   // the increments beyond n - 1 are not zero: restore the invariant
 }
 template <int CH, int L, int N>
 __device__ __forceinline__ void mw_right(const float (&x)[CH], float (&y)[CH], float il, int lane) {
   static_assert(L >= 1 && L <= CH, "window longer than a lane chunk");
-  constexpr int n = N;
   const float e0 = __shfl_sync(FULL, x[(N - 1) % CH], (N - 1) / CH);
   float h[L];
 #pragma unroll
-  for (int j = 0; j < L; j++) h[j] = __shfl_down_sync(FULL, x[j], 1);
-  float run = 0.f;
-  if (CH * (lane + 1) + L <= n) {
-    // interior lanes: no edge cases
-#pragma unroll
-    for (int j = CH - 1; j >= 0; j--) {
-      const float next = j + L < CH ? x[j + L < CH ? j + L : 0] : h[j + L >= CH ? j + L - CH : 0];
-      run += (x[j] - next) * il;
-      y[j] = run;
-    }
-  } else {
-#pragma unroll
-    for (int j = CH - 1; j >= 0; j--) {
-      const int i = CH * lane + j;
-      const float next = j + L < CH ? x[j + L < CH ? j + L : 0] : h[j + L >= CH ? j + L - CH : 0];
-      float d = (x[j] - (i + L <= n - 1 ? next : e0)) * il;
-      d = i == n - 1 ? e0 : d;
-      d = i >= n ? 0.f : d;
-      run += d;
-      y[j] = run;
-    }
+  for (int j = 0; j < L; j++) {
+    const float t = __shfl_down_sync(FULL, x[j], 1);
+    h[j] = lane == 31 ? e0 : t;
   }
-  const float off = wscan_excl_add_rev(run, lane);
+  float run = 0.f;
+#pragma unroll
+  for (int j = CH - 1; j >= 0; j--) {
+    const float next = j + L < CH ? x[j + L < CH ? j + L : 0] : h[j + L >= CH ? j + L - CH : 0];
+    run += (x[j] - next) * il;
+    y[j] = run;
+  }
+  const float off = wscan_excl_add_rev(run, lane) + e0;
 #pragma unroll
   for (int j = 0; j < CH; j++) y[j] += off;
 }
@@ -259,53 +253,59 @@ __device__ __forceinline__ void min_max(const float (&x)[CH], int lo, int hi, in
 // lane that owns the sample (bit k of lane l <-> sample CH*l + k), so merging the two search
 // directions (aggressive search = union) and sorting are free.
 // ---------------------------------------------------------------------------------------
-// per-chunk summaries: extreme values, the largest fall (v[i] - v[j], i < j) and the largest rise
-// (v[j] - v[i], i < j) inside the chunk
-struct ChunkSumm {
+// per-window summaries (a window = 32 samples, or the whole lane chunk when it is shorter): extreme
+// values, the largest fall (v[i] - v[j], i < j) and the largest rise (v[j] - v[i], i < j) inside it
+struct WinSumm {
   float vmax, vmin, fall, rise;
 };
 template <int CH>
-__device__ __forceinline__ ChunkSumm chunk_summary(const float (&x)[CH], int n, int lane) {
-  ChunkSumm s{-CUDART_INF_F, CUDART_INF_F, 0.f, 0.f};
-  if (CH * (lane + 1) <= n) {
+struct ChunkSumm {
+  static constexpr int WS = CH < 32 ? CH : 32;   // window size
+  static constexpr int NWL = CH / WS;            // windows per lane
+  WinSumm w[NWL];
+};
+template <int CH>
+__device__ __forceinline__ ChunkSumm<CH> chunk_summary(const float (&x)[CH]) {
+  // (edge-extended waves: the repeated last sample changes none of the four)
+  ChunkSumm<CH> s;
 #pragma unroll
-    for (int j = 0; j < CH; j++) {
-      s.vmax = fmaxf(s.vmax, x[j]);
-      s.vmin = fminf(s.vmin, x[j]);
-      s.fall = fmaxf(s.fall, s.vmax - x[j]);
-      s.rise = fmaxf(s.rise, x[j] - s.vmin);
-    }
-    return s;
-  }
+  for (int h = 0; h < ChunkSumm<CH>::NWL; h++) {
+    WinSumm a{-CUDART_INF_F, CUDART_INF_F, 0.f, 0.f};
 #pragma unroll
-  for (int j = 0; j < CH; j++) {
-    if (CH * lane + j < n) {
-      s.vmax = fmaxf(s.vmax, x[j]);
-      s.vmin = fminf(s.vmin, x[j]);
-      s.fall = fmaxf(s.fall, s.vmax - x[j]);
-      s.rise = fmaxf(s.rise, x[j] - s.vmin);
+    for (int k = 0; k < ChunkSumm<CH>::WS; k++) {
+      const float v = x[h * ChunkSumm<CH>::WS + k];
+      a.vmax = fmaxf(a.vmax, v);
+      a.vmin = fminf(a.vmin, v);
+      a.fall = fmaxf(a.fall, a.vmax - v);
+      a.rise = fmaxf(a.rise, v - a.vmin);
     }
+    s.w[h] = a;
   }
   return s;
 }
 
 template <int CH, bool BWD>
 __device__ __forceinline__ void peak_walk(const float* S, int n, float d_max, float d_min, float a_max, float a_min, int m,
-                                            const ChunkSumm& cs, unsigned long long& bmax, unsigned long long& bmin,
+                                            const ChunkSumm<CH>& cs, unsigned long long& bmax, unsigned long long& bmin,
                                             int& n_found_max, int& n_found_min) {
   constexpr int NTOT = 32 * CH;
-  constexpr int NW = (CH + 31) / 32;  // 32-sample windows per chunk
+  constexpr int WS = ChunkSumm<CH>::WS, NWL = ChunkSumm<CH>::NWL;
   const int lane = threadIdx.x & 31;
-  // summaries in walk order
-  const float lmax = BWD ? __shfl_sync(FULL, cs.vmax, 31 - lane) : cs.vmax;
-  const float lmin = BWD ? __shfl_sync(FULL, cs.vmin, 31 - lane) : cs.vmin;
-  // the largest drop below a running maximum that starts INSIDE the chunk, in walk order (a fall of the
-  // samples when walking forward, a rise when walking backward), and the same for the find-min state
-  const float ldrop = BWD ? __shfl_sync(FULL, cs.rise, 31 - lane) : cs.fall;
-  const float lclimb = BWD ? __shfl_sync(FULL, cs.fall, 31 - lane) : cs.rise;
-  // float32 slack of "v < fl(M - delta)" against "fl(M - v) > delta" (only used to SKIP chunks)
-  const float slack = 0x1p-20f * (fabsf(lmax) + fabsf(lmin) + d_max + d_min);
+  // summaries in walk order: logical window lane * NWL + h.  Walking backward, the largest drop below a
+  // running maximum that starts INSIDE a window is a rise of the samples (and a fall for the find-min state).
+  float lmax[NWL], lmin[NWL], ldrop[NWL], lclimb[NWL], slack[NWL];
+#pragma unroll
+  for (int h = 0; h < NWL; h++) {
+    const WinSumm& w = cs.w[BWD ? NWL - 1 - h : h];
+    lmax[h] = BWD ? __shfl_sync(FULL, w.vmax, 31 - lane) : w.vmax;
+    lmin[h] = BWD ? __shfl_sync(FULL, w.vmin, 31 - lane) : w.vmin;
+    ldrop[h] = BWD ? __shfl_sync(FULL, w.rise, 31 - lane) : w.fall;
+    lclimb[h] = BWD ? __shfl_sync(FULL, w.fall, 31 - lane) : w.rise;
+    // float32 slack of "v < fl(M - delta)" against "fl(M - v) > delta" (only used to SKIP windows)
+    slack[h] = 0x1p-20f * (fabsf(lmax[h]) + fabsf(lmin[h]) + d_max + d_min);
+  }
   int p = BWD ? NTOT - n : 0;  // walk position; sample index = BWD ? NTOT - 1 - p : p
+  const int p_begin = p;
   const int p_end = BWD ? NTOT : n;
 #define WRT_IDX(q) (BWD ? NTOT - 1 - (q) : (q))
   bool mode_max = true;
@@ -318,13 +318,12 @@ __device__ __forceinline__ void peak_walk(const float* S, int n, float d_max, fl
     const float sg = mode_max ? 1.f : -1.f;
     const float dl = mode_max ? d_max : d_min;
     const float ab = mode_max ? a_max : -a_min;
-    const int c = p / CH;
-    bool found = false;
-    // ---- exact examination of the rest of chunk c ------------------------------------------------
-    for (int w = (p - c * CH) >> 5; w < NW; w++) {
-      const int q0 = c * CH + w * 32;
+    const int W = p / WS;
+    // ---- exact examination of the rest of window W ------------------------------------------------
+    {
+      const int q0 = W * WS;
       const int q = q0 + lane;
-      const bool valid = q >= p && (w * 32 + lane) < CH && q < p_end;
+      const bool valid = q >= p && lane < WS && q < p_end;
       const float v = valid ? sg * S[widx<CH>(WRT_IDX(q))] : -CUDART_INF_F;
       const float pm = wscan_incl_max(v, lane);
       const float M = fmaxf(ev, pm);
@@ -347,8 +346,7 @@ __device__ __forceinline__ void peak_walk(const float* S, int n, float d_max, fl
         ei = WRT_IDX(q0 + ls);
         mode_max = !mode_max;
         p = q0 + ls + 1;
-        found = true;
-        break;
+        continue;
       }
       const float wm = __shfl_sync(FULL, pm, 31);
       if (wm > ev) {
@@ -357,37 +355,55 @@ __device__ __forceinline__ void peak_walk(const float* S, int n, float d_max, fl
         ev = wm;
       }
     }
-    if (found) continue;
-    // ---- next chunk that may fire (32 chunks at once) ---------------------------------------------
-    const float smx = mode_max ? lmax : -lmin;  // signed chunk max / min
-    const float smn = mode_max ? lmin : -lmax;
-    const float pmx = wscan_incl_max(lane > c ? smx : -CUDART_INF_F, lane);
-    const float ex = __shfl_up_sync(FULL, pmx, 1);
-    const float m_in = fmaxf(ev, lane == 0 ? -CUDART_INF_F : ex);  // running extreme on entry of chunk `lane`
-    const float m_full = fmaxf(m_in, smx);
-    // an event inside chunk `lane` needs a sample below fl(carry - delta), or a drop of (almost) delta below a
-    // maximum of the chunk itself
-    const float drop = mode_max ? ldrop : lclimb;
-    const unsigned b = __ballot_sync(FULL, lane > c && (m_full > ab) && ((smn < m_in - dl) || (drop > dl - slack)));
-    if (!b) break;
-    const int c2 = __ffs(b) - 1;
-    const float nev = __shfl_sync(FULL, m_in, c2);
-    if (nev > ev) {  // the extreme moved into one of the skipped chunks: first occurrence of it
-      const unsigned kb = __ballot_sync(FULL, lane > c && lane < c2 && smx == nev);
-      const int k = __ffs(kb) - 1;
-      for (int w = 0; w < NW; w++) {
-        const int q = k * CH + w * 32 + lane;
-        const bool valid = (w * 32 + lane) < CH && q < p_end && q >= (BWD ? NTOT - n : 0);
-        const float v = valid ? sg * S[widx<CH>(WRT_IDX(q))] : -CUDART_INF_F;
-        const unsigned e = __ballot_sync(FULL, valid && v == nev);
-        if (e) {
-          ei = WRT_IDX(k * CH + w * 32 + __ffs(e) - 1);
-          break;
-        }
+    // ---- next window that may fire (all windows at once) --------------------------------------------
+    float smx[NWL], smn[NWL], pmw[NWL];
+    bool act[NWL];
+    float tot = -CUDART_INF_F;
+#pragma unroll
+    for (int h = 0; h < NWL; h++) {
+      smx[h] = mode_max ? lmax[h] : -lmin[h];  // signed window max / min
+      smn[h] = mode_max ? lmin[h] : -lmax[h];
+      act[h] = lane * NWL + h > W;
+      pmw[h] = act[h] ? smx[h] : -CUDART_INF_F;
+      tot = fmaxf(tot, pmw[h]);
+    }
+    const float ex = __shfl_up_sync(FULL, wscan_incl_max(tot, lane), 1);
+    float m_in[NWL];
+    int first = 0x7fffffff;
+    m_in[0] = fmaxf(ev, lane == 0 ? -CUDART_INF_F : ex);  // running extreme on entry of the lane's first window
+#pragma unroll
+    for (int h = 0; h < NWL; h++) {
+      if (h > 0) m_in[h] = fmaxf(m_in[h - 1], pmw[h - 1]);
+      const float m_full = fmaxf(m_in[h], smx[h]);
+      // an event inside the window needs a sample below fl(carry - delta), or a drop of (almost) delta below
+      // a maximum of the window itself
+      const float drop = mode_max ? ldrop[h] : lclimb[h];
+      const unsigned b = __ballot_sync(FULL, act[h] && (m_full > ab) && ((smn[h] < m_in[h] - dl) || (drop > dl - slack[h])));
+      if (b) first = min(first, (__ffs(b) - 1) * NWL + h);
+    }
+    if (first == 0x7fffffff) break;
+    const int W2 = first;
+    float nev = __shfl_sync(FULL, m_in[0], W2 / NWL);
+#pragma unroll
+    for (int h = 1; h < NWL; h++) {
+      const float t = __shfl_sync(FULL, m_in[h], W2 / NWL);
+      if (W2 % NWL == h) nev = t;
+    }
+    if (nev > ev) {  // the extreme moved into one of the skipped windows: first occurrence of it
+      int k = 0x7fffffff;
+#pragma unroll
+      for (int h = 0; h < NWL; h++) {
+        const unsigned kb = __ballot_sync(FULL, act[h] && lane * NWL + h < W2 && smx[h] == nev);
+        if (kb) k = min(k, (__ffs(kb) - 1) * NWL + h);
       }
+      const int q = k * WS + lane;
+      const bool valid = lane < WS && q < p_end && q >= p_begin;
+      const float v = valid ? sg * S[widx<CH>(WRT_IDX(q))] : -CUDART_INF_F;
+      const unsigned e = __ballot_sync(FULL, valid && v == nev);
+      ei = WRT_IDX(k * WS + __ffs(e) - 1);
       ev = nev;
     }
-    p = c2 * CH;
+    p = W2 * WS;
   }
 #undef WRT_IDX
   n_found_max = cm;

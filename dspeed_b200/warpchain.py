@@ -299,7 +299,7 @@ class WarpChain(FusedChain):
             for k, d in enumerate(dirs):
                 dst = out.reg if k == len(dirs) - 1 else self._t("r")
                 if d == "l":
-                    self._e(f"float {dst}[CH]; mw_left<CH, {L}>({src}, {dst}, {n}, {il}, lane);")
+                    self._e(f"float {dst}[CH]; mw_left<CH, {L}, {n}>({src}, {dst}, {il}, lane);")
                 else:
                     self._e(f"float {dst}[CH]; mw_right<CH, {L}, {n}>({src}, {dst}, {il}, lane);")
                 src = dst
@@ -312,7 +312,8 @@ class WarpChain(FusedChain):
                 raise NotSpecializable("avg_current arguments")
             L = int(length)
             out = self._wout(a[2], n - L)
-            self._e(f"float {out.reg}[CH]; avg_current<CH, {L}>({w.reg}, {out.reg}, {_flit(1.0 / float(np.float32(L)))}, lane);")
+            self._e(f"float {out.reg}[CH]; avg_current<CH, {L}>({w.reg}, {out.reg}, {_flit(1.0 / float(np.float32(L)))}, lane); "
+                    f"edge_extend<CH, {n - L}>({out.reg}, lane);")
             out.nan = w.nan
             self.text.append(f"avg_current L={L} {w.reg} -> {out.reg}")
         elif name in ("min_max", "amax"):
@@ -354,7 +355,7 @@ class WarpChain(FusedChain):
         nx, nn = self._sout(nmax_t), self._sout(nmin_t)
         prm = f"{_flit(d_max)}, {_flit(d_min)}, {_flit(ab_max)}, {_flit(ab_min)}, {m}"
         self._e(f"st_chunk<CH>(S, lane, {w.reg});",
-                f"const ChunkSumm {cs} = chunk_summary<CH>({w.reg}, {n}, lane);",
+                f"const ChunkSumm<CH> {cs} = chunk_summary<CH>({w.reg});",
                 "__syncwarp();",
                 f"unsigned long long {bx} = 0ull, {bn} = 0ull; int {c0} = 0, {c1} = 0; (void){c0}; (void){c1};",
                 f"if (!({w.nan})) {{")
@@ -450,6 +451,7 @@ __global__ void __launch_bounds__(32 * WPC, {self.ctas_per_sm}) k_chain_warp(con
     __syncwarp();
     float r_in[CH];
     read_chunk_16<CH, {sg}>(raw, lane, r_in);
+    edge_extend<CH, {n}>(r_in, lane);
     __syncwarp();
     // the raw row of this warp's next waveform travels while this one is processed
     if (row + wstride < A.n_rows) stage_row_16<CH>(raw, (const uint16_t*)A.p[{pi}] + (row + wstride) * A.s[{pi}], {n}, lane);
