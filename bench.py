@@ -165,7 +165,7 @@ class ClockSampler:
             f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
             self.path = f.name
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "25",
                  "-i", str(self.gpu)], stdout=f, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -367,6 +367,7 @@ def run_b200(args, rank, world, local_rank):
             "workload": "full LEGEND ICPC HPGe chain (hpge_icpc.yaml, 34 outputs) on synthetic 8192-sample "
                         "uint16 waveforms",
             "rows_per_gpu": n, "wf_len": WF_LEN, "block_width": chain._block_width,
+            "rows_per_launch": {"device_resident": int(rows_per_launch), "host_staged": int(min(chain._block_width, n))},
             "sharding": f"events x{world} (no collective on the hot path)",
             "l2_policy": "inputs (16 GB per step) are far larger than the 126 MB L2",
             "fused_kernel": bool(fused),

@@ -291,3 +291,30 @@ def test_specialised_kernel_is_deterministic_and_matches_interpreted(synth_batch
         else:
             PT.assert_float_close(k, a[k], ref[k], rtol=5e-6, mask=t0_same)
     torch.cuda.synchronize()
+
+
+def test_code_generation_variants_agree():
+    """The generator's alternative lowerings -- cusp/zac pass 1 by the owner threads in float64 (no helper threads),
+    reductions right behind their producer (no wait filling) -- are the fallbacks for chains whose geometry does not
+    fit the default ones: they must give the same results to float32 rounding, and identical indices."""
+    from dspeed_b200 import synth
+
+    d = synth.hpge_waveforms(3000, seed=77, stress=True)
+    vals, bl = d["values"].numpy(), d["baseline"].numpy()
+    ref = run_icpc(vals, bl, block_width=3000, device="cuda")
+    for var in ("DSPEED_B200_CONV_HELPERS", "DSPEED_B200_FILL_WAIT"):
+        os.environ[var] = "0"
+        try:
+            alt = run_icpc(vals, bl, block_width=3000, device="cuda")
+        finally:
+            os.environ.pop(var, None)
+        t0_same = (alt["tp_0_est"] == ref["tp_0_est"]) | (np.isnan(alt["tp_0_est"]) & np.isnan(ref["tp_0_est"]))
+        assert t0_same.mean() > 0.999
+        for k in ref:
+            if k in EXACT:
+                assert np.array_equal(alt[k], ref[k], equal_nan=True), (var, k)
+            elif k.startswith("tp_"):
+                same = (alt[k] == ref[k]) | (np.isnan(alt[k]) & np.isnan(ref[k]))
+                assert same.mean() > 0.998, (var, k, same.mean())
+            else:
+                PT.assert_float_close(k, alt[k], ref[k], rtol=5e-6, mask=t0_same)
