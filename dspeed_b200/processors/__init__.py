@@ -20,6 +20,7 @@ chain instead passes ``fatal=<int32[4] device tensor>`` and checks once per bloc
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -547,6 +548,40 @@ def _upsampler(w_in, upsample, w_out, fatal=None):
                                     *_tail(fatal, w_out.device))
 
 
+#: 'valid' float32 convolutions of whole blocks with a generic kernel of at least this many taps run on the
+#: tensor cores (csrc/conv_tc.cu: banded Toeplitz GEMM, 3xTF32, tcgen05 + TMEM + TMA); 0 disables the path
+TC_CONV_MIN_TAPS = int(os.environ.get("DSPEED_B200_TC_CONV_MIN_TAPS", "128"))
+_tc_workspace: dict = {}
+
+
+def _convolve_valid_tc(w_in, k, w_out) -> bool:
+    """tensor-core path of `convolve_wf(..., 'v')`; False when the call does not fit it"""
+    if (TC_CONV_MIN_TAPS <= 0 or k.numel() < TC_CONV_MIN_TAPS or w_in.dtype != torch.float32 or w_out.dtype != torch.float32
+            or w_in.ndim != 2 or w_out.ndim != 2 or w_in.stride(1) != 1 or w_out.stride(1) != 1
+            or w_in.stride(0) % 4 or w_in.data_ptr() % 16 or w_in.shape[0] != w_out.shape[0]
+            or w_out.shape[1] != w_in.shape[1] - k.numel() + 1):   # (never on the row count: results must not depend on block_width)
+        return False
+    L = _lib.lib()
+    L.dspb_convolve_valid_tc_workspace.restype = C.c_int64
+    need = int(L.dspb_convolve_valid_tc_workspace(_i64(k.numel())))
+    key = (w_in.device, need)
+    ws = _tc_workspace.get(key)
+    if ws is None:
+        ws = _tc_workspace[key] = torch.empty(need, dtype=torch.float32, device=w_in.device)
+    rc = L.dspb_convolve_valid_tc_f32(_vp(w_in.data_ptr()), _i64(w_in.stride(0)), _i64(w_in.shape[0]), _i64(w_in.shape[1]),
+                                      _vp(k.data_ptr()), _i64(k.numel()), _vp(w_out.data_ptr()), _i64(w_out.stride(0)),
+                                      _vp(ws.data_ptr()), _i64(need), _vp(torch.cuda.current_stream(w_in.device).cuda_stream))
+    if rc < 0:
+        raise RuntimeError(f"dspb_convolve_valid_tc_f32: CUDA error {-rc}")
+    if rc != 0:
+        return False
+    # convolutions.py:44-46: a NaN anywhere in the waveform (or the kernel) leaves the whole output row NaN; in the
+    # GEMM a NaN sample only reaches the outputs whose band covers it
+    bad = torch.isnan(w_in).any(dim=1) | torch.isnan(k).any()
+    w_out.masked_fill_(bad[:, None], float("nan"))
+    return True
+
+
 def _convolve_common(w_in, kernel, mode_in, w_out, fatal):
     T = _out_T(w_out)
     c = _Call(T, w_out.device)
@@ -555,6 +590,8 @@ def _convolve_common(w_in, kernel, mode_in, w_out, fatal):
     wo, p = c.wave_out(w_out)
     k = kernel.reshape(-1).to(T).contiguous()
     c.keep.append(k)
+    if chr(_as_int(mode_in)) == "v" and isinstance(w_in, torch.Tensor) and _convolve_valid_tc(w_in, k, w_out):
+        return 0
     return _fn("dspb_convolve_wf", T)(*wi, _i64(c.n_rows), _i64(n), _vp(k.data_ptr()), _i64(k.numel()),
                                       _i32(_as_int(mode_in)), *wo, _i64(p), *_tail(fatal, w_out.device))
 

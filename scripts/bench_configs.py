@@ -104,8 +104,16 @@ if "C5" in SEL:
     for K in (256, 512, 1024, 2048, 4096):
         k = torch.from_numpy(rng.standard_normal(K).astype(np.float32)).to(dev)
         out = torch.empty((n, 8192 - K + 1), dtype=torch.float32, device=dev)
-        t = timed(lambda: P.convolve_wf(x, k, np.int8(ord("v")), out), reps=2, warm=3)
         flops = 2.0 * K * (8192 - K + 1)
-        print(json.dumps({"config": f"C5 convolve_wf 'valid', generic kernel K={K}, L=8192 (direct, SMEM-tiled, fp32 FMA + fp64 chunk sums)",
-                          "rows": n, "waveforms_per_s": n / t, "ms": t * 1e3, "useful_TFLOP_per_s": flops * n / t / 1e12}), flush=True)
+        for tc in (False, True):
+            P.TC_CONV_MIN_TAPS = 1 if tc else 0
+            t = timed(lambda: P.convolve_wf(x, k, np.int8(ord("v")), out), reps=2, warm=3)
+            # tensor-pipe work actually issued: 3 TF32 products over the (K + 127)-wide band of every 128-output tile
+            issued = 3 * 2.0 * 128 * (-(-(K + 127) // 32) * 32) * (-(-(8192 - K + 1) // 128)) if tc else None
+            how = ("tensor cores: banded Toeplitz GEMM, 3xTF32, tcgen05 + TMEM + TMA" if tc
+                   else "direct, SMEM-tiled, fp32 FMA + fp64 chunk sums")
+            print(json.dumps({"config": f"C5 convolve_wf 'valid', generic kernel K={K}, L=8192 ({how})",
+                              "rows": n, "waveforms_per_s": n / t, "ms": t * 1e3, "useful_TFLOP_per_s": flops * n / t / 1e12,
+                              "issued_tf32_TFLOP_per_s": issued * n / t / 1e12 if tc else None}), flush=True)
+        P.TC_CONV_MIN_TAPS = int(os.environ.get("DSPEED_B200_TC_CONV_MIN_TAPS", "128"))
 
