@@ -273,6 +273,24 @@ __global__ void k_toeplitz_tiles(const float* __restrict__ kern, int K, int nk, 
   tiles[((long long)(2 * kt + 1) * BM + oo) * BK + jj] = v - h;
 }
 
+// convolutions.py:44-46: a NaN anywhere in the waveform or in the kernel leaves the whole output row NaN (in the
+// GEMM a NaN sample only reaches the outputs whose band covers it).  One CTA per waveform, runs after the GEMM.
+__global__ void k_nan_rows(const float* __restrict__ x, long long x_stride, int L, const float* __restrict__ kern, int K,
+                           float* __restrict__ out, long long out_stride, int P) {
+  const float* row = x + (long long)blockIdx.x * x_stride;
+  int bad = 0;
+  for (int i = threadIdx.x; i < L / 4; i += blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(row)[i];
+    bad |= (v.x != v.x) | (v.y != v.y) | (v.z != v.z) | (v.w != v.w);
+  }
+  for (int i = (L / 4) * 4 + threadIdx.x; i < L; i += blockDim.x) bad |= row[i] != row[i];
+  for (int i = threadIdx.x; i < K; i += blockDim.x) bad |= kern[i] != kern[i];
+  if (__syncthreads_or(bad)) {
+    float* o = out + (long long)blockIdx.x * out_stride;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) o[i] = __int_as_float(0x7fc00000);
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -317,7 +335,7 @@ extern "C" int dspb_convolve_valid_tc_f32(const float* x, int64_t x_stride, int6
                                           int64_t K, float* out, int64_t out_stride, float* workspace,
                                           int64_t workspace_floats, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  if (K < 1 || K > L || n_rows <= 0) return DSPB_ERR_UNSUPPORTED;
+  if (K < 1 || K > L || n_rows <= 0 || n_rows > 65535LL * BN || L > 0x7fffffff) return DSPB_ERR_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(x) & 15) || (x_stride & 3) || (reinterpret_cast<uintptr_t>(workspace) & 127))
     return DSPB_ERR_UNSUPPORTED;
   const int64_t nk = (K + BM - 1 + BK - 1) / BK;
@@ -339,6 +357,7 @@ extern "C" int dspb_convolve_valid_tc_f32(const float* x, int64_t x_stride, int6
   if (e != cudaSuccess) return -(int)e;
   dim3 grid((unsigned)((P + BM - 1) / BM), (unsigned)((n_rows + BN - 1) / BN));
   k_conv_valid_tc<<<grid, NTHREADS, SMEM_BYTES, stream>>>(map_a, map_x, prm);
+  k_nan_rows<<<(unsigned)n_rows, 256, 0, stream>>>(x, x_stride, (int)L, kern, (int)K, out, out_stride, (int)P);
   e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -(int)e;
 }

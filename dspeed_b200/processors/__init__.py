@@ -573,13 +573,7 @@ def _convolve_valid_tc(w_in, k, w_out) -> bool:
                                       _vp(ws.data_ptr()), _i64(need), _vp(torch.cuda.current_stream(w_in.device).cuda_stream))
     if rc < 0:
         raise RuntimeError(f"dspb_convolve_valid_tc_f32: CUDA error {-rc}")
-    if rc != 0:
-        return False
-    # convolutions.py:44-46: a NaN anywhere in the waveform (or the kernel) leaves the whole output row NaN; in the
-    # GEMM a NaN sample only reaches the outputs whose band covers it
-    bad = torch.isnan(w_in).any(dim=1) | torch.isnan(k).any()
-    w_out.masked_fill_(bad[:, None], float("nan"))
-    return True
+    return rc == 0   # (NaN rows -> NaN outputs, convolutions.py:44-46, are handled by the launcher's second kernel)
 
 
 def _convolve_common(w_in, kernel, mode_in, w_out, fatal):

@@ -201,7 +201,8 @@ DSPB_DECLARE(_f64)
  * (csrc/conv_tc.cu: banded Toeplitz GEMM, 3xTF32 on tcgen05 / TMEM, operands staged by TMA) -- the
  * tensor-core variant of convolve_wf / fft_convolve_wf (convolutions.py:14-119) for long kernels.
  * x [n_rows, L] (row pitch x_stride elements, 16-byte aligned rows), kern [K], out [n_rows, L - K + 1],
- * workspace: dspb_convolve_valid_tc_workspace(K) floats; all on the device.  NaN rows are the caller's business. */
+ * workspace: dspb_convolve_valid_tc_workspace(K) floats; all on the device.  A NaN in a waveform or in the kernel
+ * gives an all-NaN output row (convolutions.py:44-46). */
 int64_t dspb_convolve_valid_tc_workspace(int64_t K);
 int dspb_convolve_valid_tc_f32(const float* x, int64_t x_stride, int64_t n_rows, int64_t L, const float* kern, int64_t K,
                                float* out, int64_t out_stride, float* workspace, int64_t workspace_floats, void* stream);
