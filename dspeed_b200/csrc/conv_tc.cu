@@ -1,4 +1,4 @@
-// dspeed_b200 -- 'valid' convolution of a block of waveforms with ONE generic long kernel on the
+// dspeed_b200 -- convolution ('valid'; 'full' / 'same' by zero fill) of a block of waveforms with ONE generic long kernel on the
 // 5th-generation tensor cores (north_star (3), BASELINE.json config 5; reference: convolve_wf /
 // fft_convolve_wf, processors/convolutions.py:14-119).
 //
@@ -104,6 +104,7 @@ struct Params {
   int64_t out_stride;
   int nk;   // k tiles of a band: ceil((K + BM - 1) / BK)
   int flush;  // k-tiles per accumulation window
+  int shift;  // column of x under A's diagonal for output 0: 0 ('valid'), -(K-1) ('full'), -(K-1-(K-1)/2) ('same')
 };
 
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -160,7 +161,7 @@ k_conv_valid_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         mbar_expect_tx(full_bar(s), 3 * TILE_BYTES);
         tma_load_2d(st, &map_a, full_bar(s), 0, (2 * kt) * BM);                  // A_hi tile kt
         tma_load_2d(st + TILE_BYTES, &map_a, full_bar(s), 0, (2 * kt + 1) * BM); // A_lo tile kt
-        tma_load_2d(st + 2 * TILE_BYTES, &map_x, full_bar(s), o0 + kt * BK, r0); // x[r0.., o0 + 32 kt ..]
+        tma_load_2d(st + 2 * TILE_BYTES, &map_x, full_bar(s), o0 + kt * BK + prm.shift, r0);  // out-of-range columns read as 0
       }
     }
   } else if (warp == 1) {
@@ -261,12 +262,12 @@ k_conv_valid_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 
 // The distinct tiles of the banded Toeplitz matrix of the kernel: tile kt (distance 32 kt from the
 // diagonal), element (oo, jj) = kern[K - 1 - (32 kt + jj - oo)] or 0; hi tiles at 2 kt, lo at 2 kt + 1.
-__global__ void k_toeplitz_tiles(const float* __restrict__ kern, int K, int nk, float* __restrict__ tiles) {
+__global__ void k_toeplitz_tiles(const float* __restrict__ kern, int K, int nk, int e, float* __restrict__ tiles) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)nk * BM * BK;
   if (i >= total) return;
   const int jj = (int)(i % BK), oo = (int)((i / BK) % BM), kt = (int)(i / (BK * BM));
-  const int d = BK * kt + jj - oo;
+  const int d = BK * kt + jj - oo - e;   // e: the columns of x start e samples early (16-byte aligned TMA coordinates)
   const float v = (d >= 0 && d < K) ? kern[K - 1 - d] : 0.f;
   const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
   tiles[((long long)(2 * kt) * BM + oo) * BK + jj] = h;
@@ -324,26 +325,37 @@ int make_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint
 }  // namespace
 
 // floats of workspace the launcher needs for a kernel of length K (the Toeplitz tiles, hi and lo)
-extern "C" int64_t dspb_convolve_valid_tc_workspace(int64_t K) {
-  const int64_t nk = (K + BM - 1 + BK - 1) / BK;
+extern "C" int64_t dspb_convolve_tc_workspace(int64_t K) {
+  const int64_t nk = (K + 3 + BM - 1 + BK - 1) / BK;
   return 2 * nk * BM * BK;
 }
 
-// y[r, 0:P] = valid convolution of x[r, 0:L] with kern[0:K] for n_rows waveforms; all pointers on the device,
-// x / out row pitches in elements (x: 16-byte aligned rows).  Returns 0, DSPB_ERR_UNSUPPORTED or -cudaError_t.
-extern "C" int dspb_convolve_valid_tc_f32(const float* x, int64_t x_stride, int64_t n_rows, int64_t L, const float* kern,
-                                          int64_t K, float* out, int64_t out_stride, float* workspace,
-                                          int64_t workspace_floats, void* stream_) {
+// y[r, 0:P] = convolution (numpy.convolve modes 'f' | 'v' | 's', P = L + K - 1 | L - K + 1 | L) of x[r, 0:L] with
+// kern[0:K] for n_rows waveforms; all pointers on the device, x / out row pitches in elements (x: 16-byte aligned
+// rows).  The zero padding of 'full' / 'same' is TMA's out-of-bounds fill.  Returns 0, a DSPB_FATAL_* code,
+// DSPB_ERR_UNSUPPORTED or -cudaError_t.
+extern "C" int dspb_convolve_tc_f32(const float* x, int64_t x_stride, int64_t n_rows, int64_t L, const float* kern,
+                                    int64_t K, int32_t mode_in, float* out, int64_t out_stride, int64_t p,
+                                    float* workspace, int64_t workspace_floats, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (K < 1 || K > L || n_rows <= 0 || n_rows > 65535LL * BN || L > 0x7fffffff) return DSPB_ERR_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(x) & 15) || (x_stride & 3) || (reinterpret_cast<uintptr_t>(workspace) & 127))
     return DSPB_ERR_UNSUPPORTED;
-  const int64_t nk = (K + BM - 1 + BK - 1) / BK;
+  int64_t P, shift;
+  if (mode_in == 'v') { P = L - K + 1; shift = 0; }
+  else if (mode_in == 'f') { P = L + K - 1; shift = -(K - 1); }
+  else if (mode_in == 's') { P = L; shift = -((K - 1) - (K - 1) / 2); }
+  else return DSPB_FATAL_CONV_MODE;
+  if (p != P) return DSPB_FATAL_CONV_OUTLEN;
+  // TMA wants the innermost coordinate on a 16-byte boundary: start the columns lead = 0..3 samples early and move the
+  // Toeplitz band by the same amount
+  const int64_t lead = ((shift % 4) + 4) % 4;
+  shift -= lead;
+  const int64_t nk = (K + lead + BM - 1 + BK - 1) / BK;
   if (workspace_floats < 2 * nk * BM * BK) return DSPB_ERR_UNSUPPORTED;
-  const int64_t P = L - K + 1;
   {
     const long long total = (long long)nk * BM * BK;
-    k_toeplitz_tiles<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(kern, (int)K, (int)nk, workspace);
+    k_toeplitz_tiles<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(kern, (int)K, (int)nk, (int)lead, workspace);
   }
   CUtensorMap map_a, map_x;
   int rc = make_map(&map_a, workspace, (uint64_t)(2 * nk * BM), BK, BK);
@@ -352,7 +364,7 @@ extern "C" int dspb_convolve_valid_tc_f32(const float* x, int64_t x_stride, int6
   if (rc) return rc;
   int flush = FLUSH_DEFAULT;
   if (const char* e = getenv("DSPEED_B200_TC_FLUSH")) flush = atoi(e) > 0 ? atoi(e) : FLUSH_DEFAULT;
-  Params prm{n_rows, L, K, P, out, out_stride, (int)nk, flush};
+  Params prm{n_rows, L, K, P, out, out_stride, (int)nk, flush, (int)shift};
   cudaError_t e = cudaFuncSetAttribute(k_conv_valid_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   if (e != cudaSuccess) return -(int)e;
   dim3 grid((unsigned)((P + BM - 1) / BM), (unsigned)((n_rows + BN - 1) / BN));

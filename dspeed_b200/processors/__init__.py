@@ -548,31 +548,32 @@ def _upsampler(w_in, upsample, w_out, fatal=None):
                                     *_tail(fatal, w_out.device))
 
 
-#: 'valid' float32 convolutions of whole blocks with a generic kernel of at least this many taps run on the
+#: float32 convolutions of whole blocks with a generic kernel of at least this many taps run on the
 #: tensor cores (csrc/conv_tc.cu: banded Toeplitz GEMM, 3xTF32, tcgen05 + TMEM + TMA); 0 disables the path
 TC_CONV_MIN_TAPS = int(os.environ.get("DSPEED_B200_TC_CONV_MIN_TAPS", "128"))
 _tc_workspace: dict = {}
 
 
-def _convolve_valid_tc(w_in, k, w_out) -> bool:
-    """tensor-core path of `convolve_wf(..., 'v')`; False when the call does not fit it"""
+def _convolve_tc(w_in, k, mode, w_out) -> bool:
+    """tensor-core path of `convolve_wf`; False when the call does not fit it"""
     if (TC_CONV_MIN_TAPS <= 0 or k.numel() < TC_CONV_MIN_TAPS or w_in.dtype != torch.float32 or w_out.dtype != torch.float32
             or w_in.ndim != 2 or w_out.ndim != 2 or w_in.stride(1) != 1 or w_out.stride(1) != 1
             or w_in.stride(0) % 4 or w_in.data_ptr() % 16 or w_in.shape[0] != w_out.shape[0]
-            or w_out.shape[1] != w_in.shape[1] - k.numel() + 1):   # (never on the row count: results must not depend on block_width)
+            or mode not in "fvs" or k.numel() > w_in.shape[1]):   # (never on the row count: results must not depend on block_width)
         return False
     L = _lib.lib()
-    L.dspb_convolve_valid_tc_workspace.restype = C.c_int64
-    need = int(L.dspb_convolve_valid_tc_workspace(_i64(k.numel())))
+    L.dspb_convolve_tc_workspace.restype = C.c_int64
+    need = int(L.dspb_convolve_tc_workspace(_i64(k.numel())))
     key = (w_in.device, need)
     ws = _tc_workspace.get(key)
     if ws is None:
         ws = _tc_workspace[key] = torch.empty(need, dtype=torch.float32, device=w_in.device)
-    rc = L.dspb_convolve_valid_tc_f32(_vp(w_in.data_ptr()), _i64(w_in.stride(0)), _i64(w_in.shape[0]), _i64(w_in.shape[1]),
-                                      _vp(k.data_ptr()), _i64(k.numel()), _vp(w_out.data_ptr()), _i64(w_out.stride(0)),
-                                      _vp(ws.data_ptr()), _i64(need), _vp(torch.cuda.current_stream(w_in.device).cuda_stream))
+    rc = L.dspb_convolve_tc_f32(_vp(w_in.data_ptr()), _i64(w_in.stride(0)), _i64(w_in.shape[0]), _i64(w_in.shape[1]),
+                                _vp(k.data_ptr()), _i64(k.numel()), _i32(ord(mode)), _vp(w_out.data_ptr()),
+                                _i64(w_out.stride(0)), _i64(w_out.shape[1]), _vp(ws.data_ptr()), _i64(need),
+                                _vp(torch.cuda.current_stream(w_in.device).cuda_stream))
     if rc < 0:
-        raise RuntimeError(f"dspb_convolve_valid_tc_f32: CUDA error {-rc}")
+        raise RuntimeError(f"dspb_convolve_tc_f32: CUDA error {-rc}")
     return rc == 0   # (NaN rows -> NaN outputs, convolutions.py:44-46, are handled by the launcher's second kernel)
 
 
@@ -584,7 +585,7 @@ def _convolve_common(w_in, kernel, mode_in, w_out, fatal):
     wo, p = c.wave_out(w_out)
     k = kernel.reshape(-1).to(T).contiguous()
     c.keep.append(k)
-    if chr(_as_int(mode_in)) == "v" and isinstance(w_in, torch.Tensor) and _convolve_valid_tc(w_in, k, w_out):
+    if isinstance(w_in, torch.Tensor) and _convolve_tc(w_in, k, chr(_as_int(mode_in)), w_out):
         return 0
     return _fn("dspb_convolve_wf", T)(*wi, _i64(c.n_rows), _i64(n), _vp(k.data_ptr()), _i64(k.numel()),
                                       _i32(_as_int(mode_in)), *wo, _i64(p), *_tail(fatal, w_out.device))

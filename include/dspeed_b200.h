@@ -197,15 +197,16 @@ DSPB_DECLARE(_f64)
  * (dspeed_b200/fusion.py); the kernel interprets it with one CTA per waveform: the raw
  * row is read from HBM once, all intermediates live in shared-memory slots / a
  * per-row scalar file, only requested outputs are written back. */
-/* 'valid' convolution of a block of float32 waveforms with one generic kernel on the tensor cores
+/* Convolution of a block of float32 waveforms with one generic kernel on the tensor cores
  * (csrc/conv_tc.cu: banded Toeplitz GEMM, 3xTF32 on tcgen05 / TMEM, operands staged by TMA) -- the
  * tensor-core variant of convolve_wf / fft_convolve_wf (convolutions.py:14-119) for long kernels.
- * x [n_rows, L] (row pitch x_stride elements, 16-byte aligned rows), kern [K], out [n_rows, L - K + 1],
- * workspace: dspb_convolve_valid_tc_workspace(K) floats; all on the device.  A NaN in a waveform or in the kernel
- * gives an all-NaN output row (convolutions.py:44-46). */
-int64_t dspb_convolve_valid_tc_workspace(int64_t K);
-int dspb_convolve_valid_tc_f32(const float* x, int64_t x_stride, int64_t n_rows, int64_t L, const float* kern, int64_t K,
-                               float* out, int64_t out_stride, float* workspace, int64_t workspace_floats, void* stream);
+ * x [n_rows, L] (row pitch x_stride elements, 16-byte aligned rows), kern [K], mode_in 'f'|'v'|'s',
+ * out [n_rows, p] with p = L + K - 1 | L - K + 1 | L, workspace: dspb_convolve_tc_workspace(K) floats; all on
+ * the device.  A NaN in a waveform or in the kernel gives an all-NaN output row (convolutions.py:44-46). */
+int64_t dspb_convolve_tc_workspace(int64_t K);
+int dspb_convolve_tc_f32(const float* x, int64_t x_stride, int64_t n_rows, int64_t L, const float* kern, int64_t K,
+                         int32_t mode_in, float* out, int64_t out_stride, int64_t p, float* workspace,
+                         int64_t workspace_floats, void* stream);
 
 typedef struct dspb_chain dspb_chain;
 int dspb_chain_create(const int32_t* code, int64_t n_code, const double* consts, int64_t n_consts,

@@ -7,7 +7,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def _run(x, k, tc):
+def _run(x, k, tc, mode="v"):
     import torch
 
     import dspeed_b200.processors as P
@@ -16,8 +16,9 @@ def _run(x, k, tc):
     P.TC_CONV_MIN_TAPS = 1 if tc else 0
     try:
         xd = torch.from_numpy(x).cuda()
-        out = torch.empty((x.shape[0], x.shape[1] - len(k) + 1), dtype=torch.float32, device="cuda")
-        P.convolve_wf(xd, torch.from_numpy(k).cuda(), np.int8(ord("v")), out)
+        p = {"v": x.shape[1] - len(k) + 1, "f": x.shape[1] + len(k) - 1, "s": x.shape[1]}[mode]
+        out = torch.empty((x.shape[0], p), dtype=torch.float32, device="cuda")
+        P.convolve_wf(xd, torch.from_numpy(k).cuda(), np.int8(ord(mode)), out)
         torch.cuda.synchronize()
         return out.cpu().numpy()
     finally:
@@ -56,3 +57,19 @@ def test_nan_rows_and_structured_kernel():
     ok = ~np.isnan(ref).any(axis=1)
     assert ok.sum() == 254
     assert np.abs(got[ok] - ref[ok]).max() <= 1e-5 * np.abs(ref[ok]).max()
+
+
+@pytest.mark.parametrize("mode,rows,L,K", [("f", 150, 4096, 300), ("s", 150, 4096, 301), ("s", 130, 8192, 134), ("f", 128, 1024, 1024)])
+def test_full_and_same_modes(mode, rows, L, K):
+    """the zero padding of numpy.convolve's 'full' / 'same' is TMA's out-of-bounds fill"""
+    from oracle import oracle as O
+
+    rng = np.random.default_rng(K)
+    x = (rng.normal(0, 4, (rows, L)) + 1500 * (np.arange(L)[None, :] > rng.integers(L // 4, 3 * L // 4, (rows, 1)))).astype(np.float32)
+    k = rng.standard_normal(K).astype(np.float32)
+    ref = O.convolve_wf(x, k, mode)
+    got = _run(x, k, tc=True, mode=mode)
+    assert got.shape == ref.shape
+    scale = np.abs(ref).max()
+    assert np.abs(got - ref).max() <= 4e-6 * scale, np.abs(got - ref).max() / scale
+    assert np.abs(_run(x, k, tc=False, mode=mode) - ref).max() <= 1e-5 * scale
