@@ -564,7 +564,7 @@ def _convolve_tc(w_in, k, mode, w_out) -> bool:
     L = _lib.lib()
     L.dspb_convolve_tc_workspace.restype = C.c_int64
     need = int(L.dspb_convolve_tc_workspace(_i64(k.numel())))
-    key = (w_in.device, need)
+    key = (w_in.device, need, torch.cuda.current_stream(w_in.device).cuda_stream)   # the tiles are rebuilt per call, on the call's stream
     ws = _tc_workspace.get(key)
     if ws is None:
         ws = _tc_workspace[key] = torch.empty(need, dtype=torch.float32, device=w_in.device)

@@ -16,3 +16,16 @@ jobs += [(2000, _cfg(3, 20, **k)) for k in (dict(d_max=0.0, d_min=0.0, a_max=-1e
 jobs += [(2000, _cfg(3, 20))]
 for n, cfg in jobs:
     print(n, warpchain.prebuild(cfg, wf_len=n)[0])
+
+# alternative lowerings of the ICPC chain exercised by tests/test_chain_gpu.py::test_code_generation_variants_agree
+import yaml  # noqa: E402
+
+from dspeed_b200 import codegen  # noqa: E402
+
+icpc = yaml.safe_load(open(os.path.join(REPO, "dspeed_b200", "configs", "hpge_icpc.yaml")))
+for var in ("DSPEED_B200_CONV_HELPERS", "DSPEED_B200_FILL_WAIT"):
+    os.environ[var] = "0"
+    try:
+        print(var, codegen.prebuild(icpc)[0])
+    finally:
+        os.environ.pop(var, None)
