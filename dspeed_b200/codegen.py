@@ -381,6 +381,15 @@ class SpecChain(FusedChain):
             if n != w.n:
                 raise NotSpecializable("pole_zero on a slice")
             self._node("pole_zero", ins=[(w, off, n)], tau=self._sc(a[1]), wouts=[self._wout(a[2])])
+        elif name == "double_pole_zero":
+            w, off, n = self._win(a[0], True)
+            t1, t2, fr = (self._sc(x) for x in a[1:4])
+            if n != w.n or n <= 3 or not all(x.startswith(("0x", "-0x")) for x in (t1, t2, fr)):
+                raise NotSpecializable("double_pole_zero: slice / non-constant time constants (interpreted tier)")
+            w.force_slot = True       # the two samples in front of a chunk are read from the slot
+            self._node("dpz", ins=[(w, 0, n)], tau1=float(np.float32(float.fromhex(t1))),
+                       tau2=float(np.float32(float.fromhex(t2))), frac=float(np.float32(float.fromhex(fr))),
+                       wouts=[self._wout(a[4])])
         elif name in ("trap_filter", "trap_norm"):
             w, off, n = self._win(a[0], True)
             rise, flat = int(a[1]), int(a[2])
@@ -808,10 +817,16 @@ class SpecChain(FusedChain):
         LS.append("EV_ARRIVE(15);")
         self.LS = LS
         LB = list(self.LB)
-        if self.late_idx is not None:
-            LB.insert(self.late_idx, "if (it > 0) EV_WAIT(15);   // the scalar warp is done with the previous row")
-        else:
-            LB.append("if (it > 0) EV_WAIT(15);")
+        # The "done" wait must precede the row's LAST block -> scalar event: the scalar warp cannot finish row r + 1
+        # (and arrive on barrier 15 again) before it has consumed that event, so every block warp has passed its wait for
+        # row r by then.  With the wait behind the last event (chains without slot hazards used to get it at the very end)
+        # a scalar warp with little work per row could arrive twice in one phase of barrier 15 while a block warp was
+        # still on its way to the wait: the phase completed early and the late warp deadlocked in the next one.
+        last_ev = max([k for k, ln in enumerate(LB) if "EV_ARRIVE(EVB(" in ln] + [-1])
+        pos = self.late_idx if self.late_idx is not None else len(LB)
+        if 0 <= last_ev < pos:
+            pos = last_ev
+        LB.insert(pos, "if (it > 0) EV_WAIT(15);   // the scalar warp is done with the previous row")
         if self.progress_seq:   # (inserted second: progress_idx < late_idx)
             LB.insert(self.progress_idx, "if (it > 0) EV_WAIT(14);   // the scalar warp is past its reads of these slots")
         self.LB = LB
@@ -1325,6 +1340,48 @@ class SpecChain(FusedChain):
             self.pending.add(nf)
         self.pending.add(out.name)
         self._post_store(out, o)   # the output chunk exists after the barrier
+
+    def _e_dpz(self, nd):
+        # pole_zero.py:82-198 as a geometric scan followed by a plain scan (chain_rt.cuh: dpz_local), two rounds
+        w, off, n = nd["ins"][0]
+        out = nd["wouts"][0]
+        self._need(w.nan)
+        x = self._chunk(w)
+        self._visible(w)
+        a_, b_, f = math.exp(-1.0 / nd["tau1"]), math.exp(-1.0 / nd["tau2"]), nd["frac"]
+        if not all(math.isfinite(v) for v in (a_, b_, f)):
+            raise NotSpecializable("double_pole_zero: NaN constants (the interpreted tier writes the NaN outputs)")
+        r = -1.0 * (f * b_ - f * a_ - b_)           # transfer_denom_2; transfer_denom_1 = -(1 + r)
+        n1, n2 = -1.0 * (a_ + b_), a_ * b_
+        R = r ** CHK
+        rp, rw, rl, g, cl, vt, vin, incl, tot, incl2 = (self._t(p) for p in ("rp", "rw", "rl", "g", "cl", "vt", "vin", "incl", "tot", "incl"))
+        self.static_arrays = getattr(self, "static_arrays", [])
+        self.static_arrays.append(f"__device__ const double {rl}[32] = {{{', '.join(_lit(R ** k) for k in range(32))}}};")
+        gs, acc = [], 0.0
+        for j in range(CHK):
+            acc += r ** (j + 1)
+            gs.append(acc)
+        sd = self._alloc_d(1)
+        sl = self._slot(w)
+        self._e(f"const double {rp}[5] = {{{', '.join(_lit(R ** (1 << k)) for k in range(5))}}};",
+                f"const double {rw}[5] = {{{', '.join(_lit((R ** 32) ** (1 << k)) for k in range(5))}}};",
+                f"const double {g}[16] = {{{', '.join(_lit(v) for v in gs)}}};",
+                f"double {cl}[16], {vt}; dpz_local({x}, 16 * tid >= 1 ? at({sl}, 16 * tid - 1) : 0.f, "
+                f"16 * tid >= 2 ? at({sl}, 16 * tid - 2) : 0.f, 16 * tid, {n}, {_lit(r)}, {_lit(n1)}, {_lit(n2)}, {cl}, {vt});",
+                f"const double {incl} = put_scan_geo(CSD({sd}), {vt}, {rp}, lane, warp);")
+        self.posts.append(f"const double {vin} = get_excl_geo(CSD({sd}), {incl}, {rw}, {rl}[lane], lane, warp);")
+        self.posts.append(f"const double {tot} = fma({vin}, {g}[15], {cl}[15]);")
+        self.pending.add(vin)
+        self._close_round()
+        sd2 = self._alloc_d(1)
+        self._e(f"const double {incl2} = put_scan(CSD({sd2}), {tot}, lane, warp);")
+        o, dum, win = self._t("r"), self._t("tt"), self._t("win")
+        self.posts.append(f"double {dum}; const double {win} = get_excl(CSD({sd2}), {incl2}, {tot}, lane, warp, {dum});")
+        self.posts.append(f"float {o}[16]; _Pragma(\"unroll\") for (int j = 0; j < 16; j++) "
+                          f"{o}[j] = (float)({win} + fma({vin}, {g}[j], {cl}[j]));")
+        out.nan = w.nan
+        self.pending.add(out.name)
+        self._post_store(out, o)
 
     def _e_fir_group(self, nd):
         members = nd["members"]

@@ -246,6 +246,55 @@ __device__ __forceinline__ double get_excl(const double* p, double incl, double 
   total = __shfl_sync(FULL, pin, NWP - 1);
   return __shfl_sync(FULL, pin - part, warp) + (incl - v);
 }
+// Geometric (first-order IIR) scans, s_l = v_l + R s_{l-1}: Rp[k] = R^(2^k) over lanes, Rw[k] = (R^32)^(2^k) over
+// warps, Rl = R^lane.  get_excl_geo returns the state entering this thread's chunk.
+__device__ __forceinline__ double wscan_geo(double v, const double (&Rp)[5], int lane) {
+#pragma unroll
+  for (int k = 0; k < 5; k++) {
+    const double t = __shfl_up_sync(FULL, v, 1 << k);
+    if (lane >= (1 << k)) v = fma(Rp[k], t, v);
+  }
+  return v;
+}
+__device__ __forceinline__ double put_scan_geo(double* p, double v, const double (&Rp)[5], int lane, int warp) {
+  const double incl = wscan_geo(v, Rp, lane);
+  if (lane == 31) p[warp] = incl;
+  return incl;
+}
+__device__ __forceinline__ double get_excl_geo(const double* p, double incl, const double (&Rw)[5], double Rl, int lane,
+                                               int warp) {
+  const double part = lane < NWP ? p[lane] : 0.0;
+  const double pin = wscan_geo(part, Rw, lane);   // inclusive over the warps
+  const double win = __shfl_sync(FULL, pin, warp > 0 ? warp - 1 : 0);
+  const double prev = __shfl_up_sync(FULL, incl, 1);
+  return (lane > 0 ? prev : 0.0) + (warp > 0 ? Rl * win : 0.0);
+}
+
+// double_pole_zero (pole_zero.py:82-198).  The denominator 1 + d1 z^-1 + d2 z^-2 has d1 + d2 = -1, i.e. it factors
+// into (1 - z^-1)(1 - r z^-1) with r = d2: the filter is a first-order recursion v[i] = u[i] + r v[i-1] on
+// u = x[i] + n1 x[i-1] + n2 x[i-2] followed by a running sum w = cumsum(v) (v[0] = x[0], v[1] = x[1] - x[0] reproduce
+// the reference's w[0] = x[0], w[1] = x[1]).  Chunk-local pass: cl[j] = running sum of the zero-state response,
+// vtot = its last value; the carry-in v_in of the chunk adds v_in * (r + .. + r^(j+1)) to cl[j].
+__device__ __forceinline__ void dpz_local(const float (&x)[CHK], float xm1, float xm2, int i0, int n, double r, double n1,
+                                          double n2, double (&cl)[CHK], double& vtot) {
+  double v = 0.0, c = 0.0, p1 = (double)xm1, p2 = (double)xm2;
+#pragma unroll
+  for (int j = 0; j < CHK; j++) {
+    const int i = i0 + j;
+    const double xj = (double)x[j];
+    double u = xj + n1 * p1 + n2 * p2;
+    if (i == 0) u = xj;
+    if (i == 1) u = xj - p1 - r * p1;
+    if (i >= n) u = 0.0;
+    v = fma(r, v, u);
+    c += v;
+    cl[j] = c;
+    p2 = p1;
+    p1 = xj;
+  }
+  vtot = v;
+}
+
 // float variants for running sums whose magnitude (< 2^24 times the output tolerance) allows it:
 // half the shuffles of the float64 scan
 __device__ __forceinline__ float wscan_incl_f(float v, int lane) {

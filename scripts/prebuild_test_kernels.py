@@ -29,3 +29,26 @@ for var in ("DSPEED_B200_CONV_HELPERS", "DSPEED_B200_FILL_WAIT"):
         print(var, codegen.prebuild(icpc)[0])
     finally:
         os.environ.pop(var, None)
+
+# small specialised chains of tests/test_chain_gpu.py
+dpz = {
+    "outputs": ["wf_dpz", "dpz_max", "t_max", "trapEmax"],
+    "processors": {
+        "wf_blsub": "dspeed.processors.bl_subtract(waveform, baseline, wf_blsub(unit='ADC'))",
+        "wf_dpz": {"function": "dspeed.processors.double_pole_zero(wf_blsub, 27460.5, 1200.25, 0.025, wf_dpz)", "unit": "ADC"},
+        "t_min, t_max, dpz_min, dpz_max": {"function": "dspeed.processors.min_max(wf_dpz, t_min, t_max, dpz_min, dpz_max)",
+                                           "unit": ["ns", "ns", "ADC", "ADC"]},
+        "wf_trap": {"function": "dspeed.processors.trap_norm(wf_dpz, 10*us, 3.008*us, wf_trap)", "unit": "ADC"},
+        "trapEmax": {"function": "numpy.amax(wf_trap, 1, trapEmax)", "unit": "ADC"},
+    },
+}
+tiny = {
+    "outputs": ["wf_pz", "pz_max"],
+    "processors": {
+        "wf_blsub": "dspeed.processors.bl_subtract(waveform, baseline, wf_blsub(unit='ADC'))",
+        "wf_pz": {"function": "dspeed.processors.pole_zero(wf_blsub, 27460.5, wf_pz)", "unit": "ADC"},
+        "pz_max": {"function": "numpy.amax(wf_pz, 1, pz_max)", "unit": "ADC"},
+    },
+}
+for cfg in (dpz, tiny):
+    print(codegen.prebuild(cfg)[0])

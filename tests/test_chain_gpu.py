@@ -318,3 +318,64 @@ def test_code_generation_variants_agree():
                 assert same.mean() > 0.998, (var, k, same.mean())
             else:
                 PT.assert_float_close(k, alt[k], ref[k], rtol=5e-6, mask=t0_same)
+
+
+def test_double_pole_zero_in_the_specialised_kernel():
+    """double_pole_zero (pole_zero.py:82-198) has a specialised emitter: a geometric scan followed by a plain scan.
+    The corrected waveform itself and quantities derived from it must match the float64 recursion of the oracle."""
+    from dspeed_b200 import codegen, synth, tables
+    from dspeed_b200.build_dsp import build_dsp
+    from oracle import oracle as O
+
+    d = synth.hpge_waveforms(1500, seed=21, stress=True)
+    vals, bl = d["values"].numpy(), d["baseline"].numpy()
+    cfg = {
+        "outputs": ["wf_dpz", "dpz_max", "t_max", "trapEmax"],
+        "processors": {
+            "wf_blsub": "dspeed.processors.bl_subtract(waveform, baseline, wf_blsub(unit='ADC'))",
+            "wf_dpz": {"function": "dspeed.processors.double_pole_zero(wf_blsub, 27460.5, 1200.25, 0.025, wf_dpz)", "unit": "ADC"},
+            "t_min, t_max, dpz_min, dpz_max": {"function": "dspeed.processors.min_max(wf_dpz, t_min, t_max, dpz_min, dpz_max)",
+                                               "unit": ["ns", "ns", "ADC", "ADC"]},
+            "wf_trap": {"function": "dspeed.processors.trap_norm(wf_dpz, 10*us, 3.008*us, wf_trap)", "unit": "ADC"},
+            "trapEmax": {"function": "numpy.amax(wf_trap, 1, trapEmax)", "unit": "ADC"},
+        },
+    }
+    wf = tables.WaveformTable(size=len(vals), t0=0, t0_units="ns", dt=16, dt_units="ns", values=vals)
+    out = build_dsp(tables.Table({"waveform": wf, "baseline": tables.Array(bl)}, size=len(vals)), dsp_config=cfg)
+    assert isinstance(out.proc_chain._fused, codegen.SpecChain), getattr(out.proc_chain, "_not_specialised_reason", None)
+    blsub = O.bl_subtract(vals.astype(np.float32), bl.astype(np.float32))
+    ref = O.double_pole_zero(blsub, np.float32(27460.5), np.float32(1200.25), np.float32(0.025))
+    got = np.asarray(out["wf_dpz"].values.nda)
+    scale = np.abs(ref).max()
+    assert np.abs(got - ref).max() <= 1e-6 * scale, np.abs(got - ref).max() / scale
+    PT.assert_float_close("dpz_max", out["dpz_max"].nda, ref.max(axis=1), rtol=1e-6, scale=scale)
+    trap = O.trap_norm(ref, 625, 188)
+    PT.assert_float_close("trapEmax", out["trapEmax"].nda, trap.max(axis=1), scale=scale)
+
+
+@pytest.mark.timeout(120)
+def test_tiny_chain_with_little_scalar_work_does_not_deadlock():
+    """Regression: with almost no per-event scalar work the scalar warp could post its "row done" event twice within
+    one phase of the named barrier while a block warp was still on its way to the wait for the previous row (the wait
+    sat behind the row's last block -> scalar event): the kernel hung.  The wait now precedes that event."""
+    from dspeed_b200 import codegen, synth, tables
+    from dspeed_b200.build_dsp import build_dsp
+    from oracle import oracle as O
+
+    d = synth.hpge_waveforms(4000, seed=8)
+    vals, bl = d["values"].numpy(), d["baseline"].numpy()
+    cfg = {
+        "outputs": ["wf_pz", "pz_max"],
+        "processors": {
+            "wf_blsub": "dspeed.processors.bl_subtract(waveform, baseline, wf_blsub(unit='ADC'))",
+            "wf_pz": {"function": "dspeed.processors.pole_zero(wf_blsub, 27460.5, wf_pz)", "unit": "ADC"},
+            "pz_max": {"function": "numpy.amax(wf_pz, 1, pz_max)", "unit": "ADC"},
+        },
+    }
+    wf = tables.WaveformTable(size=len(vals), t0=0, t0_units="ns", dt=16, dt_units="ns", values=vals)
+    for _ in range(3):
+        out = build_dsp(tables.Table({"waveform": wf, "baseline": tables.Array(bl)}, size=len(vals)), dsp_config=cfg)
+    assert isinstance(out.proc_chain._fused, codegen.SpecChain)
+    ref = O.pole_zero(O.bl_subtract(vals.astype(np.float32), bl.astype(np.float32)), np.float32(27460.5))
+    PT.assert_float_close("wf_pz", out["wf_pz"].values.nda, ref, rtol=1e-6)
+    PT.assert_float_close("pz_max", out["pz_max"].nda, ref.max(axis=1), rtol=1e-6, scale=np.abs(ref).max())

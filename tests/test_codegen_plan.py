@@ -71,3 +71,11 @@ def test_generated_kernel_compiles_for_sm100a(spec):
     so, cu = codegen.build_source(spec.source())
     assert os.path.exists(so) and os.path.getsize(so) > 10000
     assert "sm_100a" in " ".join(codegen._lib.NVCC_FLAGS)
+
+
+def test_done_event_wait_precedes_the_last_block_to_scalar_event(spec):
+    """the block stream's wait for "scalar warp done with the previous row" must come before the row's last
+    block -> scalar event (else a fast scalar warp can arrive twice in one barrier phase: deadlock)"""
+    src = spec.source()
+    blk = src[src.index("block stream"):src.index("scalar stream")]
+    assert blk.index("if (it > 0) EV_WAIT(15);") < blk.rindex("EV_ARRIVE(EVB(")
