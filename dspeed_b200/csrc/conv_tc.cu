@@ -33,11 +33,21 @@
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 32, STAGES = 3;
+#ifndef DSPB_TC_BN
+#define DSPB_TC_BN 128      // waveforms per CTA tile (MMA N)
+#endif
+#ifndef DSPB_TC_STAGES
+#define DSPB_TC_STAGES 3    // shared-memory ring depth
+#endif
+#ifndef DSPB_TC_CTAS
+#define DSPB_TC_CTAS 1      // CTAs per SM the kernel is sized for
+#endif
+constexpr int BM = 128, BN = DSPB_TC_BN, BK = 32, STAGES = DSPB_TC_STAGES;
 constexpr int FLUSH_DEFAULT = 2;                        // k-tiles per accumulation window
-constexpr int TILE_BYTES = BM * BK * 4;                 // 16 KB: every operand tile (BM == BN)
-constexpr int STAGE_BYTES = 4 * TILE_BYTES;             // A_hi, A_lo, B_hi, B_lo
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /* alignment */ + 256 /* barriers */;
+constexpr int TILE_BYTES = BM * BK * 4;                 // 16 KB: a tile of the Toeplitz operand
+constexpr int BTILE_BYTES = BN * BK * 4;                // a tile of waveforms
+constexpr int STAGE_BYTES = 2 * TILE_BYTES + 2 * BTILE_BYTES;   // A_hi, A_lo, B_hi, B_lo
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /* alignment */ + 256 /* barriers */ + BN * 4 /* pedestals */;
 constexpr uint32_t TMEM_COLS = 2 * BN;                  // two accumulator stages
 constexpr int NTHREADS = 192;
 constexpr uint32_t SPIN_LIMIT = 1u << 28;               // a protocol bug traps instead of hanging the GPU
@@ -104,10 +114,13 @@ struct Params {
   int64_t out_stride;
   int nk;   // k tiles of a band: ceil((K + BM - 1) / BK)
   int flush;  // k-tiles per accumulation window
+  const float* x;       // waveforms (for the pedestal c[r]) and their row pitch
+  int64_t x_stride;
+  const float* ksum;    // sum of the kernel taps (device scalar), nullptr: no pedestal removal
   int shift;  // column of x under A's diagonal for output 0: 0 ('valid'), -(K-1) ('full'), -(K-1-(K-1)/2) ('same')
 };
 
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__(NTHREADS, DSPB_TC_CTAS)
 k_conv_valid_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_x,
                 const Params prm) {
   extern __shared__ unsigned char smem_raw[];
@@ -127,6 +140,25 @@ k_conv_valid_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   const int o0 = blockIdx.x * BM;
   const int r0 = blockIdx.y * BN;
   const int nk = prm.nk;
+  // Pedestal removal ('valid' mode): y = k * (x - c) + c sum(k) with c[r] = mean(x[r, 0:64]).  The tensor core truncates when
+  // it adds into its accumulator, an error proportional to the partial sums: a large pedestal under a kernel of small
+  // area would dominate it.  The subtraction happens in the converter warps, the constant returns in the epilogue.
+  float* cvals = reinterpret_cast<float*>(base_ptr + STAGES * STAGE_BYTES + 256);
+  if (threadIdx.x >= 64 && threadIdx.x - 64 < BN) {
+    const long long r = (long long)r0 + (threadIdx.x - 64);
+    float c = 0.f;
+    if (prm.ksum && r < prm.n_rows) {   // mean of the first 64 samples (a single sample would inject its own noise)
+      const float4* row = reinterpret_cast<const float4*>(prm.x + r * prm.x_stride);
+      const int nq = (int)(prm.L < 64 ? prm.L : 64) / 4;
+      for (int i = 0; i < nq; i++) {
+        const float4 v = row[i];
+        c += (v.x + v.y) + (v.z + v.w);
+      }
+      c = nq > 0 ? c / (float)(4 * nq) : 0.f;
+      c = (c == c && fabsf(c) < 3.0e38f) ? c : 0.f;   // NaN / Inf rows are overwritten by k_nan_rows anyway
+    }
+    cvals[threadIdx.x - 64] = c;
+  }
   const int FLUSH = prm.flush;
 
   if (threadIdx.x == 0) {
@@ -158,7 +190,7 @@ k_conv_valid_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         const int s = kt % STAGES, ph = (kt / STAGES) & 1;
         mbar_wait(empty_bar(s), ph ^ 1);
         const uint32_t st = base + s * STAGE_BYTES;
-        mbar_expect_tx(full_bar(s), 3 * TILE_BYTES);
+        mbar_expect_tx(full_bar(s), 2 * TILE_BYTES + BTILE_BYTES);
         tma_load_2d(st, &map_a, full_bar(s), 0, (2 * kt) * BM);                  // A_hi tile kt
         tma_load_2d(st + TILE_BYTES, &map_a, full_bar(s), 0, (2 * kt + 1) * BM); // A_lo tile kt
         tma_load_2d(st + 2 * TILE_BYTES, &map_x, full_bar(s), o0 + kt * BK + prm.shift, r0);  // out-of-range columns read as 0
@@ -178,7 +210,7 @@ k_conv_valid_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 #pragma unroll
         for (int k = 0; k < BK / 8; k++) {
           const uint64_t a_hi = umma_desc(st + 32 * k), a_lo = umma_desc(st + TILE_BYTES + 32 * k);
-          const uint64_t b_hi = umma_desc(st + 2 * TILE_BYTES + 32 * k), b_lo = umma_desc(st + 3 * TILE_BYTES + 32 * k);
+          const uint64_t b_hi = umma_desc(st + 2 * TILE_BYTES + 32 * k), b_lo = umma_desc(st + 2 * TILE_BYTES + BTILE_BYTES + 32 * k);
           umma_tf32(acc, a_hi, b_hi, (kt % FLUSH != 0) || (k != 0));
           umma_tf32(acc, a_lo, b_hi, 1);
           umma_tf32(acc, a_hi, b_lo, 1);
@@ -223,11 +255,13 @@ k_conv_valid_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       const int s = kt % STAGES, ph = (kt / STAGES) & 1;
       mbar_wait(full_bar(s), ph);
       float4* hi = reinterpret_cast<float4*>(base_ptr + s * STAGE_BYTES + 2 * TILE_BYTES);
-      float4* lo = reinterpret_cast<float4*>(base_ptr + s * STAGE_BYTES + 3 * TILE_BYTES);
+      float4* lo = reinterpret_cast<float4*>(base_ptr + s * STAGE_BYTES + 2 * TILE_BYTES + BTILE_BYTES);
 #pragma unroll
-      for (int i4 = 0; i4 < TILE_BYTES / 16 / 128; i4++) {
+      for (int i4 = 0; i4 < BTILE_BYTES / 16 / 128; i4++) {
         const int i = i4 * 128 + t;     // same byte offset in both buffers: the swizzle is irrelevant here
-        const float4 v = hi[i];
+        float4 v = hi[i];
+        const float c = cvals[i >> 3];   // a row of the tile = 128 bytes = 8 float4 (the swizzle stays inside the row)
+        v.x -= c; v.y -= c; v.z -= c; v.w -= c;
         float4 h, l;
         h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); l.x = v.x - h.x;
         h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); l.y = v.y - h.y;
@@ -245,10 +279,11 @@ k_conv_valid_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     for (int w = (nk / FLUSH >= 1 ? nk / FLUSH - 1 : 0); w < nw; w++) drain(w);
     const long long o = (long long)o0 + 32 * q + lane;
     if (o < prm.P) {
+      const float ks = prm.ksum ? prm.ksum[0] : 0.f;
 #pragma unroll
       for (int c = 0; c < BN; c++) {
         const long long r = (long long)r0 + c;
-        if (r < prm.n_rows) prm.out[r * prm.out_stride + o] = sum[c];
+        if (r < prm.n_rows) prm.out[r * prm.out_stride + o] = fmaf(cvals[c], ks, sum[c]);
       }
     }
   }
@@ -292,6 +327,20 @@ __global__ void k_nan_rows(const float* __restrict__ x, long long x_stride, int 
   }
 }
 
+// sum of the kernel taps (float64 accumulation) -> one float behind the Toeplitz tiles
+__global__ void k_kernel_sum(const float* __restrict__ kern, int K, float* __restrict__ dst) {
+  __shared__ double part[256];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < K; i += 256) s += (double)kern[i];
+  part[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) part[threadIdx.x] += part[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) dst[0] = (float)part[0];
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -308,13 +357,13 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// 2-D float32 tensor [rows][cols] (row pitch in elements), box = 32 columns x 128 rows, 128-byte swizzle
-int make_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t pitch_elems) {
+// 2-D float32 tensor [rows][cols] (row pitch in elements), box = 32 columns x box_rows rows, 128-byte swizzle
+int make_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t pitch_elems, uint32_t box_rows) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return DSPB_ERR_UNSUPPORTED;
   const cuuint64_t dims[2] = {cols, rows};
   const cuuint64_t strides[1] = {pitch_elems * sizeof(float)};
-  const cuuint32_t box[2] = {BK, BM};
+  const cuuint32_t box[2] = {BK, box_rows};
   const cuuint32_t estr[2] = {1, 1};
   const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -327,7 +376,7 @@ int make_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint
 // floats of workspace the launcher needs for a kernel of length K (the Toeplitz tiles, hi and lo)
 extern "C" int64_t dspb_convolve_tc_workspace(int64_t K) {
   const int64_t nk = (K + 3 + BM - 1 + BK - 1) / BK;
-  return 2 * nk * BM * BK;
+  return 2 * nk * BM * BK + 32;
 }
 
 // y[r, 0:P] = convolution (numpy.convolve modes 'f' | 'v' | 's', P = L + K - 1 | L - K + 1 | L) of x[r, 0:L] with
@@ -352,19 +401,21 @@ extern "C" int dspb_convolve_tc_f32(const float* x, int64_t x_stride, int64_t n_
   const int64_t lead = ((shift % 4) + 4) % 4;
   shift -= lead;
   const int64_t nk = (K + lead + BM - 1 + BK - 1) / BK;
-  if (workspace_floats < 2 * nk * BM * BK) return DSPB_ERR_UNSUPPORTED;
+  if (workspace_floats < 2 * nk * BM * BK + 32) return DSPB_ERR_UNSUPPORTED;
+  float* ksum = workspace + 2 * nk * BM * BK;
   {
     const long long total = (long long)nk * BM * BK;
     k_toeplitz_tiles<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(kern, (int)K, (int)nk, (int)lead, workspace);
+    k_kernel_sum<<<1, 256, 0, stream>>>(kern, (int)K, ksum);
   }
   CUtensorMap map_a, map_x;
-  int rc = make_map(&map_a, workspace, (uint64_t)(2 * nk * BM), BK, BK);
+  int rc = make_map(&map_a, workspace, (uint64_t)(2 * nk * BM), BK, BK, BM);
   if (rc) return rc;
-  rc = make_map(&map_x, x, (uint64_t)n_rows, (uint64_t)L, (uint64_t)x_stride);
+  rc = make_map(&map_x, x, (uint64_t)n_rows, (uint64_t)L, (uint64_t)x_stride, BN);
   if (rc) return rc;
   int flush = FLUSH_DEFAULT;
   if (const char* e = getenv("DSPEED_B200_TC_FLUSH")) flush = atoi(e) > 0 ? atoi(e) : FLUSH_DEFAULT;
-  Params prm{n_rows, L, K, P, out, out_stride, (int)nk, flush, (int)shift};
+  Params prm{n_rows, L, K, P, out, out_stride, (int)nk, flush, x, x_stride, mode_in == 'v' ? ksum : nullptr, (int)shift};
   cudaError_t e = cudaFuncSetAttribute(k_conv_valid_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   if (e != cudaSuccess) return -(int)e;
   dim3 grid((unsigned)((P + BM - 1) / BM), (unsigned)((n_rows + BN - 1) / BN));

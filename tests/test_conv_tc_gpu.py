@@ -73,3 +73,20 @@ def test_full_and_same_modes(mode, rows, L, K):
     scale = np.abs(ref).max()
     assert np.abs(got - ref).max() <= 4e-6 * scale, np.abs(got - ref).max() / scale
     assert np.abs(_run(x, k, tc=False, mode=mode) - ref).max() <= 1e-5 * scale
+
+
+def test_pedestal_under_a_zero_area_kernel():
+    """A waveform pedestal under a kernel of (almost) zero area: the partial sums of the GEMM are far larger than the
+    result, and the tensor core truncates when it accumulates.  The kernel removes the pedestal c[r] = mean(x[r, 0:64]) before
+    the products and adds c * sum(kern) back (exact), so the error stays at the float32 level of the RESULT."""
+    from oracle import oracle as O
+
+    rng = np.random.default_rng(11)
+    x = (rng.normal(0, 4, (256, 8192)) + 3000.0).astype(np.float32)
+    k = rng.standard_normal(512).astype(np.float32)
+    k -= k.mean()
+    ref = np.stack([np.convolve(r.astype(np.float64), k.astype(np.float64), "valid") for r in x[:64]])
+    got = _run(x, k, tc=True)[:64]
+    # scale of the problem: |x| * ||k||_1 (the result itself is ~1000 x smaller)
+    assert np.abs(got - ref).max() <= 2e-7 * 3000.0 * np.abs(k).sum()
+    assert np.abs(got - ref).max() <= 1e-4 * np.abs(ref).max()
