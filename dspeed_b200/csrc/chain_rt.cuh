@@ -951,14 +951,69 @@ __device__ __forceinline__ void conv_seg_chunked(const float* X, const float (&x
   conv_seg_finish<POLY, TWO>(X, N, lt, fl, L, c, inv2S, qm, qp, eA, pw, s0, s1, k0, k1, tab, s, tid, lane, warp);
 }
 
+// Running sums of (band, chunk) pair `h` at the chunk's positions [K0, K1): the chunk is re-read from shared
+// memory, the sums of the positions before K0 are accumulated without deposits.  Branch-free: positions outside
+// the band write to a column of the band table that no band position uses (CW - 1 > (p - 1) / 16), so the
+// positions form ONE basic block and the conversions / FP64 products / stores of consecutive positions overlap.
+template <bool POLY, int K0, int K1>
+__device__ __forceinline__ void seg_deposit(const float* X, int N, int p, int CW, int PP, const int (&base)[4], int h,
+                                            double j0, float omc, const double* __restrict__ pwc, int NPW,
+                                            const float (&wm)[CHK], const float (&wp)[CHK], double* tab) {
+  int b = -1, ch = 0, bbase = 0;
+#pragma unroll
+  for (int bb = 0; bb < 4; bb++) {
+    const int c_lo = base[bb] >> 4, cnt = ((base[bb] + p - 1) >> 4) - c_lo + 1;
+    if (b < 0) {
+      if (h < cnt) { b = bb; ch = c_lo + h; bbase = base[bb]; }
+      else h -= cnt;
+    }
+  }
+  if (b < 0 || CHK * ch > N) return;
+  const int i0 = CHK * ch;
+  float xs[CHK];
+  ld_chunk(X, ch, xs);
+  float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f, r4 = 0.f;
+  float prev = i0 > 0 ? at(X, i0 - 1) : 0.f;
+  const double w0 = pwc[ch], w0i = pwc[NPW + ch];
+  const double jc0 = (double)i0 - j0, jc02 = jc0 * jc0, jc2 = 2.0 * jc0;
+  const int ob = i0 - bbase;
+  double* tb = tab + b * PP;
+#pragma unroll
+  for (int k = 0; k < K1; k++) {
+    if (k >= K0) {
+      const int o = ob + k;
+      const bool dep = (unsigned)o < (unsigned)p && i0 + k <= N;
+      double* t = tb + (dep ? (o & 15) * CW + (o >> 4) : CW - 1);
+      const double d2 = (double)r2, d3 = (double)r3;
+      t[0] = w0 * (double)r0;
+      t[4 * PP] = w0i * (double)r1;
+      t[2 * 4 * PP] = d2;
+      if (POLY) {
+        t[3 * 4 * PP] = fma(jc0, d2, d3);
+        t[4 * 4 * PP] = fma(jc02, d2, fma(jc2, d3, (double)r4));
+      }
+    }
+    float z = (xs[k] - prev) + omc * prev;
+    z = i0 + k < N ? z : 0.f;
+    prev = xs[k];
+    r0 = fmaf(wm[k], z, r0);
+    r1 = fmaf(wp[k], z, r1);
+    r2 += z;
+    if (POLY) {
+      r3 = fmaf((float)k, z, r3);
+      r4 = fmaf((float)(k * k), z, r4);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // Pass 1 with helper threads.  The chunk sums are float32 inside a 16-sample chunk (weights relative
 // to the chunk start, compile-time tables `wm` / `wp`; z = (x[k] - x[k-1]) + (1 - c) x[k-1] keeps the
 // pole-zero difference exact) and float64 across chunks (`pwc[t]` = e^{-16 t / sigma}, `pwc[NPW + t]`
-// its inverse).  Owner threads never deposit: the (band, chunk) pairs that need the running sums at
-// every position are handed to the threads beyond the end of the input (tid >= HB, idle otherwise),
-// which re-read the chunk from shared memory -- the 4 warps that used to be the critical path
-// (16 x 4 predicated bands x 5 stores) are gone and the work is spread over all 16 warps.
+// its inverse).  The (band, chunk) pairs that need the running sums at every position are handed to the
+// threads beyond the end of the input (tid >= HB, idle otherwise; first half of the positions) and to the
+// four owner warps below them (second half, after their own chunk), which re-read the chunk from shared
+// memory -- the 4 warps that used to be the critical path (16 x 4 predicated bands x 5 stores) are gone.
 // ---------------------------------------------------------------------------------------
 template <bool POLY, bool TWO, int HB, int NPW>
 __device__ __forceinline__ void conv_seg_chunked_h(const float* X, const float (&x)[CHK], int N, double sigma, int lt,
@@ -1007,56 +1062,11 @@ __device__ __forceinline__ void conv_seg_chunked_h(const float* X, const float (
         s[4] = fma(jc0 * jc0, s[2], fma(2.0 * jc0, (double)r3, (double)r4));
       }
     }
-  } else {
-    // ---- helper threads: one (band, chunk) pair each -------------------------------------------------
-    int h = tid - HB, b = -1, ch = 0, bbase = 0;
-#pragma unroll
-    for (int bb = 0; bb < 4; bb++) {
-      const int c_lo = base[bb] >> 4, cnt = ((base[bb] + p - 1) >> 4) - c_lo + 1;
-      if (b < 0) {
-        if (h < cnt) { b = bb; ch = c_lo + h; bbase = base[bb]; }
-        else h -= cnt;
-      }
-    }
-    if (b >= 0 && CHK * ch <= N) {
-      const int i0 = CHK * ch;
-      float xs[CHK];
-      ld_chunk(X, ch, xs);
-      float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f, r4 = 0.f;
-      float prev = i0 > 0 ? at(X, i0 - 1) : 0.f;
-      const double w0 = pwc[ch], w0i = pwc[NPW + ch];
-      const double jc0 = (double)i0 - j0, jc02 = jc0 * jc0, jc2 = 2.0 * jc0;
-      const int ob = i0 - bbase;
-      double* tb = tab + b * PP;
-#pragma unroll
-      for (int k = 0; k < CHK; k++) {
-        // Branch-free deposit: positions outside the band write to a column of the band table that no
-        // band position uses (CW - 1 > (p - 1) / 16), so the 16 positions form ONE basic block and the
-        // conversions / FP64 products / stores of consecutive positions overlap.
-        const int o = ob + k;
-        const bool dep = (unsigned)o < (unsigned)p && i0 + k <= N;
-        double* t = tb + (dep ? (o & 15) * CW + (o >> 4) : CW - 1);
-        const double d2 = (double)r2, d3 = (double)r3;
-        t[0] = w0 * (double)r0;
-        t[4 * PP] = w0i * (double)r1;
-        t[2 * 4 * PP] = d2;
-        if (POLY) {
-          t[3 * 4 * PP] = fma(jc0, d2, d3);
-          t[4 * 4 * PP] = fma(jc02, d2, fma(jc2, d3, (double)r4));
-        }
-        float z = (xs[k] - prev) + omc * prev;
-        z = i0 + k < N ? z : 0.f;
-        prev = xs[k];
-        r0 = fmaf(wm[k], z, r0);
-        r1 = fmaf(wp[k], z, r1);
-        r2 += z;
-        if (POLY) {
-          r3 = fmaf((float)k, z, r3);
-          r4 = fmaf((float)(k * k), z, r4);
-        }
-      }
-    }
   }
+  // ---- band deposits: (band, chunk) pair h, positions [0, 8) by the helper threads (tid >= HB, idle otherwise),
+  // positions [8, 16) by the owner threads of the four warps below them once their own chunk is done ------------
+  if (tid >= HB) seg_deposit<POLY, 0, CHK / 2>(X, N, p, CW, PP, base, tid - HB, j0, omc, pwc, NPW, wm, wp, tab);
+  else if (tid >= HB - 128) seg_deposit<POLY, CHK / 2, CHK>(X, N, p, CW, PP, base, tid - (HB - 128), j0, omc, pwc, NPW, wm, wp, tab);
   PROF_SUB(0);   // pass 1 (this thread)
   conv_seg_finish<POLY, TWO>(X, N, lt, fl, L, c, inv2S, qm, qp, eA, pw, s0, s1, k0, k1, tab, s, tid, lane, warp);
 }
