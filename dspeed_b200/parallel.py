@@ -48,6 +48,12 @@ def gather_table(tb_local, n_rows: int, dst: int = 0, group=None):
         if tables.kind_of(col) not in ("array", "aoesa"):
             raise TypeError(f"gather of column {name}: only fixed-shape columns are gathered")
         t = _column_tensor(col)
+        # unsigned 16/32/64-bit columns (e.g. the uint32 peak counters of get_multi_local_extrema) travel as the
+        # signed type of the same width: the collectives' dtype support for them varies between backends
+        wire = {torch.uint16: torch.int16, torch.uint32: torch.int32, torch.uint64: torch.int64}.get(t.dtype)
+        dtype = t.dtype
+        if wire is not None:
+            t = t.view(wire)
         # equal-sized pieces (all_gather), padded to the longest shard
         piece = t.new_zeros((longest, *t.shape[1:]))
         piece[: t.shape[0]] = t
@@ -55,6 +61,8 @@ def gather_table(tb_local, n_rows: int, dst: int = 0, group=None):
         dist.all_gather(pieces, piece, group=group)
         if rank == dst:
             cat = torch.cat([p[: e - b] for p, (b, e) in zip(pieces, sizes)], dim=0)
+            if wire is not None:
+                cat = cat.view(dtype)
             full[name] = type(col)(cat if cat.is_cuda else cat.numpy(), attrs=dict(col.attrs))
     return tables.Table(full, size=n_rows) if rank == dst else None
 

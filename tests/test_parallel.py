@@ -44,6 +44,10 @@ def _worker(rank, world, port, n_rows, q):
             "trapEmax": tables.Array((rows * 2.0).astype(np.float32), attrs={"units": "ADC"}),
             "tp_0_est": tables.Array((rows + 0.5).astype(np.float32), attrs={"units": "ns"}),
             "wf": tables.ArrayOfEqualSizedArrays(np.repeat(rows[:, None], 3, axis=1).astype(np.float32)),
+            # the SiPM chain's outputs: NaN-padded peak lists [rows, 20] and uint32 counters
+            "vt_max": tables.ArrayOfEqualSizedArrays(np.where(np.arange(20)[None, :] < (rows % 5)[:, None],
+                                                              rows[:, None] + np.arange(20)[None, :], np.nan).astype(np.float32)),
+            "n_max": tables.Array((rows % 5).astype(np.uint32)),
         }, size=e - b)
         full = parallel.gather_table(local, n_rows, dst=0)
         if rank == 0:
@@ -51,7 +55,11 @@ def _worker(rank, world, port, n_rows, q):
                   and np.array_equal(np.asarray(full["trapEmax"].nda), np.arange(n_rows, dtype=np.float32) * 2)
                   and np.array_equal(np.asarray(full["tp_0_est"].nda), np.arange(n_rows, dtype=np.float32) + 0.5)
                   and np.array_equal(np.asarray(full["wf"].nda)[:, 2], np.arange(n_rows, dtype=np.float32))
-                  and full["trapEmax"].attrs["units"] == "ADC")
+                  and full["trapEmax"].attrs["units"] == "ADC"
+                  and np.asarray(full["n_max"].nda).dtype == np.uint32
+                  and np.array_equal(np.asarray(full["n_max"].nda), (np.arange(n_rows) % 5).astype(np.uint32))
+                  and np.array_equal(np.isnan(np.asarray(full["vt_max"].nda)).sum(axis=1), 20 - np.arange(n_rows) % 5)
+                  and np.array_equal(np.asarray(full["vt_max"].nda)[1::5, 0], np.arange(n_rows, dtype=np.float32)[1::5]))
             q.put(bool(ok))
         else:
             assert full is None
