@@ -135,3 +135,17 @@ def test_units_algebra():
     assert float((128 * ureg("ns") + 2 * ureg("us")) / p) == 133.0
     assert "ns" in ureg and "ADC" not in ureg
     assert Quantity(1, "us") == Quantity(1000, "ns")
+
+
+def test_tensor_core_convolution_workspace_query():
+    """host-side entry point of csrc/conv_tc.cu (no GPU work): Toeplitz tiles hi + lo of the (K + lead + 127)-wide band
+    in 32-column tiles of 128 rows, plus the kernel-sum scalar"""
+    import ctypes as C
+
+    from dspeed_b200 import _lib
+
+    L = _lib.lib()
+    L.dspb_convolve_tc_workspace.restype = C.c_int64
+    for K in (1, 128, 1024, 4096, 5792):
+        nk = (K + 3 + 127 + 31) // 32
+        assert L.dspb_convolve_tc_workspace(C.c_int64(K)) == 2 * nk * 128 * 32 + 32

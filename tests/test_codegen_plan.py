@@ -79,3 +79,32 @@ def test_done_event_wait_precedes_the_last_block_to_scalar_event(spec):
     src = spec.source()
     blk = src[src.index("block stream"):src.index("scalar stream")]
     assert blk.index("if (it > 0) EV_WAIT(15);") < blk.rindex("EV_ARRIVE(EVB(")
+
+
+def test_double_pole_zero_is_specialised():
+    """double_pole_zero with constant time constants has an emitter (geometric scan + plain scan, two barrier rounds)"""
+    import numpy as np
+
+    from dspeed_b200 import tables
+    from dspeed_b200.processing_chain import build_processing_chain
+
+    cfg = {"outputs": ["dpz_max"], "processors": {
+        "wf_blsub": "dspeed.processors.bl_subtract(waveform, baseline, wf_blsub(unit='ADC'))",
+        "wf_dpz": {"function": "dspeed.processors.double_pole_zero(wf_blsub, 27460.5, 1200.25, 0.025, wf_dpz)", "unit": "ADC"},
+        "dpz_max": {"function": "numpy.amax(wf_dpz, 1, dpz_max)", "unit": "ADC"}}}
+    n = 4
+    wf = tables.WaveformTable(size=n, t0=0, t0_units="ns", dt=16, dt_units="ns", values=np.zeros((n, 8192), np.uint16))
+    tb = tables.Table({"waveform": wf, "baseline": tables.Array(np.zeros(n, np.uint16))}, size=n)
+    chain, _, _ = build_processing_chain(cfg, tb, block_width=16, device="meta")
+    build = codegen.SpecChain._build
+    codegen.SpecChain._build = lambda self: None
+    try:
+        sc = codegen.SpecChain(chain)
+    finally:
+        codegen.SpecChain._build = build
+    assert [nd["kind"] for nd in sc.order][:3] == ["load", "bl_sub", "dpz"]
+    src = sc.source()
+    assert "dpz_local(" in src and "put_scan_geo(" in src and "get_excl_geo(" in src
+    # the row's only block -> scalar event comes after the wait for the previous row's "done" event
+    blk = src[src.index("block stream"):src.index("scalar stream")]
+    assert blk.index("if (it > 0) EV_WAIT(15);") < blk.rindex("EV_ARRIVE(EVB(")
