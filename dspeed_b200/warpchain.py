@@ -338,8 +338,10 @@ class WarpChain(FusedChain):
         vmax_t, vmin_t, nmax_t, nmin_t = a[6:10]
         if any(not isinstance(t, torch.Tensor) for t in (vmax_t, vmin_t, nmax_t, nmin_t)):
             raise NotSpecializable("extrema outputs")
+        if vmax_t.ndim != 2 or vmin_t.ndim != 2:
+            raise NotSpecializable("extrema lists must be [block, m] variables")
         m = int(vmax_t.shape[1])
-        if vmax_t.ndim != 2 or tuple(vmin_t.shape) != tuple(vmax_t.shape) or m > 32 or not m < n:
+        if tuple(vmin_t.shape) != tuple(vmax_t.shape) or m > 32 or not m < n:
             raise NotSpecializable("extrema list shape (another tier raises the DSPFatal)")
         if not (d_max >= 0 and d_min >= 0) or float(sdir) not in (0.0, 1.0, 3.0) or np.isnan(ab_max) or np.isnan(ab_min):
             raise NotSpecializable("extrema arguments (another tier handles them)")
