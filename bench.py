@@ -151,7 +151,7 @@ def run_reference(args, rank):
 # clocks during the timed region
 # ----------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -170,7 +170,12 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """median SM clock / throttle reasons of the samples taken between wall-clock times t0 and t1 (the timed
+        region); nvidia-smi needs a few hundred ms to start, so the sampler is started before the warm-up steps and
+        the samples are selected by their timestamps (all samples under load if the region was too short for one)"""
+        import datetime
+
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.proc is None:
             return out
@@ -179,27 +184,29 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        rows = []
         try:
             for ln in open(self.path):
                 p = [x.strip() for x in ln.split(",")]
                 if len(p) < 9:
                     continue
                 try:
-                    sm.append(float(p[1]))
-                    mx.append(float(p[2]))
+                    ts = datetime.datetime.strptime(p[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    rows.append((ts, float(p[1]), float(p[2]),
+                                 [name for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                                             "sw_power_cap"), p[5:9]) if val.lower().startswith("active")]))
                 except ValueError:
                     continue
-                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
-                                     p[5:9]):
-                    if val.lower().startswith("active"):
-                        reasons.add(name)
             os.unlink(self.path)
         except Exception:
             pass
-        if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons),
-                       samples=len(sm))
+        sel = [r for r in rows if t0 is not None and t1 is not None and t0 <= r[0] <= t1]
+        window = "timed region"
+        if not sel:      # region shorter than the sampling period: the warm-up steps ran the same kernel
+            sel, window = rows, "warm-up + timed region"
+        if sel:
+            out.update(sm_mhz=float(np.median([r[1] for r in sel])), sm_max_mhz=float(max(r[2] for r in sel)),
+                       reasons=sorted({x for r in sel for x in r[3]}), samples=len(sel), window=window)
         return out
 
 
@@ -250,21 +257,23 @@ def run_b200(args, rank, world, local_rank):
         return float(t.item())
 
     # ---- device-resident throughput ---------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(warm):
         chain(tb_dev, tb_out_dev)
     chain.enable_event_timing(True)
     launches0 = chain.stats["launches"]
-    sampler = ClockSampler(local_rank)
     barrier()
-    if rank == 0:
-        sampler.start()
+    wall0 = time.time()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
         chain(tb_dev, tb_out_dev)
     e1.record()
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    wall1 = time.time()
+    clocks = sampler.stop(wall0, wall1) if rank == 0 else None
     t_dev = max_over_ranks(e0.elapsed_time(e1) * 1e-3)
     launches = chain.stats["launches"] - launches0
     timing = chain.get_timing()  # resolves the per-processor CUDA events
