@@ -303,6 +303,7 @@ class SpecChain(FusedChain):
                 raise NotSpecializable(f"input waveform dtype {rv.dtype}")
             w = Wave(len(self.waves), int(rv.shape[1]))
             w.is_input = True
+            w.int_valued = rv.dtype in (torch.uint16, torch.int16)
             self.waves[st] = w
             self._node("load", wouts=[w], ptr=self._ptr(("in", man, what)), dtype=rv.dtype, n=int(rv.shape[1]))
         off = t.storage_offset() % max(1, w.n) if t.storage_offset() else 0
@@ -731,15 +732,30 @@ class SpecChain(FusedChain):
                 for key in ("thr", "start", "walk", "t", "x", "y", "oi", "oo"):
                     if isinstance(nd.get(key), str) and not nd[key].startswith(("0x", "-0x", "CUDART")):
                         self.urgent_names.add(nd[key])
+        regions = self._plan_regions()
+        self.region_nw = None
         for k, nd in enumerate(self.order):
             self.pos = k
             self._es_later_end()
+            if k in regions:
+                # a run of nodes that only touch short waveforms: warps that own no chunk of them skip the arithmetic
+                # and only mirror the synchronisation (see _expand_regions)
+                self._close_round()
+                self.region_nw = regions[k][1]
+                self.LB.append(f"//@REGION_BEGIN {self.region_nw}")
             self.LB.append(f"// ---- [{k}] {self._describe_node(nd)}")
             self.LS.append(f"// ---- [{k}] {self._describe_node(nd)}")
             getattr(self, "_e_" + nd["kind"])(nd)
             self.LB.append("PROF_MARK(%d);" % k)
             self.LS.append("PROF_MARK_S(%d);" % k)
             self._release(k)
+            if self.region_nw is not None and any(k == e for (e, _) in regions.values()):
+                self._close_round()
+                self.LB.append("//@REGION_END")
+                self.region_nw = None
+                for w in list(self.live_regs):    # register chunks defined inside the region are out of scope
+                    w.reg = None
+                self.live_regs = []
         self._close_round()
         self._flush_s()
         # scalar outputs not stored at their definition (pass-through input scalars)
@@ -760,6 +776,78 @@ class SpecChain(FusedChain):
             raise NotSpecializable("not enough shared memory for the live waveforms")
         self.program_text = "\n".join(f"{k:3d} {self._describe_node(nd)}" for k, nd in enumerate(self.order))
         self.code = self.order  # (for len(code) users)
+
+    def _extent(self, nd):
+        """number of samples the block-stream code of a node spans (0: scalar-stream only)"""
+        kind = nd["kind"]
+        if kind in ("tpt", "ftp", "trap_pickoff", "fir_lazy", "sc_bin", "sc_neg", "sc_convert"):
+            return 0
+        if kind == "windower":
+            return nd["wouts"][0].n + CHK
+        if kind == "min_max" and (nd.get("from_conv") or any(
+                w.producer is not None and self.nodes[w.producer]["kind"] == "conv_seg" for (w, _, _) in nd["ins"])):
+            return 0    # (the convolution hands its maxima to the scalar warp itself; at worst the region is missed)
+        if kind in ("min_max", "lsf", "avg_current", "upsampler", "mw"):
+            return max([w.n for (w, _, _) in nd.get("ins", [])] + [w.n for w in nd.get("wouts", [])])
+        return CHK * NT
+
+    def _plan_regions(self):
+        """{first node: (last node, warps)} for runs of consecutive nodes whose waveforms fit into at most 12 warps"""
+        if os.environ.get("DSPEED_B200_REGIONS", "1") == "0":
+            return {}
+        lim = 12 * 32 * CHK
+        ext = [self._extent(nd) for nd in self.order]
+        regions, k = {}, 0
+        while k < len(ext):
+            if not (0 < ext[k] <= lim):
+                k += 1
+                continue
+            e = k
+            last = k
+            while e + 1 < len(ext) and ext[e + 1] <= lim:
+                e += 1
+                if ext[e] > 0:
+                    last = e
+            if sum(1 for q in range(k, last + 1) if ext[q] > 0) >= 2:
+                regions[k] = (last, -(-max(ext[k:last + 1]) // (32 * CHK)))
+            k = last + 1
+        return regions
+
+    def _nwarg(self):
+        return f", {self.region_nw}" if getattr(self, "region_nw", None) else ""
+
+    def _expand_regions(self, lines):
+        """//@REGION markers -> `if (warp < nw) { ... } else { <synchronisation only> }`.  The idle warps execute the
+        same barriers, events and scalar fetches in the same order (the hazard waits that _pipeline_rows inserted
+        included); flags that outlive the region are declared in front of it."""
+        out, k = [], 0
+        keep = re.compile(r"^\s*(BSYNC\(\)|EV_ARRIVE|EV_WAIT|if \(it > 0\) EV_WAIT|par \^= 1|s\d+ = )")
+        while k < len(lines):
+            ln = lines[k]
+            if not ln.startswith("//@REGION_BEGIN"):
+                out.append(ln)
+                k += 1
+                continue
+            nw = int(ln.split()[1])
+            e = next(i for i in range(k + 1, len(lines)) if lines[i].startswith("//@REGION_END"))
+            body, idle, decls = [], [], []
+            for b in lines[k + 1:e]:
+                m = re.match(r"^(\s*)const int (nan\w+) = (get_imax\(.*)$", b)
+                if m:
+                    decls.append(f"int {m.group(2)} = 0;")
+                    b = f"{m.group(1)}{m.group(2)} = {m.group(3)}"
+                    idle.append(b)
+                elif keep.match(b):
+                    idle.append(b)
+                body.append(b)
+            out.extend(decls)
+            out.append(f"if (warp < {nw}) {{   // ---- region: waveforms of at most {nw * 32 * CHK} samples")
+            out.extend(body)
+            out.append("} else {   // warps without a chunk of these waveforms: synchronisation only")
+            out.extend(idle)
+            out.append("}")
+            k = e + 1
+        return out
 
     def _pipeline_rows(self):
         """Software pipelining across rows.  The block stream starts row r+1 while the scalar warp is
@@ -885,6 +973,7 @@ class SpecChain(FusedChain):
             self._e(*self.posts)
             self._e("par ^= 1;")
         self.posts = []
+        self.post_mail = False
         self.pending.clear()
         self.dirty.clear()
         self.xread.clear()
@@ -913,6 +1002,8 @@ class SpecChain(FusedChain):
         (bar.arrive by the 512 block threads, bar.sync by the scalar warp)"""
         if not self.s_dirty:
             return
+        if getattr(self, "post_mail", False):
+            self._close_round()      # mailbox entries written by post-barrier code precede the event
         self.s_dirty = False
         if self.b2s_count >= 6:
             raise NotSpecializable("more block -> scalar events per row than named barriers")
@@ -1220,10 +1311,24 @@ class SpecChain(FusedChain):
         fl = [f for f in flags if f != "0"]
         return " || ".join(f"({f})" for f in fl) if fl else None
 
+    def _wrange(self, lo, hi):
+        """block warps that own a chunk of the samples [lo, hi)"""
+        return lo // (32 * CHK), min(NT // 32, -(-hi // (32 * CHK)))
+
+    def _guard(self, w0, w1):
+        """(opening, closing, number of warps) of a warp-uniform guard for the warps [w0, w1)"""
+        if w0 <= 0 and w1 >= NT // 32:
+            return "{", "}", NT // 32
+        cond = f"warp < {w1}" if w0 <= 0 else (f"warp >= {w0}" if w1 >= NT // 32 else f"warp >= {w0} && warp < {w1}")
+        return f"if ({cond}) {{", "}", w1 - w0
+
     def _e_min_max(self, nd):
-        # min_max.py:11-82 / numpy.amax: value via FMNMX, first-occurrence index via an equality pass;
-        # outputs nobody reads (and that are no chain outputs) are not computed at all.  The block
-        # warps deposit their partial results in the mailbox; the scalar warp combines them.
+        # min_max.py:11-82 / numpy.amax: value via FMNMX; outputs nobody reads (and that are no chain outputs) are not
+        # computed at all.  Only the warps that own part of the range take part; chunks inside the range run
+        # unmasked.  The block warps deposit their partial results in the mailbox; the scalar warp combines them.
+        # First-occurrence index: on the latency-critical path (a scalar the block stream waits for depends on it)
+        # every thread looks up the position of its own extremum before the block-wide result is known; otherwise
+        # the look-up happens after the round's barrier, in the one warp that owns the block extremum.
         w, off, n = nd["ins"][0]
         outs = [o if (o and o in self.used_scalars) else None for o in nd["outs"]]
         if not any(outs):
@@ -1238,57 +1343,111 @@ class SpecChain(FusedChain):
             return
         self._need(w.nan)
         r = self._chunk(w)
-        full = "true" if (off == 0 and n >= w.n and w.n % CHK == 0 and w.n == CHK * NT) else "false"
+        lo, hi = off, min(off + n, w.n)
+        t0, t1 = -(-lo // CHK), hi // CHK                  # chunks entirely inside the range
+        partial = (lo % CHK != 0) + (hi % CHK != 0)
+        w0, w1 = self._wrange(lo, hi)
+        g_open, g_close, g_n = self._guard(w0, w1)
+        rng = f", {w0}, {w1}" if g_n < NT // 32 else ""
         todo = []
-        for (it, iv, fn, put_a, get_a, put_v, get_v) in ((0, 2, "min", "put_argmin", "get_argmin", "put_fmin", "get_fmin"),
-                                                         (1, 3, "max", "put_argmax", "get_argmax", "put_fmax", "get_fmax")):
+        for (it, iv, fn, put_a, get_a, put_v, get_v, ident) in (
+                (0, 2, "min", "put_argmin", "get_argmin", "put_fmin", "get_fmin", "CUDART_INF_F"),
+                (1, 3, "max", "put_argmax", "get_argmax", "put_fmax", "get_fmax", "(-CUDART_INF_F)")):
             if outs[it] is None and outs[iv] is None:
                 continue
             m = self._t("m")
-            self._e(f"const float {m} = {fn}_local<{full}>({r}, 16 * tid, {off}, {off + n});")
-            if outs[it] is not None:
+
+            def local(f, extra=""):
+                full = f"{f}_local<true>({r}, {extra}16 * tid, {lo}, {hi})"
+                part = f"{f}_local<false>({r}, {extra}16 * tid, {lo}, {hi})"
+                if not partial and t0 == 0 and t1 * CHK >= min(w.n, w1 * 32 * CHK):
+                    return [f"  {{res}} = {full};   //@X {g_n}"]
+                return [f"  if (tid >= {t0} && tid < {t1}) {{res}} = {full};   //@X {-(-t1 // 32) - t0 // 32}",
+                        f"  else if (16 * tid < {hi} && 16 * tid + 16 > {lo}) {{res}} = {part};   //@X {max(1, partial)}"]
+
+            urgent_idx = outs[it] is not None and (outs[it] in self.urgent_names or outs[it] in self.b_needed
+                                                   or os.environ.get("DSPEED_B200_LATE_ARG", "1") == "0")
+            whole = not partial and t0 == 0 and t1 * CHK >= w.n and lo == 0
+            if (outs[it] is not None and not urgent_idx and w.is_input and whole and w.n == CHK * NT
+                    and getattr(w, "int_valued", False)):
+                # raw ADC words: value and first position in one pass (no equality look-up)
+                mb = self._mbi(2)
+                jx = self._t("jx")
+                self._e(f"int {jx}; const float {m} = arg{fn}_packed({r}, {jx});",
+                        f"{put_a}(MBI({mb}), {m}, 16 * tid + {jx}, lane, warp);")
+                todo.append((it, iv, get_a, mb, "arg"))
+                continue
+            self._e(f"float {m} = {ident};", g_open, *[ln.format(res=m) for ln in local(fn)])
+            if outs[it] is not None and (urgent_idx or w.slot is None or not w.needs_slot):
                 mb = self._mbi(2)
                 ix = self._t("ix")
-                self._e(f"const int {ix} = first_eq_local<{full}>({r}, {m}, 16 * tid, {off}, {off + n});",
-                        f"{put_a}(MBI({mb}), {m}, {ix}, lane, warp);")
-                todo.append((it, iv, get_a, mb, True))
+                self._e(f"  int {ix} = 0x7fffffff;", *[ln.format(res=ix) for ln in local("first_eq", f"{m}, ")],
+                        f"  {put_a}(MBI({mb}), {m}, {ix}, lane, warp);   //@X {g_n}", g_close)
+                todo.append((it, iv, get_a, mb, "arg"))
+            elif outs[it] is not None:
+                # the position is looked up after the barrier by the warp that holds the block extremum, which
+                # re-reads its chunk from the slot (no register chunk stays live across the barrier)
+                mb = self._mbi(2)
+                ix, q = self._t("ix"), self._t("q")
+                self._e(f"  {put_v}(MBI({mb}), {m}, lane, warp);   //@X {g_n}", g_close,
+                        f"if (tid == 0) MBI({mb + 1})[0] = 0x7fffffff;")
+                self.posts.append(f"{g_open} const float g_ = {get_v}(MBI({mb}), lane{rng});   //@X {g_n}")
+                self.posts.append(f"  if ({m} == g_) {{ int {ix} = 0x7fffffff; float {q}[16]; ld_chunk({self._slot(w)}, tid, {q});   //@X 1")
+                self.posts.extend("  " + ln.format(res=ix).replace(r + ",", q + ",").replace("//@X", "//@X 1 //")
+                                  for ln in local("first_eq", "g_, "))
+                self.posts.append(f"    if ({ix} != 0x7fffffff) atomicMin(&MBI({mb + 1})[0], {ix}); }} {g_close}   //@X 1")
+                self.post_mail = True
+                todo.append((it, iv, get_v, mb, "late"))
             else:
                 mb = self._mbi(1)
-                self._e(f"{put_v}(MBI({mb}), {m}, lane, warp);")
-                todo.append((it, iv, get_v, mb, False))
+                self._e(f"  {put_v}(MBI({mb}), {m}, lane, warp);   //@X {g_n}", g_close)
+                todo.append((it, iv, get_v, mb, "val"))
         g = self._nan_guard([self._flag_s(w.nan)])
         gq = f"({g}) ? CUDART_NAN_F : " if g else ""
         self.s_dirty = True
         self.s_seq += 1
-        for (it, iv, get, mb, with_idx) in todo:
-            if with_idx:
+        for (it, iv, get, mb, how) in todo:
+            if how == "arg":
                 v, i = self._t("v"), self._t("i")
-                self._es_later(f"float {v}; int {i}; {get}(MBI({mb}), lane, {v}, {i});", self._asg(outs[it], f"{gq}(float){i}"))
+                self._es_later(f"float {v}; int {i}; {get}(MBI({mb}), lane, {v}, {i}{rng});", self._asg(outs[it], f"{gq}(float){i}"))
                 if outs[iv]:
                     self._es_later(self._asg(outs[iv], f"{gq}{v}"))
+            elif how == "late":
+                self._es_later(self._asg(outs[it], f"{gq}(float)MBI({mb + 1})[0]"))
+                if outs[iv]:
+                    self._es_later(self._asg(outs[iv], f"{gq}{get}(MBI({mb}), lane{rng})"))
             else:
-                self._es_later(self._asg(outs[iv], f"{gq}{get}(MBI({mb}), lane)"))
+                self._es_later(self._asg(outs[iv], f"{gq}{get}(MBI({mb}), lane{rng})"))
         for o in outs:
             if o:
                 self._es_later(*self._stores(o))
                 self._def_s_later(o)
 
     def _e_lsf(self, nd):
+        # linear_slope_fit.py:11-90.  Threads whose chunk lies inside [off, off + n) run the unmasked float32-local
+        # sums, the (at most two) chunks that straddle an end the masked ones, and only the warps that hold part of
+        # the range take part in the block sum.
         w, off, n = nd["ins"][0]
         outs = nd["outs"]
         self._need(w.nan)
         r = self._chunk(w)
         mb = self._mbd(3)
         a, b, c = self._t("sy"), self._t("sxy"), self._t("syy")
-        self._e(f"double {a}, {b}, {c}; lsf_local({r}, 16 * tid, {off}, {off + n}, {a}, {b}, {c});",
-                f"put_sum(MBD({mb}), {a}, lane, warp); put_sum(MBD({mb + 1}), {b}, lane, warp); "
-                f"put_sum(MBD({mb + 2}), {c}, lane, warp);")
+        lo, hi = off, off + n
+        t0, t1 = -(-lo // CHK), hi // CHK           # chunks entirely inside the range
+        w0, w1 = lo // (32 * CHK), min(NT // 32, -(-hi // (32 * CHK)))
+        self._e(f"double {a} = 0.0, {b} = 0.0, {c} = 0.0;",
+                f"if (tid >= {t0} && tid < {t1}) lsf_local_f<true>({r}, 16 * tid, {lo}, {hi}, {a}, {b}, {c});   //@X {-(-t1 // 32) - t0 // 32}",
+                f"else if (16 * tid < {hi} && 16 * tid + 16 > {lo}) lsf_local_f<false>({r}, 16 * tid, {lo}, {hi}, {a}, {b}, {c});   //@X {(lo % CHK != 0) + (hi % CHK != 0)}",
+                f"if (warp >= {w0} && warp < {w1}) {{ put_sum(MBD({mb}), {a}, lane, warp); put_sum(MBD({mb + 1}), {b}, lane, warp); "
+                f"put_sum(MBD({mb + 2}), {c}, lane, warp); }}   //@X {w1 - w0}")
         g = self._nan_guard([self._flag_s(w.nan)])
         self.s_dirty = True
         self.s_seq += 1
         f = [self._t("f") for _ in range(4)]
-        post = (f"float {f[0]}, {f[1]}, {f[2]}, {f[3]}; lsf_finish({n}, get_sum(MBD({mb}), lane), "
-                f"get_sum(MBD({mb + 1}), lane), get_sum(MBD({mb + 2}), lane), {f[0]}, {f[1]}, {f[2]}, {f[3]});")
+        post = (f"float {f[0]}, {f[1]}, {f[2]}, {f[3]}; lsf_finish({n}, get_sum_r(MBD({mb}), lane, {w0}, {w1}), "
+                f"get_sum_r(MBD({mb + 1}), lane, {w0}, {w1}), get_sum_r(MBD({mb + 2}), lane, {w0}, {w1}), "
+                f"{f[0]}, {f[1]}, {f[2]}, {f[3]});")
         if g:
             post += f" if ({g}) {{ {f[0]} = {f[1]} = {f[2]} = {f[3]} = CUDART_NAN_F; }}"
         self._es_later(post)
@@ -1325,11 +1484,11 @@ class SpecChain(FusedChain):
         sd = self._alloc_d(1)
         tot, incl, omc = self._t("tot"), self._t("incl"), self._t("omc")
         self._e(f"const double {omc} = -expm1(-1.0 / (double)(float)({nd['tau']}));",
-                f"const double {tot} = chunk_sum_d({r});",
+                f"const double {tot} = (double)chunk_sum_f({r});",
                 f"const double {incl} = put_scan(CSD({sd}), {tot}, lane, warp);")
         o, dum = self._t("r"), self._t("tt")
         self.posts.append(f"float {o}[16]; double {dum}; "
-                          f"pz_chunk({r}, get_excl(CSD({sd}), {incl}, {tot}, lane, warp, {dum}), {omc}, {o});")
+                          f"pz_chunk_f({r}, get_excl(CSD({sd}), {incl}, {tot}, lane, warp, {dum}), {omc}, {o});")
         const_tau = nd["tau"].startswith(("0x", "-0x"))
         flags = [w.nan] + ([] if const_tau else [f"((float)({nd['tau']}) != (float)({nd['tau']}))"])
         g = self._nan_guard(flags)
@@ -1611,12 +1770,12 @@ class SpecChain(FusedChain):
         self._e(self._wmark(out.slot), f"int {pad} = 0;",
                 f"const float {tf} = (float)({nd['t0']});",
                 f"int {beg} = ({tf} == {tf}) ? (int)fminf(fmaxf({tf}, -1.0e9f), 1.0e9f) : 0; if ({beg} > {n}) {beg} = {n};",
-                f"for (int k = tid; k < {mc}; k += 512) {{ const int q = {beg} + k; float v = 0.f; "
+                f"for (int k = tid; k < {mc}; k += {32 * (self.region_nw or NT // 32)}) {{ const int q = {beg} + k; float v = 0.f; "
                 f"if (k < {m}) {{ if (!({g}) && q >= 0 && q < {n}) v = at({self._slot(w)}, q); else {{ {pad} = 1; v = CUDART_NAN_F; }} }} "
                 f"{so}[sidx(k)] = v; }}",
                 f"put_imax(CSI({si}), {pad}, lane, warp);")
         nf = f"nan{out.name}"
-        self.posts.append(f"const int {nf} = get_imax(CSI({si}), lane);")
+        self.posts.append(f"const int {nf} = get_imax(CSI({si}), lane{self._nwarg()});")
         self.pending.add(nf)
         out.nan = nf
         out.nan_elementwise = True
@@ -1675,7 +1834,8 @@ class SpecChain(FusedChain):
 
     def _e_mw(self, nd):
         # moving_windows.py:12-203 : successive boxcar means with edge-value padding, each one a
-        # chunk-local running sum of (x[i] - x[i -/+ L]) / L plus one block scan
+        # chunk-local running sum of (x[i] - x[i -/+ L]) / L plus one block scan.  Only the warps that own a
+        # chunk of the wave take part, and chunks away from the ends run the unmasked difference.
         w, off, n = nd["ins"][0]
         out = nd["wouts"][0]
         L = nd["L"]
@@ -1683,6 +1843,8 @@ class SpecChain(FusedChain):
         dirs = nd["dirs"]
         temps = []
         src = w
+        nwarg = self._nwarg()
+        g_n = self.region_nw or NT // 32
         for k, dr in enumerate(dirs):
             last = k == len(dirs) - 1
             if last:
@@ -1700,25 +1862,30 @@ class SpecChain(FusedChain):
             sh, d, tot, incl, e0, tt = (self._t(p) for p in ("r", "d", "tot", "incl", "e", "tt"))
             sd = self._alloc_d(1)
             sl = self._slot(src)
+            self._e(f"float {sh}[16], {d}[16];")
             if dr == "l":
                 # out[0] = x[0]; out[i] = out[i-1] + (x[i] - x[max(i-L,0)]) / L
-                self._e(f"float {sh}[16]; ld_shift<{-L}>({sl}, tid, {n}, {self._zc(src)}, {sh}); const float {e0} = at({sl}, 0);",
-                        f"float {d}[16]; _Pragma(\"unroll\") for (int j = 0; j < 16; j++) {{ const int i = 16 * tid + j; "
-                        f"{d}[j] = i >= {n} ? 0.f : (i == 0 ? {e0} : ({x}[j] - (i >= {L} ? {sh}[j] : {e0})) * {il}); }}",
-                        f"const float {tot} = cumsum_local({d});",
-                        f"const float {incl} = put_scan_f(CSD({sd}), {tot}, lane, warp);")
-                get = f"get_excl_f(CSD({sd}), {incl}, {tot}, lane, warp)"
+                ta, tb = -(-L // CHK), n // CHK     # chunks with every i in [L, n)
+                self._e(f"  ld_shift<{-L}>({sl}, tid, {n}, {self._zc(src)}, {sh}); const float {e0} = at({sl}, 0);   //@X {g_n}",
+                        f"  if (tid >= {ta} && tid < {tb}) {{ _Pragma(\"unroll\") for (int j = 0; j < 16; j++) {d}[j] = ({x}[j] - {sh}[j]) * {il}; }}   //@X {g_n}",
+                        f"  else {{ _Pragma(\"unroll\") for (int j = 0; j < 16; j++) {{ const int i = 16 * tid + j; "
+                        f"{d}[j] = i >= {n} ? 0.f : (i == 0 ? {e0} : ({x}[j] - (i >= {L} ? {sh}[j] : {e0})) * {il}); }} }}   //@X 2",
+                        f"const float {tot} = cumsum_local({d});   //@X {g_n}",
+                        f"const float {incl} = put_scan_f(CSD({sd}), {tot}, lane, warp);   //@X {g_n}")
+                get = f"get_excl_f(CSD({sd}), {incl}, {tot}, lane, warp{nwarg})"
             else:
                 # mirror image: out[n-1] = x[n-1]; out[i] = out[i+1] + (x[i] - x[min(i+L,n-1)]) / L
-                self._e(f"float {sh}[16]; ld_shift<{L}>({sl}, tid, {n}, {self._zc(src)}, {sh}); const float {e0} = at({sl}, {n - 1});",
-                        f"float {d}[16]; _Pragma(\"unroll\") for (int j = 0; j < 16; j++) {{ const int i = 16 * tid + j; "
-                        f"{d}[j] = i >= {n} ? 0.f : (i == {n - 1} ? {e0} : ({x}[j] - (i + {L} <= {n - 1} ? {sh}[j] : {e0})) * {il}); }}",
-                        f"const float {tot} = cumsum_local_rev({d});",
-                        f"const float {incl} = put_scan_rev_f(CSD({sd}), {tot}, lane, warp);")
-                get = f"get_excl_rev_f(CSD({sd}), {incl}, {tot}, lane, warp)"
+                ta, tb = 0, max(0, (n - L) // CHK)  # chunks with every i + L <= n - 1
+                self._e(f"  ld_shift<{L}>({sl}, tid, {n}, {self._zc(src)}, {sh}); const float {e0} = at({sl}, {n - 1});   //@X {g_n}",
+                        f"  if (tid >= {ta} && tid < {tb}) {{ _Pragma(\"unroll\") for (int j = 0; j < 16; j++) {d}[j] = ({x}[j] - {sh}[j]) * {il}; }}   //@X {g_n}",
+                        f"  else {{ _Pragma(\"unroll\") for (int j = 0; j < 16; j++) {{ const int i = 16 * tid + j; "
+                        f"{d}[j] = i >= {n} ? 0.f : (i == {n - 1} ? {e0} : ({x}[j] - (i + {L} <= {n - 1} ? {sh}[j] : {e0})) * {il}); }} }}   //@X 2",
+                        f"const float {tot} = cumsum_local_rev({d});   //@X {g_n}",
+                        f"const float {incl} = put_scan_rev_f(CSD({sd}), {tot}, lane, warp);   //@X {g_n}")
+                get = f"get_excl_rev_f(CSD({sd}), {incl}, {tot}, lane, warp{nwarg})"
             o, offv = self._t("r"), self._t("off")
-            self.posts.append(f"double {tt} = 0.0; const float {offv} = (float){get}; (void){tt};")
-            self.posts.append(f"float {o}[16]; _Pragma(\"unroll\") for (int j = 0; j < 16; j++) {o}[j] = {d}[j] + {offv};")
+            self.posts.append(f"float {o}[16]; const float {offv} = (float){get}; _Pragma(\"unroll\") for (int j = 0; j < 16; j++) "
+                              f"{o}[j] = {d}[j] + {offv};   //@X {g_n}")
             dst.nan = src.nan
             dst.reg = None
             self.pending.add(dst.name)
@@ -1911,7 +2078,7 @@ class SpecChain(FusedChain):
     def source(self) -> str:
         np_ = max(1, len(self.ptrs))
         ind = "\n        "
-        body_b = ind.join(self.LB)
+        body_b = ind.join(self._expand_regions(self.LB))
         body_s = ind.join(self.LS)
         prolog = "\n      ".join(self.prolog)
         names = sorted(set(self.svar.values()), key=lambda x: int(x[1:]))
@@ -1975,7 +2142,9 @@ __global__ void __launch_bounds__(544, 1) k_chain_spec(const __grid_constant__ A
   WaveSummary* summ = reinterpret_cast<WaveSummary*>(smem_raw + {summ_off});
   float* slots = reinterpret_cast<float*>(smem_raw + {self.fixed_bytes});
   (void)prof_ts; (void)cs; (void)summ;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // (the shuffle makes the warp index provably warp-uniform: branches on it are uniform branches and the
+  // collectives inside them need no re-convergence code)
+  const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const bool scalar_warp = warp == 16;
   int par = 0;
   if (!scalar_warp) {{

@@ -319,8 +319,8 @@ __device__ __forceinline__ float put_scan_f(double* p, float v, int lane, int wa
   return incl;
 }
 // exclusive prefix of this thread: float64 across the 16 warp totals, float inside the warp
-__device__ __forceinline__ double get_excl_f(const double* p, float incl, float v, int lane, int warp) {
-  const double part = lane < NWP ? p[lane] : 0.0;
+__device__ __forceinline__ double get_excl_f(const double* p, float incl, float v, int lane, int warp, int nw = NWP) {
+  const double part = lane < nw ? p[lane] : 0.0;   // nw: warps that took part in the scan
   double pin = part;
 #pragma unroll
   for (int o = 1; o < NWP; o <<= 1) {
@@ -334,8 +334,8 @@ __device__ __forceinline__ float put_scan_rev_f(double* p, float v, int lane, in
   if (lane == 0) p[warp] = (double)incl;
   return incl;
 }
-__device__ __forceinline__ double get_excl_rev_f(const double* p, float incl, float v, int lane, int warp) {
-  const double part = lane < NWP ? p[lane] : 0.0;
+__device__ __forceinline__ double get_excl_rev_f(const double* p, float incl, float v, int lane, int warp, int nw = NWP) {
+  const double part = lane < nw ? p[lane] : 0.0;
   double pin = part;
 #pragma unroll
   for (int o = 1; o < NWP; o <<= 1) {
@@ -363,9 +363,10 @@ __device__ __forceinline__ void put_argmax(int* p, float v, int idx, int lane, i
   const int im = __reduce_min_sync(FULL, k == km ? idx : 0x7fffffff);
   if (lane == 0) { p[warp] = (int)km; p[NWP + warp] = im; }
 }
-__device__ __forceinline__ void get_argmax(const int* p, int lane, float& v, int& idx) {
-  const unsigned k = lane < NWP ? (unsigned)p[lane] : 0u;
-  const int ii = lane < NWP ? p[NWP + lane] : 0x7fffffff;
+__device__ __forceinline__ void get_argmax(const int* p, int lane, float& v, int& idx, int w0 = 0, int w1 = NWP) {
+  const bool in = lane >= w0 && lane < w1;   // warps that deposited a partial result
+  const unsigned k = in ? (unsigned)p[lane] : 0u;
+  const int ii = in ? p[NWP + lane] : 0x7fffffff;
   const unsigned km = __reduce_max_sync(FULL, k);
   idx = __reduce_min_sync(FULL, k == km ? ii : 0x7fffffff);
   v = fkey_inv(km);
@@ -376,9 +377,10 @@ __device__ __forceinline__ void put_argmin(int* p, float v, int idx, int lane, i
   const int im = __reduce_min_sync(FULL, k == km ? idx : 0x7fffffff);
   if (lane == 0) { p[warp] = (int)km; p[NWP + warp] = im; }
 }
-__device__ __forceinline__ void get_argmin(const int* p, int lane, float& v, int& idx) {
-  const unsigned k = lane < NWP ? (unsigned)p[lane] : 0xffffffffu;
-  const int ii = lane < NWP ? p[NWP + lane] : 0x7fffffff;
+__device__ __forceinline__ void get_argmin(const int* p, int lane, float& v, int& idx, int w0 = 0, int w1 = NWP) {
+  const bool in = lane >= w0 && lane < w1;
+  const unsigned k = in ? (unsigned)p[lane] : 0xffffffffu;
+  const int ii = in ? p[NWP + lane] : 0x7fffffff;
   const unsigned km = __reduce_min_sync(FULL, k);
   idx = __reduce_min_sync(FULL, k == km ? ii : 0x7fffffff);
   v = fkey_inv(km);
@@ -388,8 +390,8 @@ __device__ __forceinline__ void put_imax(int* p, int v, int lane, int warp) {
   v = __reduce_max_sync(FULL, v);
   if (lane == 0) p[warp] = v;
 }
-__device__ __forceinline__ int get_imax(const int* p, int lane) {
-  return __reduce_max_sync(FULL, lane < NWP ? p[lane] : (int)0x80000000);
+__device__ __forceinline__ int get_imax(const int* p, int lane, int nw = NWP) {
+  return __reduce_max_sync(FULL, lane < nw ? p[lane] : (int)0x80000000);
 }
 __device__ __forceinline__ void put_imin(int* p, int v, int lane, int warp) {
   v = __reduce_min_sync(FULL, v);
@@ -448,20 +450,39 @@ __device__ __forceinline__ int first_eq_local(const float (&v)[CHK], float m, in
     if ((FULL_RANGE || (i0 + j >= lo && i0 + j < hi)) && v[j] == m) idx = i0 + j - lo;
   return idx;
 }
+// Extremum AND first position of a whole chunk in one FMNMX pass, for integer-valued samples with |x| < 2^19 (the
+// raw ADC words): 16 x + (15 - j) is exact in float32, its maximum is the largest sample at the smallest j
+// (16 x + j: the smallest sample at the smallest j).  `j` = position inside the chunk.
+__device__ __forceinline__ float argmax_packed(const float (&v)[CHK], int& j) {
+  float k = -CUDART_INF_F;
+#pragma unroll
+  for (int q = 0; q < CHK; q++) k = fmaxf(k, fmaf(v[q], 16.f, (float)(CHK - 1 - q)));
+  const float x = floorf(k * 0.0625f);
+  j = CHK - 1 - (int)fmaf(x, -16.f, k);
+  return x;
+}
+__device__ __forceinline__ float argmin_packed(const float (&v)[CHK], int& j) {
+  float k = CUDART_INF_F;
+#pragma unroll
+  for (int q = 0; q < CHK; q++) k = fminf(k, fmaf(v[q], 16.f, (float)q));
+  const float x = floorf(k * 0.0625f);
+  j = (int)fmaf(x, -16.f, k);
+  return x;
+}
 // value-only block max / min through the order-preserving key
 __device__ __forceinline__ void put_fmax(int* p, float v, int lane, int warp) {
   const unsigned km = __reduce_max_sync(FULL, fkey(v));
   if (lane == 0) p[warp] = (int)km;
 }
-__device__ __forceinline__ float get_fmax(const int* p, int lane) {
-  return fkey_inv(__reduce_max_sync(FULL, lane < NWP ? (unsigned)p[lane] : 0u));
+__device__ __forceinline__ float get_fmax(const int* p, int lane, int w0 = 0, int w1 = NWP) {
+  return fkey_inv(__reduce_max_sync(FULL, (lane >= w0 && lane < w1) ? (unsigned)p[lane] : 0u));
 }
 __device__ __forceinline__ void put_fmin(int* p, float v, int lane, int warp) {
   const unsigned km = __reduce_min_sync(FULL, fkey(v));
   if (lane == 0) p[warp] = (int)km;
 }
-__device__ __forceinline__ float get_fmin(const int* p, int lane) {
-  return fkey_inv(__reduce_min_sync(FULL, lane < NWP ? (unsigned)p[lane] : 0xffffffffu));
+__device__ __forceinline__ float get_fmin(const int* p, int lane, int w0 = 0, int w1 = NWP) {
+  return fkey_inv(__reduce_min_sync(FULL, (lane >= w0 && lane < w1) ? (unsigned)p[lane] : 0xffffffffu));
 }
 
 // linear_slope_fit.py:11-90 : sums over [lo, hi), abscissa relative to lo
@@ -514,6 +535,68 @@ __device__ __forceinline__ int pz_chunk(const float (&x)[CHK], double run, doubl
     run += xv;
   }
   return bad;
+}
+
+// ---------------------------------------------------------------------------------------
+// float32-local variants (round 2).  Inside a 16-sample chunk the sums run in float32 -- exact for the
+// integer-valued waveforms of the DAQ (|x| < 2^16: every partial sum stays below 2^24), rounding-level
+// (<= 16 ulp of a 16-term sum) for general data -- and float64 only where chunks are combined.  One
+// FADD / FFMA per sample instead of F2F + DADD / DFMA (4 + 2 issue cycles each on this part).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float chunk_sum_f(const float (&v)[CHK]) {
+  float a[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) a[j] = v[2 * j] + v[2 * j + 1];
+#pragma unroll
+  for (int j = 0; j < 4; j++) a[j] = a[2 * j] + a[2 * j + 1];
+  return (a[0] + a[1]) + (a[2] + a[3]);
+}
+// pole_zero.py:24-77 : y[i] = x[i] + (1-c) * S[i-1] with S[i-1] = E + r, E = sum of all samples in front of the
+// chunk (float64, from the block scan) and r = running sum inside the chunk (float32).  (1-c) E is rounded to
+// float32 once per chunk: <= 1.5 ulp of the output in total (the reference stores float32: 0.5 ulp).
+__device__ __forceinline__ void pz_chunk_f(const float (&x)[CHK], double excl, double omc, float (&y)[CHK]) {
+  const float oe = (float)(omc * excl), omcf = (float)omc;
+  float run = 0.f;
+#pragma unroll
+  for (int j = 0; j < CHK; j++) {
+    y[j] = x[j] + fmaf(omcf, run, oe);
+    run += x[j];
+  }
+}
+// linear_slope_fit.py:11-90 : sums over [lo, hi) with the abscissa relative to lo.  The samples are centred on one
+// sample of the chunk (c0): u = y - c0 is exact in float32 whenever it matters (a pedestal much larger than
+// the fluctuations is exactly the case in which u needs few bits), so sum u, sum j u and sum u^2 over 16 samples
+// carry no cancellation; the pedestal terms are added in float64.  FULL: the whole chunk lies inside [lo, hi).
+template <bool FULL>
+__device__ __forceinline__ void lsf_local_f(const float (&v)[CHK], int i0, int lo, int hi, double& sy, double& sxy,
+                                            double& syy) {
+  float c0 = v[0];
+  if (!FULL) {   // first sample of the chunk that lies inside the range
+    const int jf = lo - i0;
+#pragma unroll
+    for (int j = 1; j < CHK; j++) c0 = (j == jf) ? v[j] : c0;
+  }
+  float su = 0.f, sju = 0.f, suu = 0.f;
+  int m = 0, sj = 0;
+#pragma unroll
+  for (int j = 0; j < CHK; j++) {
+    if (FULL || (i0 + j >= lo && i0 + j < hi)) {
+      const float u = v[j] - c0;
+      su += u;
+      sju = fmaf((float)j, u, sju);
+      suu = fmaf(u, u, suu);
+      m++;
+      sj += j;
+    }
+  }
+  const double c = (double)c0, dm = (double)m, dsu = (double)su;
+  sy = fma(dm, c, dsu);
+  sxy = fma((double)(i0 - lo), sy, fma((double)sj, c, (double)sju));
+  syy = fma(c, fma(dm, c, dsu + dsu), (double)suu);
+}
+// block sum over the warps [w0, w1) only (the other warps hold no part of the range and deposit nothing)
+__device__ __forceinline__ double get_sum_r(const double* p, int lane, int w0, int w1) {
+  return wsum((lane >= w0 && lane < w1) ? p[lane] : 0.0);
 }
 
 // inclusive running sum inside the chunk (float), returns the chunk total

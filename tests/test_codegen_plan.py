@@ -47,9 +47,19 @@ def test_icpc_program(spec):
     assert len(spec.out_scalars) == 34
 
 
+def _block_stream(src, idle=False):
+    """block-stream text; the idle branches of the short-waveform regions (warps without a chunk of those waveforms
+    only mirror the synchronisation) are cut out (or returned alone)"""
+    blk = src[src.index("block stream"):src.index("scalar stream")]
+    pat = re.compile(r"\} else \{   // warps without a chunk.*?\n\s*\}\n", re.S)
+    if idle:
+        return "\n".join(pat.findall(blk))
+    return pat.sub("}\n", blk)
+
+
 def test_streams_and_events(spec):
     src = spec.source()
-    blk = src[src.index("block stream"):src.index("scalar stream")]
+    blk = _block_stream(src)
     sca = src[src.index("scalar stream"):]
     # threshold searches, pick-offs and output stores live in the scalar stream only
     assert "tpt_w(" in sca and "tpt_w(" not in blk
@@ -64,6 +74,18 @@ def test_streams_and_events(spec):
     assert sca.count("EV_ARRIVE(15);") == 1 and "if (it > 0) EV_WAIT(15);" in blk
     # block-only barriers never involve the scalar warp
     assert "__syncthreads()" not in blk
+
+
+def test_idle_warps_of_a_region_mirror_its_synchronisation(spec):
+    """warps that own no chunk of a region's short waveforms execute the same barriers / events in the same order"""
+    src = spec.source()
+    blk = src[src.index("block stream"):src.index("scalar stream")]
+    regions = re.findall(r"// ---- region:.*?\n(.*?)\} else \{   // warps without a chunk[^\n]*\n(.*?)\n\s*\}\n", blk, re.S)
+    assert regions, "the ICPC chain has a short-waveform region (windowed current)"
+    sync = re.compile(r"BSYNC\(\)|EV_ARRIVE\([^)]*\)\)?|EV_WAIT\([^)]*\)\)?|par \^= 1")
+    for body, idle in regions:
+        assert sync.findall(body) == sync.findall(idle)
+        assert "ld_shift" not in idle and "st_chunk_n" not in idle
 
 
 @pytest.mark.skipif(shutil.which("nvcc") is None and not os.path.exists("/usr/local/cuda/bin/nvcc"), reason="nvcc not available")
