@@ -653,7 +653,7 @@ class SpecChain(FusedChain):
         # pick-offs, scalar glue, output stores).  They meet only through named-barrier events
         # (B -> S: "partials / slots are ready", S -> B: "this scalar is ready") and at the row end,
         # so the serial per-event scalar chain runs concurrently with the block work.
-        self.LB, self.LS = [], []
+        self.LB, self.LS, self.LS_tag = [], [], []
         self.pending = set()
         self.dirty = set()
         self.xread = set()
@@ -733,6 +733,7 @@ class SpecChain(FusedChain):
                     if isinstance(nd.get(key), str) and not nd[key].startswith(("0x", "-0x", "CUDART")):
                         self.urgent_names.add(nd[key])
         regions = self._plan_regions()
+        self._plan_scalar_warps()
         self.region_nw = None
         for k, nd in enumerate(self.order):
             self.pos = k
@@ -744,10 +745,10 @@ class SpecChain(FusedChain):
                 self.region_nw = regions[k][1]
                 self.LB.append(f"//@REGION_BEGIN {self.region_nw}")
             self.LB.append(f"// ---- [{k}] {self._describe_node(nd)}")
-            self.LS.append(f"// ---- [{k}] {self._describe_node(nd)}")
+            self._ls_add([f"// ---- [{k}] {self._describe_node(nd)}"], "all")
             getattr(self, "_e_" + nd["kind"])(nd)
             self.LB.append("PROF_MARK(%d);" % k)
-            self.LS.append("PROF_MARK_S(%d);" % k)
+            self._ls_add(["PROF_MARK_S(%d);" % k], "all")
             self._release(k)
             if self.region_nw is not None and any(k == e for (e, _) in regions.values()):
                 self._close_round()
@@ -761,9 +762,9 @@ class SpecChain(FusedChain):
         # scalar outputs not stored at their definition (pass-through input scalars)
         for k, (name, pi, ct) in enumerate(self.out_scalars):
             if name not in self.stored:
-                self._es(f"if (lane == {k % 32}) (({ct}*)A.p[{pi}])[row] = ({ct}){name};")
+                self._es(f"if (lane == {k % 32}) (({ct}*)A.p[{pi}])[row] = ({ct}){name};", tag="leaf")
         self.LB.append("PROF_MARK(%d);" % len(self.order))
-        self.LS.append("PROF_MARK_S(%d);" % len(self.order))
+        self._ls_add(["PROF_MARK_S(%d);" % len(self.order)], "all")
         self.mb_bytes = (self.n_mbd * 16 * 8 + self.n_mbi * 16 * 4 + 15) & ~15
         if self.mb_bytes > self.MB_BUDGET:
             raise NotSpecializable("too many reductions for the mailbox")
@@ -776,6 +777,165 @@ class SpecChain(FusedChain):
             raise NotSpecializable("not enough shared memory for the live waveforms")
         self.program_text = "\n".join(f"{k:3d} {self._describe_node(nd)}" for k, nd in enumerate(self.order))
         self.code = self.order  # (for len(code) users)
+
+    _SKEYS = ("x", "y", "thr", "start", "walk", "t", "t0", "b", "tau", "oi", "oo")
+
+    def _plan_scalar_warps(self):
+        """Split the per-event scalar work over TWO scalar warps when it is the longer of the two pipelines.
+
+        Warp 1 (warp 16 of the CTA) owns everything a scalar the block stream waits for depends on (the path to
+        tp_0_est in the ICPC chain), publishes it, and then carries on with its share of the rest; warp 2 (warp 17)
+        takes whole dependency components of the remaining searches / pick-offs / glue.  Reductions that are only
+        finished from the mailbox (min_max, linear_slope_fit, convolution sinks) are cheap and have no scalar inputs:
+        they are evaluated by every warp that needs one of their results and stored by one.  The only scalars that
+        cross are results of warp 1's latency-critical path, handed over once per row (`xfer`, one named-barrier
+        event); warp 2 never feeds warp 1 or the block stream.
+        self.swarp: program position -> set of scalar warps; self.store_owner: position -> warp that stores the outputs
+        """
+        order = self.order
+        lit = ("0x", "-0x", "CUDART")
+        info = {}
+        for k, nd in enumerate(order):
+            kind = nd["kind"]
+            if kind in ("fir_group", "conv_seg_group"):
+                continue
+            outs = [o for o in ([nd.get("out")] + list(nd.get("outs", []))) if o]
+            ins = [nd[key] for key in self._SKEYS if isinstance(nd.get(key), str) and not nd[key].startswith(lit)]
+            if not outs:
+                continue
+            fin = kind in ("min_max", "lsf") or (kind == "ftp" and not ins and nd.get("lazy") is None and any(
+                w.producer is not None and self.nodes[w.producer]["kind"] == "conv_seg" for (w, _, _) in nd["ins"]))
+            cost = {"tpt": 10, "ftp": 8 if nd.get("lazy") is not None else 4, "trap_pickoff": 8, "min_max": 2, "lsf": 3}.get(kind, 1)
+            info[k] = dict(outs=outs, ins=ins, fin=fin, cost=cost)
+        producer = {o: k for k, d in info.items() for o in d["outs"]}
+        # glue that only depends on inputs and mailbox results (unit offsets, thresholds ...) is as cheap to repeat
+        for k in sorted(info):
+            d = info[k]
+            if not d["fin"] and order[k]["kind"].startswith("sc_") and all(
+                    i not in producer or info[producer[i]]["fin"] for i in d["ins"]):
+                d["fin"] = True
+        # urgent: ancestors of the scalars the block stream needs
+        urgent, stack = set(), [producer[n] for n in self.b_needed if n in producer]
+        while stack:
+            k = stack.pop()
+            if k in urgent:
+                continue
+            urgent.add(k)
+            stack.extend(producer[i] for i in info[k]["ins"] if i in producer)
+        self.swarp = {k: {1} for k in info}
+        self.store_owner = {k: 1 for k in info}
+        self.xfer = []
+        self.n_swarps = 1
+        regular = [k for k, d in info.items() if not d["fin"] and k not in urgent]
+        if os.environ.get("DSPEED_B200_SCALAR_WARPS", "2") == "1" or not regular:
+            return
+        # dependency components of the remaining regular nodes
+        parent = {k: k for k in regular}
+
+        def find(a):
+            while parent[a] != a:
+                parent[a] = parent[parent[a]]
+                a = parent[a]
+            return a
+
+        for k in regular:
+            for i in info[k]["ins"]:
+                pk = producer.get(i)
+                if pk in parent:
+                    parent[find(k)] = find(pk)
+        comps = {}
+        for k in regular:
+            comps.setdefault(find(k), []).append(k)
+        load = {1: sum(info[k]["cost"] for k in urgent), 2: 0}
+        assign = {}
+        for root, members in sorted(comps.items(), key=lambda kv: -sum(info[k]["cost"] for k in kv[1])):
+            wsel = 2 if load[2] <= load[1] else 1
+            load[wsel] += sum(info[k]["cost"] for k in members)
+            for k in members:
+                assign[k] = wsel
+        if load[2] < 20:
+            return      # too little to hand over: one scalar warp as before
+        self.n_swarps = 2
+        for k, wsel in assign.items():
+            self.swarp[k] = {wsel}
+            self.store_owner[k] = wsel
+        # mailbox finishers: wherever a consumer lives; chain outputs are stored by warp 2 (warp 1 keeps the critical path)
+        for k in sorted(info, reverse=True):
+            d = info[k]
+            if not d["fin"]:
+                continue
+            need = set()
+            for k2, d2 in info.items():
+                if k2 > k and any(o in d2["ins"] for o in d["outs"]):
+                    need |= self.swarp[k2]
+            if k in urgent:
+                need.add(1)
+            has_out = any(o in self.out_of for o in d["outs"])
+            if has_out or not need:
+                need.add(2)
+            self.swarp[k] = need
+            self.store_owner[k] = 2 if 2 in need else 1
+        # scalars of warp 1's regular nodes that warp 2 reads
+        for k, d in info.items():
+            if 2 in self.swarp[k] and not d["fin"]:
+                for i in d["ins"]:
+                    pk = producer.get(i)
+                    if pk is not None and not info[pk]["fin"] and self.swarp[pk] == {1} and i not in self.xfer:
+                        if pk not in urgent:
+                            raise NotSpecializable("internal: scalar warps are not independent")
+                        self.xfer.append(i)
+
+    def _split_scalar(self):
+        """tagged scalar-stream lines -> one list per scalar warp (see _plan_scalar_warps)"""
+        ns = self.n_swarps
+        streams = {wn: [] for wn in range(1, ns + 1)}
+        tags = {wn: [] for wn in range(1, ns + 1)}
+        for tag, ln in zip(self.LS_tag, self.LS):
+            if tag in ("all", "sync"):
+                targets = range(1, ns + 1)
+            elif tag == "leaf":
+                targets = [ns]
+            else:
+                targets = sorted(w_ for w_ in self.swarp.get(tag, {1}) if w_ <= ns)
+            for wn in targets:
+                if "/*store*/" in ln and not isinstance(tag, str) and self.store_owner.get(tag, 1) != wn and len(targets) > 1:
+                    continue
+                if wn > 1 and ln.startswith("PROF_MARK_S("):
+                    ln = ln.replace("PROF_MARK_S(", "PROF_MARK_S2(")
+                streams[wn].append(ln)
+                tags[wn].append(tag)
+        if ns == 2 and self.xfer:
+            if self.n_bc + len(self.xfer) > 16:
+                raise NotSpecializable("too many scalars cross between the streams")
+            cell = {n: 15 - i for i, n in enumerate(self.xfer)}
+            owner = {n: next(k for k, nd in enumerate(self.order)
+                             if n == nd.get("out") or n in [o for o in nd.get("outs", []) if o]) for n in self.xfer}
+            # warp 1: each scalar goes to its cell behind the node that defines it, the event behind the last one
+            last_line = {}
+            for idx, tag in enumerate(tags[1]):
+                for n, k in owner.items():
+                    if tag == k:
+                        last_line[n] = idx
+            ins_at = {}
+            for n, idx in last_line.items():
+                ins_at.setdefault(idx, []).append(f"if (lane == 0) bc[{cell[n]}] = (double){n};")
+            ev = max(last_line.values())
+            out1 = []
+            for idx, ln in enumerate(streams[1]):
+                out1.append(ln)
+                out1.extend(ins_at.get(idx, []))
+                if idx == ev:
+                    out1.append("EV_ARRIVE(EVX);   // hand-over to the second scalar warp")
+            streams[1] = out1
+            # warp 2: fetched in front of the first node that reads one of them
+            users = set()
+            for k, nd in enumerate(self.order):
+                if 2 in self.swarp.get(k, set()) and any(nd.get(key) in cell for key in self._SKEYS):
+                    users.add(k)
+            first = next(idx for idx, tag in enumerate(tags[2]) if tag in users)
+            fetch = ["EV_WAIT(EVX);"] + [self._asg(n, f"bc[{cell[n]}]") for n in self.xfer]
+            streams[2] = streams[2][:first] + fetch + streams[2][first:]
+        return streams
 
     def _extent(self, nd):
         """number of samples the block-stream code of a node spans (0: scalar-stream only)"""
@@ -850,27 +1010,31 @@ class SpecChain(FusedChain):
         return out
 
     def _pipeline_rows(self):
-        """Software pipelining across rows.  The block stream starts row r+1 while the scalar warp is
+        """Software pipelining across rows.  The block stream starts row r+1 while the scalar warps are
         still finishing row r; mailbox / broadcast cells and the B -> S event barriers alternate with
         the row parity, and two waits protect the shared-memory slots: before its first write to
-        the slot of the wave the scalar warp reads last, the block stream waits for "scalar warp done
+        the slot of a wave a scalar warp reads late, the block stream waits for "scalar warps done
         with the previous row" (barrier 15); for the writes before that point (the head: raw-data
-        front end, scratch tables) it waits for a progress event (barrier 14) that
-        the scalar warp posts right after its last read of any slot the head overwrites."""
+        front end, scratch tables) it waits for a progress event (barrier 14) that every scalar warp
+        posts right after its last read of any slot the head overwrites."""
         def overlap(a, b):
             return a[0] == b[0] and a[1] < b[2] and b[1] < a[2]
 
-        reads = []          # (seq, region) of scalar-warp slot reads, in program order
-        for ln in self.LS:
-            if ln.startswith("//@R "):
-                sl, c0, c1, seq = (int(x) for x in ln.split()[1:5])
-                reads.append((seq, (sl, c0, c1)))
+        self.SW = self._split_scalar()          # scalar warp -> lines
+        ns = self.n_swarps
+        reads = {}          # warp -> [(ordinal, line index, region)] of slot reads, in program order
+        for wn, lines in self.SW.items():
+            reads[wn] = []
+            for idx, ln in enumerate(lines):
+                if ln.startswith("//@R "):
+                    sl, c0, c1 = (int(x) for x in ln.split()[1:4])
+                    reads[wn].append((len(reads[wn]) + 1, idx, (sl, c0, c1)))
         writes = []         # (LB index, region as seen from the previous row's frame)
         for k, ln in enumerate(self.LB):
             if ln.startswith("//@W "):
                 sl, c0, c1 = (int(x) for x in ln.split()[1:4])
                 writes.append((k, (self._rot(sl) if sl < 1000 else sl, c0, c1)))
-        # group the block stream's writes by node; need[k] = latest scalar-warp read (of the previous
+        # group the block stream's writes by node; need[w][k] = latest read of scalar warp w (of the previous
         # row) that node k's writes collide with
         node_of, cur = {}, -1
         starts = {}
@@ -879,34 +1043,40 @@ class SpecChain(FusedChain):
                 cur += 1
                 starts[cur] = k
             node_of[k] = cur
-        need = {}
+        need = {wn: {} for wn in reads}
         for k, reg in writes:
-            q = max([seq for seq, r in reads if overlap(reg, r)] + [0])
-            need[node_of[k]] = max(need.get(node_of[k], 0), q)
+            for wn in reads:
+                q = max([o for o, _, r in reads[wn] if overlap(reg, r)] + [0])
+                need[wn][node_of[k]] = max(need[wn].get(node_of[k], 0), q)
         self.late_idx, self.progress_idx, self.progress_seq = None, None, 0
-        hot = sorted(nk for nk, q in need.items() if q > 0)
+        hot = sorted({nk for wn in need for nk, q in need[wn].items() if q > 0})
+        prog = {wn: 0 for wn in reads}      # ordinal of the read behind which warp wn posts its progress event
         if hot:
             first = hot[0]
-            self.progress_seq = need[first]          # early group: covered by the progress event
+            prog = {wn: need[wn].get(first, 0) for wn in reads}   # early group: covered by the progress event
             self.progress_idx = starts[first]
-            later = [nk for nk in hot if need[nk] > self.progress_seq]
+            self.progress_seq = 1
+            later = [nk for nk in hot if any(need[wn].get(nk, 0) > prog[wn] for wn in reads)]
             if later:
-                self.late_idx = starts[later[0]]     # everything beyond waits for "scalar warp done"
-            last_seq = max(seq for seq, _ in reads)
-            if self.progress_seq >= last_seq:
-                # the first collision is already with the scalar warp's last read
+                self.late_idx = starts[later[0]]     # everything beyond waits for "scalar warps done"
+            if all(prog[wn] >= len(reads[wn]) for wn in reads if reads[wn]):
+                # the first collision is already with the scalar warps' last reads
                 self.late_idx, self.progress_idx, self.progress_seq = starts[first], None, 0
-        # scalar stream: progress event after node `progress_seq`, done event at the end
-        LS = list(self.LS)
-        if self.progress_seq:
-            k = next(i for i, ln in enumerate(LS) if ln.startswith("//@R ") and int(ln.split()[4]) == self.progress_seq)
-            nxt = next((i for i in range(k + 1, len(LS)) if LS[i].startswith("// ---- [")), len(LS))
-            LS.insert(nxt, "EV_ARRIVE(14);")
-        LS.append("EV_ARRIVE(15);")
-        self.LS = LS
+        # scalar streams: progress event behind read `prog[w]` (at the next node header), done event at the end
+        for wn in list(self.SW):
+            LS = list(self.SW[wn])
+            if self.progress_seq:
+                if prog[wn] > 0:
+                    k = next(idx for o, idx, _ in reads[wn] if o == prog[wn])
+                    nxt = next((i for i in range(k + 1, len(LS)) if LS[i].startswith("// ---- [")), len(LS))
+                else:
+                    nxt = 0     # nothing of this warp collides: it may be overwritten right away
+                LS.insert(nxt, "EV_ARRIVE(14);")
+            LS.append("EV_ARRIVE(15);")
+            self.SW[wn] = LS
         LB = list(self.LB)
-        # The "done" wait must precede the row's LAST block -> scalar event: the scalar warp cannot finish row r + 1
-        # (and arrive on barrier 15 again) before it has consumed that event, so every block warp has passed its wait for
+        # The "done" wait must precede the row's LAST block -> scalar event: the scalar warps cannot finish row r + 1
+        # (and arrive on barrier 15 again) before they have consumed that event, so every block warp has passed its wait for
         # row r by then.  With the wait behind the last event (chains without slot hazards used to get it at the very end)
         # a scalar warp with little work per row could arrive twice in one phase of barrier 15 while a block warp was
         # still on its way to the wait: the phase completed early and the late warp deadlocked in the next one.
@@ -914,9 +1084,11 @@ class SpecChain(FusedChain):
         pos = self.late_idx if self.late_idx is not None else len(LB)
         if 0 <= last_ev < pos:
             pos = last_ev
-        LB.insert(pos, "if (it > 0) EV_WAIT(15);   // the scalar warp is done with the previous row")
+        # (never inside a short-waveform region: its idle branch is generated from these lines, see _expand_regions,
+        # which copies the waits, but keep the wait on the common path where the hazard analysis put it)
+        LB.insert(pos, "if (it > 0) EV_WAIT(15);   // the scalar warps are done with the previous row")
         if self.progress_seq:   # (inserted second: progress_idx < late_idx)
-            LB.insert(self.progress_idx, "if (it > 0) EV_WAIT(14);   // the scalar warp is past its reads of these slots")
+            LB.insert(self.progress_idx, "if (it > 0) EV_WAIT(14);   // the scalar warps are past their reads of these slots")
         self.LB = LB
 
     def _describe_node(self, nd):
@@ -935,21 +1107,29 @@ class SpecChain(FusedChain):
         """block stream"""
         self.LB.extend(lines)
 
-    def _es(self, *lines, urgent=False):
+    def _ls_add(self, lines, tag=None):
+        """scalar-stream lines, tagged with the program position of the node they belong to ("all": every scalar
+        warp, "sync": block -> scalar events, "leaf": the last scalar warp); see _split_scalar"""
+        tag = self.pos if tag is None else tag
+        for ln in lines:
+            self.LS.append(ln)
+            self.LS_tag.append(tag)
+
+    def _es(self, *lines, urgent=False, tag=None):
         """scalar stream"""
         self._flush_s(urgent)
-        self.LS.extend(lines)
+        self._ls_add(lines, tag)
 
     def _es_later(self, *lines):
         """scalar-stream code that only consumes mailbox partials: consecutive reductions are
         collected and released behind ONE block -> scalar event.  A node's block that feeds a scalar
         the block stream waits for is released first (and alone, when the consumer is on that path)."""
-        self._cur_def.extend(lines)
+        self._cur_def.extend((self.pos, ln) for ln in lines)
 
     def _es_later_end(self):
         """end of a node: file its deferred block as urgent or not"""
         if self._cur_def:
-            urgent = any(re.match(rf"\s*{n} = ", ln) for ln in self._cur_def for n in self.urgent_names)
+            urgent = any(re.match(rf"\s*{n} = ", ln) for _, ln in self._cur_def for n in self.urgent_names)
             (self.s_deferred_urgent if urgent else self.s_deferred).extend(self._cur_def)
             self._cur_def = []
 
@@ -959,10 +1139,12 @@ class SpecChain(FusedChain):
             self._sync_s()
         if self.s_deferred_urgent:
             d, self.s_deferred_urgent = self.s_deferred_urgent, []
-            self.LS.extend(d)
+            for tag, ln in d:
+                self._ls_add([ln], tag)
         if self.s_deferred and not urgent:
             d, self.s_deferred = self.s_deferred, []
-            self.LS.extend(d)
+            for tag, ln in d:
+                self._ls_add([ln], tag)
 
     def _round_open(self):
         return bool(self.posts or self.nd_used or self.ni_used or self.pending)
@@ -1005,12 +1187,12 @@ class SpecChain(FusedChain):
         if getattr(self, "post_mail", False):
             self._close_round()      # mailbox entries written by post-barrier code precede the event
         self.s_dirty = False
-        if self.b2s_count >= 6:
+        if self.b2s_count >= 5:
             raise NotSpecializable("more block -> scalar events per row than named barriers")
         eid = self.b2s_count
         self.b2s_count += 1
         self._e(f"EV_ARRIVE(EVB({eid}));")
-        self.LS.append(f"EV_WAIT(EVB({eid}));")
+        self._ls_add([f"EV_WAIT(EVB({eid}));"], "sync")
 
     def _is_s(self, e):
         return e is not None and self.sdom.get(str(e)) == "s"
@@ -1063,7 +1245,7 @@ class SpecChain(FusedChain):
             self.s_dirty = True
             self._sync_s()
             nm = flag + "_s"
-            self._es(f"const int {nm} = MBI({k})[0];")
+            self._es(f"const int {nm} = MBI({k})[0];", tag="all")
             self.flag_s[flag] = nm
         return self.flag_s[flag]
 
@@ -1074,7 +1256,7 @@ class SpecChain(FusedChain):
             raise NotSpecializable("internal: scalar-warp access to a register-only wave")
         self._sync_s()
         self.s_seq += 1
-        w.s_last = self.s_seq
+        w.s_last = self.s_seq if self.swarp.get(self.pos, {1}) == {1} else 10 ** 9   # (no event proves the 2nd warp's progress)
         self._es(f"//@R {w.slot[0]} {w.slot[1]} {w.slot[1] + w.slot[2]} {self.s_seq}")
 
     @staticmethod
@@ -1094,7 +1276,7 @@ class SpecChain(FusedChain):
         """statements (scalar warp) that write a just-defined scalar to its output columns: results
         leave the register file as soon as they are final"""
         self.stored.add(name)
-        return [f"if (lane == {k % 32}) (({ct}*)A.p[{pi}])[row] = ({ct}){name};" for (pi, ct, k) in self.out_of.get(name, [])]
+        return [f"if (lane == {k % 32}) (({ct}*)A.p[{pi}])[row] = ({ct}){name};   /*store*/" for (pi, ct, k) in self.out_of.get(name, [])]
 
     def _mbd(self, k=1):
         b = self.n_mbd
@@ -2079,7 +2261,10 @@ class SpecChain(FusedChain):
         np_ = max(1, len(self.ptrs))
         ind = "\n        "
         body_b = ind.join(self._expand_regions(self.LB))
-        body_s = ind.join(self.LS)
+        ns = self.n_swarps
+        nthr = NT + 32 * ns
+        body_s = ind.join(self.SW[1])
+        body_s2 = ind.join(self.SW[2]) if ns == 2 else ""
         prolog = "\n      ".join(self.prolog)
         names = sorted(set(self.svar.values()), key=lambda x: int(x[1:]))
         decl = " ".join(f"{ty} " + ", ".join(n for n in names if self.stype[n] == ty) + ";"
@@ -2100,10 +2285,14 @@ class SpecChain(FusedChain):
         return f"""// generated by dspeed_b200/codegen.py -- do not edit
 #define DSPB_PSP {self.psp}
 #define DSPB_PROF_OFF (2048 + 8192)
-// the 16 block warps synchronise on named barrier 1; the scalar warp (warp 16) never joins it
+// the 16 block warps synchronise on named barrier 1; the scalar warps (warp 16 ...) never join it
 #define BSYNC() asm volatile("bar.sync 1, 512;" ::: "memory")
-#define EV_ARRIVE(id) asm volatile("bar.arrive %0, 544;" ::"r"(id) : "memory")
-#define EV_WAIT(id) asm volatile("bar.sync %0, 544;" ::"r"(id) : "memory")
+// events between the block stream and the scalar warps: counted arrivals on named barriers.  Barrier 0 (scalar warp 1
+// -> block stream) involves the 512 block threads and ONE scalar warp, the block -> scalar events and the progress /
+// done events (14 / 15) all {ns} scalar warp(s), the hand-over between the scalar warps (EVX) only those two.
+#define EV_COUNT(id) ((id) == 0 ? 544 : ((id) == 12 || (id) == 13) ? 64 : {nthr})
+#define EV_ARRIVE(id) asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(EV_COUNT(id)) : "memory")
+#define EV_WAIT(id) asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(EV_COUNT(id)) : "memory")
 #include "chain_rt.cuh"
 using namespace dspb;
 using namespace crt;
@@ -2129,13 +2318,21 @@ struct Args {{
 // per-node SM cycles of both streams of CTA 0, accumulated in shared memory (time between consecutive
 // marks of a stream, waits included), flushed when the CTA exits; rows overlap as in production
 #define PROF_MARK(k) if (A.prof && tid == 0 && (k) < 128) {{ const long long t_ = clock64(); prof_ts[k] += t_ - prof_prev; prof_prev = t_; }}
-#define PROF_MARK_S(k) if (A.prof && lane == 0 && (k) < 128) {{ const long long t_ = clock64(); prof_ts[128 + (k)] += t_ - prof_prev; prof_prev = t_; }}
+#define PROF_MARK_SX(k) if (A.prof && lane == 0 && (k) < 128) {{ const long long t_ = clock64(); prof_ts[128 + (k)] += t_ - prof_prev; prof_prev = t_; }}
+#ifdef DSPB_PROF_S2     // the scalar-stream stamps come from the SECOND scalar warp
+#define PROF_MARK_S(k)
+#define PROF_MARK_S2(k) PROF_MARK_SX(k)
+#else
+#define PROF_MARK_S(k) PROF_MARK_SX(k)
+#define PROF_MARK_S2(k)
+#endif
 #else
 #define PROF_MARK(k)
 #define PROF_MARK_S(k)
+#define PROF_MARK_S2(k)
 #endif
 
-__global__ void __launch_bounds__(544, 1) k_chain_spec(const __grid_constant__ Args A) {{
+__global__ void __launch_bounds__({nthr}, 1) k_chain_spec(const __grid_constant__ Args A) {{
   extern __shared__ __align__(16) unsigned char smem_raw[];
   CScr* cs = reinterpret_cast<CScr*>(smem_raw + 2048);
   long long* prof_ts = reinterpret_cast<long long*>(smem_raw + 2048 + 8192);
@@ -2145,7 +2342,7 @@ __global__ void __launch_bounds__(544, 1) k_chain_spec(const __grid_constant__ A
   // (the shuffle makes the warp index provably warp-uniform: branches on it are uniform branches and the
   // collectives inside them need no re-convergence code)
   const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
-  const bool scalar_warp = warp == 16;
+  const bool scalar_warp = warp >= 16;
   int par = 0;
   if (!scalar_warp) {{
     zero_pads(slots, {self.slot_words}, {self.nchunks}, 0, {self.n_slots}, tid);
@@ -2154,7 +2351,7 @@ __global__ void __launch_bounds__(544, 1) k_chain_spec(const __grid_constant__ A
   int it = 0;
   {prefetch_init}
 #ifdef DSPB_PROFILE
-  for (int k = tid; k < 256; k += 544) prof_ts[k] = 0;
+  for (int k = tid; k < 256; k += {nthr}) prof_ts[k] = 0;
   __syncthreads();
   long long prof_prev = clock64();
 #endif
@@ -2166,19 +2363,24 @@ __global__ void __launch_bounds__(544, 1) k_chain_spec(const __grid_constant__ A
     double* mbd = reinterpret_cast<double*>(smem_raw + {mbd_off} + {self.MB_BUDGET} * rp);  // block warps -> scalar warp
     int* mbi = reinterpret_cast<int*>(smem_raw + {mbi_off} + {self.MB_BUDGET} * rp);
     (void)bc; (void)mbd; (void)mbi;
-#define EVB(k) (2 + 6 * rp + (k))
+#define EVB(k) (2 + 5 * rp + (k))
+#define EVX (12 + rp)
     {{
       {decl}
       {prolog}
       if (!scalar_warp) {{
         // =============================== block stream (warps 0-15) ===============================
         {body_b}
-      }} else {{
+      }} else if (warp == 16) {{
         // =============================== scalar stream (warp 16) =================================
         {body_s}
+      }} else {{
+        // =============================== second scalar stream (warp 17) ===========================
+        {body_s2}
       }}
     }}
 #undef EVB
+#undef EVX
   }}
   // consume the scalar warp's last "done" / "progress" events
   if (!scalar_warp && it > 0) {{
@@ -2188,7 +2390,7 @@ __global__ void __launch_bounds__(544, 1) k_chain_spec(const __grid_constant__ A
 #ifdef DSPB_PROFILE
   __syncthreads();
   if (A.prof && blockIdx.x == 0)
-    for (int k = tid; k < N_NODES && k < 128; k += 544) {{
+    for (int k = tid; k < N_NODES && k < 128; k += {nthr}) {{
       A.prof[k] += prof_ts[k];
       A.prof[N_NODES + k] += prof_ts[128 + k];
       if (k < 32) A.prof[2 * N_NODES + k] += prof_ts[96 + k];   // PROF_SUB stamps inside routines
@@ -2213,7 +2415,7 @@ extern "C" int chain_launch(const void* const* ptrs, long long n_ptrs, long long
   cudaError_t e = cudaFuncSetAttribute(k_chain_spec, cudaFuncAttributeMaxDynamicSharedMemorySize, {self.smem_bytes});
   if (e != cudaSuccess) return -(int)e;
   const int grid = (int)(n_rows < num_sms ? n_rows : num_sms);
-  k_chain_spec<<<grid, 544, {self.smem_bytes}, (cudaStream_t)stream>>>(a);
+  k_chain_spec<<<grid, {nthr}, {self.smem_bytes}, (cudaStream_t)stream>>>(a);
   e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -(int)e;
 }}

@@ -50,36 +50,67 @@ def test_icpc_program(spec):
 def _block_stream(src, idle=False):
     """block-stream text; the idle branches of the short-waveform regions (warps without a chunk of those waveforms
     only mirror the synchronisation) are cut out (or returned alone)"""
-    blk = src[src.index("block stream"):src.index("scalar stream")]
+    blk = src[src.index("block stream (warps 0-15)"):src.index("scalar stream (warp 16)")]
     pat = re.compile(r"\} else \{   // warps without a chunk.*?\n\s*\}\n", re.S)
     if idle:
         return "\n".join(pat.findall(blk))
     return pat.sub("}\n", blk)
 
 
+def _scalar_streams(src):
+    """texts of the scalar warps' streams (warp 16, and warp 17 when the scalar work is split)"""
+    a = src.index("scalar stream (warp 16)")
+    b = src.find("second scalar stream (warp 17)")
+    end = src.index("#undef EVB")
+    return [src[a:b], src[b:end]] if b >= 0 else [src[a:end]]
+
+
 def test_streams_and_events(spec):
     src = spec.source()
     blk = _block_stream(src)
-    sca = src[src.index("scalar stream"):]
-    # threshold searches, pick-offs and output stores live in the scalar stream only
+    streams = _scalar_streams(src)
+    sca = streams[0]
+    # threshold searches, pick-offs and output stores live in the scalar streams only
     assert "tpt_w(" in sca and "tpt_w(" not in blk
-    assert "A.p[" in sca and "st_chunk_n" not in sca
-    # every block -> scalar event has exactly one arrive and one wait, in the same order
+    assert all("A.p[" in st and "st_chunk_n" not in st for st in streams)
+    # every block -> scalar event has exactly one arrive and one wait per scalar warp, in the same order
     arr = re.findall(r"EV_ARRIVE\(EVB\((\d+)\)\)", blk)
-    wait = re.findall(r"EV_WAIT\(EVB\((\d+)\)\)", sca)
-    assert arr == wait and 1 <= len(arr) <= 6
-    # the scalar published to the block stream (tp_0_est -> windower) crosses once
+    for st in streams:
+        assert re.findall(r"EV_WAIT\(EVB\((\d+)\)\)", st) == arr
+    assert 1 <= len(arr) <= 5
+    # the scalar published to the block stream (tp_0_est -> windower) crosses once, from the first scalar warp
     assert blk.count("EV_WAIT(0);") == 1 and sca.count("EV_ARRIVE(0);") == 1
-    # cross-row pipelining: "done" event per row, consumed before the next row's first colliding write
-    assert sca.count("EV_ARRIVE(15);") == 1 and "if (it > 0) EV_WAIT(15);" in blk
-    # block-only barriers never involve the scalar warp
+    assert all("EV_ARRIVE(0);" not in st for st in streams[1:])
+    # cross-row pipelining: "done" event per row and scalar warp, consumed before the next row's first colliding write
+    assert all(st.count("EV_ARRIVE(15);") == 1 for st in streams) and "if (it > 0) EV_WAIT(15);" in blk
+    assert len({st.count("EV_ARRIVE(14);") for st in streams}) == 1
+    # block-only barriers never involve the scalar warps
     assert "__syncthreads()" not in blk
+
+
+def test_scalar_work_is_split_over_two_warps(spec):
+    """the ICPC chain's 11 dependent threshold searches are the longer pipeline: the path to tp_0_est stays on the first
+    scalar warp, whole dependency components of the rest go to the second one, which receives tp_0_est exactly once"""
+    assert spec.n_swarps == 2
+    src = spec.source()
+    s1, s2 = _scalar_streams(src)
+    assert s1.count("tpt_w(") + s2.count("tpt_w(") == 11 and s1.count("tpt_w(") >= 2 and s2.count("tpt_w(") >= 2
+    assert s1.count("EV_ARRIVE(EVX);") == 1 and s2.count("EV_WAIT(EVX);") == 1 and "EV_ARRIVE(EVX)" not in s2
+    # the hand-over follows the search that produces tp_0_est and precedes every use in the second warp
+    assert s1.index("EV_ARRIVE(0);") < s1.index("EV_ARRIVE(EVX);")
+    assert s2.index("EV_WAIT(EVX);") < s2.index("tpt_w(")
+    # every output column is stored exactly once
+    stores = re.findall(r"\(\(float\*\)A\.p\[(\d+)\]\)\[row\] = ", s1 + s2)
+    assert len(stores) == len(set(stores)) == len(spec.out_scalars)
+    # launch: 16 block warps + 2 scalar warps, events counted accordingly
+    assert "__launch_bounds__(576, 1)" in src and "<<<grid, 576," in src
+    assert "? 64 : 576)" in src
 
 
 def test_idle_warps_of_a_region_mirror_its_synchronisation(spec):
     """warps that own no chunk of a region's short waveforms execute the same barriers / events in the same order"""
     src = spec.source()
-    blk = src[src.index("block stream"):src.index("scalar stream")]
+    blk = src[src.index("block stream (warps 0-15)"):src.index("scalar stream (warp 16)")]
     regions = re.findall(r"// ---- region:.*?\n(.*?)\} else \{   // warps without a chunk[^\n]*\n(.*?)\n\s*\}\n", blk, re.S)
     assert regions, "the ICPC chain has a short-waveform region (windowed current)"
     sync = re.compile(r"BSYNC\(\)|EV_ARRIVE\([^)]*\)\)?|EV_WAIT\([^)]*\)\)?|par \^= 1")
@@ -99,7 +130,7 @@ def test_done_event_wait_precedes_the_last_block_to_scalar_event(spec):
     """the block stream's wait for "scalar warp done with the previous row" must come before the row's last
     block -> scalar event (else a fast scalar warp can arrive twice in one barrier phase: deadlock)"""
     src = spec.source()
-    blk = src[src.index("block stream"):src.index("scalar stream")]
+    blk = _block_stream(src)
     assert blk.index("if (it > 0) EV_WAIT(15);") < blk.rindex("EV_ARRIVE(EVB(")
 
 
@@ -128,5 +159,5 @@ def test_double_pole_zero_is_specialised():
     src = sc.source()
     assert "dpz_local(" in src and "put_scan_geo(" in src and "get_excl_geo(" in src
     # the row's only block -> scalar event comes after the wait for the previous row's "done" event
-    blk = src[src.index("block stream"):src.index("scalar stream")]
+    blk = src[src.index("block stream (warps 0-15)"):src.index("scalar stream (warp 16)")]
     assert blk.index("if (it > 0) EV_WAIT(15);") < blk.rindex("EV_ARRIVE(EVB(")
