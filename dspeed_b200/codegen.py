@@ -44,6 +44,8 @@ log = logging.getLogger("dspeed")
 
 CHK = 16
 NT = 512
+# block scans of filter running sums entirely in float32 (chain_rt.cuh: put_scan_ff / get_excl_ff); "0": float64 across warps
+_FF = "ff" if os.environ.get("DSPEED_B200_F32_SCANS", "1") != "0" else "f"
 MAX_SMEM = 227 * 1024
 CACHE_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_chains")
 _build_lock = threading.Lock()
@@ -606,7 +608,7 @@ class SpecChain(FusedChain):
             if wpos is not None:
                 wave_last = {}
                 for k, nd in enumerate(order):
-                    for m in (nd["members"] if nd["kind"] in ("fir_group", "conv_seg_group") else [nd]):
+                    for m in (nd["members"] if nd["kind"] in ("fir_group", "conv_seg_group", "tpt_chain") else [nd]):
                         for (w, _, _) in m.get("ins", []):
                             wave_last[w.id] = k
                 best = None
@@ -625,11 +627,12 @@ class SpecChain(FusedChain):
                     order.insert(wpos - 1, nd)     # wpos shifted by one after the pop
                     w = nd["ins"][0][0]
                     w.force_slot = True
+        order = self._chain_searches(order)
         self.order = order
         # last use positions (in emission order) for slot liveness
         pos = {}
         for k, nd in enumerate(order):
-            members = nd["members"] if nd["kind"] in ("fir_group", "conv_seg_group") else [nd]
+            members = nd["members"] if nd["kind"] in ("fir_group", "conv_seg_group", "tpt_chain") else [nd]
             for m in members:
                 pos[m["idx"]] = k
         for w in self.waves.values():
@@ -643,6 +646,73 @@ class SpecChain(FusedChain):
                     local &= nd["kind"] in ("min_max", "lsf", "bl_sub", "pole_zero")
             first = pos.get(w.producer, 0) if w.producer is not None else 0
             w.needs_slot = not (local and w.last - first <= 6) or getattr(w, "force_slot", False)
+
+    def _chain_searches(self, order):
+        """Backward threshold searches on one waveform in which each search starts at the result of the previous one
+        (tp_95 <- tp_99, tp_90 <- tp_95 ...) become ONE node: the scalar warp resolves them in a single walk
+        (chain_rt.cuh: tpt_chain_bwd).  Nodes between the members (threshold glue, unrelated searches) move in front
+        of the chain when their inputs are ready there, else behind it; a member whose threshold depends on the
+        chain itself ends it."""
+        if os.environ.get("DSPEED_B200_TPT_CHAINS", "1") == "0":
+            return order
+        lit = ("0x", "-0x", "CUDART")
+
+        def sins(nd):
+            vals = []
+            for key in self._SKEYS:
+                v = nd.get(key)
+                if isinstance(v, str) and not v.startswith(lit):
+                    vals.append(v)
+            return vals
+
+        def souts(nd):
+            return [o for o in ([nd.get("out")] + list(nd.get("outs", []))) if o]
+
+        def is_bwd(nd):
+            return nd["kind"] == "tpt" and nd["walk"].startswith(lit[:2]) and float.fromhex(nd["walk"]) == 0.0
+
+        k = 0
+        while k < len(order):
+            head = order[k]
+            if not is_bwd(head):
+                k += 1
+                continue
+            members, pos_m = [head], [k]
+            q = k + 1
+            while q < len(order):
+                nd = order[q]
+                if (is_bwd(nd) and nd["ins"][0][0] is head["ins"][0][0] and nd["start"] == members[-1]["out"]
+                        and nd["fatal"] is not None):
+                    members.append(nd)
+                    pos_m.append(q)
+                q += 1
+            if len(members) < 2 or len(members) > 8:
+                k += 1
+                continue
+            # nodes between the first and the last member
+            chain_outs = {m["out"] for m in members}
+            between = [order[q] for q in range(pos_m[0] + 1, pos_m[-1]) if q not in pos_m]
+            front, back, tainted = [], [], set(chain_outs)
+            ok = True
+            for nd in between:
+                if nd["kind"] in ("fir_group", "conv_seg_group") or nd.get("wouts") or nd["kind"] in ("load", "store_wave"):
+                    ok = False      # block-stream work inside the span: leave the program alone
+                    break
+                if any(i in tainted for i in sins(nd)):
+                    back.append(nd)
+                    tainted.update(souts(nd))
+                else:
+                    front.append(nd)
+            # a member must not depend on anything that moved behind the chain
+            moved_back = {o for nd in back for o in souts(nd)}
+            if not ok or any(i in moved_back for m in members for i in sins(m)):
+                k += 1
+                continue
+            node = dict(kind="tpt_chain", idx=head["idx"], members=members, ins=[head["ins"][0]], outs=[m["out"] for m in members],
+                        thrs=[m["thr"] for m in members], start=head["start"], fatal=head["fatal"])
+            order = order[:pos_m[0]] + front + [node] + back + order[pos_m[-1] + 1:]
+            k = pos_m[0] + len(front) + 1
+        return order
 
     # ------------------------------------------------------------------------------------
     # emission
@@ -801,11 +871,13 @@ class SpecChain(FusedChain):
                 continue
             outs = [o for o in ([nd.get("out")] + list(nd.get("outs", []))) if o]
             ins = [nd[key] for key in self._SKEYS if isinstance(nd.get(key), str) and not nd[key].startswith(lit)]
+            ins += [t for t in nd.get("thrs", []) if not t.startswith(lit)]
             if not outs:
                 continue
             fin = kind in ("min_max", "lsf") or (kind == "ftp" and not ins and nd.get("lazy") is None and any(
                 w.producer is not None and self.nodes[w.producer]["kind"] == "conv_seg" for (w, _, _) in nd["ins"]))
-            cost = {"tpt": 10, "ftp": 8 if nd.get("lazy") is not None else 4, "trap_pickoff": 8, "min_max": 2, "lsf": 3}.get(kind, 1)
+            cost = {"tpt": 10, "tpt_chain": 10 + 2 * len(nd.get("members", [])), "ftp": 8 if nd.get("lazy") is not None else 4,
+                    "trap_pickoff": 8, "min_max": 2, "lsf": 3}.get(kind, 1)
             info[k] = dict(outs=outs, ins=ins, fin=fin, cost=cost)
         producer = {o: k for k, d in info.items() for o in d["outs"]}
         # glue that only depends on inputs and mailbox results (unit offsets, thresholds ...) is as cheap to repeat
@@ -940,7 +1012,7 @@ class SpecChain(FusedChain):
     def _extent(self, nd):
         """number of samples the block-stream code of a node spans (0: scalar-stream only)"""
         kind = nd["kind"]
-        if kind in ("tpt", "ftp", "trap_pickoff", "fir_lazy", "sc_bin", "sc_neg", "sc_convert"):
+        if kind in ("tpt", "tpt_chain", "ftp", "trap_pickoff", "fir_lazy", "sc_bin", "sc_neg", "sc_convert"):
             return 0
         if kind == "windower":
             return nd["wouts"][0].n + CHK
@@ -1027,8 +1099,8 @@ class SpecChain(FusedChain):
             reads[wn] = []
             for idx, ln in enumerate(lines):
                 if ln.startswith("//@R "):
-                    sl, c0, c1 = (int(x) for x in ln.split()[1:4])
-                    reads[wn].append((len(reads[wn]) + 1, idx, (sl, c0, c1)))
+                    sl, c0, c1, seq = (int(x) for x in ln.split()[1:5])
+                    reads[wn].append((seq, idx, (sl, c0, c1)))     # (seq: one number per reading node, increasing)
         writes = []         # (LB index, region as seen from the previous row's frame)
         for k, ln in enumerate(self.LB):
             if ln.startswith("//@W "):
@@ -1059,18 +1131,31 @@ class SpecChain(FusedChain):
             later = [nk for nk in hot if any(need[wn].get(nk, 0) > prog[wn] for wn in reads)]
             if later:
                 self.late_idx = starts[later[0]]     # everything beyond waits for "scalar warps done"
-            if all(prog[wn] >= len(reads[wn]) for wn in reads if reads[wn]):
+            if all(prog[wn] >= max(o for o, _, _ in reads[wn]) for wn in reads if reads[wn]):
                 # the first collision is already with the scalar warps' last reads
                 self.late_idx, self.progress_idx, self.progress_seq = starts[first], None, 0
+        # A scalar warp must not post the progress event of row r + 1 before every block warp has consumed the one of
+        # row r (counted arrivals: a second arrival in the same phase completes it early and the late block warp hangs in
+        # the next one).  It therefore posts behind its wait for the first block -> scalar event that the block stream
+        # signals AFTER its own progress wait: passing that wait proves that all block warps are beyond theirs.
+        safe_ev = None
+        if self.progress_seq:
+            m = next((re.search(r"EV_ARRIVE\(EVB\((\d+)\)\)", ln) for ln in self.LB[self.progress_idx:]
+                      if "EV_ARRIVE(EVB(" in ln), None)
+            if m is None:
+                self.late_idx, self.progress_idx, self.progress_seq = starts[first], None, 0
+            else:
+                safe_ev = f"EV_WAIT(EVB({m.group(1)}));"
         # scalar streams: progress event behind read `prog[w]` (at the next node header), done event at the end
         for wn in list(self.SW):
             LS = list(self.SW[wn])
             if self.progress_seq:
                 if prog[wn] > 0:
-                    k = next(idx for o, idx, _ in reads[wn] if o == prog[wn])
+                    k = max(idx for o, idx, _ in reads[wn] if o == prog[wn])
                     nxt = next((i for i in range(k + 1, len(LS)) if LS[i].startswith("// ---- [")), len(LS))
                 else:
                     nxt = 0     # nothing of this warp collides: it may be overwritten right away
+                nxt = max(nxt, LS.index(safe_ev) + 1)
                 LS.insert(nxt, "EV_ARRIVE(14);")
             LS.append("EV_ARRIVE(15);")
             self.SW[wn] = LS
@@ -1798,7 +1883,7 @@ class SpecChain(FusedChain):
                     self._e("}")
                 sd = self._alloc_d(1)
                 self._e(f"const float {tot} = cumsum_local({d});",
-                        f"const float {incl} = put_scan_f(CSD({sd}), {tot}, lane, warp);")
+                        f"const float {incl} = put_scan_{_FF}(CSD({sd}), {tot}, lane, warp);")
                 ex = None
                 if m["extra"]:
                     kx = self._t("kx")
@@ -1819,7 +1904,9 @@ class SpecChain(FusedChain):
                 sc = _flit(m["scale"])
                 extra = f" + get_sum(CSD({ex}), lane)" if ex is not None else ""
                 self.posts.append(
-                    f"const float {off} = (float)((get_excl_f(CSD({sd}), {incl}, {tot}, lane, warp){extra}) * (double){sc});")
+                    f"const float {off} = (float)((get_excl_{_FF}(CSD({sd}), {incl}, {tot}, lane, warp){extra}) * (double){sc});"
+                    if ex is not None or _FF == "f" else
+                    f"const float {off} = get_excl_ff(CSD({sd}), {incl}, {tot}, lane, warp) * {sc};")
                 self.posts.append(f"float {o}[16]; _Pragma(\"unroll\") for (int j = 0; j < 16; j++) {o}[j] = fmaf({d}[j], {sc}, {off});")
                 out.nan = w.nan
                 self.pending.add(out.name)
@@ -1842,6 +1929,28 @@ class SpecChain(FusedChain):
                  f"if ({f} && lane == 0) raise_fatal(A.fatal ? A.fatal + 4 * {nd['fatal']} : nullptr, {f}, A.row0 + row);",
                  *self._stores(nd["out"]), urgent=nd["out"] in self.b_needed)
         self._def_s(nd["out"])
+
+    def _e_tpt_chain(self, nd):
+        w, off, n = nd["ins"][0]
+        self._s_wave(w)
+        f, th, res = self._t("f"), self._t("th"), self._t("tc")
+        g = self._nan_guard([self._flag_s(w.nan)])
+        if getattr(w, "scatter", False):
+            raise NotSpecializable("threshold search on a scattered waveform")
+        if not self.summ[w.id][1]:
+            self._es(f"//@R {1000 + self.summ[w.id][0]} 0 1 {self.s_seq}")
+        K = len(nd["members"])
+        start = f"(float)({nd['start']})" if not g else f"(({g}) ? CUDART_NAN_F : (float)({nd['start']}))"
+        lines = [f"int {f} = 0; float {res}[{K}];",
+                 f"{{ const float {th}[{K}] = {{{', '.join('(float)(' + t + ')' for t in nd['thrs'])}}};",
+                 f"  tpt_chain_bwd<{K}>({self._slot(w)}, {self._summ(w)}, {n}, {th}, {start}, {res}, {f}, lane); }}",
+                 f"if ({f} && lane == 0) raise_fatal(A.fatal ? A.fatal + 4 * {nd['fatal']} : nullptr, {f}, A.row0 + row);"]
+        for j, m in enumerate(nd["members"]):
+            lines.append(self._asg(m["out"], f"{res}[{j}]"))
+            lines.extend(self._stores(m["out"]))
+        self._es(*lines, urgent=any(m["out"] in self.b_needed for m in nd["members"]))
+        for m in nd["members"]:
+            self._def_s(m["out"])
 
     def _e_trap_pickoff(self, nd):
         # trap_filters.py:230-301 : the normalised trapezoid at ONE index from two window sums,
@@ -2053,8 +2162,8 @@ class SpecChain(FusedChain):
                         f"  else {{ _Pragma(\"unroll\") for (int j = 0; j < 16; j++) {{ const int i = 16 * tid + j; "
                         f"{d}[j] = i >= {n} ? 0.f : (i == 0 ? {e0} : ({x}[j] - (i >= {L} ? {sh}[j] : {e0})) * {il}); }} }}   //@X 2",
                         f"const float {tot} = cumsum_local({d});   //@X {g_n}",
-                        f"const float {incl} = put_scan_f(CSD({sd}), {tot}, lane, warp);   //@X {g_n}")
-                get = f"get_excl_f(CSD({sd}), {incl}, {tot}, lane, warp{nwarg})"
+                        f"const float {incl} = put_scan_{_FF}(CSD({sd}), {tot}, lane, warp);   //@X {g_n}")
+                get = f"get_excl_{_FF}(CSD({sd}), {incl}, {tot}, lane, warp{nwarg})"
             else:
                 # mirror image: out[n-1] = x[n-1]; out[i] = out[i+1] + (x[i] - x[min(i+L,n-1)]) / L
                 ta, tb = 0, max(0, (n - L) // CHK)  # chunks with every i + L <= n - 1
@@ -2063,8 +2172,8 @@ class SpecChain(FusedChain):
                         f"  else {{ _Pragma(\"unroll\") for (int j = 0; j < 16; j++) {{ const int i = 16 * tid + j; "
                         f"{d}[j] = i >= {n} ? 0.f : (i == {n - 1} ? {e0} : ({x}[j] - (i + {L} <= {n - 1} ? {sh}[j] : {e0})) * {il}); }} }}   //@X 2",
                         f"const float {tot} = cumsum_local_rev({d});   //@X {g_n}",
-                        f"const float {incl} = put_scan_rev_f(CSD({sd}), {tot}, lane, warp);   //@X {g_n}")
-                get = f"get_excl_rev_f(CSD({sd}), {incl}, {tot}, lane, warp{nwarg})"
+                        f"const float {incl} = put_scan_rev_{_FF}(CSD({sd}), {tot}, lane, warp);   //@X {g_n}")
+                get = f"get_excl_rev_{_FF}(CSD({sd}), {incl}, {tot}, lane, warp{nwarg})"
             o, offv = self._t("r"), self._t("off")
             self.posts.append(f"float {o}[16]; const float {offv} = (float){get}; _Pragma(\"unroll\") for (int j = 0; j < 16; j++) "
                               f"{o}[j] = {d}[j] + {offv};   //@X {g_n}")

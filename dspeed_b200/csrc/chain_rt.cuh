@@ -329,6 +329,40 @@ __device__ __forceinline__ double get_excl_f(const double* p, float incl, float 
   }
   return __shfl_sync(FULL, pin - part, warp) + (double)(incl - v);
 }
+// all-float32 variants for running sums that ARE the float32 result (filter outputs: every partial sum is a value of
+// the output waveform, so rounding it to float32 costs half an ulp of that output, like the reference's own
+// sequential float32 accumulation): one shuffle per level instead of two, no conversions.  The scratch cell is the
+// first half of the collective's double[NWP] row.
+__device__ __forceinline__ float put_scan_ff(double* p, float v, int lane, int warp) {
+  const float incl = wscan_incl_f(v, lane);
+  if (lane == 31) reinterpret_cast<float*>(p)[warp] = incl;
+  return incl;
+}
+__device__ __forceinline__ float get_excl_ff(const double* p, float incl, float v, int lane, int warp, int nw = NWP) {
+  const float part = lane < nw ? reinterpret_cast<const float*>(p)[lane] : 0.f;
+  float pin = part;
+#pragma unroll
+  for (int o = 1; o < NWP; o <<= 1) {
+    const float t = __shfl_up_sync(FULL, pin, o);
+    if (lane >= o) pin += t;
+  }
+  return __shfl_sync(FULL, pin - part, warp) + (incl - v);
+}
+__device__ __forceinline__ float put_scan_rev_ff(double* p, float v, int lane, int warp) {
+  const float incl = wscan_incl_rev_f(v, lane);
+  if (lane == 0) reinterpret_cast<float*>(p)[warp] = incl;
+  return incl;
+}
+__device__ __forceinline__ float get_excl_rev_ff(const double* p, float incl, float v, int lane, int warp, int nw = NWP) {
+  const float part = lane < nw ? reinterpret_cast<const float*>(p)[lane] : 0.f;
+  float pin = part;
+#pragma unroll
+  for (int o = 1; o < NWP; o <<= 1) {
+    const float t = __shfl_down_sync(FULL, pin, o);
+    if (lane + o < NWP) pin += t;
+  }
+  return __shfl_sync(FULL, pin - part, warp) + (incl - v);
+}
 __device__ __forceinline__ float put_scan_rev_f(double* p, float v, int lane, int warp) {
   const float incl = wscan_incl_rev_f(v, lane);
   if (lane == 0) p[warp] = (double)incl;
@@ -839,6 +873,58 @@ __device__ __forceinline__ float tpt_w(const float* w, const WaveSummary* sm, in
   if (!(t_start >= 0.f && t_start < (float)n)) { fatal = DSPB_FATAL_TSTART_RANGE; return CUDART_NAN_F; }
   const int hit = search_cross_w(w, sm, n, thr, (int)t_start, walk == 1.0f, 1, lane);
   return hit < 0 ? CUDART_NAN_F : (float)hit;
+}
+
+// K backward searches on one waveform, each starting where the previous one ended (time_point_thresh.py:84-92 applied
+// K times: tp_95 from tp_99, tp_90 from tp_95 ... in the LEGEND chains).  The crossings of a rising edge lie within a
+// few samples of each other, so one walk over 32-sample windows serves all thresholds: the window's sample pairs stay
+// in registers while consecutive thresholds are resolved in it (compare + ballot per threshold, no further loads),
+// and only an empty window moves on (three plain windows, then the two-level summary).  Semantics per search are
+// those of tpt_w: the first start is validated like any t_start, a search without a crossing (or with a NaN
+// threshold) yields NaN and so do all later ones (their start is NaN).
+template <int K>
+__device__ __forceinline__ void tpt_chain_bwd(const float* w, const WaveSummary* sm, int n, const float (&thr)[K],
+                                              float t_start, float (&out)[K], int& fatal, int lane) {
+  fatal = 0;
+#pragma unroll
+  for (int k = 0; k < K; k++) out[k] = CUDART_NAN_F;
+  if (t_start != t_start) return;
+  if (floorf(t_start) != t_start) { fatal = DSPB_FATAL_TSTART_NONINT; return; }
+  if (!(t_start >= 0.f && t_start < (float)n)) { fatal = DSPB_FATAL_TSTART_RANGE; return; }
+  int pos = (int)t_start;   // start of the current search (inclusive)
+  int base = pos;           // lane l of the current window looks at the pair (base - l - 1, base - l)
+  bool have = false;
+  float a = 0.f, b = 0.f;
+  int i = 0;
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    const float t = thr[k];
+    if (pos < 1 || t != t) return;
+    int found = -1, tries = 0;
+#pragma unroll 1
+    while (true) {
+      if (!have) {
+        i = base - lane;
+        a = i >= 1 ? at(w, i - 1) : 0.f;
+        b = i >= 1 ? at(w, i) : 0.f;
+        have = true;
+      }
+      const bool hit = i >= 1 && i <= pos && ((a < t && t <= b) || (a > t && t >= b));
+      const unsigned m = __ballot_sync(FULL, hit);
+      if (m) { found = base - (__ffs(m) - 1); break; }
+      base -= 32;
+      have = false;
+      if (base < 1) break;
+      if (++tries >= 3) {
+        found = search_cross_far(w, sm, n, t, base, false, 1, lane);
+        if (found >= 1) base = found;
+        break;
+      }
+    }
+    if (found < 1) return;
+    out[k] = (float)found;
+    pos = found;
+  }
 }
 
 // =========================================================================================

@@ -39,7 +39,11 @@ def test_icpc_program(spec):
     # the raw row is loaded once; filters of one input are evaluated together; cusp + zac share
     # one evaluation; the trapezoid that is only picked off is never materialised
     assert kinds.count("load") == 1 and kinds.count("fir_group") == 1 and kinds.count("conv_seg_group") == 1
-    assert kinds.count("fir_lazy") == 1 and kinds.count("tpt") == 11
+    # 11 threshold searches: tp_95 ... tp_01 (each starting at the previous result) are one combined walk
+    assert kinds.count("fir_lazy") == 1 and kinds.count("tpt") == 4 and kinds.count("tpt_chain") == 1
+    chain = next(nd for nd in spec.order if nd["kind"] == "tpt_chain")
+    assert len(chain["members"]) == 7 and chain["start"] == next(nd["out"] for nd in spec.order if nd["kind"] == "tpt" and
+                                                               nd["out"] == chain["start"])
     assert [c[0] for c in spec.conv_lowering] == ["runs", "seg", "seg"] and spec.cse_skipped == 1
     # reductions follow their producer (they read the chunk from registers)
     assert kinds[:4] == ["load", "min_max", "bl_sub", "lsf"]
@@ -94,11 +98,12 @@ def test_scalar_work_is_split_over_two_warps(spec):
     assert spec.n_swarps == 2
     src = spec.source()
     s1, s2 = _scalar_streams(src)
-    assert s1.count("tpt_w(") + s2.count("tpt_w(") == 11 and s1.count("tpt_w(") >= 2 and s2.count("tpt_w(") >= 2
+    assert s1.count("tpt_w(") + s2.count("tpt_w(") == 4 and (s1 + s2).count("tpt_chain_bwd<7>(") == 1
+    assert "tpt_w(" in s1 and ("tpt_w(" in s2 or "tpt_chain_bwd" in s2)
     assert s1.count("EV_ARRIVE(EVX);") == 1 and s2.count("EV_WAIT(EVX);") == 1 and "EV_ARRIVE(EVX)" not in s2
     # the hand-over follows the search that produces tp_0_est and precedes every use in the second warp
     assert s1.index("EV_ARRIVE(0);") < s1.index("EV_ARRIVE(EVX);")
-    assert s2.index("EV_WAIT(EVX);") < s2.index("tpt_w(")
+    assert s2.index("EV_WAIT(EVX);") < min(s2.find(x) for x in ("tpt_w(", "tpt_chain_bwd") if x in s2)
     # every output column is stored exactly once
     stores = re.findall(r"\(\(float\*\)A\.p\[(\d+)\]\)\[row\] = ", s1 + s2)
     assert len(stores) == len(set(stores)) == len(spec.out_scalars)
