@@ -55,6 +55,7 @@ def parse_args():
     ap.add_argument("--rows", type=int, default=int(os.environ.get("DSPB_BENCH_ROWS", ROWS_PER_GPU)))
     ap.add_argument("--block-width", type=int, default=int(os.environ.get("DSPB_BENCH_BLOCK", 0)) or None)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the other BASELINE.json configurations (C1, C4, C5)")
     # bounded CPU sample: ~10-15 s of work on a 16-thread host at ~10 k wf/s (the chain is O(rows))
     ap.add_argument("--cpu-rows", type=int, default=int(os.environ.get("DSPB_BENCH_CPU_ROWS", 98304)))
     return ap.parse_args()
@@ -82,13 +83,20 @@ def hbm_peak():
 CPU_CHUNK = 8192   # rows per oracle call (the reference also walks its input in buffer_len chunks, build_dsp.py:399-407)
 
 
-def _cpu_pass(chains, vals, bl, consts, cores):
+def _cpu_pass(chains, vals, bl, consts, cores, keep=None):
+    """one pass of the CPU oracle chain over the sample; `keep` (a dict) collects its output columns"""
+    parts = []
     for lo in range(0, len(vals), CPU_CHUNK):
-        chains.icpc_chain(vals[lo:lo + CPU_CHUNK], bl[lo:lo + CPU_CHUNK], consts=consts, keep_waveforms=False,
-                          conv="library", threads=cores)
+        o = chains.icpc_chain(vals[lo:lo + CPU_CHUNK], bl[lo:lo + CPU_CHUNK], consts=consts, keep_waveforms=False,
+                              conv="library", threads=cores)
+        if keep is not None:
+            parts.append(o)
+    if keep is not None and parts:
+        for k in parts[0]:
+            keep[k] = np.concatenate([np.asarray(p[k]) for p in parts])
 
 
-def cpu_chain_throughput(n_rows: int, repeats: int = 1, vals=None, bl=None):
+def cpu_chain_throughput(n_rows: int, repeats: int = 1, vals=None, bl=None, keep=None):
     """waveforms/s of the CPU oracle ICPC chain on `n_rows` synthetic waveforms using all
     host threads (OpenMP over rows, like LEGEND production parallelises over files)."""
     from dspeed_b200 import synth
@@ -104,10 +112,45 @@ def cpu_chain_throughput(n_rows: int, repeats: int = 1, vals=None, bl=None):
     best = None
     for _ in range(max(1, repeats)):
         t = time.perf_counter()
-        _cpu_pass(chains, vals, bl, consts, cores)
+        _cpu_pass(chains, vals, bl, consts, cores, keep=keep)
         dt = time.perf_counter() - t
         best = dt if best is None else min(best, dt)
     return n_rows / best, cores, best
+
+
+def genuine_reference():
+    """The unmodified reference (`dspeed` + its lgdo / lh5 / pint dependencies), when this box can import it: from
+    baseline/_ref (the offline pip install of /root/reference) or the environment.  Returns (module, None) or
+    (None, why not).  The reference is pure Python + numba; in the build container its dependencies have no wheels,
+    so this normally reports why and the arm times the C restatement instead (kind "port")."""
+    ref = os.path.join(REPO, "baseline", "_ref")
+    if os.path.isdir(ref) and ref not in sys.path:
+        sys.path.append(ref)
+    try:
+        import dspeed  # noqa: F401
+        import lgdo  # noqa: F401
+        from dspeed import build_dsp  # noqa: F401
+        return dspeed, None
+    except Exception as e:   # ImportError, or a broken partial install
+        return None, f"{type(e).__name__}: {e}"
+
+
+def run_genuine_reference(dspeed_mod, vals, bl, steps):
+    """times dspeed.build_dsp (numba gufuncs, stock code path) on an in-memory lgdo table of the sample"""
+    import lgdo
+
+    from dspeed import build_dsp
+
+    n = len(vals)
+    wf = lgdo.WaveformTable(size=n, t0=0, t0_units="ns", dt=16, dt_units="ns", values=vals)
+    tb = lgdo.Table(col_dict={"waveform": wf, "baseline": lgdo.Array(bl)}, size=n)
+    cfg = load_config()
+    db = {"pz": {"tau": 27460.5}}
+    build_dsp(raw_in=tb, dsp_config=cfg, database=db, n_entries=min(n, 256))   # numba warm-up
+    t = time.perf_counter()
+    for _ in range(steps):
+        build_dsp(raw_in=tb, dsp_config=cfg, database=db)
+    return (time.perf_counter() - t) / steps
 
 
 def run_reference(args, rank):
@@ -122,6 +165,26 @@ def run_reference(args, rank):
     cores = O.set_threads(os.cpu_count() or 1)
     d = synth.hpge_waveforms(n, seed=2026, stress=True)
     vals, bl = d["values"].numpy(), d["baseline"].numpy()
+    ref_mod, why_not = genuine_reference()
+    if ref_mod is not None:
+        try:
+            dt = run_genuine_reference(ref_mod, vals, bl, steps)
+            v = n / dt
+            sample = (f"{n} synthetic 8192-sample waveforms per step through the unmodified dspeed.build_dsp "
+                      f"(numba gufuncs, in-memory lgdo table, block_width 16), 1 process")
+            line = {
+                "impl": "reference", "metric": "waveforms/s for HPGe DSP chain", "value": v, "unit": "waveforms/s",
+                "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "full LEGEND ICPC HPGe chain (34 outputs), 8192-sample uint16 waveforms",
+                           "rows_per_step": n},
+                "cpu_baseline": {"value": v, "unit": "waveforms/s", "cores": 1, "kind": "reference", "sample": sample},
+                "e2e": {"value": v, "unit": "waveforms/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            }
+            print(json.dumps(line), flush=True)
+            return
+        except Exception as e:
+            why_not = f"dspeed imported but build_dsp failed: {type(e).__name__}: {e}"
     consts = chains.icpc_constants()
     for _ in range(min(warm, 1)):
         chains.icpc_chain(vals[: min(n, 256)], bl[: min(n, 256)], consts=consts, keep_waveforms=False,
@@ -141,7 +204,8 @@ def run_reference(args, rank):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "full LEGEND ICPC HPGe chain (34 outputs), 8192-sample uint16 waveforms",
                    "rows_per_step": n},
-        "cpu_baseline": {"value": v, "unit": "waveforms/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "waveforms/s", "cores": cores, "kind": "port", "sample": sample,
+                         "genuine_reference_unavailable": why_not},
         "e2e": {"value": v, "unit": "waveforms/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -321,7 +385,9 @@ def run_b200(args, rank, world, local_rank):
     achieved = algo / k_time / 1e9
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": _traffic_from_profile(dom_name, rows_per_launch), "kernel": dom_name, "kernel_share_of_step": share,
+        "traffic": _traffic_from_profile(dom_name, rows_per_launch),
+        "traffic_source": "profiles/dominant_kernel_traffic.json (ncu --set full capture of this kernel, bytes per row x rows)",
+        "kernel": dom_name, "kernel_share_of_step": share,
         "kernel_ms_per_launch": k_time * 1e3, "rows_per_launch": rows_per_launch,
         "algorithmic_bytes_per_waveform": ALGO_BYTES_PER_WF, "peak_source": peak_src,
         "chain_frac_of_hbm_roofline": (value / world) * ALGO_BYTES_PER_WF / 1e9 / peak,
@@ -371,14 +437,32 @@ def run_b200(args, rank, world, local_rank):
         checksum = None
 
     # ---- CPU baseline (rank 0, single-GPU run only) --------------------------------------------
-    cpu = None
+    cpu, parity, other = None, None, None
     if rank == 0 and world == 1:
         mc = min(args.cpu_rows, n)   # the first rows of the very batch the GPU processed
-        v, cores, secs = cpu_chain_throughput(mc, vals=vals_d[:mc].cpu().numpy(), bl=bl_d[:mc].cpu().numpy())
+        vals_c, bl_c = vals_d[:mc].cpu().numpy(), bl_d[:mc].cpu().numpy()
+        oracle_out = {}
+        v, cores, secs = cpu_chain_throughput(mc, vals=vals_c, bl=bl_c, keep=oracle_out)
         cpu = {"value": v, "unit": "waveforms/s", "cores": cores, "kind": "port",
                "sample": f"{mc} of the same synthetic waveforms ({secs:.1f} s of CPU work), CPU oracle "
                          f"chain (C restatement of the reference's numba processors; convolutions through the "
                          f"reference's own numpy.convolve / scipy fftconvolve calls), {cores} threads"}
+        # ---- the benchmarked launch checks itself: the device-resident outputs of the last timed step against the
+        # oracle outputs of the same rows (tolerances of tests/parity.py; oracle/parity_check.py) ----------------
+        from oracle import chains
+        from oracle import parity_check
+
+        got = {k: tb_out_dev[k].nda[:mc].cpu().numpy() for k in out_names}
+        parity = parity_check.icpc_report(
+            got, oracle_out, waves_of=lambda rows: chains.icpc_chain(vals_c[rows], bl_c[rows], keep_waveforms=True))
+        parity["path"] = "device-resident one-launch path, rows [0, %d) of the timed batch" % mc
+    if rank == 0 and world == 1 and not args.no_configs:
+        del tb_dev, vals_d, bl_d, data
+        torch.cuda.empty_cache()
+        sys.path.insert(0, os.path.join(REPO, "scripts"))
+        import bench_configs
+
+        other = bench_configs.run_all(dev)
 
     if world > 1:
         dist.barrier()
@@ -400,9 +484,12 @@ def run_b200(args, rank, world, local_rank):
             "output_gather_ms": gather_ms,
         },
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-        "output_checksum_trapEmax": checksum,
+        "parity": parity, "configs": other, "output_checksum_trapEmax": checksum,
     }
     print(json.dumps(line), flush=True)
+    if parity is not None and not parity["ok"]:
+        print("bench.py: the benchmarked launch does not match the oracle: " + "; ".join(parity["violations"]), file=sys.stderr)
+        sys.exit(3)
 
 
 def _traffic_from_profile(kernel_name: str, rows_per_launch: int):

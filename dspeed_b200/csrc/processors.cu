@@ -938,6 +938,11 @@ extern "C" const char* dspb_fatal_message(int code) {
     case DSPB_FATAL_RF_SHORT: return "The length of the waveform must be larger than len(b) for the filter to work safely";
     case DSPB_FATAL_SHAPE: return "array shapes do not match the processor signature";
     case DSPB_FATAL_KERNEL_ARGS: return "invalid kernel-generator arguments";
+    case DSPB_FATAL_HIST_LEN: return "length borders_out must be exactly 1 + length of weights_out";
+    case DSPB_FATAL_HIST_NAN: return "input data contains nan";
+    case DSPB_FATAL_HPS_NAN: return "nan in input weights";
+    case DSPB_FATAL_HPS_LEN: return "length edges_in must be exactly 1 + length of weights_in";
+    case DSPB_FATAL_HPS_WIDTH_TYPE: return "Unknown width_type, must be [0...4]";
     case DSPB_ERR_ROW_TOO_LONG: return "waveform too long for the shared-memory resident layout";
     case DSPB_ERR_UNSUPPORTED: return "argument combination not supported by the device implementation";
   }

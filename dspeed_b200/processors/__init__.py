@@ -150,8 +150,9 @@ def raise_if_fatal(fatal: torch.Tensor, processor: str | None = None, wf_range=N
 class DeviceProcessor:
     """A CUDA processor obeying the gufunc protocol of the reference."""
 
-    def __init__(self, name, signature, types, impl, nout, doc=""):
+    def __init__(self, name, signature, types, impl, nout, doc="", out_args=None):
         self.__name__ = name
+        self.out_args = out_args      # positions of the output arguments when they are not the last `nout` ones
         self.__doc__ = doc
         self.signature = signature
         self.types = list(types)
@@ -198,7 +199,7 @@ class DeviceProcessor:
         dargs = []
         outs = []
         for i, a in enumerate(args):
-            is_out = i >= nargs - self.nout
+            is_out = (i in self.out_args) if self.out_args is not None else i >= nargs - self.nout
             if isinstance(a, np.ndarray) and a.ndim > 0:
                 if is_out:
                     if not a.flags.writeable:
@@ -249,9 +250,9 @@ def _tail(fatal, dev):
 _REGISTRY: dict[str, DeviceProcessor] = {}
 
 
-def _register(name, signature, types, nout):
+def _register(name, signature, types, nout, out_args=None):
     def deco(f):
-        p = DeviceProcessor(name, signature, types, f, nout, f.__doc__ or "")
+        p = DeviceProcessor(name, signature, types, f, nout, f.__doc__ or "", out_args)
         _REGISTRY[name] = p
         globals()[name] = p
         __all__.append(name)
@@ -676,6 +677,195 @@ def _t0_filter(rise, fall, kernel, fatal=None):
     r = (lambda v: float(np.float32(_as_float(v)))) if T == torch.float32 else _as_float
     return _fn("dspb_t0_filter", T)(_f64(r(rise)), _f64(r(fall)), _vp(k.data_ptr()), _i64(k.numel()),
                                     _stream_ptr(kernel.device))
+
+
+# ---- the rest of the SiPM / LAr chain (tests/configs/sipm-dsp-config.json; csrc/sipm.cu) -----------------------------
+def _list2d(c, a, T, what):
+    """[n_rows, m] list-valued operand (histogram weights / borders, index lists) -> (tensor, ptr, row stride, m)"""
+    t = a if a.ndim == 2 else a.unsqueeze(0)
+    if t.dtype != T:
+        raise TypeError(f"{what} dtype {t.dtype} does not match the {T} type loop")
+    if t.shape[-1] > 1 and t.stride(-1) != 1:
+        t = t.contiguous()
+    c.keep.append(t)
+    rs = 0 if t.shape[0] == 1 and c.n_rows > 1 else t.stride(0)
+    return t, _vp(t.data_ptr()), _i64(rs), t.shape[-1]
+
+
+@_register("histogram", "(n),(m),(p)", ["fff->", "ddd->"], 2)
+def _histogram(w_in, weights_out, borders_out, fatal=None):
+    """histogram.py:14-89"""
+    T = _out_T(weights_out)
+    c = _Call(T, weights_out.device)
+    c.rows_from(w_in, weights_out)
+    wi, n = c.wave_in(w_in)
+    _, wp, wrs, m = _list2d(c, weights_out, T, "weights_out")
+    _, bp, brs, p = _list2d(c, borders_out, T, "borders_out")
+    return _fn("dspb_histogram", T)(*wi, _i64(c.n_rows), _i64(n), wp, wrs, _i64(m), bp, brs, _i64(p),
+                                    *_tail(fatal, weights_out.device))
+
+
+@_register("histogram_around_mode", "(n),(),(),(m),(p)", ["fffff->", "ddddd->"], 2)
+def _histogram_around_mode(w_in, center, bin_width, weights_out, borders_out, fatal=None):
+    """histogram.py:92-204"""
+    T = _out_T(weights_out)
+    c = _Call(T, weights_out.device)
+    c.rows_from(w_in, center, bin_width, weights_out)
+    wi, n = c.wave_in(w_in)
+    _, wp, wrs, m = _list2d(c, weights_out, T, "weights_out")
+    _, bp, brs, p = _list2d(c, borders_out, T, "borders_out")
+    return _fn("dspb_histogram_around_mode", T)(*wi, _i64(c.n_rows), _i64(n), *c.scalar_in(center), *c.scalar_in(bin_width),
+                                                wp, wrs, _i64(m), bp, brs, _i64(p), *_tail(fatal, weights_out.device))
+
+
+@_register("histogram_stats", "(n),(m),(),(),(),()", ["ffffff->", "dddddd->"], 3, out_args=(2, 3, 4))
+def _histogram_stats(weights_in, edges_in, mode_out, max_out, fwhm_out, max_in, fatal=None):
+    """histogram_stats.py:146-261 (outputs are arguments 3-5, `max_in` is the last INPUT, like the reference)"""
+    T = _out_T(max_out)
+    c = _Call(T, max_out.device)
+    c.rows_from(weights_in, max_out)
+    _, wp, wrs, m = _list2d(c, weights_in.to(T) if weights_in.dtype != T else weights_in, T, "weights_in")
+    _, ep, ers, p = _list2d(c, edges_in.to(T) if edges_in.dtype != T else edges_in, T, "edges_in")
+    return _fn("dspb_histogram_stats", T)(wp, wrs, _i64(m), ep, ers, _i64(p), _i64(c.n_rows), c.scalar_out(mode_out),
+                                          c.scalar_out(max_out), c.scalar_out(fwhm_out), *c.scalar_in(max_in),
+                                          *_tail(fatal, max_out.device))
+
+
+@_register("histogram_peakstats", "(n),(m),(),(),()->(),()", ["fffii->ff", "dddii->dd"], 2)
+def _histogram_peakstats(weights_in, edges_in, max_in, skip_zeroes, width_type, mode_out, width_out, fatal=None):
+    """histogram_stats.py:12-143"""
+    T = _out_T(mode_out)
+    c = _Call(T, mode_out.device)
+    c.rows_from(weights_in, mode_out)
+    _, wp, wrs, m = _list2d(c, weights_in.to(T) if weights_in.dtype != T else weights_in, T, "weights_in")
+    _, ep, ers, p = _list2d(c, edges_in.to(T) if edges_in.dtype != T else edges_in, T, "edges_in")
+    return _fn("dspb_histogram_peakstats", T)(wp, wrs, _i64(m), ep, ers, _i64(p), _i64(c.n_rows), *c.scalar_in(max_in),
+                                              _i32(_as_int(skip_zeroes)), _i32(_as_int(width_type)), c.scalar_out(mode_out),
+                                              c.scalar_out(width_out), *_tail(fatal, mode_out.device))
+
+
+@_register("peak_snr_threshold", "(n),(m),(),()->(m),()", ["ffff->fI", "dddd->dI"], 2)
+def _peak_snr_threshold(w_in, idx_in, ratio_in, width_in, idx_out, n_idx_out, fatal=None):
+    """peak_snr_threshold.py:11-71"""
+    T = _out_T(idx_out)
+    c = _Call(T, idx_out.device)
+    c.rows_from(w_in, idx_out)
+    wi, n = c.wave_in(w_in)
+    _, ip, irs, m = _list2d(c, idx_in, T, "idx_in")
+    _, op, ors, mo = _list2d(c, idx_out, T, "idx_out")
+    assert mo == m and n_idx_out.dtype == torch.uint32
+    return _fn("dspb_peak_snr_threshold", T)(*wi, _i64(c.n_rows), _i64(n), ip, irs, _i64(m), *c.scalar_in(ratio_in),
+                                             *c.scalar_in(width_in), op, ors, _vp(n_idx_out.data_ptr()),
+                                             *_tail(fatal, idx_out.device))
+
+
+@_register("multi_a_filter", "(n),(m)->(m)", ["ff->f", "dd->d"], 1)
+def _multi_a_filter(w_in, vt_maxs_in, va_max_out, fatal=None):
+    """multi_a_filter.py:11-57"""
+    T = _out_T(va_max_out)
+    c = _Call(T, va_max_out.device)
+    c.rows_from(w_in, va_max_out)
+    wi, n = c.wave_in(w_in)
+    _, ip, irs, m = _list2d(c, vt_maxs_in, T, "vt_maxs_in")
+    _, op, ors, mo = _list2d(c, va_max_out, T, "va_max_out")
+    assert mo == m
+    return _fn("dspb_multi_a_filter", T)(*wi, _i64(c.n_rows), _i64(n), ip, irs, _i64(m), op, ors,
+                                         *_tail(fatal, va_max_out.device))
+
+
+@_register("reflected_convolve_wf", "(n),(m),(p)", ["fff->", "ddd->"], 1)
+def _reflected_convolve_wf(w_in, kernel, w_out, fatal=None):
+    """convolutions.py:122-182"""
+    T = _out_T(w_out)
+    c = _Call(T, w_out.device)
+    c.rows_from(w_in, w_out)
+    wi, n = c.wave_in(w_in)
+    wo, _ = c.wave_out(w_out, n)
+    k = kernel.reshape(-1).to(T).contiguous()
+    c.keep.append(k)
+    return _fn("dspb_reflected_convolve_wf", T)(*wi, _i64(c.n_rows), _i64(n), _vp(k.data_ptr()), _i64(k.numel()), *wo,
+                                                *_tail(fatal, w_out.device))
+
+
+@_register("gaussian_filter1d", "(),(),(n)", ["fff->", "ddd->"], 1)
+def _gaussian_filter1d(sigma, truncate, weights, fatal=None):
+    """gaussian_filter1d.py:46-82"""
+    T, k = _kernel_out(weights)
+    return _fn("dspb_gaussian_filter1d", T)(_f64(_as_float(sigma)), _f64(_as_float(truncate)), _vp(k.data_ptr()),
+                                            _i64(k.numel()), _stream_ptr(weights.device))
+
+
+@_register("moving_slope", "(n)", ["f->", "d->"], 1)
+def _moving_slope(kernel, fatal=None):
+    """kernels.py:64-103"""
+    T, k = _kernel_out(kernel)
+    return _fn("dspb_moving_slope", T)(_vp(k.data_ptr()), _i64(k.numel()), _stream_ptr(kernel.device))
+
+
+@_register("step", "(),(n)", ["ff->", "dd->"], 1)
+def _step(weight_pos, kernel, fatal=None):
+    """kernels.py:106-142"""
+    T, k = _kernel_out(kernel)
+    return _fn("dspb_step", T)(_f64(_as_float(weight_pos)), _vp(k.data_ptr()), _i64(k.numel()), _stream_ptr(kernel.device))
+
+
+@_register("dplms", "(n,n),(m),(),(),(),()->(n)", ["ffffff->f", "dddddd->d"], 1)
+def _dplms(noise_mat, reference, a1, a2, a3, ff, kernel, fatal=None):
+    """energy_kernels.py:160-272 -- the DPLMS optimum filter (set-up time, const-folded by the chain compiler).  The
+    penalised normal equations (a1 N + a2 R + a3 1 1^T) x = r are assembled and solved in float64 ON THE DEVICE
+    (torch.linalg.solve: cuSOLVER LU, a library call at set-up time like the reference's numpy.linalg.solve); the
+    kernel is the flipped solution, normalised by the maximum of its 'valid' convolution with the reference pulse."""
+    T, k = _kernel_out(kernel)
+    dev = kernel.device
+    length = k.numel()
+
+    def dev64(x):
+        t = x if isinstance(x, torch.Tensor) else torch.as_tensor(np.asarray(x))
+        return t.to(device=dev, dtype=T).to(torch.float64)     # values as the loop's type holds them
+
+    nm = dev64(noise_mat)
+    if nm.ndim == 3:
+        nm = nm[0]
+    ref = dev64(reference).reshape(-1)
+    a1, a2, a3, ff = (float(np.dtype("f4" if T == torch.float32 else "f8").type(_as_float(v))) for v in (a1, a2, a3, ff))
+
+    def bad(msg):
+        e = DSPFatal(msg)
+        e.code = 0
+        raise e
+
+    if nm.shape[0] != length:
+        bad("The length of the filter is not consistent with the noise matrix")
+    if ref.numel() <= 0:
+        bad("The length of the reference signal must be positive")
+    if a1 <= 0:
+        bad("The penalized coefficient for the noise must be positive")
+    if a2 <= 0:
+        bad("The penalized coefficient for the reference must be positive")
+    if a3 <= 0:
+        bad("The penalized coefficient for the zero area must be positive")
+    if ff <= 0:
+        bad("The penalized coefficient for the ref matrix must be positive")
+    if ff != 1:
+        bad("The penalized coefficient for the ref matrix must be 0 or 1")
+    ssize = ref.numel()
+    flo, fhi = int(ssize / 2 - length / 2), int(ssize / 2 + length / 2)
+    ref_mat = torch.zeros((length, length), dtype=torch.float64, device=dev)
+    ref_sig = torch.zeros(length, dtype=torch.float64, device=dev)
+    shifts = (-1, 0, 1)
+    for i in shifts:
+        seg = ref[flo + i: fhi + i]
+        ref_mat += torch.outer(seg, seg)
+        ref_sig += seg
+    ref_mat /= len(shifts)
+    mat = a1 * nm + a2 * ref_mat + a3
+    sol = torch.linalg.solve(mat, ref_sig)
+    k.copy_(torch.flip(sol, (0,)).to(T))                 # kernel[:] = np.flip(solve(...)) (stored in the loop's type)
+    # y = np.convolve(reference, kernel, 'valid'); kernel /= max(y)
+    kk = k.to(torch.float64)
+    y = torch.nn.functional.conv1d(ref.view(1, 1, -1), torch.flip(kk, (0,)).view(1, 1, -1)).view(-1)
+    k.copy_((k.to(torch.float64) / y.max()).to(T) if T == torch.float64 else (k / y.max().to(T)))
+    return 0
 
 
 def __getattr__(name):

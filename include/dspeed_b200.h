@@ -80,6 +80,11 @@ enum {
   DSPB_FATAL_RF_SHORT = 28,         /* recursive_filter.py:68-71 */
   DSPB_FATAL_SHAPE = 29,            /* gufunc core-dimension mismatch (numpy raises) */
   DSPB_FATAL_KERNEL_ARGS = 30,      /* energy_kernels.py:51-61, kernels.py:49-56 */
+  DSPB_FATAL_HIST_LEN = 31,         /* histogram.py:64-65, 152-153 */
+  DSPB_FATAL_HIST_NAN = 32,         /* histogram.py:157-158 */
+  DSPB_FATAL_HPS_NAN = 33,          /* histogram_stats.py:84-85 */
+  DSPB_FATAL_HPS_LEN = 34,          /* histogram_stats.py:88-89, 221-222 */
+  DSPB_FATAL_HPS_WIDTH_TYPE = 35,   /* histogram_stats.py:142-143 */
   DSPB_ERR_ROW_TOO_LONG = 100,      /* waveform does not fit the shared-memory resident layout */
   DSPB_ERR_UNSUPPORTED = 101
 };
@@ -191,6 +196,44 @@ const char* dspb_fatal_message(int code);
 
 DSPB_DECLARE(_f32)
 DSPB_DECLARE(_f64)
+
+/* ---- the rest of the SiPM / LAr chain (tests/configs/sipm-dsp-config.json), csrc/sipm.cu ------------------------
+ * List-valued operands (histogram weights / borders, index lists) are [n_rows, m] arrays of the loop's type with a row
+ * stride in elements. */
+#define DSPB_DECLARE_SIPM(SFX)                                                                                           \
+  /* histogram.py:14-89   weights[m], borders[m + 1] of the row's min..max range */                                      \
+  int dspb_histogram##SFX(DSPB_WAVE_IN(w_in), int64_t n_rows, int64_t n, void* weights, int64_t weights_rs,              \
+                          int64_t n_bins, void* borders, int64_t borders_rs, int64_t n_borders, DSPB_TAIL);             \
+  /* histogram.py:92-204   bins of width bin_width centred on `center` (NaN: on the mode of the row) */                  \
+  int dspb_histogram_around_mode##SFX(DSPB_WAVE_IN(w_in), int64_t n_rows, int64_t n, DSPB_SCALAR(center),                \
+                                      DSPB_SCALAR(bin_width), void* weights, int64_t weights_rs, int64_t n_bins,        \
+                                      void* borders, int64_t borders_rs, int64_t n_borders, DSPB_TAIL);                 \
+  /* histogram_stats.py:146-261   mode index, left edge of the mode bin, half width at half maximum */                   \
+  int dspb_histogram_stats##SFX(const void* weights, int64_t weights_rs, int64_t n_bins, const void* edges,              \
+                                int64_t edges_rs, int64_t n_edges, int64_t n_rows, void* mode_out, void* max_out,       \
+                                void* fwhm_out, DSPB_SCALAR(max_in), DSPB_TAIL);                                        \
+  /* histogram_stats.py:12-143   centre of the mode bin, FWHM / HWHM variants */                                         \
+  int dspb_histogram_peakstats##SFX(const void* weights, int64_t weights_rs, int64_t n_bins, const void* edges,          \
+                                    int64_t edges_rs, int64_t n_edges, int64_t n_rows, DSPB_SCALAR(max_in),             \
+                                    int32_t skip_zeroes, int32_t width_type, void* mode_out, void* width_out,           \
+                                    DSPB_TAIL);                                                                         \
+  /* peak_snr_threshold.py:11-71   candidates whose local minimum / value ratio is below ratio_in; count uint32 */       \
+  int dspb_peak_snr_threshold##SFX(DSPB_WAVE_IN(w_in), int64_t n_rows, int64_t n, const void* idx_in,                    \
+                                   int64_t idx_in_rs, int64_t m, DSPB_SCALAR(ratio_in), DSPB_SCALAR(width_in),          \
+                                   void* idx_out, int64_t idx_out_rs, void* n_idx_out, DSPB_TAIL);                      \
+  /* multi_a_filter.py:11-57   waveform values at the (integer) times of the list, NaN padded */                         \
+  int dspb_multi_a_filter##SFX(DSPB_WAVE_IN(w_in), int64_t n_rows, int64_t n, const void* vt_maxs_in, int64_t vt_rs,     \
+                               int64_t m, void* va_max_out, int64_t va_rs, DSPB_TAIL);                                  \
+  /* convolutions.py:122-182   'same' convolution of the reflect-padded waveform */                                      \
+  int dspb_reflected_convolve_wf##SFX(DSPB_WAVE_IN(w_in), int64_t n_rows, int64_t n, const void* kernel, int64_t m,      \
+                                      DSPB_WAVE_OUT(w_out), DSPB_TAIL);                                                 \
+  /* set-up time kernel generators: gaussian_filter1d.py:46-82, kernels.py:64-103, kernels.py:106-142 */                \
+  int dspb_gaussian_filter1d##SFX(double sigma, double truncate, void* weights, int64_t length, void* stream);          \
+  int dspb_moving_slope##SFX(void* kernel, int64_t length, void* stream);                                               \
+  int dspb_step##SFX(double weight_pos, void* kernel, int64_t length, void* stream);
+
+DSPB_DECLARE_SIPM(_f32)
+DSPB_DECLARE_SIPM(_f64)
 
 /* ---- fused waveform-resident chain program (see DESIGN.md "chain compiler") ---------
  * A program is a flat int32/double blob produced by the host chain compiler

@@ -356,7 +356,114 @@ def sipm_chain(P, synth):
     return o
 
 
+def sipm_processor_cases(P, synth):
+    """the processors of the reference's SiPM chain (tests/configs/sipm-dsp-config.json) and the remaining kernel
+    generators, float32 and float64 type loops, on 12 synthetic SiPM rows + the reference tests' own vectors"""
+    import dspeed.processors.gaussian_filter1d as G
+    from dspeed.processors.convolutions import reflected_convolve_wf
+    from dspeed.processors.histogram import histogram, histogram_around_mode
+    from dspeed.processors.histogram_stats import histogram_peakstats, histogram_stats
+    from dspeed.processors.multi_a_filter import multi_a_filter
+    from dspeed.processors.peak_snr_threshold import peak_snr_threshold
+
+    g = {}
+    d = synth.sipm_waveforms(12, seed=777)
+    vals = d["values"].numpy()
+    n_rows, L = vals.shape
+    g["values"] = vals
+    for dt in (np.float32, np.float64):
+        t = "f" if dt == np.float32 else "d"
+        # --- gaussian kernels (sipm-dsp-config.json:4-16: width 1, trunc 4 -> 9 taps)
+        for (sig, trunc) in ((1.0, 4.0), (2.5, 3.0)):
+            k = np.zeros(int(trunc * sig + 0.5) * 2 + 1, dt)
+            G.gaussian_filter1d(dt(sig), dt(trunc), k)
+            g[f"gaus_{t}_{sig}_{trunc}"] = k
+        k = g[f"gaus_{t}_1.0_4.0"]
+        w = vals.astype(dt)
+        wg = np.zeros((n_rows, L), dt)
+        reflected_convolve_wf(w, k, wg)
+        g[f"wf_gaus_{t}"] = wg
+        k2 = g[f"gaus_{t}_2.5_3.0"]
+        wg2 = np.zeros((n_rows, L), dt)
+        reflected_convolve_wf(w, k2, wg2)
+        g[f"wf_gaus2_{t}"] = wg2
+        curr = np.zeros((n_rows, L - 5), dt)
+        P.avg_current(wg, 5, curr)
+        g[f"curr_{t}"] = curr
+        hw, hb = np.zeros((n_rows, 100), dt), np.zeros((n_rows, 101), dt)
+        histogram(curr, hw, hb)
+        g[f"hist_w_{t}"], g[f"hist_b_{t}"] = hw, hb
+        idx, mx, fw = np.zeros(n_rows, dt), np.zeros(n_rows, dt), np.zeros(n_rows, dt)
+        histogram_stats(hw, hb, idx, mx, fw, dt(np.nan))
+        g[f"hs_idx_{t}"], g[f"hs_max_{t}"], g[f"hs_fwhm_{t}"] = idx, mx, fw
+        idx2, mx2, fw2 = np.zeros(n_rows, dt), np.zeros(n_rows, dt), np.zeros(n_rows, dt)
+        histogram_stats(hw, hb, idx2, mx2, fw2, dt(0.5))
+        g[f"hs2_idx_{t}"], g[f"hs2_max_{t}"], g[f"hs2_fwhm_{t}"] = idx2, mx2, fw2
+        # histogram around the mode (mode search / given centre), then the peak statistics in every mode
+        for tag, center, bw, nb in (("a", np.nan, 1.0, 101), ("b", np.nan, 0.5, 64), ("c", 3.0, 2.0, 31)):
+            aw, ab = np.zeros((n_rows, nb), dt), np.zeros((n_rows, nb + 1), dt)
+            histogram_around_mode(curr, dt(center), dt(bw), aw, ab)
+            g[f"ham_w_{tag}_{t}"], g[f"ham_b_{tag}_{t}"] = aw, ab
+            for skip in (0, 1):
+                for wt in range(5):
+                    mo, wo = np.zeros(n_rows, dt), np.zeros(n_rows, dt)
+                    histogram_peakstats(aw, ab, dt(np.nan), np.int32(skip), np.int32(wt), mo, wo)
+                    g[f"hps_mode_{tag}_{skip}_{wt}_{t}"], g[f"hps_width_{tag}_{skip}_{wt}_{t}"] = mo, wo
+            mo, wo = np.zeros(n_rows, dt), np.zeros(n_rows, dt)
+            histogram_peakstats(aw, ab, dt(1.25), np.int32(0), np.int32(0), mo, wo)
+            g[f"hps_mode_{tag}_given_{t}"], g[f"hps_width_{tag}_given_{t}"] = mo, wo
+        # raw-waveform histogram of integer ADC values (aliasing case of the reference's doc-string)
+        rw, rb = np.zeros((n_rows, 40), dt), np.zeros((n_rows, 41), dt)
+        histogram(w, rw, rb)
+        g[f"hist_raw_w_{t}"], g[f"hist_raw_b_{t}"] = rw, rb
+        # peak finding with a per-row absolute threshold (3 * fwhm), SNR cut, amplitudes
+        vmax, vmin = np.zeros((n_rows, 20), dt), np.zeros((n_rows, 20), dt)
+        nmax, nmin = np.zeros(n_rows, np.uint32), np.zeros(n_rows, np.uint32)
+        for r in range(n_rows):
+            P.get_multi_local_extrema(curr[r], dt(5), dt(0.1), dt(1), dt(3) * fw[r], dt(0), vmax[r], vmin[r], nmax[r:r + 1], nmin[r:r + 1])
+        g[f"vt_max_{t}"], g[f"vt_min_{t}"], g[f"n_max_{t}"], g[f"n_min_{t}"] = vmax, vmin, nmax, nmin
+        for tag, ratio, width in (("a", 0.8, 10), ("b", 0.3, 4)):
+            trig, no = np.zeros((n_rows, 20), dt), np.zeros(n_rows, np.uint32)
+            peak_snr_threshold(curr, vmax, dt(ratio), dt(width), trig, no)
+            g[f"trig_{tag}_{t}"], g[f"n_trig_{tag}_{t}"] = trig, no
+            en = np.zeros((n_rows, 20), dt)
+            multi_a_filter(curr, trig, en)
+            g[f"energies_{tag}_{t}"] = en
+    # reference KATs (tests/processors/test_histogram.py:9-19)
+    v = np.arange(100) * 2 / 3
+    hw, hb = np.zeros(66), np.zeros(67)
+    histogram(v, hw, hb)
+    g["kat_hist_in"], g["kat_hist_w"], g["kat_hist_b"] = v, hw, hb
+    for tag, wi in (("a", [1, 2, 2, 2, 3, 4, 5]), ("b", [1, 2, 2, 2, 3, 4, 5, 100]), ("c", [1, 2, 2, 2, 3, 4, 5, -100])):
+        wi = np.array(wi, np.float32)
+        aw, ab = np.zeros(11, np.float32), np.zeros(12, np.float32)
+        histogram_around_mode(wi, np.float32(np.nan), np.float32(1.0), aw, ab)
+        g[f"kat_ham_in_{tag}"], g[f"kat_ham_w_{tag}"], g[f"kat_ham_b_{tag}"] = wi, aw, ab
+    # dplms: the reference test's 50 x 50 noise matrix (tests/processors/dplms_noise_mat.dat) and delta reference
+    nmat = np.array([[float(x) for x in ln.split(" ")] for ln in open("/root/reference/tests/processors/dplms_noise_mat.dat")])
+    ref = np.zeros(100)
+    ref[49:50] = 1
+    g["dplms_nmat"], g["dplms_ref"] = nmat, ref
+    for dt in (np.float32, np.float64):
+        t = "f" if dt == np.float32 else "d"
+        k = np.zeros(50, dt)
+        P.dplms(nmat.astype(dt), ref.astype(dt), dt(1), dt(1), dt(1), dt(1), k)
+        g[f"dplms_{t}_1111"] = k
+        k = np.zeros(50, dt)
+        rr = (1 - np.exp(-np.arange(100) / 5.0)) * np.exp(-np.arange(100) / 400.0)
+        P.dplms(nmat.astype(dt), rr.astype(dt), dt(50), dt(0.1), dt(1), dt(1), k)
+        g[f"dplms_{t}_pulse"] = k
+        g["dplms_ref_pulse"] = rr
+    return g
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "sipm":
+        P = import_reference()
+        out_dir = os.path.join(REPO, "tests", "golden")
+        np.savez_compressed(os.path.join(out_dir, "sipm_processors.npz"), **sipm_processor_cases(P, load_synth()))
+        print("sipm_processors.npz", os.path.getsize(os.path.join(out_dir, "sipm_processors.npz")))
+        return
     P = import_reference()
     synth = load_synth()
     out_dir = os.path.join(REPO, "tests", "golden")
@@ -379,6 +486,7 @@ def main():
     np.savez_compressed(os.path.join(out_dir, "processors.npz"), **processor_cases(P))
     np.savez_compressed(os.path.join(out_dir, "kernels.npz"), **kernel_cases(P))
     np.savez_compressed(os.path.join(out_dir, "sipm_chain.npz"), **sipm_chain(P, synth))
+    np.savez_compressed(os.path.join(out_dir, "sipm_processors.npz"), **sipm_processor_cases(P, synth))
     for f in sorted(os.listdir(out_dir)):
         print(f, os.path.getsize(os.path.join(out_dir, f)))
 
