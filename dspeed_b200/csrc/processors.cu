@@ -445,7 +445,7 @@ struct RecursiveFilter {
 // ---------------------------------------------------------------------------------
 template <typename T>
 struct MultiLocalExtrema {
-  Wave in; int n; T d_max, d_min; T dir; T abs_max, abs_min; T *vt_max, *vt_min; int m;
+  Wave in; int n; T d_max, d_min; T dir; Scalar<T> abs_max_s, abs_min_s; T *vt_max, *vt_min; int m;   // (thresholds may be per-row)
   uint32_t *n_max, *n_min;
   __device__ static void walk(const T* s, int n, bool fwd, T d_max, T d_min, T abs_max, T abs_min,
                               float* v_max, float* v_min, int m, int& c_max, int& c_min) {
@@ -476,6 +476,7 @@ struct MultiLocalExtrema {
   }
   __device__ void operator()(long long row, T* s, Scratch* sc) const {
     const int nan_in = stage_in<T>(s, in, row, n);
+    const T abs_max = abs_max_s.get(row), abs_min = abs_min_s.get(row);
     T* omax = vt_max + row * m;
     T* omin = vt_min + row * m;
     for (int i = threadIdx.x; i < m; i += NT) { omax[i] = nan_of<T>(); omin[i] = nan_of<T>(); }
@@ -816,7 +817,8 @@ int trap_static_check(int64_t n, int32_t rise, int32_t flat) {
   }                                                                                                \
   extern "C" int dspb_get_multi_local_extrema##SFX(                                                \
       DSPB_WAVE_IN(w_in), int64_t n_rows, int64_t n, double a_delta_max, double a_delta_min,       \
-      double search_direction, double a_abs_max, double a_abs_min, void* vt_max, void* vt_min,     \
+      double search_direction, DSPB_SCALAR(a_abs_max), DSPB_SCALAR(a_abs_min), void* vt_max,       \
+      void* vt_min,                                                                                \
       int64_t m, uint32_t* n_max, uint32_t* n_min, DSPB_TAIL) {                                    \
     using T = T_;                                                                                  \
     (void)fatal;                                                                                   \
@@ -826,8 +828,8 @@ int trap_static_check(int64_t n, int32_t rise, int32_t flat) {
       if (!((T)a_delta_max >= 0) || !((T)a_delta_min >= 0)) return DSPB_FATAL_GMLE_DELTA;          \
       if (!(dir == 0 || dir == 1 || dir == 2 || dir == 3)) return DSPB_FATAL_GMLE_DIR;             \
     }                                                                                              \
-    MultiLocalExtrema<T> b{WIN(w_in), (int)n, (T)a_delta_max, (T)a_delta_min, dir, (T)a_abs_max,   \
-                           (T)a_abs_min, (T*)vt_max, (T*)vt_min, (int)m, n_max, n_min};            \
+    MultiLocalExtrema<T> b{WIN(w_in), (int)n, (T)a_delta_max, (T)a_delta_min, dir, SC(a_abs_max),  \
+                           SC(a_abs_min), (T*)vt_max, (T*)vt_min, (int)m, n_max, n_min};           \
     return launch_rows<T>(b, n_rows, 1, n, stream, 4 * (size_t)m * sizeof(float) + 16);            \
   }                                                                                                \
   extern "C" int dspb_recursive_filter##SFX(DSPB_WAVE_IN(w_in), int64_t n_rows, int64_t n,         \

@@ -404,6 +404,63 @@ __global__ void k_step(T* out, int n) {
   }
 }
 
+// ---- VectorOfVectors output compaction (LGDOVectorOfVectorsIOManager.write, processing_chain.py:2230-2260) ---------
+// A variable-length output lives in the chain as a padded [rows, width] block plus a length variable; the ragged column
+// stores `flattened_data` and `cumulative_length` (end offsets).  One CTA turns the block's lengths into end offsets
+// (chunked inclusive scan with a carried total, clamped to the block width like the reference's per-row slice),
+// then one warp per row copies its entries to their place -- the padded block never leaves the device.
+__global__ void __launch_bounds__(1024) k_vov_offsets(const uint32_t* lens, long long n_rows, int width, long long base,
+                                                       long long* ends, uint32_t* cum_out) {
+  __shared__ long long warp_tot[32];
+  __shared__ long long carry;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry = base;
+  __syncthreads();
+  for (long long r0 = 0; r0 < n_rows; r0 += 1024) {
+    const long long r = r0 + threadIdx.x;
+    long long v = 0;
+    if (r < n_rows) {
+      const uint32_t l = lens[r];
+      v = l < (uint32_t)width ? l : (uint32_t)width;
+    }
+    long long inc = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      const long long t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) warp_tot[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+      long long w = warp_tot[lane];
+      for (int o = 1; o < 32; o <<= 1) {
+        const long long t = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += t;
+      }
+      warp_tot[lane] = w;
+    }
+    __syncthreads();
+    const long long end = carry + (wid ? warp_tot[wid - 1] : 0) + inc;
+    if (r < n_rows) {
+      ends[r] = end;
+      cum_out[r] = (uint32_t)end;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) carry += warp_tot[31];
+    __syncthreads();
+  }
+}
+template <typename E>
+__global__ void k_vov_scatter(const E* block, long long row_stride, const uint32_t* lens, int width, const long long* ends,
+                              long long n_rows, long long base, E* flat) {
+  const long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= n_rows) return;
+  uint32_t l = lens[row];
+  if (l > (uint32_t)width) l = (uint32_t)width;
+  const long long dst = ends[row] - (long long)l - base;
+  for (uint32_t j = lane; j < l; j += 32) flat[dst + j] = block[row * row_stride + j];
+}
+
 int grid_rows(long long n_rows) { return (int)(n_rows < 148LL * 16 ? n_rows : 148LL * 16); }
 int last_error() {
   const cudaError_t e = cudaGetLastError();
@@ -521,3 +578,30 @@ int last_error() {
 
 DSPB_DEFINE_SIPM(_f32, float)
 DSPB_DEFINE_SIPM(_f64, double)
+
+// VectorOfVectors compaction: lens uint32[n_rows] -> ends int64[n_rows] (absolute end offsets, first row starts at
+// `base`) and cumulative_length uint32[n_rows]; then block [n_rows, width] (elements of elem_bytes = 4 or 8) ->
+// flat[0 .. ends[n_rows-1] - base).  All pointers are device pointers.
+extern "C" int dspb_vov_offsets(const uint32_t* lens, int64_t n_rows, int64_t width, int64_t base, int64_t* ends,
+                                uint32_t* cumulative_length, void* stream) {
+  if (n_rows <= 0) return 0;
+  k_vov_offsets<<<1, 1024, 0, (cudaStream_t)stream>>>(lens, n_rows, (int)width, base, (long long*)ends, cumulative_length);
+  return last_error();
+}
+extern "C" int dspb_vov_compact(const void* block, int64_t row_stride, int32_t elem_bytes, const uint32_t* lens,
+                                int64_t width, const int64_t* ends, int64_t n_rows, int64_t base, void* flat, void* stream) {
+  if (n_rows <= 0) return 0;
+  const unsigned grid = (unsigned)((n_rows * 32 + 255) / 256);
+  if (elem_bytes == 4)
+    k_vov_scatter<uint32_t><<<grid, 256, 0, (cudaStream_t)stream>>>((const uint32_t*)block, row_stride, lens, (int)width,
+                                                                   (const long long*)ends, n_rows, base, (uint32_t*)flat);
+  else if (elem_bytes == 8)
+    k_vov_scatter<uint64_t><<<grid, 256, 0, (cudaStream_t)stream>>>((const uint64_t*)block, row_stride, lens, (int)width,
+                                                                   (const long long*)ends, n_rows, base, (uint64_t*)flat);
+  else if (elem_bytes == 2)
+    k_vov_scatter<uint16_t><<<grid, 256, 0, (cudaStream_t)stream>>>((const uint16_t*)block, row_stride, lens, (int)width,
+                                                                   (const long long*)ends, n_rows, base, (uint16_t*)flat);
+  else
+    return DSPB_ERR_UNSUPPORTED;
+  return last_error();
+}

@@ -43,8 +43,9 @@ from typing import Any
 import numpy as np
 import torch
 
-from . import numpy_bridge, tables
+from . import _lib, numpy_bridge, tables
 from . import processors as device_processors
+from .processors import _i32, _i64, _vp
 from .errors import DSPFatal, ProcessingChainError
 from .tables import kind_of
 from .units import Quantity, Unit, as_unit, from_foreign, is_in_registry, to_period_units, ureg
@@ -1391,13 +1392,46 @@ class VectorOfVectorsIOManager(IOManager):
         self._count(pad.nbytes, False)
 
     def write(self, start: int, end: int) -> None:
+        """The padded [block, width] buffer is compacted ON THE DEVICE (csrc/sipm.cu: scan of the lengths -> end offsets
+        and `cumulative_length`, one warp per row scatters its entries); only the ragged data and the offsets cross to
+        the host column -- or nothing at all when the column's arrays are device tensors."""
         self._ensure_raw(start, end)
-        vals = self.raw_var[: end - start].cpu().numpy()
-        lens = self.len_var[: end - start].cpu().numpy().astype(np.int64)
+        nrow = end - start
+        if nrow <= 0:
+            return
+        blk = self.raw_var[:nrow]
+        dev = blk.device
+        lens = self.len_var[:nrow]
+        if lens.dtype != torch.uint32:
+            lens = lens.to(torch.int64).clamp_(min=0).to(torch.uint32)
+        lens = lens.contiguous()
         if len(self.io_vov) < end:
             self.io_vov.resize(end)
-        self.io_vov._set_vector_unsafe(start, vals, lens)
-        self._count(vals.nbytes, True)
+        cl = self.io_vov.cumulative_length.nda
+        base = int(cl[start - 1]) if start > 0 else 0
+        L = _lib.lib()
+        stream = _vp(torch.cuda.current_stream(dev).cuda_stream)
+        ends = torch.empty(nrow, dtype=torch.int64, device=dev)
+        cum = torch.empty(nrow, dtype=torch.uint32, device=dev)
+        width = int(blk.shape[1]) if blk.ndim == 2 else 1
+        rc = L.dspb_vov_offsets(_vp(lens.data_ptr()), _i64(nrow), _i64(width), _i64(base), _vp(ends.data_ptr()),
+                                _vp(cum.data_ptr()), stream)
+        if rc:
+            raise RuntimeError(f"dspb_vov_offsets: error {rc}")
+        total = int(ends[-1].item()) - base          # (one 8-byte read back: the size of the ragged payload)
+        flat_d = torch.empty(max(total, 1), dtype=blk.dtype, device=dev)
+        rc = L.dspb_vov_compact(_vp(blk.data_ptr()), _i64(blk.stride(0)), _i32(blk.element_size()), _vp(lens.data_ptr()),
+                                _i64(width), _vp(ends.data_ptr()), _i64(nrow), _i64(base), _vp(flat_d.data_ptr()), stream)
+        if rc:
+            raise RuntimeError(f"dspb_vov_compact: error {rc}")
+        need = base + total
+        if need > len(self.io_vov.flattened_data):
+            self.io_vov.flattened_data.resize(need)
+        fd = _as_tensor(self.io_vov.flattened_data.nda)
+        fd[base:need].copy_(flat_d[:total])
+        _as_tensor(cl)[start:end].copy_(cum)
+        if not fd.is_cuda:
+            self._count(total * blk.element_size() + 4 * nrow, True)
 
     def __str__(self) -> str:
         return f"{self.var} linked to VectorOfVectors(vector_len={self.var.vector_len}, attrs={self.io_vov.attrs})"
@@ -1499,7 +1533,8 @@ def _resolve_function(module_name: str, func_name: str):
     """processor callable named by a recipe.  ``dspeed.processors.X`` resolves to the
     CUDA processor of the same name; numpy / scipy functions are resolved as such and
     mapped to a device implementation when bound (or rejected: no CPU fallback)."""
-    if module_name in _MODULE_ALIASES:
+    # (the reference's configs also name the processor's own sub-module, e.g. "dspeed.processors.histogram")
+    if module_name in _MODULE_ALIASES or any(module_name.startswith(m + ".") for m in _MODULE_ALIASES):
         try:
             return getattr(device_processors, func_name)
         except AttributeError as e:

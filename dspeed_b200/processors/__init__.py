@@ -621,7 +621,7 @@ def _get_multi_local_extrema(w_in, a_delta_max_in, a_delta_min_in, search_direct
     m = vmx.shape[-1]
     return _fn("dspb_get_multi_local_extrema", T)(
         *wi, _i64(c.n_rows), _i64(n), _f64(_as_float(a_delta_max_in)), _f64(_as_float(a_delta_min_in)),
-        _f64(_as_float(search_direction)), _f64(_as_float(a_abs_max_in)), _f64(_as_float(a_abs_min_in)),
+        _f64(_as_float(search_direction)), *c.scalar_in(a_abs_max_in), *c.scalar_in(a_abs_min_in),
         _vp(vmx.data_ptr()), _vp(vmn.data_ptr()), _i64(m), _vp(n_max_out.data_ptr()), _vp(n_min_out.data_ptr()),
         *_tail(fatal, vt_max_out.device))
 

@@ -179,8 +179,9 @@ const char* dspb_fatal_message(int code);
   /* get_multi_local_extrema.py:12-306 ; vt_max/vt_min [n_rows, m], n_max/n_min uint32 [n_rows] */ \
   int dspb_get_multi_local_extrema##SFX(DSPB_WAVE_IN(w_in), int64_t n_rows, int64_t n,             \
                                         double a_delta_max, double a_delta_min,                    \
-                                        double search_direction, double a_abs_max,                 \
-                                        double a_abs_min, void* vt_max, void* vt_min, int64_t m,   \
+                                        double search_direction, DSPB_SCALAR(a_abs_max),           \
+                                        DSPB_SCALAR(a_abs_min), void* vt_max, void* vt_min,        \
+                                        int64_t m,                                                 \
                                         uint32_t* n_max, uint32_t* n_min, DSPB_TAIL);              \
   /* recursive_filter.py:12-93 ; a[p], b[q] host doubles (q <= 3) */                               \
   int dspb_recursive_filter##SFX(DSPB_WAVE_IN(w_in), int64_t n_rows, int64_t n, const double* a,   \
@@ -234,6 +235,15 @@ DSPB_DECLARE(_f64)
 
 DSPB_DECLARE_SIPM(_f32)
 DSPB_DECLARE_SIPM(_f64)
+
+/* VectorOfVectors output compaction on the device (LGDOVectorOfVectorsIOManager.write, processing_chain.py:2230-2260):
+ * lens uint32[n_rows] (clamped to `width`) -> absolute end offsets int64[n_rows] starting from `base` and the column's
+ * cumulative_length uint32[n_rows]; then the padded block [n_rows, width] of elem_bytes (2 / 4 / 8) byte elements ->
+ * flat[0 .. ends[n_rows - 1] - base). */
+int dspb_vov_offsets(const uint32_t* lens, int64_t n_rows, int64_t width, int64_t base, int64_t* ends,
+                     uint32_t* cumulative_length, void* stream);
+int dspb_vov_compact(const void* block, int64_t row_stride, int32_t elem_bytes, const uint32_t* lens, int64_t width,
+                     const int64_t* ends, int64_t n_rows, int64_t base, void* flat, void* stream);
 
 /* ---- fused waveform-resident chain program (see DESIGN.md "chain compiler") ---------
  * A program is a flat int32/double blob produced by the host chain compiler

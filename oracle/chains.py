@@ -150,3 +150,31 @@ def sipm_chain(values: np.ndarray, baseline: np.ndarray, keep_waveforms: bool = 
     if keep_waveforms:
         o.update(wf_blsub=blsub, wf_mw=mw, curr=curr)
     return o
+
+
+def sipm_lar_chain(values: np.ndarray, gauss_width: float = 1.0, gauss_trunc: float = 4.0, dt_ns: float = 16.0) -> dict:
+    """The reference's SiPM / LAr chain (tests/configs/sipm-dsp-config.json), sequenced like processing_chain.py does:
+    the float64 gaussian kernel forces the float64 type loops downstream.  Returns the padded per-row lists, their
+    lengths and the ragged (VectorOfVectors) form of the two outputs; `trigger_pos` in ns ((idx + t0 / dt) * dt)."""
+    from oracle import sipm_oracle as S
+
+    o = {}
+    k = S.gaussian_filter1d(gauss_width, gauss_trunc, np.float64)
+    wf_gaus = S.reflected_convolve_wf(values.astype(np.float64), k)
+    curr = O.avg_current(wf_gaus, 5)
+    hw, hb = S.histogram(curr, 100)
+    _, _, fwhm = S.histogram_stats(hw, hb, np.nan)
+    n_rows = len(values)
+    vmax = np.empty((n_rows, 20))
+    nmax = np.empty(n_rows, np.uint32)
+    for r in range(n_rows):      # per-row absolute threshold 3 * fwhm (the C oracle takes one value per call)
+        vm, _, nm, _ = O.get_multi_local_extrema(curr[r], 5.0, 0.1, 1, 3.0 * fwhm[r], 0.0, 20)
+        vmax[r], nmax[r] = vm, nm
+    trig, no = S.peak_snr_threshold(curr, vmax, 0.8, 10)
+    en = S.multi_a_filter(curr, trig)
+    o.update(curr=curr, fwhm=fwhm, vt_max_candidate=vmax, n_max=nmax, trigger_pos_samples=trig, n_trig=no, energies_padded=en)
+    o["cumulative_length"] = np.cumsum(no.astype(np.int64)).astype(np.uint32)
+    mask = np.arange(20)[None, :] < no[:, None]
+    o["trigger_pos_flat"] = trig[mask] * dt_ns
+    o["energies_flat"] = en[mask]
+    return o

@@ -82,6 +82,47 @@ def test_reference_config_compiles_to_the_same_plan():
     assert a[1] == b[1] and a[2] == b[2] and a[3] == b[3]
 
 
+REF_SIPM = "/root/reference/tests/configs/sipm-dsp-config.json"
+SIPM_LAR = os.path.join(os.path.dirname(ICPC), "sipm_lar.yaml")
+
+
+def sipm_plan(cfg, db=None):
+    from dspeed_b200 import synth
+
+    n = 8
+    wf = tables.WaveformTable(size=n, t0=0, t0_units="ns", dt=16, dt_units="ns",
+                              values=synth.sipm_waveforms(n, seed=1)["values"].numpy())
+    chain, _, tb_out = build_processing_chain(cfg, tables.Table({"waveform": wf}, size=n), db_dict=db, block_width=16, device="meta")
+    return chain, [str(pm) for pm in chain._proc_managers], {k: (type(v).__name__, dict(v.attrs)) for k, v in tb_out.items()}
+
+
+def test_sipm_lar_plan():
+    """the reference's SiPM chain: float64 loops forced by the 'd' gaussian kernel, a per-event threshold expression,
+    variable-length (VectorOfVectors) outputs whose lengths are other outputs of the chain"""
+    chain, procs, cols = sipm_plan(yaml.safe_load(open(SIPM_LAR)))
+    assert procs == [
+        "reflected_convolve_wf(waveform, gaus_kernel, wf_gaus)", "avg_current(wf_gaus, 5, curr)",
+        "histogram(curr, hist_weights, hist_borders)", "histogram_stats(hist_weights, hist_borders, idx_out_c, max_out, fwhm, nan)",
+        "multiply(3, fwhm, (3*fwhm))",
+        "get_multi_local_extrema(curr, 5, 0.1, 1, (3*fwhm), 0, vt_max_candidate_out, vt_min_out, n_max_out, n_min_out)",
+        "peak_snr_threshold(curr, vt_max_candidate_out, 0.8, 10, trigger_pos, no_out)", "multi_a_filter(curr, trigger_pos, energies)"]
+    assert cols == {"energies": ("VectorOfVectors", {"units": "ADC"}), "trigger_pos": ("VectorOfVectors", {"units": "ns"})}
+    v = chain._vars_dict
+    assert str(v["wf_gaus"].dtype) == "float64" and str(v["curr"].dtype) == "float64" and v["curr"].shape == (1995,)
+    assert v["gaus_kernel"].is_const and v["gaus_kernel"].shape == (9,)          # const-folded at build time
+    assert v["trigger_pos"].vector_len is v["no_out"] and v["energies"].shape == (20,)
+    # database override of the kernel width changes the (const-folded) kernel length
+    chain2, _, _ = sipm_plan(yaml.safe_load(open(SIPM_LAR)), db={"gauss": {"width": 2, "trunc": 3}})
+    assert chain2._vars_dict["gaus_kernel"].shape == (13,)
+
+
+@pytest.mark.skipif(not os.path.exists(REF_SIPM), reason="reference tree not present (GPU box)")
+def test_reference_sipm_config_compiles_to_the_same_plan():
+    a = sipm_plan(json.load(open(REF_SIPM)))
+    b = sipm_plan(yaml.safe_load(open(SIPM_LAR)))
+    assert a[1] == b[1] and a[2] == b[2]
+
+
 def test_database_overrides_and_errors():
     cfg = yaml.safe_load(open(ICPC))
     _, procs, _, _ = plan(cfg, db={"ttrap": {"rise": "8*us", "flat": "2*us"}, "pz": {"tau": "400*us"}})
