@@ -42,6 +42,13 @@ SIn<T> mk_sin(const void* p, int64_t stride, double imm) {
   return SIn<T>{reinterpret_cast<const T*>(p), stride, (T)imm};
 }
 
+// start + i * step with both roundings (np.linspace / numba evaluate the product and the sum separately; the compiler
+// would contract them into one FMA)
+template <typename T>
+__device__ __forceinline__ double lin(T start, int i, double step) {
+  return __dadd_rn((double)start, __dmul_rn((double)i, step));
+}
+
 // block-wide min / max / any-NaN of a row (TPB threads); results broadcast through shared memory
 template <typename T>
 __device__ void row_minmax(const void* w, int dt, long long base, int n, T& mn, T& mx, int& has_nan, T* sh) {
@@ -110,7 +117,7 @@ __global__ void __launch_bounds__(TPB) k_histogram(const void* w, long long w_rs
     const T b0 = mn;   // borders[0] = (T)(double)mn
     if (need_pass1) {
       if (!MODE)
-        for (int i = threadIdx.x; i <= nb; i += TPB) bo[i] = i == nb ? mx : (T)((double)mn + (double)i * step);
+        for (int i = threadIdx.x; i <= nb; i += TPB) bo[i] = i == nb ? mx : (T)lin(mn, i, step);
       if (delta != 0.0) {
         for (int i = threadIdx.x; i < n; i += TPB) {
           const T v = ldw<T>(w, w_dt, base + i);
@@ -136,7 +143,7 @@ __global__ void __launch_bounds__(TPB) k_histogram(const void* w, long long w_rs
           int am = 0;
           for (int i = 1; i < nb; i++)
             if (cnt[i] > cnt[am]) am = i;
-          const T bam = am == nb ? mx : (T)((double)mn + (double)am * step);
+          const T bam = am == nb ? mx : (T)lin(mn, am, step);
           c = (double)bam + 0.5 * delta;
           c = rint(c / (double)bw) * (double)bw;
         }
@@ -144,10 +151,11 @@ __global__ void __launch_bounds__(TPB) k_histogram(const void* w, long long w_rs
       s_center = c;
     }
     __syncthreads();
-    const double hist_min = s_center - (double)bw * (double)(nb / 2) - 0.5 * (double)bw;
+    // (explicit roundings: numpy evaluates every product and sum separately, the compiler would contract them into FMAs)
+    const double hist_min = __dsub_rn(__dsub_rn(s_center, __dmul_rn((double)bw, (double)(nb / 2))), 0.5 * (double)bw);
     for (int i = threadIdx.x; i <= nb; i += TPB) {
       cnt[i] = 0;
-      bo[i] = (T)(hist_min + (double)bw * (double)i);
+      bo[i] = (T)__dadd_rn(hist_min, __dmul_rn((double)bw, (double)i));
     }
     __syncthreads();
     const T e0 = (T)hist_min;

@@ -772,6 +772,27 @@ class FusedChain:
             return man.io_wf.t0.nda
         return man.io_array.nda if hasattr(man, "io_array") else man.io_buf
 
+    @staticmethod
+    def _t0_source(chain, out_man):
+        """input `t0` column that a waveform output's per-event offset variable mirrors (same block buffer), or
+        NotFusable when the offset is derived (another unit system / a conversion): those chains take the
+        per-processor path, where the conversion managers fill it"""
+        from . import processing_chain as pc
+
+        for m in chain._input_managers.values():
+            if (isinstance(m, pc.WaveformIOManager) and m.variable_t0 and isinstance(out_man.t0_var, torch.Tensor)
+                    and _storage(m.t0_var) == _storage(out_man.t0_var)
+                    and m.t0_var.storage_offset() == out_man.t0_var.storage_offset()):
+                return m.io_wf.t0.nda
+        raise NotFusable("waveform output whose per-event t0 is not an input column")
+
+    def _check_outputs(self, chain):
+        from . import processing_chain as pc
+
+        for man in chain._output_managers.values():
+            if isinstance(man, pc.WaveformIOManager) and man.variable_t0:
+                self._t0_source(chain, man)
+
     def _resident(self, src) -> bool:
         """is this input column consumed in place (already on the device, same dtype, unit stride)?"""
         idx, man, what, buf, staging = src
@@ -893,7 +914,15 @@ class FusedChain:
                 chain.stats["launches"] += 1
                 chain.stats["blocks"] += 1
                 for out_man in copied:
-                    out_man.write(begin, end)
+                    if isinstance(out_man, pc.WaveformIOManager) and out_man.variable_t0:
+                        # per-event t0 of a waveform output: the rows of the input column the offset variable mirrors
+                        # (the block's offset buffer is only a staging area here, and not even that for device-resident
+                        # inputs or chains whose kernel never reads t0)
+                        col = self._t0_source(chain, out_man)
+                        t = col if isinstance(col, torch.Tensor) else torch.from_numpy(np.asarray(col))
+                        out_man.write(begin, end, t0_src=t[begin:end])
+                    else:
+                        out_man.write(begin, end)
             compute.synchronize()
             # data-dependent DSPFatal conditions are recorded on the device with their row: one
             # check per call (the reference raises after the offending block, :1156-1159)
@@ -926,12 +955,14 @@ def try_fuse(chain) -> bool:
         # short waveforms (<= 2048 samples): one warp per waveform, vector outputs supported
         try:
             chain._fused = warpchain.WarpChain(chain)
+            chain._fused._check_outputs(chain)
             log.debug(f"warp-per-waveform chain kernel:\n{chain._fused.program_text}")
             return True
         except NotFusable as e:
             chain._not_warp_reason = str(e)
         try:
             chain._fused = codegen.SpecChain(chain)
+            chain._fused._check_outputs(chain)
             log.debug(f"specialised chain kernel:\n{chain._fused.program_text}")
             return True
         except NotFusable as e:
@@ -939,6 +970,7 @@ def try_fuse(chain) -> bool:
             chain._not_specialised_reason = str(e)
     try:
         chain._fused = FusedChain(chain)
+        chain._fused._check_outputs(chain)
         log.debug(f"fused chain program:\n{chain._fused.program_text}")
         return True
     except NotFusable as e:

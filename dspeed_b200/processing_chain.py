@@ -1352,6 +1352,10 @@ class VectorOfVectorsIOManager(IOManager):
         self.raw_var = None
         self.len_var = var.vector_len.get_buffer()
         self.set_buffer(io_vov)
+        if var.shape is not auto:
+            # the buffer in the column's unit system now: a coordinate variable (e.g. peak positions in ns) gets its
+            # conversion manager appended at build time, not after the first block has already run
+            self.raw_var = self.var.get_buffer(self.unit)
 
     def set_buffer(self, io_vov) -> None:
         if "units" not in io_vov.attrs and self.var.unit is not None:
@@ -1501,7 +1505,9 @@ class WaveformIOManager(IOManager):
             src = _as_tensor(self.io_wf.t0.nda)[start:end]
             self.t0_var[0 : end - start].copy_(src, non_blocking=True)
 
-    def write(self, start: int, end: int) -> None:
+    def write(self, start: int, end: int, t0_src=None) -> None:
+        """`t0_src`: the per-event offsets of rows [start, end) when the caller did not fill the block's offset
+        variable (the fused tiers never run the input managers' read(): they hand over the input column's rows)"""
         if len(self.io_wf) < end:
             self.io_wf.resize(end)
         if not self._is_output_target:
@@ -1509,7 +1515,8 @@ class WaveformIOManager(IOManager):
             self._is_output_target = True
         self.val_ioman.write(start, end)
         if self.variable_t0:
-            _as_tensor(self.io_wf.t0.nda)[start:end].copy_(self.t0_var[0 : end - start], non_blocking=True)
+            src = self.t0_var[0 : end - start] if t0_src is None else t0_src
+            _as_tensor(self.io_wf.t0.nda)[start:end].copy_(src, non_blocking=True)
 
     def __str__(self) -> str:
         return f"{self.wf_var} linked to WaveformTable(values({self.val_ioman}))"

@@ -692,12 +692,20 @@ def _list2d(c, a, T, what):
     return t, _vp(t.data_ptr()), _i64(rs), t.shape[-1]
 
 
+def _rows_of_wave(c, w_in, *more):
+    """row count of a call whose list-valued operands have their own core dimensions: a 1-D waveform is ONE row"""
+    if isinstance(w_in, torch.Tensor) and w_in.ndim == 1:
+        c.n_rows = 1
+        return 1
+    return c.rows_from(w_in, *[m for m in more if isinstance(m, torch.Tensor) and m.ndim >= 2])
+
+
 @_register("histogram", "(n),(m),(p)", ["fff->", "ddd->"], 2)
 def _histogram(w_in, weights_out, borders_out, fatal=None):
     """histogram.py:14-89"""
     T = _out_T(weights_out)
     c = _Call(T, weights_out.device)
-    c.rows_from(w_in, weights_out)
+    _rows_of_wave(c, w_in, weights_out)
     wi, n = c.wave_in(w_in)
     _, wp, wrs, m = _list2d(c, weights_out, T, "weights_out")
     _, bp, brs, p = _list2d(c, borders_out, T, "borders_out")
@@ -710,7 +718,7 @@ def _histogram_around_mode(w_in, center, bin_width, weights_out, borders_out, fa
     """histogram.py:92-204"""
     T = _out_T(weights_out)
     c = _Call(T, weights_out.device)
-    c.rows_from(w_in, center, bin_width, weights_out)
+    _rows_of_wave(c, w_in, weights_out)
     wi, n = c.wave_in(w_in)
     _, wp, wrs, m = _list2d(c, weights_out, T, "weights_out")
     _, bp, brs, p = _list2d(c, borders_out, T, "borders_out")
@@ -723,7 +731,7 @@ def _histogram_stats(weights_in, edges_in, mode_out, max_out, fwhm_out, max_in, 
     """histogram_stats.py:146-261 (outputs are arguments 3-5, `max_in` is the last INPUT, like the reference)"""
     T = _out_T(max_out)
     c = _Call(T, max_out.device)
-    c.rows_from(weights_in, max_out)
+    _rows_of_wave(c, weights_in)
     _, wp, wrs, m = _list2d(c, weights_in.to(T) if weights_in.dtype != T else weights_in, T, "weights_in")
     _, ep, ers, p = _list2d(c, edges_in.to(T) if edges_in.dtype != T else edges_in, T, "edges_in")
     return _fn("dspb_histogram_stats", T)(wp, wrs, _i64(m), ep, ers, _i64(p), _i64(c.n_rows), c.scalar_out(mode_out),
@@ -736,7 +744,7 @@ def _histogram_peakstats(weights_in, edges_in, max_in, skip_zeroes, width_type, 
     """histogram_stats.py:12-143"""
     T = _out_T(mode_out)
     c = _Call(T, mode_out.device)
-    c.rows_from(weights_in, mode_out)
+    _rows_of_wave(c, weights_in)
     _, wp, wrs, m = _list2d(c, weights_in.to(T) if weights_in.dtype != T else weights_in, T, "weights_in")
     _, ep, ers, p = _list2d(c, edges_in.to(T) if edges_in.dtype != T else edges_in, T, "edges_in")
     return _fn("dspb_histogram_peakstats", T)(wp, wrs, _i64(m), ep, ers, _i64(p), _i64(c.n_rows), *c.scalar_in(max_in),
@@ -749,7 +757,7 @@ def _peak_snr_threshold(w_in, idx_in, ratio_in, width_in, idx_out, n_idx_out, fa
     """peak_snr_threshold.py:11-71"""
     T = _out_T(idx_out)
     c = _Call(T, idx_out.device)
-    c.rows_from(w_in, idx_out)
+    _rows_of_wave(c, w_in, idx_out)
     wi, n = c.wave_in(w_in)
     _, ip, irs, m = _list2d(c, idx_in, T, "idx_in")
     _, op, ors, mo = _list2d(c, idx_out, T, "idx_out")
@@ -764,7 +772,7 @@ def _multi_a_filter(w_in, vt_maxs_in, va_max_out, fatal=None):
     """multi_a_filter.py:11-57"""
     T = _out_T(va_max_out)
     c = _Call(T, va_max_out.device)
-    c.rows_from(w_in, va_max_out)
+    _rows_of_wave(c, w_in, va_max_out)
     wi, n = c.wave_in(w_in)
     _, ip, irs, m = _list2d(c, vt_maxs_in, T, "vt_maxs_in")
     _, op, ors, mo = _list2d(c, va_max_out, T, "va_max_out")

@@ -379,3 +379,44 @@ def test_tiny_chain_with_little_scalar_work_does_not_deadlock():
     ref = O.pole_zero(O.bl_subtract(vals.astype(np.float32), bl.astype(np.float32)), np.float32(27460.5))
     PT.assert_float_close("wf_pz", out["wf_pz"].values.nda, ref, rtol=1e-6)
     PT.assert_float_close("pz_max", out["pz_max"].nda, ref.max(axis=1), rtol=1e-6, scale=np.abs(ref).max())
+
+
+@pytest.mark.parametrize("case", ["host_blocks", "device_resident", "kernel_ignores_t0"])
+def test_waveform_outputs_carry_the_per_event_t0(case):
+    """A waveform OUTPUT copies the per-event t0 of its rows (reference WaveformIOManager.write, processing_chain.py:
+    2344-2360).  The fused tiers never run the input managers' read(), so the offsets come straight from the input
+    column: more than two host-staged blocks (both staging sets), device-resident inputs (nothing staged), and a chain
+    whose kernel never reads t0 at all."""
+    import torch
+
+    from dspeed_b200 import synth, tables
+    from dspeed_b200.build_dsp import build_dsp
+
+    n = 1000
+    d = synth.hpge_waveforms(n, seed=9)
+    vals, bl = d["values"].numpy(), d["baseline"].numpy()
+    t0 = (np.arange(n, dtype=np.float64) * 48.0 + 160.0)          # ns, a different offset for every event
+    dt = np.full(n, 16.0)
+    cfg = {"outputs": ["wf_blsub", "wf_max"] + ([] if case == "kernel_ignores_t0" else ["tp_max"]), "processors": {
+        "tp_min, tp_max, wf_min, wf_max": {"function": "dspeed.processors.min_max(waveform, tp_min, tp_max, wf_min, wf_max)",
+                                           "unit": ["ns", "ns", "ADC", "ADC"]},
+        "wf_blsub": "dspeed.processors.bl_subtract(waveform, baseline, wf_blsub(unit='ADC'))"}}
+    if case == "device_resident":
+        dev = torch.device("cuda", 0)
+        vals_t, bl_t = torch.from_numpy(vals).to(dev), torch.from_numpy(bl).to(dev)
+        t0_t, dt_t = torch.from_numpy(t0).to(dev), torch.from_numpy(dt).to(dev)
+    else:
+        vals_t, bl_t, t0_t, dt_t = vals, bl, t0, dt
+    wf = tables.WaveformTable(size=n, t0=tables.Array(t0_t, attrs={"units": "ns"}), dt=tables.Array(dt_t, attrs={"units": "ns"}),
+                              values=vals_t)
+    out = build_dsp(tables.Table({"waveform": wf, "baseline": tables.Array(bl_t)}, size=n), dsp_config=cfg, block_width=300)
+    assert out.proc_chain._fused is not None, getattr(out.proc_chain, "_not_fused_reason", None)
+    got_t0 = out["wf_blsub"].t0.nda
+    got_t0 = got_t0.cpu().numpy() if hasattr(got_t0, "cpu") else np.asarray(got_t0)
+    assert np.array_equal(got_t0, t0)
+    w = out["wf_blsub"].values.nda
+    w = w.cpu().numpy() if hasattr(w, "cpu") else np.asarray(w)
+    assert np.array_equal(w, vals.astype(np.float32) - bl.astype(np.float32)[:, None])
+    if case != "kernel_ignores_t0":
+        tp = np.asarray(out["tp_max"].nda.cpu() if hasattr(out["tp_max"].nda, "cpu") else out["tp_max"].nda)
+        assert np.array_equal(tp, (np.argmax(vals, 1) * 16.0 + t0).astype(np.float32))

@@ -48,6 +48,13 @@ def _worker(rank, world, port, n_rows, q):
             "vt_max": tables.ArrayOfEqualSizedArrays(np.where(np.arange(20)[None, :] < (rows % 5)[:, None],
                                                               rows[:, None] + np.arange(20)[None, :], np.nan).astype(np.float32)),
             "n_max": tables.Array((rows % 5).astype(np.uint32)),
+            # variable-length (VectorOfVectors) column: row r holds r % 4 entries r, r + 0.5, ...
+            "trigger_pos": tables.VectorOfVectors(
+                flattened_data=np.concatenate([r + 0.5 * np.arange(r % 4) for r in rows] + [np.zeros(0)]).astype(np.float64),
+                cumulative_length=np.cumsum(rows % 4).astype(np.uint32), attrs={"units": "ns"}),
+            # waveform output with a per-event t0
+            "wf_out": tables.WaveformTable(size=e - b, t0=tables.Array(rows * 16.0, attrs={"units": "ns"}), dt=16, dt_units="ns",
+                                           values=np.repeat(rows[:, None], 4, axis=1).astype(np.float32)),
         }, size=e - b)
         full = parallel.gather_table(local, n_rows, dst=0)
         if rank == 0:
@@ -59,7 +66,13 @@ def _worker(rank, world, port, n_rows, q):
                   and np.asarray(full["n_max"].nda).dtype == np.uint32
                   and np.array_equal(np.asarray(full["n_max"].nda), (np.arange(n_rows) % 5).astype(np.uint32))
                   and np.array_equal(np.isnan(np.asarray(full["vt_max"].nda)).sum(axis=1), 20 - np.arange(n_rows) % 5)
-                  and np.array_equal(np.asarray(full["vt_max"].nda)[1::5, 0], np.arange(n_rows, dtype=np.float32)[1::5]))
+                  and np.array_equal(np.asarray(full["vt_max"].nda)[1::5, 0], np.arange(n_rows, dtype=np.float32)[1::5])
+                  and np.array_equal(np.asarray(full["trigger_pos"].cumulative_length.nda), np.cumsum(np.arange(n_rows) % 4))
+                  and all(np.array_equal(full["trigger_pos"][r], r + 0.5 * np.arange(r % 4)) for r in range(n_rows))
+                  and full["trigger_pos"].attrs["units"] == "ns"
+                  and np.array_equal(np.asarray(full["wf_out"].t0.nda), np.arange(n_rows) * 16.0)
+                  and np.array_equal(np.asarray(full["wf_out"].values.nda)[:, 3], np.arange(n_rows, dtype=np.float32))
+                  and float(np.asarray(full["wf_out"].dt.nda)[0]) == 16.0)
             q.put(bool(ok))
         else:
             assert full is None
@@ -67,8 +80,10 @@ def _worker(rank, world, port, n_rows, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_rows", [11, 64])
+@pytest.mark.parametrize("n_rows", [1, 11, 64])
 def test_gather_of_output_tables_gloo_world2(n_rows):
+    """one packed gather for every fixed-shape column (+ one for the ragged payloads); n_rows = 1: rank 1's shard is
+    empty"""
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
