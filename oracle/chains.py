@@ -155,7 +155,10 @@ def sipm_chain(values: np.ndarray, baseline: np.ndarray, keep_waveforms: bool = 
 def sipm_lar_chain(values: np.ndarray, gauss_width: float = 1.0, gauss_trunc: float = 4.0, dt_ns: float = 16.0) -> dict:
     """The reference's SiPM / LAr chain (tests/configs/sipm-dsp-config.json), sequenced like processing_chain.py does:
     the float64 gaussian kernel forces the float64 type loops downstream.  Returns the padded per-row lists, their
-    lengths and the ragged (VectorOfVectors) form of the two outputs; `trigger_pos` in ns ((idx + t0 / dt) * dt)."""
+    lengths and the ragged (VectorOfVectors) form of the two outputs.  `trigger_pos` stays a SAMPLE index although the
+    config labels it "ns": wf_gaus / curr are declared with their own length expressions ("(n),(m),(p)" signature),
+    so they inherit no coordinate grid from `waveform` (processing_chain.py:1654-1715) and nothing downstream is a
+    coordinate -- the same quirk SURVEY Appendix C notes for tp_aoe_max of the ICPC chain."""
     from oracle import sipm_oracle as S
 
     o = {}
@@ -175,6 +178,6 @@ def sipm_lar_chain(values: np.ndarray, gauss_width: float = 1.0, gauss_trunc: fl
     o.update(curr=curr, fwhm=fwhm, vt_max_candidate=vmax, n_max=nmax, trigger_pos_samples=trig, n_trig=no, energies_padded=en)
     o["cumulative_length"] = np.cumsum(no.astype(np.int64)).astype(np.uint32)
     mask = np.arange(20)[None, :] < no[:, None]
-    o["trigger_pos_flat"] = trig[mask] * dt_ns
+    o["trigger_pos_flat"] = trig[mask]
     o["energies_flat"] = en[mask]
     return o

@@ -46,7 +46,7 @@ def test_sipm_lar_chain_matches_oracle(block_width):
     assert np.abs(en - o["energies_flat"]).max() <= 1e-12 * np.abs(o["energies_flat"]).max()
     # row access of the ragged column
     r = int(np.argmax(o["n_trig"]))
-    assert np.array_equal(out["trigger_pos"][r], o["trigger_pos_samples"][r, : o["n_trig"][r]] * 16.0)
+    assert np.array_equal(out["trigger_pos"][r], o["trigger_pos_samples"][r, : o["n_trig"][r]])
 
 
 def test_vov_compaction_kernels():
