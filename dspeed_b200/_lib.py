@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 LIB_PATH = os.path.join(_HERE, "libdspeed_b200.so")
-SOURCES = ["processors.cu", "conv.cu", "fused.cu", "conv_tc.cu", "sipm.cu"]
+SOURCES = ["processors.cu", "conv.cu", "fused.cu", "conv_tc.cu", "sipm.cu", "glue.cu"]
 HEADERS = ["common.cuh", "row_ops.cuh", "conv_ops.cuh", "conv_seg.cuh"]
 
 NVCC_FLAGS = [

@@ -236,6 +236,27 @@ DSPB_DECLARE(_f64)
 DSPB_DECLARE_SIPM(_f32)
 DSPB_DECLARE_SIPM(_f64)
 
+/* ---- numpy-level glue (csrc/glue.cu): the ufuncs of the expression parser (processing_chain.py:46-59), `where`
+ * (where.py:12-54), round / floor / ceil / trunc to nearest (round_to_nearest.py:11-200), unit conversion
+ * (unit_conversion.py:16-78), astype (processing_chain.py:1269-1300) -- out[r, j] = op(a[r, j], b[r, j], c[r, j]).
+ *   op    0 add 1 subtract 2 multiply 3 divide 4 floor_divide 5 negative 6 absolute 7 sqrt 8 maximum 9 minimum
+ *         16 equal 17 not_equal 18 less 19 less_equal 20 greater 21 greater_equal 22 isnan 23 isfinite
+ *         32 where(a ? b : c) 33 copy (astype) 40..43 b * {rint, floor, ceil, trunc}(a / b) 48 (a + b) * ratio - c
+ *   loop  the type operands are converted to and the operation runs in: 0 float32, 1 float64, 2 int64
+ *   dtype codes: DSPB_F32 .. DSPB_U32 (0..5), 6 int64, 7 bool, 8 int8, 9 uint8, 10 uint64
+ *   an operand is (ptr, row stride, column stride, dtype, immediate): ptr NULL = the immediate; stride 0 broadcasts
+ *   mode (op 48): 0 none 1 rint 2 floor 3 ceil 4 trunc */
+int dspb_glue(int32_t op, int32_t loop, int64_t rows, int64_t inner, void* out, int64_t out_rs, int32_t out_dt,
+              const void* a, int64_t a_rs, int64_t a_cs, int32_t a_dt, double a_imm,
+              const void* b, int64_t b_rs, int64_t b_cs, int32_t b_dt, double b_imm,
+              const void* c, int64_t c_rs, int64_t c_cs, int32_t c_dt, double c_imm, double ratio, int32_t mode,
+              void* stream);
+/* get.py:10-91: out[r] = a[r, idx[r]] (negative indices wrap); use_default: `dflt` replaces out-of-range / NaN entries,
+ * else an out-of-range index records fatal code 32 */
+int dspb_glue_get(int32_t loop, int64_t rows, const void* a, int64_t a_rs, int32_t a_dt, int64_t n, const void* idx,
+                  int64_t idx_rs, int32_t idx_dt, double idx_imm, const void* dflt, int64_t dflt_rs, int32_t dflt_dt,
+                  double dflt_imm, int32_t use_default, void* out, int32_t out_dt, int32_t* fatal, void* stream);
+
 /* VectorOfVectors output compaction on the device (LGDOVectorOfVectorsIOManager.write, processing_chain.py:2230-2260):
  * lens uint32[n_rows] (clamped to `width`) -> absolute end offsets int64[n_rows] starting from `base` and the column's
  * cumulative_length uint32[n_rows]; then the padded block [n_rows, width] of elem_bytes (2 / 4 / 8) byte elements ->

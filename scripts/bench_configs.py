@@ -160,8 +160,9 @@ def conv_kernels(K, dev):
         rng = np.random.default_rng(K)
         lag = np.abs(np.arange(K)[:, None] - np.arange(K)[None, :])
         nmat = (np.eye(K) * 16.0 + 4.0 * np.exp(-lag / 64.0)).astype(np.float32)
-        ref = (1.0 - np.exp(-np.arange(K) / max(4.0, 0.02 * K))).astype(np.float32)
-        ref *= np.exp(-np.arange(K) / 27460.5).astype(np.float32)
+        t = np.arange(2 * K) - K // 2            # reference pulse of twice the kernel length (energy_kernels.py:232-246)
+        ref = np.where(t >= 0, (1.0 - np.exp(-np.clip(t, 0, None) / max(4.0, 0.02 * K))) * np.exp(-np.clip(t, 0, None) / 27460.5), 0.0)
+        ref = ref.astype(np.float32)
         kd = torch.empty(K, dtype=torch.float32, device=dev)
         P.dplms(torch.from_numpy(nmat).to(dev), torch.from_numpy(ref).to(dev), np.float32(1.0), np.float32(1.0), np.float32(1.0),
                 np.float32(1.0), kd)
