@@ -1627,7 +1627,7 @@ class SpecChain(FusedChain):
             def local(f, extra=""):
                 full = f"{f}_local<true>({r}, {extra}16 * tid, {lo}, {hi})"
                 part = f"{f}_local<false>({r}, {extra}16 * tid, {lo}, {hi})"
-                if not partial and t0 == 0 and t1 * CHK >= min(w.n, w1 * 32 * CHK):
+                if not partial and t0 <= w0 * 32 and t1 >= min(w1 * 32, NT):     # every thread of the guarded warps is interior
                     return [f"  {{res}} = {full};   //@X {g_n}"]
                 return [f"  if (tid >= {t0} && tid < {t1}) {{res}} = {full};   //@X {-(-t1 // 32) - t0 // 32}",
                         f"  else if (16 * tid < {hi} && 16 * tid + 16 > {lo}) {{res}} = {part};   //@X {max(1, partial)}"]

@@ -125,6 +125,9 @@ def icpc_report(got: dict, o: dict, waves_of=None, dt_ns: float = 16.0) -> dict:
                         viol.append(f"tp_aoe_max: row {int(r)} differs ({g[r]} vs {o[k][r]})")
                         continue
                     w = cav[j]
+                    if not (0 <= g[r] < len(w)):
+                        viol.append(f"tp_aoe_max: row {int(r)}: index {g[r]} outside the waveform")
+                        continue
                     if abs(float(w[int(g[r])]) - float(w[int(o[k][r])])) > FLOAT_RTOL * np.abs(w).max():
                         viol.append(f"tp_aoe_max: row {int(r)} moved from {o[k][r]} to {g[r]} and the samples differ")
                 if len(bad) > max(1, n // 1000):

@@ -128,7 +128,12 @@ def test_where_and_ternary(raw_tbl):
     assert np.all(np.where(wf < 12100, 0, wf) == wvals(out, "test1")[0])
     assert np.all(np.where(wf < 12100, wf, 0) == wvals(out, "test2")[0])
     tp_min = col(out, "tp_min")
-    for name, first, second in (("test3", tp_min[0], 1), ("test4", tp_min[0], 1000), ("test5", 1, tp_min[1]), ("test6", 1000, tp_min[1])):
+    # a time constant chosen against a coordinate variable becomes a coordinate on that variable's grid (reference
+    # :1392-1409: const / period, is_coord of the variable), so on output it is shifted by the event's t0 like the
+    # variable itself -- the reference test sees the bare constants only because its file has t0 = 0; here row 1 has
+    # t0 = 32 ns
+    for name, first, second in (("test3", tp_min[0], 1 + 32), ("test4", tp_min[0], 1000 + 32), ("test5", 1, tp_min[1]),
+                                ("test6", 1000, tp_min[1])):
         assert out[name].attrs["units"] == "ns", name
         assert col(out, name)[0] == first and col(out, name)[1] == second, name
     with pytest.raises(ProcessingChainError):          # a time and an amplitude have no common unit
