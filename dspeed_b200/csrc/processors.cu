@@ -945,6 +945,8 @@ extern "C" const char* dspb_fatal_message(int code) {
     case DSPB_FATAL_HPS_NAN: return "nan in input weights";
     case DSPB_FATAL_HPS_LEN: return "length edges_in must be exactly 1 + length of weights_in";
     case DSPB_FATAL_HPS_WIDTH_TYPE: return "Unknown width_type, must be [0...4]";
+    case DSPB_FATAL_RCCR2_NAN: return "RC-CR^2 filter produced nans in output.";
+    case DSPB_FATAL_INJ_FRAC: return "frac must be between zero and one.";
     case DSPB_ERR_ROW_TOO_LONG: return "waveform too long for the shared-memory resident layout";
     case DSPB_ERR_UNSUPPORTED: return "argument combination not supported by the device implementation";
   }

@@ -469,6 +469,75 @@ __global__ void k_vov_scatter(const E* block, long long row_stride, const uint32
   for (uint32_t j = lane; j < l; j += 32) flat[dst + j] = block[row * row_stride + j];
 }
 
+// ---- generic recursive (IIR) filters of any order, one thread per row ----------------------------------------------
+// recursive_filter.py:12-93 for len(b) > 3 (the order <= 2 case is the parallel affine scan of processors.cu): the
+// reference's loop itself -- float64 circular buffer initialised with init_out, feed-forward padded with init_in.
+// Rows are independent, so a warp works on 32 rows; the recursion is sequential along the waveform by nature.
+struct IirCoef {
+  double a[16], b[16];
+  int p, q;
+};
+template <typename T>
+__global__ void k_iir_general(const void* w, long long w_rs, int w_dt, long long n_rows, int n, IirCoef cf, SIn<T> init_in,
+                              SIn<T> init_out, T* out, long long o_rs) {
+  const long long row = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (row >= n_rows) return;
+  const long long base = row * w_rs;
+  T* o = out + row * o_rs;
+  const T ii = init_in.get(row), io = init_out.get(row);
+  bool bad = ii != ii || io != io;
+  for (int i = 0; i < n && !bad; i++) {
+    const T v = ldw<T>(w, w_dt, base + i);
+    bad = v != v;
+  }
+  if (bad) {
+    for (int i = 0; i < n; i++) o[i] = (T)NAN;
+    return;
+  }
+  double circ[16];
+  for (int j = 0; j < cf.q; j++) circ[j] = (double)io;
+  for (int i = 0; i < n; i++) {
+    const int ib = i % cf.q;
+    double acc = 0.0;
+    for (int j = 0; j < cf.p; j++) acc = __dadd_rn(acc, __dmul_rn(cf.a[j], j <= i ? (double)ldw<T>(w, w_dt, base + i - j) : (double)ii));
+    for (int j = 1; j < cf.q; j++) {
+      int k = ib - j;
+      if (k < 0) k += cf.q;
+      acc = __dsub_rn(acc, __dmul_rn(cf.b[j], circ[k]));
+    }
+    acc /= cf.b[0];
+    circ[ib] = acc;
+    o[i] = (T)acc;
+  }
+}
+// rc_cr2.py:11-93: matched z-transform RC-CR^2 shaper, float64 state seeded with the first three INPUT samples; the
+// first three outputs are not written by the reference (its output buffers start as zeros: so do they here)
+template <typename T>
+__global__ void k_rc_cr2(const void* w, long long w_rs, int w_dt, long long n_rows, int n, SIn<T> tau_in, T* out, long long o_rs,
+                         int* fatal) {
+  const long long row = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (row >= n_rows) return;
+  const long long base = row * w_rs;
+  T* o = out + row * o_rs;
+  const T tau = tau_in.get(row);
+  const double af = exp(-1.0 / (double)tau);         // (numba: int / float32 is float64, so both loops use float64 here)
+  const double d2 = -3.0 * af, d3 = 3.0 * af * af, d4 = -(af * af * af);
+  double t0 = (double)ldw<T>(w, w_dt, base), t1 = n > 1 ? (double)ldw<T>(w, w_dt, base + 1) : 0.0,
+         t2 = n > 2 ? (double)ldw<T>(w, w_dt, base + 2) : 0.0;
+  bool bad = false;
+  for (int i = 0; i < 3 && i < n; i++) o[i] = (T)0;
+  for (int i = 3; i < n; i++) {
+    const double x0 = (double)ldw<T>(w, w_dt, base + i), x1 = (double)ldw<T>(w, w_dt, base + i - 1),
+                 x2 = (double)ldw<T>(w, w_dt, base + i - 2);
+    const double t3 = __dadd_rn(__dadd_rn(__dadd_rn(__dsub_rn(__dsub_rn(__dmul_rn(-d2, t2), __dmul_rn(d3, t1)), __dmul_rn(d4, t0)), x0),
+                                          __dmul_rn(-2.0, x1)), x2);
+    o[i] = (T)t3;
+    bad |= (t3 != t3);
+    t0 = t1; t1 = t2; t2 = t3;
+  }
+  if (bad) raise_fatal(fatal, DSPB_FATAL_RCCR2_NAN, row);
+}
+
 int grid_rows(long long n_rows) { return (int)(n_rows < 148LL * 16 ? n_rows : 148LL * 16); }
 int last_error() {
   const cudaError_t e = cudaGetLastError();
@@ -562,6 +631,30 @@ int last_error() {
     if (e != cudaSuccess) return -(int)e;                                                                                \
     kern<<<grid_rows(n_rows), TPB, smem, (cudaStream_t)stream>>>(w_in, w_in_row_stride, w_in_dtype, n_rows, (int)n,        \
                                                                  (const T*)kernel, (int)m, (T*)w_out, w_out_row_stride);  \
+    return last_error();                                                                                                 \
+  }                                                                                                                      \
+  extern "C" int dspb_recursive_filter_general##SFX(DSPB_WAVE_IN(w_in), int64_t n_rows, int64_t n, const double* a,        \
+                                                    int64_t p, const double* b, int64_t q, DSPB_SCALAR(init_in),           \
+                                                    DSPB_SCALAR(init_out), DSPB_WAVE_OUT(w_out), DSPB_TAIL) {             \
+    using T = T_;                                                                                                        \
+    (void)fatal;                                                                                                         \
+    if (q == 0) return DSPB_FATAL_RF_B_SCALAR;                                                                            \
+    if (n <= q) return DSPB_FATAL_RF_SHORT;                                                                               \
+    if (p > 16 || q > 16) return DSPB_ERR_UNSUPPORTED;                                                                    \
+    if (n_rows <= 0) return 0;                                                                                           \
+    IirCoef cf;                                                                                                          \
+    cf.p = (int)p; cf.q = (int)q;                                                                                        \
+    for (int j = 0; j < 16; j++) { cf.a[j] = j < p ? a[j] : 0.0; cf.b[j] = j < q ? b[j] : 0.0; }                          \
+    k_iir_general<T><<<(unsigned)((n_rows + 31) / 32), 32, 0, (cudaStream_t)stream>>>(                                    \
+        w_in, w_in_row_stride, w_in_dtype, n_rows, (int)n, cf, SIN(init_in), SIN(init_out), (T*)w_out, w_out_row_stride);  \
+    return last_error();                                                                                                 \
+  }                                                                                                                      \
+  extern "C" int dspb_rc_cr2##SFX(DSPB_WAVE_IN(w_in), int64_t n_rows, int64_t n, DSPB_SCALAR(t_tau), DSPB_WAVE_OUT(w_out), \
+                                  DSPB_TAIL) {                                                                           \
+    using T = T_;                                                                                                        \
+    if (n_rows <= 0) return 0;                                                                                           \
+    k_rc_cr2<T><<<(unsigned)((n_rows + 31) / 32), 32, 0, (cudaStream_t)stream>>>(                                         \
+        w_in, w_in_row_stride, w_in_dtype, n_rows, (int)n, SIN(t_tau), (T*)w_out, w_out_row_stride, fatal);               \
     return last_error();                                                                                                 \
   }                                                                                                                      \
   extern "C" int dspb_gaussian_filter1d##SFX(double sigma, double truncate, void* weights, int64_t length,                \

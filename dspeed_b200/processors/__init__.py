@@ -639,9 +639,146 @@ def _recursive_filter(w_in, a, b, init_in, init_out, w_out, fatal=None):
     if np.isnan(av).any() or np.isnan(bv).any():
         w_out.fill_(float("nan"))
         return 0
+    if bv.size > 3 or av.size > 8:      # beyond the order-2 affine scan: the sequential float64 recursion (csrc/sipm.cu)
+        return _fn("dspb_recursive_filter_general", T)(
+            *wi, _i64(c.n_rows), _i64(n), av.ctypes.data_as(_vp), _i64(av.size), bv.ctypes.data_as(_vp), _i64(bv.size),
+            *c.scalar_in(init_in), *c.scalar_in(init_out), *wo, *_tail(fatal, w_out.device))
     return _fn("dspb_recursive_filter", T)(
         *wi, _i64(c.n_rows), _i64(n), av.ctypes.data_as(_vp), _i64(av.size), bv.ctypes.data_as(_vp), _i64(bv.size),
         *c.scalar_in(init_in), *c.scalar_in(init_out), *wo, *_tail(fatal, w_out.device))
+
+
+# ---- the IIR family built on recursive_filter (pole_zero.py:201-342, rc_cr2.py, iir_filter.py) ------------------------
+def _rc_exp(tau) -> float:
+    """pole_zero.py:13-20"""
+    tau = _as_float(tau)
+    return float(np.exp(-1.0 / tau)) if tau != 0 else 0.0
+
+
+def _first_sample(w_in, T):
+    """w_in[..., 0] as a per-row scalar of the loop's type"""
+    w = w_in if w_in.ndim == 2 else w_in.unsqueeze(0)
+    return w[:, 0].to(T).contiguous()
+
+
+@_register("convolve_exp", "(n),()->(n)", ["ff->f", "dd->d"], 1)
+def _convolve_exp(w_in, tau, w_out, fatal=None):
+    """pole_zero.py:201-232: recursive_filter with a = [1], b = [1, -exp(-1 / tau)], both histories = w_in[0]"""
+    T = _out_T(w_out)
+    x0 = _first_sample(w_in, T)
+    tau_t = np.float32(_as_float(tau)) if T == torch.float32 else _as_float(tau)
+    return _recursive_filter.impl(w_in, np.ones(1), np.array([1.0, -_rc_exp(tau_t)]), x0, x0, w_out, fatal=fatal)
+
+
+@_register("convolve_damped_oscillator", "(n),(),(),()->(n)", ["fddd->f", "dddd->d"], 1)
+def _convolve_damped_oscillator(w_in, tau, omega, phase, w_out, fatal=None):
+    """pole_zero.py:235-281"""
+    T = _out_T(w_out)
+    x0 = _first_sample(w_in, T)
+    rc, om, ph = _rc_exp(tau), _as_float(omega), _as_float(phase)
+    a = np.array([np.cos(ph), -rc * np.cos(om - ph)])
+    b = np.array([1.0, -2 * rc * np.cos(om), rc * rc])
+    return _recursive_filter.impl(w_in, a, b, x0, x0, w_out, fatal=fatal)
+
+
+@_register("inject_damped_oscillation", "(n),(),(),(),()->(n)", ["fdddd->f", "ddddd->d"], 1)
+def _inject_damped_oscillation(w_in, tau, omega, phase, frac, w_out, fatal=None):
+    """pole_zero.py:284-342"""
+    T = _out_T(w_out)
+    fr = _as_float(frac)
+    if not 0 <= fr <= 1:
+        return 37      # DSPB_FATAL_INJ_FRAC ("frac must be between zero and one.")
+    x0 = _first_sample(w_in, T)
+    rc, om, ph = _rc_exp(tau), _as_float(omega), _as_float(phase)
+    cw, cp, cwp = np.cos(om), np.cos(ph), np.cos(om - ph)
+    a = np.array([1 + fr * cp, -(2 * rc * cw + fr * cp + fr * rc * cwp), rc * (rc + fr * cwp)])
+    b = np.array([1.0, -2 * rc * cw, rc * rc])
+    return _recursive_filter.impl(w_in, a, b, x0, 0.0, w_out, fatal=fatal)
+
+
+@_register("rc_cr2", "(n),()->(n)", ["ff->f", "dd->d"], 1)
+def _rc_cr2(w_in, t_tau, w_out, fatal=None):
+    """rc_cr2.py:11-93"""
+    T = _out_T(w_out)
+    c = _Call(T, w_out.device)
+    c.rows_from(w_in, t_tau, w_out)
+    wi, n = c.wave_in(w_in)
+    wo, _ = c.wave_out(w_out, n)
+    return _fn("dspb_rc_cr2", T)(*wi, _i64(c.n_rows), _i64(n), *c.scalar_in(t_tau), *wo, *_tail(fatal, w_out.device))
+
+
+def _iir_processor(a, b, name, init_out):
+    """iir_filter.py:103-113, 161-170, 219-228: a (n)->(n) processor running recursive_filter with designed coefficients;
+    input history w_in[0], output history `init_out` * w_in[0]"""
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+
+    def impl(w_in, w_out, fatal=None):
+        T = _out_T(w_out)
+        x0 = _first_sample(w_in, T)
+        io = 0.0 if init_out == 0 else (x0 if init_out == 1 else (x0.to(torch.float64) * init_out).to(T))
+        return _recursive_filter.impl(w_in, a, b, x0, io, w_out, fatal=fatal)
+
+    return DeviceProcessor(name, "(n)->(n)", ["ff->f", "dd->d"], impl, 1, "recursive_filter with scipy.signal-designed coefficients")
+
+
+def _f_samp(f_samp):
+    """a waveform variable stands for its sampling frequency (iir_filter.py:71-72)"""
+    if hasattr(f_samp, "period") and hasattr(f_samp, "proc_chain"):
+        return 1 / f_samp.period
+    return f_samp
+
+
+def _norm_freq(freq, f_samp, two):
+    def one(f):
+        return float(2 * f / f_samp) if f_samp is not None else float(f)
+
+    if two:
+        if not (hasattr(freq, "__len__") and len(freq) == 2):
+            raise DSPFatal("bandpass / bandstop filter requires two freq values")
+        fc = [one(f) for f in freq]
+        ok = all(0 <= f <= 1 for f in fc)
+    else:
+        fc = one(freq)
+        ok = 0 <= fc <= 1
+    if not ok:
+        raise DSPFatal("Critical frequency must be positive and < nyquist frequency")
+    return fc
+
+
+def iir_filter(freq, order, rp=None, rs=None, f_samp=None, ftype="butter", btype="lowpass"):
+    """iir_filter.py:18-113 -- factory (``init_args`` of a recipe): designs the filter with scipy.signal.iirfilter on the
+    host at set-up time (the reference does the same) and returns the device processor that applies it."""
+    import scipy.signal as sg
+
+    f_samp = _f_samp(f_samp)
+    if btype in ("lowpass", "highpass"):
+        fc = _norm_freq(freq, f_samp, False)
+    elif btype in ("bandpass", "bandstop"):
+        fc = _norm_freq(freq, f_samp, True)
+    else:
+        raise DSPFatal("Invalid type of filter")
+    a, b = sg.iirfilter(order, fc, rp=rp, rs=rs, btype=btype, ftype=ftype)
+    return _iir_processor(a, b, f"{ftype}({freq}, {order}, {btype})", float(np.sum(a) / np.sum(b)))
+
+
+def notch_filter(freq, bandwidth, f_samp=None):
+    """iir_filter.py:115-170"""
+    import scipy.signal as sg
+
+    a, b = sg.iirnotch(_norm_freq(freq, _f_samp(f_samp), False), float(freq / bandwidth))
+    return _iir_processor(a, b, f"notch({freq}, {bandwidth})", 1)
+
+
+def peak_filter(freq, bandwidth, f_samp=None):
+    """iir_filter.py:173-228"""
+    import scipy.signal as sg
+
+    a, b = sg.iirpeak(_norm_freq(freq, _f_samp(f_samp), False), float(freq / bandwidth))
+    return _iir_processor(a, b, f"peak({freq}, {bandwidth})", 0)
+
+
+__all__ += ["iir_filter", "notch_filter", "peak_filter"]
 
 
 # ---- set-up time kernel generators (const-folded by the chain compiler) ------------------

@@ -85,6 +85,8 @@ enum {
   DSPB_FATAL_HPS_NAN = 33,          /* histogram_stats.py:84-85 */
   DSPB_FATAL_HPS_LEN = 34,          /* histogram_stats.py:88-89, 221-222 */
   DSPB_FATAL_HPS_WIDTH_TYPE = 35,   /* histogram_stats.py:142-143 */
+  DSPB_FATAL_RCCR2_NAN = 36,        /* rc_cr2.py:92-93 */
+  DSPB_FATAL_INJ_FRAC = 37,         /* pole_zero.py:316-317 */
   DSPB_ERR_ROW_TOO_LONG = 100,      /* waveform does not fit the shared-memory resident layout */
   DSPB_ERR_UNSUPPORTED = 101
 };
@@ -228,6 +230,13 @@ DSPB_DECLARE(_f64)
   /* convolutions.py:122-182   'same' convolution of the reflect-padded waveform */                                      \
   int dspb_reflected_convolve_wf##SFX(DSPB_WAVE_IN(w_in), int64_t n_rows, int64_t n, const void* kernel, int64_t m,      \
                                       DSPB_WAVE_OUT(w_out), DSPB_TAIL);                                                 \
+  /* recursive_filter.py:12-93 for any order (a[p], b[q] host doubles, p, q <= 16): the sequential float64 recursion */   \
+  int dspb_recursive_filter_general##SFX(DSPB_WAVE_IN(w_in), int64_t n_rows, int64_t n, const double* a, int64_t p,      \
+                                         const double* b, int64_t q, DSPB_SCALAR(init_in), DSPB_SCALAR(init_out),       \
+                                         DSPB_WAVE_OUT(w_out), DSPB_TAIL);                                              \
+  /* rc_cr2.py:11-93 */                                                                                                 \
+  int dspb_rc_cr2##SFX(DSPB_WAVE_IN(w_in), int64_t n_rows, int64_t n, DSPB_SCALAR(t_tau), DSPB_WAVE_OUT(w_out),          \
+                       DSPB_TAIL);                                                                                      \
   /* set-up time kernel generators: gaussian_filter1d.py:46-82, kernels.py:64-103, kernels.py:106-142 */                \
   int dspb_gaussian_filter1d##SFX(double sigma, double truncate, void* weights, int64_t length, void* stream);          \
   int dspb_moving_slope##SFX(void* kernel, int64_t length, void* stream);                                               \

@@ -457,7 +457,55 @@ def sipm_processor_cases(P, synth):
     return g
 
 
+def iir_cases(P, synth):
+    """the IIR family (pole_zero.py:201-342, rc_cr2.py, iir_filter.py) on 3 HPGe rows (1024 samples around the pulse); the iir_filter factories need
+    pint, so their scipy.signal designs are repeated here and applied with the reference's own recursive_filter"""
+    import scipy.signal as sg
+    from dspeed.processors.pole_zero import convolve_damped_oscillator, convolve_exp, inject_damped_oscillation
+    from dspeed.processors.rc_cr2 import rc_cr2
+
+    d = synth.hpge_waveforms(3, seed=4242)
+    vals = d["values"].numpy()[:, 3600:4624].copy()
+    bl = d["baseline"].numpy()
+    g = {"values": vals, "baseline": bl}
+    for dt in (np.float32, np.float64):
+        t = "f" if dt == np.float32 else "d"
+        w = (vals.astype(dt) - bl.astype(dt)[:, None])
+        for tau in (50.0, 400.5):
+            o = np.zeros_like(w)
+            convolve_exp(w, dt(tau), o)
+            g[f"cexp_{t}_{tau}"] = o
+            o = np.zeros_like(w)
+            rc_cr2(w, dt(tau), o)
+            g[f"rccr2_{t}_{tau}"] = o
+        o = np.zeros_like(w)
+        convolve_damped_oscillator(w, 120.0, 0.3, 0.7, o)
+        g[f"cdo_{t}"] = o
+        o = np.zeros_like(w)
+        inject_damped_oscillation(w, 120.0, 0.3, 0.7, 0.05, o)
+        g[f"ido_{t}"] = o
+        for tag, (a, b, gain) in {
+            "butter4_lp": (*sg.iirfilter(4, 0.1, btype="lowpass", ftype="butter"), None),
+            "cheby1_3_hp": (*sg.iirfilter(3, 0.2, rp=1.0, btype="highpass", ftype="cheby1"), None),
+            "butter2_bp": (*sg.iirfilter(2, [0.05, 0.2], btype="bandpass", ftype="butter"), None),
+            "notch": (*sg.iirnotch(0.24, 10.0), 1.0),
+            "peak": (*sg.iirpeak(0.24, 10.0), 0.0),
+        }.items():
+            if gain is None:
+                gain = sum(a) / sum(b)
+            o = np.zeros_like(w)
+            P.recursive_filter(w, a, b, w[..., 0], (gain * w[..., 0]).astype(dt), o)
+            g[f"iir_{tag}_{t}"] = o
+    return g
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "iir":
+        P = import_reference()
+        out_dir = os.path.join(REPO, "tests", "golden")
+        np.savez_compressed(os.path.join(out_dir, "iir_family.npz"), **iir_cases(P, load_synth()))
+        print("iir_family.npz", os.path.getsize(os.path.join(out_dir, "iir_family.npz")))
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "sipm":
         P = import_reference()
         out_dir = os.path.join(REPO, "tests", "golden")
@@ -487,6 +535,7 @@ def main():
     np.savez_compressed(os.path.join(out_dir, "kernels.npz"), **kernel_cases(P))
     np.savez_compressed(os.path.join(out_dir, "sipm_chain.npz"), **sipm_chain(P, synth))
     np.savez_compressed(os.path.join(out_dir, "sipm_processors.npz"), **sipm_processor_cases(P, synth))
+    np.savez_compressed(os.path.join(out_dir, "iir_family.npz"), **iir_cases(P, synth))
     for f in sorted(os.listdir(out_dir)):
         print(f, os.path.getsize(os.path.join(out_dir, f)))
 
