@@ -160,7 +160,7 @@ class FusedChain:
                     all_vars.append(prm)
         self.var_of_storage = {}
         for v in all_vars:
-            bufs = v._buffer if isinstance(v._buffer, list) else [(v._buffer, None)]
+            bufs = v.all_buffers()
             for b, _ in bufs:
                 if isinstance(b, torch.Tensor):
                     self.var_of_storage.setdefault(_storage(b), v)

@@ -43,7 +43,7 @@ from typing import Any
 import numpy as np
 import torch
 
-from . import _lib, numpy_bridge, tables
+from . import _lib, binding, numpy_bridge, recipe, tables
 from . import processors as device_processors
 from .processors import _i32, _i64, _vp
 from .errors import DSPFatal, ProcessingChainError
@@ -167,7 +167,7 @@ class ProcChainVar:
         assert isinstance(proc_chain, ProcessingChain) and isinstance(name, str)
         self.proc_chain = proc_chain
         self.name = name
-        self._buffer = None
+        self._native, self._native_system, self._twins = None, None, []
         self.shape = shape
         self.dtype = dtype
         self.grid = grid
@@ -201,43 +201,73 @@ class ProcChainVar:
             value.update_auto(shape=(), grid=None, unit=None, is_coord=False)
         super().__setattr__(name, value)
 
-    # -- buffers -------------------------------------------------------------------
-    def _make_buffer(self) -> torch.Tensor:
-        lead = 1 if self.is_const else self.proc_chain._block_width
-        return torch.zeros((lead,) + self.shape, dtype=_np2t(self.dtype), device=self.proc_chain.device)
+    # -- device storage -----------------------------------------------------------------------------------------------
+    # A variable owns ONE block buffer in its native unit system (`_native`; coordinates: samples of the producing
+    # waveform's grid).  When somebody asks for it in another unit system (an output column in ns, another waveform's
+    # grid after slicing) a converted twin is created once and a conversion step is appended to the chain behind the
+    # producer; `_twins` remembers them per unit system.  `_native_system` is set by the first request that names one.
+    def _allocate(self) -> torch.Tensor:
+        if self._native is None:
+            for what in ("shape", "dtype"):
+                if getattr(self, what) is auto:
+                    raise ProcessingChainError(f"cannot deduce {what} of {self.name}")
+            rows = 1 if self.is_const else self.proc_chain._block_width
+            self._native = torch.zeros((rows,) + self.shape, dtype=_np2t(self.dtype), device=self.proc_chain.device)
+        return self._native
 
-    def get_buffer(self, unit=None) -> torch.Tensor:
-        if self._buffer is None:
-            if self.shape is auto:
-                raise ProcessingChainError(f"cannot deduce shape of {self.name}")
-            if self.dtype is auto:
-                raise ProcessingChainError(f"cannot deduce dtype of {self.name}")
-            self._buffer = self._make_buffer()
-
+    def _unit_system(self, unit):
+        """the unit system a request means: the variable's own by default; a registry unit stands for a grid of that
+        period without offset; anything else (None, 'ADC', ...) is no system at all"""
         if unit is None:
             unit = self.grid if self.is_coord else self.unit
         if not isinstance(unit, CoordinateGrid) and is_in_registry(unit):
             unit = CoordinateGrid(unit)
+        return unit
 
-        if isinstance(self._buffer, torch.Tensor):
-            if self.is_coord is True:
-                if not isinstance(self.grid, CoordinateGrid) and unit is not None:
-                    self.grid = CoordinateGrid(unit)
-            if not isinstance(unit, CoordinateGrid):
-                return self._buffer
-            # first request in a unit system: remember which one the native buffer is in
-            self._buffer = [(self._buffer, unit)]
+    def get_buffer(self, unit=None) -> torch.Tensor:
+        native = self._allocate()
+        system = self._unit_system(unit)
+        if self._native_system is None and not self._twins:
+            if self.is_coord is True and not isinstance(self.grid, CoordinateGrid) and system is not None:
+                self.grid = CoordinateGrid(system)     # a coordinate without a grid adopts the first system asked for
+            if not isinstance(system, CoordinateGrid):
+                return native
+            self._native_system = system                # the first named system is the one the native buffer is in
+        if not isinstance(system, CoordinateGrid) or system == self._native_system:
+            return native
+        for twin, twin_system in self._twins:
+            if twin_system == system:
+                return twin
+        step = UnitConversionManager(self, system)
+        self._twins.append((step.out_buffer, system))
+        self.proc_chain._proc_managers.append(step)
+        log.debug(f"added conversion: {step}")
+        return step.out_buffer
 
-        if not isinstance(unit, CoordinateGrid):
-            return self._buffer[0][0]
-        for buff, buf_u in self._buffer:
-            if buf_u == unit:
-                return buff
-        conversion_manager = UnitConversionManager(self, unit)
-        self._buffer.append((conversion_manager.out_buffer, unit))
-        self.proc_chain._proc_managers.append(conversion_manager)
-        log.debug(f"added conversion: {conversion_manager}")
-        return conversion_manager.out_buffer
+    def all_buffers(self) -> list:
+        """[(tensor, unit system or None)] of everything this variable has allocated (chain compilers map storages back
+        to variables with it)"""
+        if self._native is None:
+            return []
+        return [(self._native, self._native_system)] + list(self._twins)
+
+    # legacy view of the storage: a tensor, or [(tensor, system), ...] once unit systems are involved
+    @property
+    def _buffer(self):
+        if self._native is None:
+            return None
+        if self._native_system is None and not self._twins:
+            return self._native
+        return self.all_buffers()
+
+    @_buffer.setter
+    def _buffer(self, value):
+        if value is None:
+            self._native, self._native_system, self._twins = None, None, []
+        elif isinstance(value, list):
+            (self._native, self._native_system), self._twins = value[0], list(value[1:])
+        else:
+            self._native, self._native_system, self._twins = value, None, []
 
     @property
     def buffer(self):
@@ -943,11 +973,6 @@ class ProcessorManager:
     deduces ``auto`` variables, converts unit-carrying scalars to samples and binds the
     device buffers -- the launch descriptor of a block step (reference :1485-1803)."""
 
-    @dataclass
-    class DimInfo:
-        length: int
-        grid: Any
-
     def __init__(self, proc_chain, func, params, kw_params=None, signature=None, types=None, grid=None) -> None:
         assert isinstance(proc_chain, ProcessingChain) and callable(func) and isinstance(params, Collection)
         kw_params = kw_params or {}
@@ -963,163 +988,53 @@ class ProcessorManager:
         self.host_func = func
         self.processor = numpy_bridge.device_equivalent(func, signature)
 
+        # ---- the call's launch descriptor (binding.py): type loop, shape solution, lowered operands ------------------
         self.signature = signature if signature is not None else getattr(self.processor, "signature", None)
         if self.signature is None:
-            self.signature = ",".join(["()"] * self.processor.nin) + "->" + ",".join(["()"] * self.processor.nout)
-
+            self.signature = binding.scalar_layout(self.processor.nin, self.processor.nout)
+        layouts = binding.core_dims(self.signature)
+        operands = self.params + list(self.kw_params.values())
+        if len(layouts) != len(operands):
+            raise ProcessingChainError(
+                f"expected {len(layouts)} arguments from signature {self.signature}; found "
+                f"{len(operands)}: ({', '.join(str(p) for p in operands)})")
+        arrays = [p if isinstance(p, (ProcChainVar, np.ndarray)) else None for p in operands]
         if types is None:
             types = list(getattr(self.processor, "types", None) or [])
-        if not types:
-            raise ProcessingChainError(f"could not find a type signature list for {func.__name__}. "
-                                       "Please supply a valid list of types.")
-        if isinstance(types, str) or not isinstance(types, Collection):
-            types = [types]
-        found_types = [t.replace("->", "") for t in types]
-
-        dims_list = re.findall(r"\((.*?)\)", self.signature)
-        all_params = list(it.chain(self.params, self.kw_params.values()))
-        if len(dims_list) != len(all_params):
-            raise ProcessingChainError(
-                f"expected {len(dims_list)} arguments from signature {self.signature}; found "
-                f"{len(all_params)}: ({', '.join(str(p) for p in all_params)})")
-
-        dims_dict: dict[str, ProcessorManager.DimInfo] = {}
-        outerdims: list[ProcessorManager.DimInfo] = []
-        bw = proc_chain._block_width
-
-        # pass 1: restrict the type loop and collect dimension lengths / grids
-        for ipar, (dims, param) in enumerate(zip(dims_list, all_params)):
-            if not isinstance(param, (ProcChainVar, np.ndarray)):
-                continue
-            if param.dtype is not auto:
-                ch = np.dtype(param.dtype).char
-                found_types = [t for t in found_types if np.can_cast(ch, t[ipar])]
-            if param.shape is auto:
-                continue
-            fun_dims = list(outerdims) + [d.strip() for d in dims.split(",") if d.strip()]
-            arr_dims = list(param.shape)
-            arr_grid = param.grid if (isinstance(param, ProcChainVar) and param.grid is not auto
-                                      and not param.is_coord) else None
-            if not grid:
-                grid = arr_grid
-            for i in range(max(len(fun_dims), len(arr_dims))):
-                fd = fun_dims[-i - 1] if i < len(fun_dims) else None
-                ad = arr_dims[-i - 1] if i < len(arr_dims) else (bw if i == len(arr_dims) else None)
-                if isinstance(fd, str):
-                    if fd in dims_dict:
-                        this = dims_dict[fd]
-                        if not ad or this.length != ad:
-                            raise ProcessingChainError(
-                                f"failed to broadcast array dimensions for {func.__name__}. Could not find "
-                                f"consistent value for dimension {fd}")
-                        if not this.grid:
-                            this.grid = arr_grid
-                    else:
-                        dims_dict[fd] = self.DimInfo(ad, arr_grid)
-                elif not fd:
-                    outerdims.insert(0, self.DimInfo(ad, arr_grid))
-                elif not ad:
-                    continue
-                elif fd.length != ad:
-                    if len(fun_dims) > len(arr_dims):
-                        arr_dims.insert(len(arr_dims) - i, 1)
-                    elif len(fun_dims) < len(arr_dims):
-                        outerdims.insert(len(fun_dims) - i, self.DimInfo(ad, arr_grid))
-                        fun_dims.insert(len(fun_dims) - i, ad)
-                    else:
-                        raise ProcessingChainError(
-                            f"failed to broadcast array dimensions for {func.__name__}. Input arrays do not "
-                            f"have consistent outer dimensions; found {tuple(arr_dims)} for {param}")
-                elif not fd.grid:
-                    outerdims[len(fun_dims) - 1 - i].grid = arr_grid
-                arr_grid = None  # only the innermost dimension carries a grid
-
-        if not found_types:
-            raise ProcessingChainError(
-                f"could not find a type signature matching the types of the variables given for {self} "
-                f"(types: {types})")
-        self.types = [np.dtype(t) for t in found_types[0]]
-
-        if not grid:
-            for param in all_params:
-                if isinstance(param, ProcChainVar) and param.is_coord is True:
-                    grid = param.grid
-                    break
-        self.grid = grid
-
-        # pass 2: deduce auto variables, convert scalars, bind buffers
-        named = it.chain(zip(it.repeat(None), self.params), self.kw_params.items())
-        for (arg_name, param), dims, dtype in zip(named, dims_list, self.types):
-            dim_list = list(outerdims)
-            for d in (x.strip() for x in dims.split(",")):
-                if not d:
-                    continue
-                if d not in dims_dict:
-                    if isinstance(param, np.ndarray):
-                        dims_dict[d] = self.DimInfo(len(param), None)
-                    else:
-                        raise ProcessingChainError(f"could not deduce dimension {d} for {param}")
-                dim_list.append(dims_dict[d])
-            shape = tuple(d.length for d in dim_list)
-            this_grid = dim_list[-1].grid if dim_list else None
-
-            if isinstance(param, ProcChainVar):
-                unit = None
-                is_coord = False
-                if param.is_coord is True and grid is not None:
-                    unit = str(grid.period.u)
-                    this_grid = grid
-                elif (is_in_registry(param.unit) and grid is not None
-                      and ureg.is_compatible_with(grid.period, param.unit)):
-                    is_coord = True
-                    this_grid = grid
-                param.update_auto(shape=shape, dtype=np.dtype(dtype), grid=this_grid, unit=unit, is_coord=is_coord)
-                buf = param.get_buffer(grid if param.is_coord else None)
-                arshape = list(buf.shape)
-                for idim in range(-1, -1 - len(shape), -1):
-                    if len(arshape) < -idim or arshape[idim] != shape[idim]:
-                        arshape.insert(len(arshape) + idim + 1, 1)
-                bound = buf.reshape(arshape) if list(buf.shape) != arshape else buf
-            elif isinstance(param, str):
-                bound = param
-                if np.issubdtype(dtype, np.integer):
-                    try:
-                        bound = np.frombuffer(param.encode("ascii"), dtype).reshape(shape)
-                    except ValueError:
-                        raise ProcessingChainError(
-                            f"could not convert string '{param}' into byte-array of type {dtype} and shape {shape}")
-                    if bound.size == 1:
-                        bound = int(bound.reshape(-1)[0])
-            elif isinstance(param, np.ndarray):
-                bound = torch.from_numpy(np.ascontiguousarray(param.astype(dtype))).to(proc_chain.device)
-            elif param is not None:
-                if isinstance(param, Unit):
-                    param = Quantity(1.0, param)
-                if isinstance(param, Quantity):
-                    if param.u.dimensionless:
-                        param = float(param)
-                    elif not isinstance(grid, CoordinateGrid):
-                        raise ProcessingChainError(
-                            f"could not find valid conversion for {param}; CoordinateGrid is {grid}")
-                    else:
-                        try:
-                            param = to_period_units(param, grid.period)
-                        except ValueError as e:
-                            raise ProcessingChainError(str(e)) from e
-                if np.issubdtype(dtype, np.integer):
-                    bound = dtype.type(np.round(param))
-                else:
-                    bound = dtype.type(param)
-            else:
-                bound = None
-
-            if arg_name is None:
+        solution, call_grid = binding.solve_shapes(layouts, arrays, proc_chain._block_width, func.__name__)
+        self.types = binding.pick_type_loop(types, arrays, self if types else func.__name__)
+        # sampling grid of the call: given, else the first gridded operand's, else that of a coordinate operand
+        self.grid = grid or call_grid or next((p.grid for p in operands if isinstance(p, ProcChainVar) and p.is_coord is True), None)
+        keys = [None] * len(self.params) + list(self.kw_params.keys())
+        for key, opnd, names, dtype in zip(keys, operands, layouts, self.types):
+            missing = [n for n in names if n not in solution.core]
+            if missing:
+                raise ProcessingChainError(f"could not deduce dimension {missing[0]} for {opnd}")
+            axes = solution.axes_of(names)
+            bound = self._lower(opnd, dtype, tuple(ax.extent for ax in axes), axes[-1].grid if axes else None)
+            if key is None:
                 self.args.append(bound)
             else:
-                self.kwargs[arg_name] = bound
+                self.kwargs[key] = bound
 
         self._sync_timing = bool(int(os.environ.get("DSPEED_B200_TIMING", "0")))
         self.fatal = proc_chain._new_fatal_slot(self)
+
+    def _lower(self, opnd, dtype: np.dtype, shape: tuple, axis_grid):
+        """one operand -> what the kernels take: a broadcastable view of the variable's block buffer (deducing the
+        variable's open properties from the solution first), a scalar in samples, byte codes, or a device constant"""
+        if isinstance(opnd, ProcChainVar):
+            unit, is_coord, grid_override = binding.coordinate_role(opnd, self.grid)
+            opnd.update_auto(shape=shape, dtype=np.dtype(dtype), grid=grid_override if grid_override is not None else axis_grid,
+                             unit=unit, is_coord=is_coord)
+            return binding.block_view(opnd.get_buffer(self.grid if opnd.is_coord else None), shape)
+        if isinstance(opnd, str):
+            return binding.text_operand(opnd, dtype, shape)
+        if isinstance(opnd, np.ndarray):
+            return torch.from_numpy(np.ascontiguousarray(opnd.astype(dtype))).to(self.proc_chain.device)
+        if opnd is None:
+            return None
+        return binding.scalar_in_samples(opnd, dtype, self.grid, CoordinateGrid)
 
     def execute(self) -> None:
         start = time.perf_counter()
@@ -1152,56 +1067,45 @@ class UnitConversionManager(ProcessorManager):
     (reference :1806-1908 and processors/unit_conversion.py:16-78)."""
 
     def __init__(self, var: ProcChainVar, unit, mode=None, out_dtype=None) -> None:
-        self.proc_chain = var.proc_chain
         if mode not in (None, "round", "floor", "ceil", "trunc"):
             raise ProcessingChainError("Mode must be round, floor, ceil or trunc")
+        self.proc_chain = var.proc_chain
         self.mode = mode
-        self.host_func = numpy_bridge.convert
-        self.processor = numpy_bridge.convert
-
-        to_offset = 0
-        if isinstance(unit, CoordinateGrid):
-            to_offset = unit.get_offset()
-            unit = unit.period
-        if isinstance(var._buffer, list):
-            from_buffer, from_unit = var._buffer[0]
-        else:
-            from_buffer = var._buffer
-            from_unit = var.unit
-            if isinstance(from_unit, str) and from_unit in ureg:
-                from_unit = ureg.Quantity(from_unit)
-
+        self.host_func = self.processor = numpy_bridge.convert
+        stored = var.all_buffers()[0] if var._native_system is not None or var._twins else (var._buffer, None)
+        source, source_system = stored
+        if source_system is None:                    # a plain value in its own unit (no grid involved so far)
+            source_system = var.unit
+            if isinstance(source_system, str) and source_system in ureg:
+                source_system = ureg.Quantity(source_system)
         self.params = [var]
-        self.kw_params = {"from": from_unit, "to": unit}
+        self.kw_params = {"from": source_system, "to": unit.period if isinstance(unit, CoordinateGrid) else unit}
+        ratio, shift_in, shift_out = self._terms(source_system, unit)
 
-        if isinstance(from_unit, CoordinateGrid):
-            ratio = from_unit.get_period(unit)
-            from_offset = from_unit.get_offset()
-        elif isinstance(from_unit, (Unit, Quantity)):
-            if isinstance(unit, str):
-                unit = ureg.Quantity(unit)
-            from_q = from_unit if isinstance(from_unit, Quantity) else Quantity(1.0, from_unit)
-            to_q = unit if isinstance(unit, Quantity) else Quantity(1.0, unit)
-            ratio = float(from_q / to_q)
-            from_offset = 0
-        else:
-            ratio = 1 / float(unit) if not isinstance(unit, Quantity) else 1.0 / unit.m
-            from_offset = 0
-
-        def expand(off):
-            if isinstance(off, torch.Tensor):
-                return off.reshape(off.shape[0], *[1] * (from_buffer.ndim - off.ndim))
-            return off
+        def per_row(x):     # per-event offsets broadcast along the variable's own axes
+            return x.reshape(x.shape[0], *[1] * (source.ndim - x.ndim)) if isinstance(x, torch.Tensor) else x
 
         self.in_is_int = not np.issubdtype(var.dtype, np.floating)
-        odt = np.dtype(out_dtype) if out_dtype is not None else var.dtype
-        self.out_buffer = torch.zeros_like(from_buffer, dtype=_np2t(odt))
-        self.args = [from_buffer, expand(from_offset), expand(to_offset), ratio, self.out_buffer]
+        self.out_buffer = torch.zeros_like(source, dtype=_np2t(np.dtype(out_dtype) if out_dtype is not None else var.dtype))
+        self.args = [source, per_row(shift_in), per_row(shift_out), ratio, self.out_buffer]
         self.kwargs = {}
-        self.time_total = 0.0
-        self.n_calls = 0
-        self._sync_timing = False
+        self.time_total, self.n_calls, self._sync_timing = 0.0, 0, False
         self.fatal = self.proc_chain._new_fatal_slot(self)
+
+    @staticmethod
+    def _terms(source, target):
+        """(ratio, offset_in, offset_out) of ``(x + offset_in) * ratio - offset_out``: `x` counted in `source` (a grid:
+        samples from its offset; a unit / quantity: multiples of it) expressed in `target`"""
+        shift_out = 0
+        if isinstance(target, CoordinateGrid):
+            shift_out, target = target.get_offset(), target.period
+        if isinstance(source, CoordinateGrid):
+            return source.get_period(target), source.get_offset(), shift_out
+        if isinstance(source, (Unit, Quantity)):
+            one = lambda u: u if isinstance(u, Quantity) else Quantity(1.0, u)   # noqa: E731
+            return float(one(source) / one(ureg.Quantity(target) if isinstance(target, str) else target)), 0, shift_out
+        # a unitless count: 1 / (size of the target unit)
+        return (1.0 / target.m if isinstance(target, Quantity) else 1 / float(target)), 0, shift_out
 
     def execute(self) -> None:
         start = time.perf_counter()
@@ -1551,294 +1455,137 @@ def _resolve_function(module_name: str, func_name: str):
 
 
 def build_processing_chain(processors, tb_in=None, db_dict=None, outputs=None, block_width=None, device=None):
-    """Compile a JSON/YAML/dict recipe into a :class:`ProcessingChain`
-    (reference :2363-2872; same schema, same dependency resolution, same constant folding).
+    """Compile a JSON/YAML/dict recipe into a :class:`ProcessingChain` (same schema and semantics as the reference's
+    build_processing_chain, :2363-2872).  Parsing and scheduling live in :mod:`dspeed_b200.recipe`; this function
+    instantiates the scheduled steps on a chain and links the table columns.
 
     Returns ``(proc_chain, field_mask, tb_out)``."""
-    db_parser = re.compile(r"(?![^\w_.])db\.[\w_.]+")
-
-    if isinstance(processors, str):
-        with open(processors) as f:
-            from yaml import safe_load
-
-            processors = safe_load(f)
-    elif processors is None:
-        processors = {}
-    elif isinstance(processors, MutableMapping):
-        processors = deepcopy(processors)
-    else:
-        raise ValueError("processors must be a dict, json/yaml file, or None")
-
+    n_rows = len(tb_in) if tb_in is not None else 1
+    chain = ProcessingChain(block_width, n_rows, device=device)
+    steps, config_outputs, db = recipe.parse(processors, db_dict, lambda text: chain.get_variable(text, True),
+                                             ProcessingChain.module_list, ProcessingChain.func_list)
     if outputs is None:
-        if "outputs" not in processors:
+        if config_outputs is None:
             raise ValueError("outputs not provided")
-        outputs = processors["outputs"]
-    if "processors" in processors:
-        processors = processors["processors"]
-    processors = dict(processors)
+        outputs = config_outputs
+    ordered, columns, copies, produced = recipe.schedule(steps, outputs)
 
-    buffer_len = len(tb_in) if tb_in is not None else 1
-    proc_chain = ProcessingChain(block_width, buffer_len, device=device)
-
-    def db_substitute(arg, node):
-        """replace ``db.a.b`` tokens by database values or the node's defaults"""
-        for db_var in db_parser.findall(arg):
-            try:
-                db_node = db_dict
-                for db_key in db_var[3:].split("."):
-                    db_node = db_node[db_key]
-            except (KeyError, TypeError):
-                try:
-                    db_node = node["defaults"][db_var]
-                except (KeyError, TypeError):
-                    raise ProcessingChainError(
-                        f"did not find {db_var} in database, and could not find default value.")
-            arg = db_node if arg == db_var else arg.replace(db_var, str(db_node))
-            if not isinstance(arg, str):
-                break
-        return arg
-
-    # ---- normalise every node into module / function / args, find prerequisites -------
-    multi_out_procs = {}
-    for key, node in processors.items():
-        keys = [k for k in re.split(",| ", key) if k != ""]
-        if len(keys) > 1:
-            for k in keys:
-                multi_out_procs[k] = key
-        if isinstance(node, str):
-            node = {"function": node}
-            processors[key] = node
-        if "function" not in node:
-            raise ProcessingChainError(f"no function given for parameter {key}")
-        function = node["function"]
-        f_parse = ast.parse(function, mode="eval").body
-        mod_err = f"Module specified twice for parameter {key}"
-        args_err = f"Cannot specify arguments if function is expr for parameter {key}"
-        seg = lambda n: function[n.col_offset : n.end_col_offset]  # noqa: E731
-        if isinstance(f_parse, ast.Name):
-            pass
-        elif isinstance(f_parse, ast.Attribute):
-            module = seg(f_parse.value)
-            if module in ProcessingChain.module_list and "args" not in node:
-                node["module"] = None
-                node["args"] = [function]
-            else:
-                node["function"] = f_parse.attr
-                if "module" in node:
-                    raise ProcessingChainError(mod_err)
-                node["module"] = module
-        elif isinstance(f_parse, ast.Call):
-            if "args" in node:
-                raise ProcessingChainError(args_err)
-            if isinstance(f_parse.func, ast.Name) and f_parse.func.id in ProcessingChain.func_list \
-                    and "module" not in node:
-                node["module"] = None
-                node["args"] = [function]
-            elif isinstance(f_parse.func, ast.Name):
-                node["function"] = f_parse.func.id
-                node["args"] = [seg(a) for a in f_parse.args + f_parse.keywords]
-            elif isinstance(f_parse.func, ast.Attribute):
-                node["function"] = f_parse.func.attr
-                if "module" in node:
-                    raise ProcessingChainError(mod_err)
-                node["module"] = seg(f_parse.func.value)
-                node["args"] = [seg(a) for a in f_parse.args + f_parse.keywords]
-        else:
-            if "args" in node:
-                raise ProcessingChainError(args_err)
-            if "module" in node:
-                raise ProcessingChainError(mod_err)
-            node["module"] = None
-            node["args"] = [function]
-        if "module" not in node:
-            raise ProcessingChainError(f"Could not find module for parameter {key}")
-        if "args" not in node:
-            raise ProcessingChainError(f"Could not find args for parameter {key}")
-
-        args = node["args"]
-        for i, arg in enumerate(args):
-            if isinstance(arg, str):
-                args[i] = db_substitute(arg, node)
-
-        if "prereqs" not in node:
-            prereqs = []
-            for arg in args:
-                if not isinstance(arg, str):
-                    continue
-                for prereq in proc_chain.get_variable(arg, True):
-                    if prereq not in prereqs and prereq not in keys:
-                        prereqs.append(prereq)
-            node["prereqs"] = prereqs
-        log.debug(f"prereqs for {key} are {node['prereqs']}")
-
-    processors.update(multi_out_procs)
-
-    # ---- dependency order from the requested outputs only ----------------------------
-    def resolve(par, resolved, leafs, unresolved=None):
-        unresolved = [] if unresolved is None else unresolved
-        if par in resolved:
-            return
-        if par in unresolved:
-            raise ProcessingChainError(f"Circular references detected for parameter '{par}'")
-        node = processors.get(par)
-        if node is None:
-            if par not in leafs:
-                leafs.append(par)
-            return
-        if isinstance(node, str):
-            resolve(node, resolved, leafs, unresolved)
-            return
-        unresolved.append(par)
-        for edge in node["prereqs"]:
-            resolve(edge, resolved, leafs, unresolved)
-        resolved.append(par)
-        unresolved.remove(par)
-
-    proc_par_list, input_par_list, copy_par_list, out_par_list = [], [], [], []
-    for out_par in outputs:
-        if out_par not in processors:
-            copy_par_list.append(out_par)
-        else:
-            resolve(out_par, proc_par_list, input_par_list)
-            out_par_list.append(out_par)
-
-    for input_par in input_par_list:
-        if tb_in is None or input_par not in tb_in:
-            log.warning(f"'{input_par}' not found in input files or dsp config.")
+    for name in columns:
+        if tb_in is None or name not in tb_in:
+            log.warning(f"'{name}' not found in input files or dsp config.")
         try:
-            proc_chain.link_input_buffer(input_par, tb_in[input_par])
+            chain.link_input_buffer(name, tb_in[name])
         except Exception as e:
-            raise ProcessingChainError(f"Exception raised while linking input buffer '{input_par}'.") from e
+            raise ProcessingChainError(f"Exception raised while linking input buffer '{name}'.") from e
 
-    # ---- add the processors ------------------------------------------------------------
-    for proc_par in proc_par_list:
-        recipe = processors[proc_par]
+    for step in ordered:
         try:
-            if recipe["module"] is None:
-                assert len(recipe["args"]) == 1
-                fun_var = proc_chain.get_variable(recipe["args"][0])
-                if isinstance(fun_var, ProcChainVar):
-                    new_var = proc_chain.add_variable(name=proc_par, dtype=fun_var.dtype, shape=fun_var.shape,
-                                                      grid=fun_var.grid, unit=fun_var.unit,
-                                                      is_coord=fun_var.is_coord)
-                    new_var._buffer = fun_var._buffer
-                    new_var.alias_of = fun_var
-                else:
-                    new_var = proc_chain.set_constant(varname=proc_par, val=fun_var)
-                continue
-
-            func = _resolve_function(recipe["module"], recipe["function"])
-            args = recipe["args"]
-            new_vars = [k for k in re.split(",| ", proc_par) if k != ""]
-
-            if "unit" in recipe:
-                for i, name in enumerate(new_vars):
-                    unit = recipe.get("unit", auto)
-                    if isinstance(unit, list):
-                        unit = unit[i]
-                    proc_chain.add_variable(name, unit=unit)
-
-            kwargs = dict(recipe.get("kwargs", {}))
-            kwargs.update({k: recipe[k] for k in ("signature", "types", "coord_grid") if k in recipe})
-
-            if "init_args" in recipe:
-                init_args, init_kwargs = [], {}
-                for arg in recipe["init_args"]:
-                    if not isinstance(arg, str):
-                        init_args.append(arg)
-                        continue
-                    arg = db_substitute(arg, recipe)
-                    if isinstance(arg, str):
-                        arg = proc_chain.get_variable(arg)
-                    if isinstance(arg, MutableMapping):
-                        init_kwargs.update(arg)
-                    else:
-                        init_args.append(arg)
-                func = func(*init_args, **init_kwargs)
-
-            params, kw_params, out_params = [], {}, []
-            is_const = True
-            for param in args:
-                if isinstance(param, str):
-                    param = proc_chain.get_variable(param)
-                if isinstance(param, MutableMapping):
-                    kw_params.update(param)
-                    param = list(param.values())[0]
-                elif isinstance(param, str):
-                    params.append(param)  # a string literal (e.g. the mode character 's')
-                else:
-                    params.append(param)
-                if isinstance(param, ProcChainVar):
-                    if param.name in new_vars:
-                        out_params.append(param)
-                    elif not param.is_const:
-                        is_const = False
-
-            if is_const:
-                # every input is a constant: run once now, outputs become constants
-                # (this is how cusp_kernel / zac_kernel / t0_kernel are made)
-                if out_params:
-                    for param in out_params:
-                        param.is_const = True
-                    proc_man = ProcessorManager(proc_chain, func, params, kw_params, kwargs.get("signature", None),
-                                                kwargs.get("types", None))
-                    if proc_chain.device.type != "meta":
-                        proc_man.execute()
-                        proc_chain._raise_recorded_fatal(0, 0)
-                    for param in out_params:
-                        # provenance of folded constants: lets the fusion compiler recognise
-                        # e.g. a cusp/zac kernel and verify an analytic model against it
-                        param.const_origin = (proc_man.processor.__name__, list(proc_man.args))
-                else:
-                    const_val = func(*params, **kw_params)
-                    if len(new_vars) == 1:
-                        const_val = [const_val]
-                    for var, val in zip(new_vars, const_val):
-                        proc_chain.set_constant(var, val)
-            else:
-                coord_grid = kwargs.get("coord_grid", None)
-                proc_man = ProcessorManager(proc_chain, func, params, kw_params, kwargs.get("signature", None),
-                                            kwargs.get("types", None),
-                                            CoordinateGrid(coord_grid) if coord_grid is not None else None)
-                proc_chain._proc_managers.append(proc_man)
-                log.debug(f"added processor: {proc_man}")
+            _instantiate(chain, step, db)
         except Exception as e:
-            raise ProcessingChainError("Exception raised while attempting to add processor:\n"
-                                       + json.dumps(recipe, indent=2, default=str)) from e
+            raise ProcessingChainError("Exception raised while attempting to add processor:\n" + recipe.describe(step)) from e
 
-    # ---- output table ------------------------------------------------------------------
-    tb_out = tables.Table(size=buffer_len)
-    for copy_par in copy_par_list:
-        if tb_in is None or copy_par not in tb_in:
-            log.warning(f"'{copy_par}' not found in input files or dsp . Building output without it!")
+    tb_out = tables.Table(size=n_rows)
+    for name in copies:          # requested names that no step produces: copied through from the input table
+        if tb_in is None or name not in tb_in:
+            log.warning(f"'{name}' not found in input files or dsp . Building output without it!")
             continue
         try:
-            proc_chain.link_input_buffer(copy_par, tb_in[copy_par])
-            buf_out = proc_chain.link_output_buffer(copy_par)
-            buf_out.attrs.update(getattr(tb_in[copy_par], "attrs", {}))
-            buf_out.resize(len(tb_out))
-            tb_out.add_field(copy_par, buf_out)
+            chain.link_input_buffer(name, tb_in[name])
+            col = chain.link_output_buffer(name)
+            col.attrs.update(getattr(tb_in[name], "attrs", {}))
+            col.resize(len(tb_out))
+            tb_out.add_field(name, col)
         except Exception as e:
-            raise ProcessingChainError(f"Exception raised while linking copy buffer '{copy_par}'.") from e
-
-    for out_par in out_par_list:
+            raise ProcessingChainError(f"Exception raised while linking copy buffer '{name}'.") from e
+    for name in produced:
         try:
-            buf_out = proc_chain.link_output_buffer(out_par)
-            recipe = processors[out_par]
-            if isinstance(recipe, str):
-                recipe = processors[recipe]
-            buf_out.attrs.update(recipe.get("lh5_attrs", {}))
-            if description := recipe.get("description"):
-                buf_out.attrs["description"] = description
-            buf_out.resize(len(tb_out))
-            tb_out.add_field(out_par, buf_out)
+            col = chain.link_output_buffer(name)
+            entry = steps[name].entry
+            col.attrs.update(entry.get("lh5_attrs", {}))
+            if text := entry.get("description"):
+                col.attrs["description"] = text
+            col.resize(len(tb_out))
+            tb_out.add_field(name, col)
         except Exception as e:
-            raise ProcessingChainError(f"Exception raised while linking output buffer {out_par}.") from e
+            raise ProcessingChainError(f"Exception raised while linking output buffer {name}.") from e
 
-    field_mask = input_par_list + copy_par_list
-    proc_chain.recipe_info = {"proc_par_list": proc_par_list, "outputs": list(outputs)}
-    if proc_chain.device.type == "cuda" and os.environ.get("DSPEED_B200_FUSE", "1") != "0":
+    chain.recipe_info = {"proc_par_list": [st.key for st in ordered], "outputs": list(outputs)}
+    if chain.device.type == "cuda" and os.environ.get("DSPEED_B200_FUSE", "1") != "0":
         from . import fusion
 
-        fusion.try_fuse(proc_chain)
-    return (proc_chain, field_mask, tb_out)
+        fusion.try_fuse(chain)
+    return (chain, columns + copies, tb_out)
+
+
+def _instantiate(chain: ProcessingChain, step, db) -> None:
+    """one scheduled recipe step -> variables + (a launch descriptor | folded constants | an alias)"""
+    entry = step.entry
+    if step.module is None:
+        # a bare expression: the grammar builds whatever processors it needs; the name becomes an alias of the result
+        value = chain.get_variable(step.args[0])
+        if isinstance(value, ProcChainVar):
+            var = chain.add_variable(name=step.key, dtype=value.dtype, shape=value.shape, grid=value.grid, unit=value.unit,
+                                     is_coord=value.is_coord)
+            var._buffer = value._buffer
+            var.alias_of = value
+        else:
+            chain.set_constant(varname=step.key, val=value)
+        return
+
+    func = _resolve_function(step.module, step.function)
+    if "unit" in entry:
+        for i, name in enumerate(step.outputs):
+            unit = entry["unit"]
+            chain.add_variable(name, unit=unit[i] if isinstance(unit, list) else unit)
+    options = dict(entry.get("kwargs", {}))
+    options.update({k: entry[k] for k in ("signature", "types", "coord_grid") if k in entry})
+
+    if "init_args" in entry:        # the named callable is a factory (iir_filter, ...): call it with these first
+        pos, named = [], {}
+        for arg in entry["init_args"]:
+            if isinstance(arg, str):
+                arg = db.substitute(arg, entry)
+                if isinstance(arg, str):
+                    arg = chain.get_variable(arg)
+            if isinstance(arg, MutableMapping):
+                named.update(arg)
+            else:
+                pos.append(arg)
+        func = func(*pos, **named)
+
+    operands, keyword_operands, results = [], {}, []
+    all_const = True
+    for arg in step.args:
+        value = chain.get_variable(arg) if isinstance(arg, str) else arg
+        if isinstance(value, MutableMapping):      # name=value in the argument list
+            keyword_operands.update(value)
+            value = list(value.values())[0]
+        else:
+            operands.append(value)                  # variables, numbers, quantities, string literals ('s', 'n', ...)
+        if isinstance(value, ProcChainVar):
+            if value.name in step.outputs:
+                results.append(value)
+            elif not value.is_const:
+                all_const = False
+
+    if not all_const:
+        grid = options.get("coord_grid")
+        man = ProcessorManager(chain, func, operands, keyword_operands, options.get("signature"), options.get("types"),
+                               CoordinateGrid(grid) if grid is not None else None)
+        chain._proc_managers.append(man)
+        log.debug(f"added processor: {man}")
+    elif results:
+        # constant folding: every input is a constant, so the processor runs once now and its outputs are constants
+        # (cusp / zac / t0 / gaussian kernels); the provenance lets the chain compilers recognise structured kernels
+        for var in results:
+            var.is_const = True
+        man = ProcessorManager(chain, func, operands, keyword_operands, options.get("signature"), options.get("types"))
+        if chain.device.type != "meta":
+            man.execute()
+            chain._raise_recorded_fatal(0, 0)
+        for var in results:
+            var.const_origin = (man.processor.__name__, list(man.args))
+    else:
+        values = func(*operands, **keyword_operands)
+        for name, val in zip(step.outputs, [values] if len(step.outputs) == 1 else values):
+            chain.set_constant(name, val)

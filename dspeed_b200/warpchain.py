@@ -70,7 +70,7 @@ class WarpChain(FusedChain):
                 if hasattr(prm, "proc_chain") and prm not in all_vars:
                     all_vars.append(prm)
         for v in all_vars:
-            bufs = v._buffer if isinstance(v._buffer, list) else [(v._buffer, None)]
+            bufs = v.all_buffers()
             for b, _ in bufs:
                 if isinstance(b, torch.Tensor):
                     self.var_of_storage.setdefault(_storage(b), v)
