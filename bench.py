@@ -275,6 +275,75 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------
+# host side of the end-to-end leg: where a rank runs and what the box can deliver
+# ----------------------------------------------------------------------------------------
+def bind_rank_to_its_gpu(local_rank: int, world: int) -> dict:
+    """Pin this rank to a private slice of the host cores that are local to its GPU (NVML CPU affinity = the cores of
+    the GPU's NUMA node) BEFORE any pinned buffer is allocated: first touch then places the staging pages on that node,
+    and the ranks' copy / launch threads do not migrate across each other.  Returns what was done (reported)."""
+    info = {"cpus": None, "numa_cpus_of_gpu": None}
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        local = [c for c in range(n_cpu) if (words[c // 64] >> (c % 64)) & 1]
+        allowed = sorted(set(local) & set(os.sched_getaffinity(0))) or sorted(os.sched_getaffinity(0))
+        info["numa_cpus_of_gpu"] = f"{allowed[0]}-{allowed[-1]} ({len(allowed)})" if allowed else None
+        # ranks whose GPUs share these cores split them evenly (contiguous slices)
+        sharers = []
+        for g in range(world):
+            try:
+                w = pynvml.nvmlDeviceGetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(g), (n_cpu + 63) // 64)
+                if list(w) == list(words):
+                    sharers.append(g)
+            except Exception:
+                pass
+        sharers = sharers or [local_rank]
+        k, m = sharers.index(local_rank) if local_rank in sharers else 0, len(sharers)
+        per = max(1, len(allowed) // m)
+        mine = allowed[k * per:(k + 1) * per] or allowed
+        os.sched_setaffinity(0, mine)
+        info["cpus"] = f"{mine[0]}-{mine[-1]} ({len(mine)})"
+    except Exception as e:      # no NVML / not permitted: run unbound, and say so
+        info["error"] = f"{type(e).__name__}: {e}"
+    return info
+
+
+def h2d_ceiling(torch, dist, dev, world, nbytes=1 << 30, seconds=1.0):
+    """What the box delivers when every rank does nothing but copy pinned host memory to its GPU at the same time (plain
+    cudaMemcpyAsync of `nbytes` blocks, two in flight): GB/s of the slowest rank.  The end-to-end rate is reported as a
+    fraction of this, so a value that stops scaling with the number of ranks shows up as the HOST's limit."""
+    src = [torch.empty(nbytes, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+    for s_ in src:
+        s_.fill_(1)
+    dst = [torch.empty(nbytes, dtype=torch.uint8, device=dev) for _ in range(2)]
+    streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    n = 0
+    while time.perf_counter() - t0 < seconds:
+        for k in range(2):
+            with torch.cuda.stream(streams[k]):
+                dst[k].copy_(src[k], non_blocking=True)
+        n += 2
+        for st in streams:
+            st.synchronize()
+    dt = time.perf_counter() - t0
+    rate = n * nbytes / dt / 1e9
+    if world > 1:
+        t = torch.tensor([rate], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        rate = float(t.item())
+    del src, dst
+    return rate
+
+
+# ----------------------------------------------------------------------------------------
 # the B200 arm
 # ----------------------------------------------------------------------------------------
 def run_b200(args, rank, world, local_rank):
@@ -284,6 +353,7 @@ def run_b200(args, rank, world, local_rank):
     from dspeed_b200 import synth, tables
     from dspeed_b200.processing_chain import build_processing_chain
 
+    binding_info = bind_rank_to_its_gpu(local_rank, world)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -430,8 +500,15 @@ def run_b200(args, rank, world, local_rank):
         barrier()
         wall = time.perf_counter() - t
         t_e2e = max_over_ranks(max(f0.elapsed_time(f1) * 1e-3, wall))
+        ceiling = h2d_ceiling(torch, dist, dev, world)
+        h2d_rate = (h1 - h0) * steps / t_e2e / 1e9        # GB/s per GPU actually moved inside the timed region
         e2e = {"value": world * m * steps / t_e2e, "unit": "waveforms/s", "h2d_bytes_per_step": h1 - h0,
-               "d2h_bytes_per_step": d1 - d0, "ms_per_step": t_e2e / steps * 1e3, "rows_per_gpu": m}
+               "d2h_bytes_per_step": d1 - d0, "ms_per_step": t_e2e / steps * 1e3, "rows_per_gpu": m,
+               "h2d_gbs_per_gpu": h2d_rate, "h2d_ceiling_gbs_per_gpu": ceiling,
+               "frac_of_h2d_ceiling": h2d_rate / ceiling if ceiling else None,
+               "h2d_ceiling_how": f"all {world} rank(s) copying 1 GiB pinned blocks to their GPUs simultaneously "
+                                  f"(cudaMemcpyAsync, 2 in flight), slowest rank",
+               "rank0_host_binding": binding_info}
         checksum = float(np.nansum(np.asarray(tb_out_host["trapEmax"].nda, np.float64)[:m]))
     else:
         checksum = None

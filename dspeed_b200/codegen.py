@@ -1742,21 +1742,37 @@ class SpecChain(FusedChain):
             out.nan = nf
         self._store(out, o)
 
+    def _runtime_const(self, literal: str) -> str:
+        """A database constant that changes per channel / run without changing the program (the pole-zero time
+        constant): passed through the launch arguments (Args.c[]) instead of being baked into the source, so that
+        chains that differ only in such values share ONE compiled kernel."""
+        self.rt_consts = getattr(self, "rt_consts", [])
+        self.rt_consts.append(float.fromhex(literal))
+        return f"A.c[{len(self.rt_consts) - 1}]"
+
     def _e_pole_zero(self, nd):
         w, off, n = nd["ins"][0]
         out = nd["wouts"][0]
+        omc_arg = None
+        if nd["tau"].startswith(("0x", "-0x")) and os.environ.get("DSPEED_B200_BAKE_CONSTANTS", "0") != "1":
+            # 1 - exp(-1 / tau) of the float32 time constant, evaluated once on the host in float64
+            tau32 = float(np.float32(float.fromhex(nd["tau"])))
+            if tau32 == tau32 and tau32 != 0.0:
+                omc_arg = self._runtime_const((-math.expm1(-1.0 / tau32)).hex())
+        const_tau_arg = omc_arg is not None
         self._need_all(nd["tau"])
         self._need(w.nan)
         r = self._chunk(w)
         sd = self._alloc_d(1)
         tot, incl, omc = self._t("tot"), self._t("incl"), self._t("omc")
-        self._e(f"const double {omc} = -expm1(-1.0 / (double)(float)({nd['tau']}));",
+        self._e(f"const double {omc} = {omc_arg};" if omc_arg is not None else
+                f"const double {omc} = -expm1(-1.0 / (double)(float)({nd['tau']}));",
                 f"const double {tot} = (double)chunk_sum_f({r});",
                 f"const double {incl} = put_scan(CSD({sd}), {tot}, lane, warp);")
         o, dum = self._t("r"), self._t("tt")
         self.posts.append(f"float {o}[16]; double {dum}; "
                           f"pz_chunk_f({r}, get_excl(CSD({sd}), {incl}, {tot}, lane, warp, {dum}), {omc}, {o});")
-        const_tau = nd["tau"].startswith(("0x", "-0x"))
+        const_tau = nd["tau"].startswith(("0x", "-0x")) or const_tau_arg
         flags = [w.nan] + ([] if const_tau else [f"((float)({nd['tau']}) != (float)({nd['tau']}))"])
         g = self._nan_guard(flags)
         if g:
@@ -2408,12 +2424,14 @@ using namespace crt;
 namespace {{
 constexpr int NP = {np_};
 constexpr int N_NODES = {len(self.order) + 1};
+constexpr int NC = {max(1, len(getattr(self, "rt_consts", [])))};   // run-time scalar constants (database values)
 struct Args {{
   const void* p[NP];
   long long s[NP];
   long long n_rows, row0;
   int* fatal;
   long long* prof;
+  double c[NC];
 }};
 {arrays}
 // logical slot k of this row: physical slot k (even rows) or (k + {self.total_slots // 2}) % {self.total_slots} (odd rows)
@@ -2519,6 +2537,8 @@ extern "C" int chain_launch(const void* const* ptrs, long long n_ptrs, long long
   for (int i = 0; i < n_ptrs; i++) {{ a.p[i] = ptrs[i]; a.s[i] = strides[i]; }}
   a.n_rows = n_rows;
   a.row0 = strides[n_ptrs];
+  const double* consts = reinterpret_cast<const double*>(strides + n_ptrs + 1);   // NC doubles behind the row offset
+  for (int i = 0; i < NC; i++) a.c[i] = consts[i];
   a.fatal = fatal;
   a.prof = prof;
   cudaError_t e = cudaFuncSetAttribute(k_chain_spec, cudaFuncAttributeMaxDynamicSharedMemorySize, {self.smem_bytes});
@@ -2542,7 +2562,12 @@ extern "C" int chain_launch(const void* const* ptrs, long long n_ptrs, long long
 
     def _launch(self, arr, n, n_rows, fatal_ptr, stream):
         prof = C.c_void_p(self.d_prof.data_ptr()) if self.d_prof is not None else C.c_void_p(0)
-        return self.lib.chain_launch(C.cast(arr, C.c_void_p), C.c_int64(n), C.c_int64(n_rows), C.c_void_p(fatal_ptr), prof,
+        # the launch table: n pointers, n strides, the row offset, then the run-time constants (doubles)
+        consts = list(getattr(self, "rt_consts", [])) or [0.0]
+        ext = (C.c_int64 * (2 * n + 1 + len(consts)))()
+        C.memmove(ext, arr, 8 * (2 * n + 1))
+        C.memmove(C.byref(ext, 8 * (2 * n + 1)), (C.c_double * len(consts))(*consts), 8 * len(consts))
+        return self.lib.chain_launch(C.cast(ext, C.c_void_p), C.c_int64(n), C.c_int64(n_rows), C.c_void_p(fatal_ptr), prof,
                                      C.c_int(self.num_sms), C.c_void_p(stream))
 
     def profile(self, run, repeats=1):
@@ -2582,17 +2607,54 @@ def _headers_digest() -> str:
     return h.hexdigest()
 
 
+def cache_dirs():
+    """where compiled chain kernels live: the in-tree cache (prebuilt by build(); travels with the repository) first,
+    then a per-user cache for installations whose package directory is read-only ($DSPEED_B200_CACHE overrides)"""
+    user = os.environ.get("DSPEED_B200_CACHE") or os.path.join(
+        os.environ.get("XDG_CACHE_HOME", os.path.join(os.path.expanduser("~"), ".cache")), "dspeed_b200", "chains")
+    return [CACHE_DIR, user]
+
+
 def build_source(src: str, flags=()):
-    """compile one generated kernel for sm_100a (cached by content hash)"""
+    """compile one generated kernel for sm_100a (cached by content hash).  Safe across processes (torchrun ranks with a
+    cold cache): an exclusive file lock per kernel, the source written through a private temporary and renamed, the
+    library likewise.  A cache that cannot be written raises NotSpecializable: the chain falls back to the interpreted
+    program instead of crashing."""
+    import fcntl
+
     extra = list(flags) + os.environ.get("DSPEED_B200_NVCC_EXTRA", "").split()   # experiments: -D switches
     tag = hashlib.sha1((src + _headers_digest() + " ".join(extra)).encode()).hexdigest()[:16]
-    os.makedirs(CACHE_DIR, exist_ok=True)
-    so = os.path.join(CACHE_DIR, f"chain_{tag}.so")
-    cu = os.path.join(CACHE_DIR, f"chain_{tag}.cu")
-    with _build_lock:
+    for d in cache_dirs():                          # a kernel that exists anywhere is used as is
+        so = os.path.join(d, f"chain_{tag}.so")
+        if os.path.exists(so):
+            return so, os.path.join(d, f"chain_{tag}.cu")
+    cache = None
+    for d in cache_dirs():
+        try:
+            os.makedirs(d, exist_ok=True)
+            if os.access(d, os.W_OK):
+                cache = d
+                break
+        except OSError:
+            continue
+    if cache is None:
+        raise NotSpecializable("no writable cache directory for the generated kernel (set DSPEED_B200_CACHE)")
+    so = os.path.join(cache, f"chain_{tag}.so")
+    cu = os.path.join(cache, f"chain_{tag}.cu")
+    try:
+        lock_file = open(os.path.join(cache, f".chain_{tag}.lock"), "w")
+    except OSError as e:
+        raise NotSpecializable(f"cannot lock the kernel cache: {e}")
+    with _build_lock, lock_file:
+        fcntl.flock(lock_file, fcntl.LOCK_EX)
         if not os.path.exists(so):
-            with open(cu, "w") as f:
-                f.write(src)
+            try:
+                tmp_cu = cu + f".tmp{os.getpid()}"
+                with open(tmp_cu, "w") as f:
+                    f.write(src)
+                os.replace(tmp_cu, cu)
+            except OSError as e:
+                raise NotSpecializable(f"cannot write the generated kernel: {e}")
             tmp = so + f".tmp{os.getpid()}"
             cmd = [_lib._nvcc(), *_lib.NVCC_FLAGS, *extra, "-I", _lib.INCLUDE, "-I", _lib.CSRC, "-o", tmp, cu]
             env = dict(os.environ)

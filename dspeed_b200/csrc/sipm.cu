@@ -510,8 +510,8 @@ __global__ void k_iir_general(const void* w, long long w_rs, int w_dt, long long
     o[i] = (T)acc;
   }
 }
-// rc_cr2.py:11-93: matched z-transform RC-CR^2 shaper, float64 state seeded with the first three INPUT samples; the
-// first three outputs are not written by the reference (its output buffers start as zeros: so do they here)
+// rc_cr2.py:11-93: matched z-transform RC-CR^2 shaper, float64 state seeded with the first three input samples, which
+// are also the first three outputs
 template <typename T>
 __global__ void k_rc_cr2(const void* w, long long w_rs, int w_dt, long long n_rows, int n, SIn<T> tau_in, T* out, long long o_rs,
                          int* fatal) {
@@ -524,8 +524,16 @@ __global__ void k_rc_cr2(const void* w, long long w_rs, int w_dt, long long n_ro
   const double d2 = -3.0 * af, d3 = 3.0 * af * af, d4 = -(af * af * af);
   double t0 = (double)ldw<T>(w, w_dt, base), t1 = n > 1 ? (double)ldw<T>(w, w_dt, base + 1) : 0.0,
          t2 = n > 2 ? (double)ldw<T>(w, w_dt, base + 2) : 0.0;
-  bool bad = false;
-  for (int i = 0; i < 3 && i < n; i++) o[i] = (T)0;
+  bool bad = tau != tau;
+  for (int i = 0; i < n && !bad; i++) {
+    const T v = ldw<T>(w, w_dt, base + i);
+    bad = v != v;
+  }
+  if (bad) {                                   // NaN in, NaN out (rc_cr2.py:46-49)
+    for (int i = 0; i < n; i++) o[i] = (T)NAN;
+    return;
+  }
+  for (int i = 0; i < 3 && i < n; i++) o[i] = ldw<T>(w, w_dt, base + i);   // the first three samples pass through
   for (int i = 3; i < n; i++) {
     const double x0 = (double)ldw<T>(w, w_dt, base + i), x1 = (double)ldw<T>(w, w_dt, base + i - 1),
                  x2 = (double)ldw<T>(w, w_dt, base + i - 2);
@@ -652,6 +660,7 @@ int last_error() {
   extern "C" int dspb_rc_cr2##SFX(DSPB_WAVE_IN(w_in), int64_t n_rows, int64_t n, DSPB_SCALAR(t_tau), DSPB_WAVE_OUT(w_out), \
                                   DSPB_TAIL) {                                                                           \
     using T = T_;                                                                                                        \
+    if (n <= 3) return DSPB_FATAL_DPZ_SHORT;                                                                              \
     if (n_rows <= 0) return 0;                                                                                           \
     k_rc_cr2<T><<<(unsigned)((n_rows + 31) / 32), 32, 0, (cudaStream_t)stream>>>(                                         \
         w_in, w_in_row_stride, w_in_dtype, n_rows, (int)n, SIN(t_tau), (T*)w_out, w_out_row_stride, fatal);               \

@@ -82,7 +82,7 @@ def check_against(got, o, n_rows):
             assert np.array_equal(g[t0_ok], ref[t0_ok], equal_nan=True), k
         else:
             PT.assert_float_close(k, g, ref, mask=t0_ok, rtol=3e-5 if k == "dt_eff" else PT.FLOAT_RTOL)
-    assert t0_ok.mean() > 0.99
+    assert (~t0_ok).mean() <= 1e-3      # rows whose tp_0_est crossing is marginal: at most 0.1 %
 
 
 @pytest.fixture(scope="module")
@@ -216,13 +216,29 @@ def test_minimal_energy_chain():
     raw_scale = float(vals[:, :750].max())
     PT.assert_float_close("bl_mean", out["bl_mean"].nda, o["bl_mean"], scale=raw_scale)
     PT.assert_float_close("bl_std", out["bl_std"].nda, o["bl_std"], scale=raw_scale)
+    # ... and against float64 arithmetic on the same samples the device values are exact to float32 rounding of the
+    # RESULT (sigma ~ 4 ADC), i.e. at least as close to the truth as the reference's recursion is
+    x = vals[:, :750].astype(np.float64)
+    mean64, std64 = x.mean(1), x.std(1, ddof=1)
+    g_mean, g_std = np.asarray(out["bl_mean"].nda, np.float64), np.asarray(out["bl_std"].nda, np.float64)
+    assert np.abs(g_mean - mean64).max() <= 1.2e-7 * raw_scale
+    assert np.abs(g_std - std64).max() <= 3e-7 * std64.max()
+    assert np.abs(g_std - std64).max() <= np.abs(o["bl_std"].astype(np.float64) - std64).max() + 1e-7 * std64.max()
     PT.assert_float_close("trapEmax", out["trapEmax"].nda, o["trapEmax"])
     PT.assert_float_close("trapEpick", out["trapEpick"].nda, o["trapEpick"])
-    # arg-max of a float waveform can move between (nearly) tied samples of the flat top;
-    # the picked-off energy above is the physical quantity.  Index must agree whenever the
-    # oracle's maximum is unique to within the float tolerance.
+    # arg-max of the trapezoid: bit-exact, except rows where the device picked another sample of the flat top that
+    # the ORACLE's own waveform holds equal to its maximum within the float tolerance (a tie decided by rounding)
+    from oracle import oracle as O
+
     tp = np.asarray(out["tp_max"].nda) / 16.0
-    assert (tp == o["tp_max"]).mean() > 0.9
+    moved = np.flatnonzero(tp != o["tp_max"])
+    if len(moved):
+        mean, _, _, _ = O.linear_slope_fit(vals[moved].astype(np.float32)[:, :750])
+        trap = O.trap_norm(O.pole_zero(O.bl_subtract(vals[moved].astype(np.float32), mean), np.float32(27460.5)), 625, 188)
+        tol = PT.FLOAT_RTOL * np.abs(trap).max(1)
+        at_dev = trap[np.arange(len(moved)), tp[moved].astype(int)]
+        assert np.all(np.abs(at_dev - trap.max(1)) <= tol), "tp_max moved to a sample that is not a tie of the maximum"
+    assert len(moved) <= 0.15 * len(tp)     # (a 188-sample flat top with sigma-4 noise: ties within 1e-5 are common)
 
 
 def test_sipm_chain():
@@ -235,7 +251,7 @@ def test_sipm_chain():
     d = synth.sipm_waveforms(2000, seed=9)
     vals, bl = d["values"].numpy(), d["baseline"].numpy()
     cfg = {
-        "outputs": ["vt_max", "vt_min", "n_max", "n_min", "curr"],
+        "outputs": ["vt_max", "vt_min", "n_max", "n_min", "curr", "wf_mw"],
         "processors": {
             "wf_blsub": "dspeed.processors.bl_subtract(waveform, baseline, wf_blsub(unit='ADC'))",
             "wf_mw": {"function": "dspeed.processors.moving_window_multi(wf_blsub, 8, 2, 0, wf_mw)", "unit": "ADC"},
@@ -255,6 +271,16 @@ def test_sipm_chain():
     same_rows = np.all((np.asarray(out["vt_max"].nda) / 16.0 == o["vt_max"]) | (np.isnan(out["vt_max"].nda) & np.isnan(o["vt_max"])), axis=1)
     assert same_rows.mean() > 0.98, same_rows.mean()
     assert (np.asarray(out["n_max"].nda) == o["n_max"]).mean() > 0.98
+    # ... and EVERY row is bit-exact when the oracle's peak finder walks the device's own smoothed waveform: the rows
+    # above differ only through float rounding of the boxcar sums in front of a marginal delta comparison
+    from oracle import oracle as O
+
+    mw_dev = np.asarray(out["wf_mw"].values.nda if hasattr(out["wf_mw"], "t0") else out["wf_mw"].nda)
+    PT.assert_float_close("wf_mw", mw_dev, o["wf_mw"])
+    vmax, vmin, nmax, nmin = O.get_multi_local_extrema(mw_dev, 12.0, 6.0, 3, 15.0, 1000.0, 20)
+    assert np.array_equal(np.asarray(out["vt_max"].nda) / 16.0, vmax, equal_nan=True)
+    assert np.array_equal(np.asarray(out["vt_min"].nda) / 16.0, vmin, equal_nan=True)
+    assert np.array_equal(np.asarray(out["n_max"].nda), nmax) and np.array_equal(np.asarray(out["n_min"].nda), nmin)
     PT.assert_float_close("curr", out["curr"].values.nda if hasattr(out["curr"], "values") and not callable(out["curr"].values) else out["curr"].nda, o["curr"], rtol=2e-5)
     assert o["n_max"].max() >= 3
 
@@ -273,6 +299,27 @@ def test_specialised_kernel_is_deterministic_and_matches_interpreted(synth_batch
     for k in runs[0]:
         for r in runs[1:]:
             assert np.array_equal(runs[0][k], r[k], equal_nan=True), k
+    # (compute-sanitizer is closed on the GPU pool, profiles/r02_compute_sanitizer_closed.log; this is the race / sync
+    # check in its place.)  The same rows with other pipelining patterns: 7 persistent CTAs (~1700 rows each, the three
+    # streams overlap all the time) and one row per CTA and launch (no cross-row overlap at all) -- bit-identical
+    from dspeed_b200 import codegen
+
+    launch = codegen.SpecChain._launch
+    try:
+        for n_cta, bw in ((7, 12000), (148, 148)):
+            def patched(self, arr, n, n_rows, fatal_ptr, stream, _n=n_cta):
+                sms, self.num_sms = self.num_sms, _n
+                try:
+                    return launch(self, arr, n, n_rows, fatal_ptr, stream)
+                finally:
+                    self.num_sms = sms
+            codegen.SpecChain._launch = patched
+            m = 12000 if bw == 12000 else 1480
+            other = run_icpc(vals[:m], bl[:m], block_width=bw, device="cuda")
+            for k in runs[0]:
+                assert np.array_equal(runs[0][k][:m], other[k], equal_nan=True), (k, n_cta)
+    finally:
+        codegen.SpecChain._launch = launch
     os.environ["DSPEED_B200_SPECIALIZE"] = "0"
     try:
         ref = run_icpc(vals, bl, block_width=12000, device="cuda")

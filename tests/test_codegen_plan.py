@@ -6,6 +6,7 @@ import os
 import re
 import shutil
 
+import numpy as np
 import pytest
 import yaml
 
@@ -166,3 +167,34 @@ def test_double_pole_zero_is_specialised():
     # the row's only block -> scalar event comes after the wait for the previous row's "done" event
     blk = src[src.index("block stream (warps 0-15)"):src.index("scalar stream (warp 16)")]
     assert blk.index("if (it > 0) EV_WAIT(15);") < blk.rindex("EV_ARRIVE(EVB(")
+
+
+def test_database_constants_do_not_change_the_kernel():
+    """chains that differ only in a per-channel / per-run database value (the pole-zero time constant) share ONE compiled
+    kernel: the value travels through the launch arguments (Args.c[]), not through the source text"""
+    import yaml
+
+    from dspeed_b200 import tables
+    from dspeed_b200.processing_chain import build_processing_chain
+
+    n = 4
+    srcs, consts = [], []
+    for tau in ("439.368*us", "431.2*us"):
+        cfg = yaml.safe_load(open(os.path.join(os.path.dirname(codegen.__file__), "configs", "hpge_icpc.yaml")))
+        wf = tables.WaveformTable(size=n, t0=0, t0_units="ns", dt=16, dt_units="ns", values=np.zeros((n, 8192), np.uint16))
+        tb = tables.Table({"waveform": wf, "baseline": tables.Array(np.zeros(n, np.uint16))}, size=n)
+        # (the trapezoid / timing part of the chain: the cusp and zac kernels depend on the decay time by construction)
+        chain, _, _ = build_processing_chain(cfg, tb, db_dict={"pz": {"tau": tau}}, block_width=16, device="meta",
+                                             outputs=["trapEmax", "tp_0_est", "tp_50", "pz_std", "wf_max", "dt_eff"])
+        build = codegen.SpecChain._build
+        codegen.SpecChain._build = lambda self: None
+        try:
+            sc = codegen.SpecChain(chain)
+        finally:
+            codegen.SpecChain._build = build
+        srcs.append(sc.source())
+        consts.append(list(sc.rt_consts))
+    assert srcs[0] == srcs[1] and "A.c[0]" in srcs[0]
+    assert consts[0] != consts[1] and len(consts[0]) == 1
+    assert abs(consts[0][0] - (1 - np.exp(-1 / np.float64(np.float32(439368.0 / 16))))) < 1e-15
+    assert abs(consts[1][0] - (1 - np.exp(-1 / np.float64(np.float32(431200.0 / 16))))) < 1e-15
