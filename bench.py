@@ -425,6 +425,8 @@ def run_b200(args, rank, world, local_rank):
         from dspeed_b200 import parallel
 
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        del_me = parallel.gather_table(tb_out_dev, world * n, dst=0)    # untimed: NCCL sets up its point-to-point channels
+        del del_me
         barrier()
         g0.record()
         full = parallel.gather_table(tb_out_dev, world * n, dst=0)

@@ -1304,7 +1304,9 @@ class SpecChain(FusedChain):
             self.s2b[name] = (eid, k, self.s_seq)
 
     def _need_all(self, *exprs):
-        """scalars the block stream must hold: wait for the scalar warp's event and fetch them"""
+        """scalars the block stream must hold: wait for the scalar warp's event and fetch them (or close the round that
+        defines a scalar the block warps finish themselves)"""
+        self._need(*exprs)
         for e in exprs:
             if self._is_s(e):
                 name = str(e)
@@ -1708,6 +1710,18 @@ class SpecChain(FusedChain):
                 f"else if (16 * tid < {hi} && 16 * tid + 16 > {lo}) lsf_local_f<false>({r}, 16 * tid, {lo}, {hi}, {a}, {b}, {c});   //@X {(lo % CHK != 0) + (hi % CHK != 0)}",
                 f"if (warp >= {w0} && warp < {w1}) {{ put_sum(MBD({mb}), {a}, lane, warp); put_sum(MBD({mb + 1}), {b}, lane, warp); "
                 f"put_sum(MBD({mb + 2}), {c}, lane, warp); }}   //@X {w1 - w0}")
+        # A mean the BLOCK stream itself needs next (baseline -> bl_subtract): every block warp finishes that one sum
+        # after the round's barrier (16 loads + a warp sum) instead of waiting for the scalar warp's round trip --
+        # mailbox event, float64 finishing of all four results, broadcast cell, event back -- with the SM idle.
+        if outs[0] and outs[0] in self.b_needed and os.environ.get("DSPEED_B200_BLOCK_MEAN", "1") != "0":
+            sd = self._alloc_d(1)
+            gb = self._nan_guard([w.nan])
+            self._e(f"if (warp >= {w0} && warp < {w1}) put_sum(CSD({sd}), {a}, lane, warp);   //@X {w1 - w0}")
+            self.posts.append(self._asg(outs[0], f"{'(' + gb + ') ? CUDART_NAN_F : ' if gb else ''}"
+                                                 f"(float)(get_sum_r(CSD({sd}), lane, {w0}, {w1}) / (double){n})"))
+            self.pending.add(outs[0])
+            self.b_needed.discard(outs[0])        # (no publication by the scalar warp)
+            self.block_finished = getattr(self, "block_finished", set()) | {outs[0]}
         g = self._nan_guard([self._flag_s(w.nan)])
         self.s_dirty = True
         self.s_seq += 1
@@ -1722,6 +1736,8 @@ class SpecChain(FusedChain):
             if outs[k]:
                 self._es_later(self._asg(outs[k], f[k]), *self._stores(outs[k]))
                 self._def_s_later(outs[k])
+                if outs[k] in getattr(self, "block_finished", ()):
+                    self.sdom[outs[k]] = "both"       # the block stream computed its own copy
 
     def _e_bl_sub(self, nd):
         w, off, n = nd["ins"][0]
