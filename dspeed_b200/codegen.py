@@ -115,7 +115,9 @@ class SpecChain(FusedChain):
     # ------------------------------------------------------------------------------------
     # analysis
     # ------------------------------------------------------------------------------------
-    def _compile(self, chain):
+    def _compile(self, chain, slot_limit=None):
+        entry_state = dict(self.__dict__)        # a second planning pass starts from exactly this state
+        self._slot_limit = slot_limit
         managers = list(chain._proc_managers)
         self.n_managers = len(managers)
         self.meta = chain.device.type == "meta"
@@ -218,6 +220,16 @@ class SpecChain(FusedChain):
             self.out_of.setdefault(name, []).append((pi, ct, k))
         self._schedule()
         self._emit_kernel()
+        # Small chains need few shared-memory slots: a second pass with the pool cut to what the first one used makes
+        # room for TWO resident CTAs per SM (two waveforms in flight hide each other's barrier and shuffle latencies)
+        # (pool = 2 x the logical slots: the two row frames are then disjoint, the strongest form of the rotation rule)
+        need = max(2, 2 * self.logical_slots_used)
+        if (slot_limit is None and need < self.total_slots
+                and os.environ.get("DSPEED_B200_OCCUPANCY", "2") != "1"
+                and self.fixed_bytes + need * self.slot_words * 4 <= (MAX_SMEM - 2048) // 2):
+            self.__dict__.clear()
+            self.__dict__.update(entry_state)
+            return self._compile(chain, slot_limit=need)
         self._build()
 
     # -- operands ----------------------------------------------------------------------------
@@ -786,6 +798,8 @@ class SpecChain(FusedChain):
         if total_slots < 2:
             raise NotSpecializable("waveforms too long for the shared-memory resident layout")
         total_slots -= total_slots % 2       # two frames of the pool alternate with the row parity
+        if self._slot_limit:
+            total_slots = min(total_slots, self._slot_limit)
         self.free_cols = [(k, 0, self.nchunks) for k in range(total_slots)]
         self.total_slots = total_slots
         self.written_slots = set()
@@ -840,6 +854,7 @@ class SpecChain(FusedChain):
             raise NotSpecializable("too many reductions for the mailbox")
         # Scratch + CScr/bc + prof stamps + mailbox (two row parities) + summaries
         self.fixed_bytes = 2048 + 8192 + 2048 + 2 * self.MB_BUDGET + self.n_summ * 4224
+        self.logical_slots_used = self.n_slots
         self.n_slots = self.total_slots
         self.smem_bytes = self.fixed_bytes + self.n_slots * self.slot_words * 4
         self._pipeline_rows()
@@ -2404,6 +2419,7 @@ class SpecChain(FusedChain):
         body_b = ind.join(self._expand_regions(self.LB))
         ns = self.n_swarps
         nthr = NT + 32 * ns
+        occ = getattr(self, "occ", 1)
         body_s = ind.join(self.SW[1])
         body_s2 = ind.join(self.SW[2]) if ns == 2 else ""
         prolog = "\n      ".join(self.prolog)
@@ -2475,7 +2491,7 @@ struct Args {{
 #define PROF_MARK_S2(k)
 #endif
 
-__global__ void __launch_bounds__({nthr}, 1) k_chain_spec(const __grid_constant__ Args A) {{
+__global__ void __launch_bounds__({nthr}, {occ}) k_chain_spec(const __grid_constant__ Args A) {{
   extern __shared__ __align__(16) unsigned char smem_raw[];
   CScr* cs = reinterpret_cast<CScr*>(smem_raw + 2048);
   long long* prof_ts = reinterpret_cast<long long*>(smem_raw + 2048 + 8192);
@@ -2559,7 +2575,8 @@ extern "C" int chain_launch(const void* const* ptrs, long long n_ptrs, long long
   a.prof = prof;
   cudaError_t e = cudaFuncSetAttribute(k_chain_spec, cudaFuncAttributeMaxDynamicSharedMemorySize, {self.smem_bytes});
   if (e != cudaSuccess) return -(int)e;
-  const int grid = (int)(n_rows < num_sms ? n_rows : num_sms);
+  const long long ctas = (long long)num_sms * {occ};      // persistent CTAs: {occ} resident per SM
+  const int grid = (int)(n_rows < ctas ? n_rows : ctas);
   k_chain_spec<<<grid, {nthr}, {self.smem_bytes}, (cudaStream_t)stream>>>(a);
   e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -(int)e;
@@ -2567,6 +2584,13 @@ extern "C" int chain_launch(const void* const* ptrs, long long n_ptrs, long long
 """
 
     def _build(self):
+        # two resident CTAs per SM when shared memory allows it and the register budget (65536 / (2 x threads)) costs
+        # no spills; else one CTA with the full register file
+        self.occ = 1
+        if self.smem_bytes <= (MAX_SMEM - 2048) // 2 and os.environ.get("DSPEED_B200_OCCUPANCY", "2") != "1":
+            self.occ = 2
+            if spill_bytes(build_source(self.source())[0]) > 0:
+                self.occ = 1
         src = self.source()
         self.lib_path, self.src_path = build_source(src)
         self.handle = C.c_void_p(1)  # marks "runnable" for can_run()
@@ -2672,19 +2696,32 @@ def build_source(src: str, flags=()):
             except OSError as e:
                 raise NotSpecializable(f"cannot write the generated kernel: {e}")
             tmp = so + f".tmp{os.getpid()}"
-            cmd = [_lib._nvcc(), *_lib.NVCC_FLAGS, *extra, "-I", _lib.INCLUDE, "-I", _lib.CSRC, "-o", tmp, cu]
+            cmd = [_lib._nvcc(), *_lib.NVCC_FLAGS, "-Xptxas", "-v", *extra, "-I", _lib.INCLUDE, "-I", _lib.CSRC,
+                   "-o", tmp, cu]
             env = dict(os.environ)
             env.pop("CC", None)
             env.pop("CXX", None)
             log.info("compiling specialised chain kernel: " + " ".join(cmd))
             try:
-                subprocess.run(cmd, env=env, check=True, capture_output=True, text=True)
+                done = subprocess.run(cmd, env=env, check=True, capture_output=True, text=True)
             except FileNotFoundError as e:
                 raise NotSpecializable(f"nvcc not available: {e}")
             except subprocess.CalledProcessError as e:
                 raise RuntimeError(f"nvcc failed on {cu}:\n{e.stderr[-4000:]}")
+            spilled = sum(int(m) for m in re.findall(r"(\d+) bytes spill stores", done.stderr))
+            with open(so + ".spills", "w") as f:     # ptxas' verdict travels with the library (see spill_bytes)
+                f.write(str(spilled))
             os.replace(tmp, so)
     return so, cu
+
+
+def spill_bytes(so: str) -> int:
+    """bytes of register spill stores ptxas reported when `so` was built (0 if unknown)"""
+    try:
+        with open(so + ".spills") as f:
+            return int(f.read())
+    except (OSError, ValueError):
+        return 0
 
 
 def load_chain_lib(path: str) -> C.CDLL:

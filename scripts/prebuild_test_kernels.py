@@ -52,3 +52,8 @@ tiny = {
 }
 for cfg in (dpz, tiny):
     print(codegen.prebuild(cfg)[0])
+
+# the minimal energy chain of BASELINE.json config 1 (scripts/bench_configs.py measures it)
+from scripts.bench_configs import C1_CFG  # noqa: E402
+
+print(codegen.prebuild(C1_CFG, with_baseline=False)[0])
