@@ -1733,7 +1733,7 @@ class SpecChain(FusedChain):
             gb = self._nan_guard([w.nan])
             self._e(f"if (warp >= {w0} && warp < {w1}) put_sum(CSD({sd}), {a}, lane, warp);   //@X {w1 - w0}")
             self.posts.append(self._asg(outs[0], f"{'(' + gb + ') ? CUDART_NAN_F : ' if gb else ''}"
-                                                 f"(float)(get_sum_r(CSD({sd}), lane, {w0}, {w1}) / (double){n})"))
+                                                 f"(float)div_by(get_sum_r(CSD({sd}), lane, {w0}, {w1}), (double){n}, 1.0 / (double){n})"))
             self.pending.add(outs[0])
             self.b_needed.discard(outs[0])        # (no publication by the scalar warp)
             self.block_finished = getattr(self, "block_finished", set()) | {outs[0]}
@@ -1874,7 +1874,20 @@ class SpecChain(FusedChain):
             for mi, m in enumerate(batch):
                 out = m["wouts"][0]
                 d, tot, incl = self._t("d"), self._t("tot"), self._t("incl")
-                self._e(f"float {d}[16];", f"_Pragma(\"unroll\") for (int j = 0; j < 16; j++) {d}[j] = 0.f;")
+                self._e(f"float {d}[16];")
+                fresh = [True]      # the first term ASSIGNS the accumulators (no 0 + x additions, no zero fill)
+
+                def acc(c, term, ind=""):
+                    loop = f"{ind}_Pragma(\"unroll\") for (int j = 0; j < 16; j++) "
+                    if fresh[0]:
+                        fresh[0] = False
+                        rhs = term if c == 1.0 else f"-{term}" if c == -1.0 else f"{_flit(c)} * {term}"
+                        return f"{loop}{d}[j] = {rhs};"
+                    if c == 1.0:
+                        return f"{loop}{d}[j] += {term};"
+                    if c == -1.0:
+                        return f"{loop}{d}[j] -= {term};"
+                    return f"{loop}{d}[j] = fmaf({_flit(c)}, {term}, {d}[j]);"
                 # Taps whose offsets lie within 16 samples of each other share ONE span load
                 # (16 + width samples, 128-bit loads): the filters are shared-memory-bandwidth
                 # bound, so a cluster costs (16 + width) / 4 loads instead of 5 per tap.  Inside a
@@ -1892,11 +1905,7 @@ class SpecChain(FusedChain):
                     cluster = taps[k:e + 1]
                     k = e + 1
                     if len(cluster) == 1 and ts0 == 0:
-                        c = cluster[0][1]
-                        if c == 1.0:
-                            self._e(f"_Pragma(\"unroll\") for (int j = 0; j < 16; j++) {d}[j] += {own}[j];")
-                        else:
-                            self._e(f"_Pragma(\"unroll\") for (int j = 0; j < 16; j++) {d}[j] = fmaf({_flit(c)}, {own}[j], {d}[j]);")
+                        self._e(acc(cluster[0][1], f"{own}[j]"))
                         continue
                     width = cluster[-1][0] - ts0
                     cnt = 16 + width
@@ -1914,18 +1923,15 @@ class SpecChain(FusedChain):
                             cm = sum(x[1] for x in cluster[q:q + run]) / run
                             lo = ts0 + width - (ts + run - 1)      # v index of the oldest sample of the window at j = 0
                             ws = self._t("ws")
-                            self._e(f"  float {ws} = 0.f; _Pragma(\"unroll\") for (int u = 0; u < {run}; u++) {ws} += {v}[{lo} + u];",
-                                    f"  _Pragma(\"unroll\") for (int j = 0; j < 16; j++) {{ {d}[j] = fmaf({_flit(cm)}, {ws}, {d}[j]); "
+                            upd = f"{d}[j] = {_flit(cm)} * {ws};" if fresh[0] else f"{d}[j] = fmaf({_flit(cm)}, {ws}, {d}[j]);"
+                            fresh[0] = False
+                            self._e(f"  float {ws} = {v}[{lo}]; _Pragma(\"unroll\") for (int u = 1; u < {run}; u++) {ws} += {v}[{lo} + u];",
+                                    f"  _Pragma(\"unroll\") for (int j = 0; j < 16; j++) {{ {upd} "
                                     f"if (j < 15) {ws} += {v}[{lo} + j + {run}] - {v}[{lo} + j]; }}")
                             q += run
                             continue
                         off = ts0 + width - ts
-                        if c == 1.0:
-                            self._e(f"  _Pragma(\"unroll\") for (int j = 0; j < 16; j++) {d}[j] += {v}[j + {off}];")
-                        elif c == -1.0:
-                            self._e(f"  _Pragma(\"unroll\") for (int j = 0; j < 16; j++) {d}[j] -= {v}[j + {off}];")
-                        else:
-                            self._e(f"  _Pragma(\"unroll\") for (int j = 0; j < 16; j++) {d}[j] = fmaf({_flit(c)}, {v}[j + {off}], {d}[j]);")
+                        self._e(acc(c, f"{v}[j + {off}]", "  "))
                         q += 1
                     self._e("}")
                 sd = self._alloc_d(1)

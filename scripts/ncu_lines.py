@@ -76,3 +76,22 @@ for k, c in inst.most_common(top):
 print("-- opcode mix")
 for k, c in ops.most_common(25):
     print(f"{100 * c / ti:5.1f}%  {k}")
+
+# optional: per-source-line counts of one file (4th argument = file basename, e.g. warp_rt.cuh)
+if len(sys.argv) > 4:
+    want = sys.argv[4]
+    per_line = collections.Counter()
+    per_line_s = collections.Counter()
+    for r, k in zip(rows, seq):
+        if not k or os.path.basename(k[0]) != want:
+            continue
+        try:
+            per_line[k[1]] += int(r[ci])
+            per_line_s[k[1]] += int(r[cs])
+        except ValueError:
+            pass
+    lines = srcs.get([f for f in srcs if os.path.basename(f) == want][0], [])
+    print(f"-- per line of {want} (% of all warp instructions, % of samples)")
+    for ln in sorted(per_line):
+        if per_line[ln] * 1000 > ti or per_line_s[ln] * 300 > ts:
+            print(f"{100 * per_line[ln] / ti:5.2f}% {100 * per_line_s[ln] / max(ts, 1):5.2f}%  {ln:5d}: {lines[ln - 1].strip()[:110] if ln <= len(lines) else ''}")
