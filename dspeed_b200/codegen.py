@@ -278,7 +278,7 @@ class SpecChain(FusedChain):
                 if src.dtype not in (torch.float32, torch.float64):
                     self.never_nan.add(name)
                 pi = self._ptr(("in", man, what))
-                self.prolog.append(self._asg(name, f"((const {_CTYPE[src.dtype]}*)A.p[{pi}])[row * A.s[{pi}]]"))
+                self.prolog.append((name, _CTYPE[src.dtype], pi))
             return self.svar[st]
         if x is None:
             raise NotSpecializable("None argument")
@@ -2343,7 +2343,10 @@ class SpecChain(FusedChain):
         pairs = sum(((bb + p - 1) >> 4) - (bb >> 4) + 1 for bb in bases)
         helpers = os.environ.get("DSPEED_B200_CONV_HELPERS", "1") != "0" and pairs <= NT - hb and 16.0 * nch / sigma < 600.0
         tmpl = f"{'true' if poly else 'false'}, {'true' if two else 'false'}"
-        args_a = (f"{self._slot(w)}, {x}, {n}, {_lit(sigma)}, {int(lt)}, {int(fl)}, {int(L)}, {_lit(c)}, {_lit(inv2S)}, "
+        # c = exp(-1 / decay) is the only number of the model that comes from the (per-channel) decay constant: a launch
+        # argument, so that channels share the compiled kernel
+        c_arg = _lit(c) if os.environ.get("DSPEED_B200_BAKE_CONSTANTS", "0") == "1" else self._runtime_const(float(c).hex())
+        args_a = (f"{self._slot(w)}, {x}, {n}, {_lit(sigma)}, {int(lt)}, {int(fl)}, {int(L)}, {c_arg}, {_lit(inv2S)}, "
                   f"{_lit(math.exp(-1.0 / sigma))}, {_lit(math.exp(1.0 / sigma))}, {_lit(math.exp((L - 1) / sigma))}, {pw}")
         args_b = (f"{so[0]}, {so[1]}, {sinks[0]}, {sinks[1]}, reinterpret_cast<double*>(SLOT({scratch[0][0]})), "
                   f"tid, lane, warp);")
@@ -2428,7 +2431,20 @@ class SpecChain(FusedChain):
         occ = getattr(self, "occ", 1)
         body_s = ind.join(self.SW[1])
         body_s2 = ind.join(self.SW[2]) if ns == 2 else ""
-        prolog = "\n      ".join(self.prolog)
+        # per-event input scalars (baseline, t0 ...) are requested one row ahead, like the raw chunk: the block stream
+        # needs them a few hundred instructions into the row, an HBM latency it would otherwise wait out every row
+        prolog, scalar_prefetch = [], []
+        for k, (name, ct, pi) in enumerate(self.prolog):
+            ld = f"((const {ct}*)A.p[{pi}])[%s * A.s[{pi}]]"
+            if not any(nd.get(key) == name for nd in self.nodes for key in ("b", "tau", "t0")):
+                # only the scalar stream reads it (late in the row: the load has long completed): no extra registers
+                prolog.append(self._asg(name, ld % "row"))
+                continue
+            scalar_prefetch.append(f"{ct} pin{k} = 0; if (blockIdx.x < A.n_rows) pin{k} = {ld % '(long long)blockIdx.x'};")
+            prolog.append(self._asg(name, f"pin{k}"))
+            prolog.append(f"if (row + gridDim.x < A.n_rows) pin{k} = {ld % '(row + gridDim.x)'};")
+        prolog = "\n      ".join(prolog)
+        scalar_prefetch = "\n  ".join(scalar_prefetch)
         names = sorted(set(self.svar.values()), key=lambda x: int(x[1:]))
         decl = " ".join(f"{ty} " + ", ".join(n for n in names if self.stype[n] == ty) + ";"
                         for ty in ("float", "double") if any(self.stype[n] == ty for n in names))
@@ -2515,6 +2531,7 @@ __global__ void __launch_bounds__({nthr}, {occ}) k_chain_spec(const __grid_const
   }}
   int it = 0;
   {prefetch_init}
+  {scalar_prefetch}
 #ifdef DSPB_PROFILE
   for (int k = tid; k < 256; k += {nthr}) prof_ts[k] = 0;
   __syncthreads();
