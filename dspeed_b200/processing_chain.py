@@ -27,28 +27,23 @@ from __future__ import annotations
 
 import ast
 import importlib
-import itertools as it
-import json
 import logging
 import os
-import re
 import time
 from collections.abc import Collection, MutableMapping
-from copy import deepcopy
 from dataclasses import dataclass
-from functools import partial
 from numbers import Real
 from typing import Any
 
 import numpy as np
 import torch
 
-from . import _lib, binding, numpy_bridge, recipe, tables
+from . import _lib, binding, grammar, numpy_bridge, recipe, tables
 from . import processors as device_processors
 from .processors import _i32, _i64, _vp
 from .errors import DSPFatal, ProcessingChainError
 from .tables import kind_of
-from .units import Quantity, Unit, as_unit, from_foreign, is_in_registry, to_period_units, ureg
+from .units import Quantity, Unit, as_unit, from_foreign, is_in_registry, ureg
 
 log = logging.getLogger("dspeed")
 
@@ -63,22 +58,6 @@ DEFAULT_BLOCK_WIDTH = 16384
 
 class EndExecute(Exception):
     """raised by an input manager when the chunk is exhausted (reference :41-42)"""
-
-
-ast_ops_dict = {
-    ast.Add: (np.add, "{}+{}"),
-    ast.Sub: (np.subtract, "{}-{}"),
-    ast.Mult: (np.multiply, "{}*{}"),
-    ast.Div: (np.divide, "{}/{}"),
-    ast.FloorDiv: (np.floor_divide, "{}//{}"),
-    ast.USub: (np.negative, "-{}"),
-    ast.Eq: (np.equal, "{}=={}"),
-    ast.NotEq: (np.not_equal, "{}!={}"),
-    ast.Lt: (np.less, "{}<{}"),
-    ast.LtE: (np.less_equal, "{}<={}"),
-    ast.Gt: (np.greater, "{}>{}"),
-    ast.GtE: (np.greater_equal, "{}>={}"),
-}
 
 
 def fatal_message(code: int) -> str:
@@ -553,20 +532,20 @@ class ProcessingChain:
 
     # -- expression grammar (reference :718-1130) ------------------------------------
     def get_variable(self, expr: str, get_names_only: bool = False, expr_only: bool = False) -> Any:
-        """Parse ``expr``: a variable name (created on first use), ``name(shape, dtype,
-        ...)`` declarations, arithmetic / comparison / ternary expressions (each emits a
-        processor), ``wf[a:b:c]`` views, ``round/floor/ceil/trunc/astype/where/isnan/
-        isfinite/len`` calls, unit names, ``np.pi``-style constants and ``kw=expr``."""
-        names: list[str] = []
+        """Evaluate ``expr`` in the chain's expression language (:mod:`dspeed_b200.grammar`): a variable name (created
+        on first use), ``name(shape, dtype, ...)`` declarations, arithmetic / comparison / ternary expressions (each
+        emits a processor), ``wf[a:b:c]`` views, ``round/floor/ceil/trunc/astype/where/isnan/isfinite/len`` calls, unit
+        names, ``np.pi``-style constants and ``kw=expr``.  ``get_names_only``: only list the variable names the text
+        mentions (nothing is created)."""
         try:
             stmt = ast.parse(expr).body[0]
-            var = self._parse_expr(stmt.value, expr, get_names_only, names)
+            if get_names_only:
+                return grammar.names_read(stmt.value, expr, type(self))
+            var = grammar.Evaluator(self, expr)(stmt.value)
         except ProcessingChainError:
             raise
         except Exception as e:
             raise ProcessingChainError("Could not parse expression:\n  " + expr) from e
-        if get_names_only:
-            return names
         if isinstance(stmt, ast.Expr):
             return var
         if isinstance(stmt, ast.Assign) and len(stmt.targets) == 1:
@@ -576,393 +555,33 @@ class ProcessingChain:
         raise ProcessingChainError("Could not parse expression:\n  " + expr)
 
     def _emit(self, func, params) -> None:
+        """append one glue processor (an element-wise ufunc of the expression language) to the chain"""
         proc_man = ProcessorManager(self, func, params)
         self._proc_managers.append(proc_man)
         log.debug(f"added processor: {proc_man}")
 
-    def _parse_expr(self, node, expr: str, dry_run: bool, var_name_list: list[str]) -> Any:
-        if node is None:
-            return None
-
-        if isinstance(node, ast.List):
-            return np.array(ast.literal_eval(expr[node.col_offset : node.end_col_offset]))
-
-        if isinstance(node, ast.Constant):
-            return node.value
-
-        if isinstance(node, ast.Name):
-            if node.id in ureg:
-                return ureg(node.id)
-            var_name_list.append(node.id)
-            if dry_run:
-                return None
-            val = self._vars_dict.get(node.id, None)
-            if val is None:
-                val = self.add_variable(node.id)
-            return val
-
-        if isinstance(node, ast.BinOp):
-            lhs = self._parse_expr(node.left, expr, dry_run, var_name_list)
-            rhs = self._parse_expr(node.right, expr, dry_run, var_name_list)
-            if rhs is None or lhs is None:
-                return None
-            op, op_form = ast_ops_dict[type(node.op)]
-            lv, rv = isinstance(lhs, ProcChainVar), isinstance(rhs, ProcChainVar)
-            if not (lv or rv):
-                return _fold_constant(op, lhs, rhs)
-            name = "(" + op_form.format(str(lhs), str(rhs)) + ")"
-            if lv and rv:
-                if is_in_registry(lhs.unit) and is_in_registry(rhs.unit):
-                    unit = op(Quantity(1.0, as_unit(lhs.unit)), Quantity(1.0, as_unit(rhs.unit))).u
-                    if unit.dimensionless:
-                        unit = None
-                elif lhs.unit is not None and rhs.unit is not None:
-                    if type(node.op) in (ast.Mult, ast.Div, ast.FloorDiv):
-                        unit = op_form.format(str(lhs.unit), str(rhs.unit))
-                    else:
-                        unit = str(lhs.unit)
-                elif lhs.unit is not None:
-                    unit = lhs.unit
-                else:
-                    unit = rhs.unit
-                out = ProcChainVar(self, name, grid=None if lhs.is_coord and rhs.is_coord else auto,
-                                   is_coord=(False if lhs.is_coord is True and rhs.is_coord is True else auto),
-                                   unit=unit)
-            elif lv:
-                out = ProcChainVar(self, name, unit=lhs.unit, is_coord=lhs.is_coord)
-            else:
-                out = ProcChainVar(self, name, unit=rhs.unit, is_coord=rhs.is_coord)
-            self._emit(op, [lhs, rhs, out])
-            return out
-
-        if isinstance(node, ast.UnaryOp):
-            operand = self._parse_expr(node.operand, expr, dry_run, var_name_list)
-            if operand is None:
-                return None
-            op, op_form = ast_ops_dict[type(node.op)]
-            if isinstance(operand, ProcChainVar):
-                out = ProcChainVar(self, "(" + op_form.format(str(operand)) + ")", operand.shape, operand.dtype,
-                                   operand.grid, operand.unit, operand.is_coord)
-                self._emit(op, [operand, out])
-                return out
-            return op(operand)
-
-        if isinstance(node, ast.Compare):
-            lhs = self._parse_expr(node.left, expr, dry_run, var_name_list)
-            if len(node.comparators) != 1:
-                raise ProcessingChainError("Compound comparisons are not supported.")
-            rhs = self._parse_expr(node.comparators[0], expr, dry_run, var_name_list)
-            if rhs is None or lhs is None:
-                return None
-            op, op_form = ast_ops_dict[type(node.ops[0])]
-            if not (isinstance(lhs, ProcChainVar) or isinstance(rhs, ProcChainVar)):
-                return _fold_constant(op, lhs, rhs)
-            out = ProcChainVar(self, "(" + op_form.format(str(lhs), str(rhs)) + ")")
-            self._emit(op, [lhs, rhs, out])
-            return out
-
-        if isinstance(node, ast.Subscript):
-            return self._parse_subscript(node, expr, dry_run, var_name_list)
-
-        if isinstance(node, ast.IfExp):
-            condition = self._parse_expr(node.test, expr, dry_run, var_name_list)
-            a = self._parse_expr(node.body, expr, dry_run, var_name_list)
-            b = self._parse_expr(node.orelse, expr, dry_run, var_name_list)
-            return self._where(condition, a, b)
-
-        if isinstance(node, ast.Attribute):
-            module = expr[node.value.col_offset : node.value.end_col_offset]
-            if module in self.module_list:
-                attr = getattr(self.module_list[module], node.attr)
-                if not isinstance(attr, Real):
-                    raise ProcessingChainError(f"Attribute {node.attr} from {module} is not an int or float...")
-                return attr
-            val = self._parse_expr(node.value, expr, dry_run, var_name_list)
-            if val is None:
-                return None
-            return getattr(val, node.attr)
-
-        if isinstance(node, ast.Call):
-            func = self.func_list.get(node.func.id, None)
-            args = [self._parse_expr(arg, expr, dry_run, var_name_list) for arg in node.args]
-            kwargs = {kw.arg: self._parse_expr(kw.value, expr, dry_run, var_name_list) for kw in node.keywords}
-            if func is not None:
-                return func(self, *args, **kwargs) if not dry_run else None
-            if self._validate_name(node.func.id):
-                var_name = node.func.id
-                var_name_list.append(var_name)
-                if var_name in self._vars_dict:
-                    var = self._vars_dict[var_name]
-                    var.update_auto(*args, **kwargs)
-                    return var
-                if not dry_run:
-                    return self.add_variable(var_name, **{**_decl_args(args), **kwargs})
-                return None
-            raise ProcessingChainError(f"do not recognize call to {node.func.id}")
-
-        raise ProcessingChainError(f"cannot parse AST nodes of type {type(node).__name__}")
-
-    def _parse_subscript(self, node, expr, dry_run, var_name_list):
-        """``wf[i]`` / ``wf[a:b:c]``: views sharing the parent's buffer, with the grid
-        period scaled by the step and the offset shifted by the start (reference :947-1071)"""
-        val = self._parse_expr(node.value, expr, dry_run, var_name_list)
-        if val is None:
-            return None
-        if not isinstance(val, ProcChainVar) or not len(val.shape) > 0:
-            raise ProcessingChainError("Cannot apply subscript to", node.value)
-
-        def get_index(slice_value, var_len=None):
-            ret = self._parse_expr(slice_value, expr, dry_run, var_name_list)
-            if ret is None or isinstance(ret, ProcChainVar):
-                return ret
-            if isinstance(ret, Quantity):
-                ret = float(ret / val.period)
-            if isinstance(ret, Real):
-                round_ret = int(round(ret))
-                if abs(ret - round_ret) > 0.0001:
-                    log.warning(f"slice value is non-integer. Rounding to {round_ret}")
-                ret = round_ret
-            if ret < 0 and var_len is not None:
-                ret = self.get_variable(f"{var_len}{ret}")
-            return ret
-
-        if isinstance(node.slice, ast.Tuple):
-            raise ProcessingChainError("Tuple still isn't implemented...")
-
-        if not isinstance(node.slice, ast.Slice):
-            index = get_index(node.slice, val.vector_len)
-            if isinstance(index, int):
-                out_buf = val.buffer[..., index]
-                out_name = f"{str(val)}[{index}]"
-                out_grid = val.grid if val.is_coord else None
-            else:
-                out = ProcChainVar(self, name=f"{str(val)}[{index}]", shape=(), dtype=val.dtype,
-                                   grid=val.grid if val.is_coord else None, unit=val.unit, is_coord=val.is_coord)
-                default = np.nan if np.issubdtype(val.dtype, np.floating) else np.iinfo(val.dtype).max
-                self._emit(numpy_bridge.get_default, [val, index, default, out])
-                return out
-        else:
-            sl = slice(get_index(node.slice.lower), get_index(node.slice.upper), get_index(node.slice.step))
-            if any(isinstance(x, ProcChainVar) for x in (sl.start, sl.stop, sl.step)):
-                raise ProcessingChainError("Slice values must be constants")
-            out_buf = val.buffer[..., sl]
-            out_name = "{}[{}:{}{}]".format(str(val), "" if sl.start is None else str(sl.start),
-                                            "" if sl.stop is None else str(sl.stop),
-                                            "" if sl.step is None else ":" + str(sl.step))
-            if val.grid is None:
-                out_grid = None
-            else:
-                pd = val.period
-                if sl.step is not None:
-                    pd = pd * sl.step
-                off = val.offset
-                if sl.start is not None and sl.start > 0:
-                    start = sl.start * val.period
-                    if isinstance(off, ProcChainVar):
-                        new_off = ProcChainVar(self, name=f"({str(off)}+{str(start)})", is_coord=True)
-                        self._emit(np.add, [off, start, new_off])
-                        off = new_off
-                    else:
-                        off = off + start
-                out_grid = CoordinateGrid(pd, off)
-
-        out = ProcChainVar(self, out_name, shape=tuple(out_buf.shape[1:]), dtype=val.dtype, grid=out_grid,
-                           unit=val.unit, is_coord=val.is_coord)
-        out._buffer = [(out_buf, val._buffer[0][1])] if out.is_coord else out_buf
-        out.view_of = (val, node.slice)
-        return out
-
     def _validate_name(self, name: str, raise_exception: bool = False) -> bool:
-        isgood = bool(re.match(r"\A\w+$", name)) and name not in self.func_list and name not in ureg \
-            and name not in self.module_list
-        if raise_exception and not isgood:
+        ok = grammar.is_variable_name(name, type(self))
+        if raise_exception and not ok:
             raise ProcessingChainError(f"{name} is not a valid variable name")
-        return isgood
+        return ok
 
-    # -- helper functions callable inside expressions (reference :1177-1482) -----------
-    def _length(self, var):
-        if var is None:
-            return None
-        if not isinstance(var, ProcChainVar):
-            raise ProcessingChainError(f"cannot call len() on {var}")
-        if var.vector_len is not None:
-            return var.vector_len
-        if not len(var.shape) == 1:
-            raise ProcessingChainError(f"{var} has wrong number of dims")
-        return var.shape[0]
-
-    def _round(self, var, to_nearest=1, dtype=None, mode="round"):
-        """round a value / a coordinate onto a grid (reference :1193-1266)"""
-        fun = getattr(numpy_bridge, f"{mode}_to_nearest", None)
-        if fun is None:
-            raise ProcessingChainError("Mode must be round, floor, ceil or trunc")
-        if var is None:
-            return None
-        to_nearest = from_foreign(to_nearest)
-        if not isinstance(var, ProcChainVar):
-            host = numpy_bridge.HOST_ROUNDERS[mode]
-            if isinstance(var, Quantity) and isinstance(to_nearest, Quantity):
-                return host(float(var / Quantity(1.0, to_nearest.u)), to_nearest.m) * Quantity(1.0, to_nearest.u)
-            if isinstance(var, Quantity):
-                var = float(var)
-            return host(var, to_nearest)
-        name = f"{mode}({var}, {to_nearest})"
-        dtype = np.dtype(dtype) if dtype is not None else var.dtype
-        if var.is_coord:
-            if isinstance(to_nearest, Real):
-                grid = CoordinateGrid(var.grid.period * to_nearest, var.grid.offset)
-            elif isinstance(to_nearest, (Unit, Quantity)):
-                grid = CoordinateGrid(to_nearest, var.grid.offset)
-            else:
-                grid = to_nearest
-            out = ProcChainVar(self, name, var.shape, dtype, grid, var.unit, var.is_coord)
-            conversion_manager = UnitConversionManager(var, grid, mode=mode, out_dtype=dtype)
-            out._buffer = conversion_manager.out_buffer
-            self._proc_managers.append(conversion_manager)
-            log.debug(f"added conversion: {conversion_manager}")
-        else:
-            out = ProcChainVar(self, name, var.shape, dtype, var.grid, var.unit, var.is_coord)
-            self.add_processor(fun, var, to_nearest, out)
-        return out
-
-    def _astype(self, var, dtype):
-        dtype = np.dtype(dtype)
-        if var is None:
-            return None
-        if not isinstance(var, ProcChainVar):
-            raise ProcessingChainError(f"cannot call astype() on {var}")
-        out = ProcChainVar(self, f"{var}.astype(`{dtype.char}`)", var.shape, dtype, var.grid, var.unit, var.is_coord)
-        self._emit(numpy_bridge.make_astype(var.dtype, dtype), [var, out])
-        return out
-
-    def _isnan(self, var):
-        if var is None:
-            return None
-        if not isinstance(var, ProcChainVar):
-            return np.isnan(var)
-        out = ProcChainVar(self, f"isnan({var})", var.shape, "bool", var.grid, var.unit, var.is_coord)
-        self._emit(np.isnan, [var, out])
-        return out
-
-    def _isfinite(self, var):
-        if var is None:
-            return None
-        if not isinstance(var, ProcChainVar):
-            return np.isfinite(var)
-        out = ProcChainVar(self, f"isfinite({var})", var.shape, "bool", var.grid, var.unit, var.is_coord)
-        self._emit(np.isfinite, [var, out])
-        return out
+    # -- helper functions callable inside expressions: dspeed_b200.grammar.HELPERS -------
+    def _add_conversion(self, var, grid, out, mode=None, out_dtype=None) -> None:
+        """append the unit conversion that expresses coordinate `var` on `grid` and writes into `out`"""
+        conversion = UnitConversionManager(var, grid, mode=mode, out_dtype=out_dtype)
+        out._buffer = conversion.out_buffer
+        self._proc_managers.append(conversion)
+        log.debug(f"added conversion: {conversion}")
 
     def _where(self, condition, a, b, dtype=auto):
-        """``where(cond, a, b)`` / ``a if cond else b`` with unit reconciliation
-        (reference :1345-1442)"""
-        if condition is None:
-            return None
-        if not (isinstance(condition, ProcChainVar) and condition.dtype == "?"):
-            raise ProcessingChainError(f"{condition} must be a boolean variable")
-        a, b = from_foreign(a), from_foreign(b)
-        name = f"where({condition}, {a}, {b})"
-        av, bv = isinstance(a, ProcChainVar), isinstance(b, ProcChainVar)
-        if av and bv:
-            if a.period != b.period:
-                raise ProcessingChainError(f"Cannot select between {a} and {b} with different periods")
-            if a.is_coord != b.is_coord:
-                raise ProcessingChainError(f"Cannot select between {a} and {b} with different is_coord")
-            is_coord = a.is_coord
-            if a.offset == b.offset:
-                grid = a.grid
-            else:
-                grid = CoordinateGrid(a.period, self._where(condition, a.offset, b.offset))
-            unit_a = as_unit(a.unit) if is_in_registry(a.unit) else a.unit
-            unit_b = as_unit(b.unit) if is_in_registry(b.unit) else b.unit
-            if unit_a == unit_b or not unit_b:
-                unit = unit_a
-            elif not unit_a:
-                unit = unit_b
-            else:
-                raise ProcessingChainError(f"{a} and {b} do not have compatible units")
-        elif av or bv:
-            var, const = (a, b) if av else (b, a)
-            grid = var.grid
-            is_coord = var.is_coord
-            if not var.unit:
-                unit = None
-            elif not isinstance(const, Quantity):
-                unit = var.unit
-            elif is_in_registry(var.unit):
-                unit = var.period if is_coord else Quantity(1, as_unit(var.unit))
-                if av:
-                    b = float(const / (1 * unit))
-                else:
-                    a = float(const / (1 * unit))
-            else:
-                raise ProcessingChainError(f"{a} and {b} do not have compatible units")
-        else:
-            grid = None
-            is_coord = False
-            if isinstance(a, Quantity) and isinstance(b, Quantity):
-                unit = a.u
-                b = float(b / Quantity(1.0, unit))
-                a = a.m
-            elif isinstance(a, Quantity):
-                unit, a = a.u, a.m
-            elif isinstance(b, Quantity):
-                unit, b = b.u, b.m
-            else:
-                unit = None
-        out = ProcChainVar(self, name, auto, dtype, grid, unit, is_coord)
-        self._emit(numpy_bridge.where, [condition, a, b, out])
-        return out
+        return grammar.h_where(self, condition, a, b, dtype)
 
-    def _loadlh5(self, path_to_file, path_in_file):
-        try:
-            import lh5
-        except ImportError as e:
-            raise ProcessingChainError("loadlh5() needs the legend-lh5io package") from e
-        try:
-            loaded = lh5.read(path_in_file, path_to_file)
-            return loaded.value if hasattr(loaded, "value") else loaded.nda
-        except (ValueError, OSError):
-            raise ProcessingChainError(f"LH5 file not found: {path_to_file}")
-
-    func_list = {
-        "len": _length,
-        "isfinite": _isfinite,
-        "isnan": _isnan,
-        "round": partial(_round, mode="round"),
-        "floor": partial(_round, mode="floor"),
-        "ceil": partial(_round, mode="ceil"),
-        "trunc": partial(_round, mode="trunc"),
-        "astype": _astype,
-        "where": _where,
-        "loadlh5": _loadlh5,
-    }
+    func_list = grammar.HELPERS
     module_list = {"np": np, "numpy": np}
-
-
-def _decl_args(args) -> dict:
-    """``name(shape, dtype, grid, unit, is_coord)``: positional declaration arguments follow
-    the ProcChainVar / update_auto order (the reference forwards them positionally to
-    add_variable, whose order differs -- reference :1117-1120); map them to keywords."""
-    return dict(zip(["shape", "dtype", "grid", "unit", "is_coord"], args))
-
-
-def _fold_constant(op, lhs, rhs):
-    """binary op on two constants, evaluated at build time (reference :839-845)"""
-    lhs, rhs = from_foreign(lhs), from_foreign(rhs)
-    if isinstance(lhs, (Quantity, Unit)) or isinstance(rhs, (Quantity, Unit)):
-        pyop = {np.add: lambda a, b: a + b, np.subtract: lambda a, b: a - b, np.multiply: lambda a, b: a * b,
-                np.divide: lambda a, b: a / b, np.floor_divide: lambda a, b: a // b,
-                np.equal: lambda a, b: a == b, np.not_equal: lambda a, b: not (a == b),
-                np.less: lambda a, b: a < b, np.less_equal: lambda a, b: a <= b,
-                np.greater: lambda a, b: a > b, np.greater_equal: lambda a, b: a >= b}[op]
-        ret = pyop(lhs, rhs)
-        if isinstance(ret, Unit):
-            ret = Quantity(1.0, ret)
-        if isinstance(ret, Quantity) and ret.u.dimensionless:
-            ret = float(ret)
-        return ret
-    return op(lhs, rhs)
+    #: the classes the expression evaluator instantiates
+    Variable = ProcChainVar
+    Grid = CoordinateGrid
 
 
 # ======================================================================================
