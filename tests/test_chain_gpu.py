@@ -467,3 +467,48 @@ def test_waveform_outputs_carry_the_per_event_t0(case):
     if case != "kernel_ignores_t0":
         tp = np.asarray(out["tp_max"].nda.cpu() if hasattr(out["tp_max"].nda, "cpu") else out["tp_max"].nda)
         assert np.array_equal(tp, (np.argmax(vals, 1) * 16.0 + t0).astype(np.float32))
+
+
+def test_one_launch_million_row_path_matches_oracle():
+    """BASELINE.json's full size: 1 M x 8192 device-resident waveforms processed by ONE launch (persistent CTAs striding
+    over the rows).  Three 34 816-row windows of that batch -- its head, its middle and its tail, 104 448 rows -- are
+    checked against the CPU oracle with the chain rules of oracle/parity_check.py (the checker bench.py applies to its
+    own timed outputs); every output row of the batch must have been written."""
+    import torch
+
+    from dspeed_b200 import synth, tables
+    from dspeed_b200.processing_chain import build_processing_chain
+    from oracle import chains, parity_check
+    from oracle import oracle as O
+
+    dev = torch.device("cuda", 0)
+    n = 1_000_000
+    if torch.cuda.get_device_properties(dev).total_memory < 40e9:
+        pytest.skip("needs 17 GB of device memory for the batch")
+    d = synth.hpge_waveforms(n, seed=4242, device=dev, stress=True)
+    wf = tables.WaveformTable(size=n, t0=tables.Array(d["t0"], attrs={"units": "ns"}),
+                              dt=tables.Array(d["dt"], attrs={"units": "ns"}), values=d["values"])
+    tb = tables.Table({"waveform": wf, "baseline": tables.Array(d["baseline"])}, size=n)
+    cfg = yaml.safe_load(open(ICPC))
+    chain, _, tb_out = build_processing_chain(cfg, tb, device=dev)
+    out = tables.Table({k: tables.Array(torch.full((n,), -7.25e30, dtype=torch.float32, device=dev)) for k in tb_out}, size=n)
+    chain(tb, out)
+    torch.cuda.synchronize()
+    assert chain._fused is not None and chain._fused.rows_per_launch == n      # one launch over the whole batch
+    for k in out:
+        assert not bool((out[k].nda == -7.25e30).any()), f"{k}: rows left unwritten"
+    threads = O.set_threads(os.cpu_count() or 1)
+    consts = chains.icpc_constants()
+    m = 34816
+    for lo in (0, n // 2 - m // 2, n - m):
+        vals = d["values"][lo:lo + m].cpu().numpy()
+        bl = d["baseline"][lo:lo + m].cpu().numpy()
+        parts = [chains.icpc_chain(vals[a:a + 8192], bl[a:a + 8192], consts=consts, keep_waveforms=False, conv="library",
+                                   threads=threads) for a in range(0, m, 8192)]
+        o = {k: np.concatenate([np.asarray(p[k]) for p in parts]) for k in parts[0]}
+        got = {k: out[k].nda[lo:lo + m].cpu().numpy() for k in out}
+
+        rep = parity_check.icpc_report(got, o, waves_of=lambda rows, v=vals, b=bl: chains.icpc_chain(v[rows], b[rows],
+                                                                                                   keep_waveforms=True))
+        assert rep["ok"], (lo, rep["violations"])
+        assert rep["max_rel_err"] <= 1e-5
