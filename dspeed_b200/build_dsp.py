@@ -300,14 +300,53 @@ def _chain_first(first, rest):
     yield from rest
 
 
-def _concat_tables(parts):
+def _concat_data(arrays):
+    """row-wise concatenation of numpy arrays or torch tensors (a mixed list ends up on the host)"""
+    import numpy as np
+    import torch
+
+    if all(isinstance(a, torch.Tensor) for a in arrays):
+        return torch.cat(list(arrays))
+    return np.concatenate([a.cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a) for a in arrays])
+
+
+def _concat_columns(cols):
+    """one output column from the same column of consecutive chunks, whatever its kind (the reference appends chunks
+    generically through lh5 / lgdo; here: arrays, arrays of equal-sized arrays, waveform tables, vectors of vectors,
+    nested tables; data on the host or on the device)"""
     import numpy as np
 
+    first = cols[0]
+    kind = tables.kind_of(first)
+    if kind == "vov":
+        ends, base = [], 0
+        for c in cols:
+            cl = c.cumulative_length.nda
+            cl = cl.cpu().numpy() if hasattr(cl, "cpu") else np.asarray(cl)
+            ends.append(cl.astype(np.int64) + base)
+            base = int(ends[-1][-1]) if len(cl) else base
+        flat = [c.flattened_data.nda[: int(c.cumulative_length.nda[-1]) if len(c) else 0] for c in cols]
+        return tables.VectorOfVectors(flattened_data=tables.Array(_concat_data(flat), attrs=dict(first.flattened_data.attrs)),
+                                      cumulative_length=tables.Array(np.concatenate(ends).astype(np.uint32)),
+                                      attrs=dict(first.attrs))
+    if kind == "wftable":
+        t0, dt, values = (_concat_columns([getattr(c, f) if f != "values" else tables.wf_values(c) for c in cols])
+                          for f in ("t0", "dt", "values"))
+        return tables.WaveformTable(size=len(t0), t0=t0, dt=dt, values=values, attrs=dict(first.attrs))
+    if kind == "table":
+        out = tables.Table(size=sum(len(c) for c in cols), attrs=dict(first.attrs))
+        for k in first:
+            out.add_field(k, _concat_columns([c[k] for c in cols]))
+        return out
+    if kind in ("array", "aoesa"):
+        return type(first)(_concat_data([c.nda for c in cols]), attrs=dict(first.attrs))
+    raise TypeError(f"cannot concatenate output columns of kind {kind}")
+
+
+def _concat_tables(parts):
     out = tables.Table(size=sum(len(p) for p in parts), attrs=parts[0].attrs)
     for k in parts[0]:
-        cols = [p[k] for p in parts]
-        nda = np.concatenate([np.asarray(c.nda) for c in cols])
-        out.add_field(k, type(cols[0])(nda, attrs=cols[0].attrs))
+        out.add_field(k, _concat_columns([p[k] for p in parts]))
     return out
 
 
