@@ -526,6 +526,21 @@ def run_b200(args, rank, world, local_rank):
                "sample": f"{mc} of the same synthetic waveforms ({secs:.1f} s of CPU work), CPU oracle "
                          f"chain (C restatement of the reference's numba processors; convolutions through the "
                          f"reference's own numpy.convolve / scipy fftconvolve calls), {cores} threads"}
+        # how the reference itself runs: ONE thread (numba gufunc target "cpu"), on a smaller sample of the same rows
+        from oracle import chains as _chains
+        from oracle import oracle as _O
+
+        m1 = min(4096, mc)
+        _O.set_threads(1)
+        try:
+            t1 = time.perf_counter()
+            _chains.icpc_chain(vals_c[:m1], bl_c[:m1], consts=_chains.icpc_constants(), keep_waveforms=False,
+                               conv="library", threads=1)
+            t1 = time.perf_counter() - t1
+        finally:
+            _O.set_threads(cores)
+        cpu["one_thread"] = {"value": m1 / t1, "unit": "waveforms/s", "cores": 1,
+                             "sample": f"the first {m1} of those rows ({t1:.1f} s)"}
         # ---- the benchmarked launch checks itself: the device-resident outputs of the last timed step against the
         # oracle outputs of the same rows (tolerances of tests/parity.py; oracle/parity_check.py) ----------------
         from oracle import chains

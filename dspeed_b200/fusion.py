@@ -815,6 +815,11 @@ class FusedChain:
                 staging[stage] = torch.empty_like(buf)
             dst = staging[stage]
             t = col if isinstance(col, torch.Tensor) else torch.from_numpy(col)
+            if not t.is_cuda and not getattr(self, "_warned_pageable", False) and not t.is_pinned():
+                # a copy from pageable memory is staged by the driver and synchronous: no overlap with the kernels
+                self._warned_pageable = True
+                log.warning("input column %r lives in pageable host memory: host-to-device copies will not overlap the "
+                            "kernels (allocate it with dspeed_b200.tables.pinned_empty, or torch .pin_memory())", what)
             n = end - begin
             with torch.cuda.stream(copy_stream):
                 dst[:n].copy_(t[begin:end], non_blocking=True)
