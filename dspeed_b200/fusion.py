@@ -819,7 +819,8 @@ class FusedChain:
                 # a copy from pageable memory is staged by the driver and synchronous: no overlap with the kernels
                 self._warned_pageable = True
                 log.warning("input column %r lives in pageable host memory: host-to-device copies will not overlap the "
-                            "kernels (allocate it with dspeed_b200.tables.pinned_empty, or torch .pin_memory())", what)
+                            "kernels (allocate it with dspeed_b200.tables.pinned_empty, or torch .pin_memory())",
+                            f"{getattr(getattr(man, 'var', None), 'name', '?')}.{what}")
             n = end - begin
             with torch.cuda.stream(copy_stream):
                 dst[:n].copy_(t[begin:end], non_blocking=True)
