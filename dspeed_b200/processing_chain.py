@@ -979,7 +979,10 @@ class WaveformIOManager(IOManager):
         self.var = variable
         if (self.wf_var.grid is auto and isinstance(dt_units, str) and dt_units in ureg
                 and isinstance(t0_units, str) and t0_units in ureg):
-            dt0 = float(np.asarray(_host_view(wf_table.dt.nda)[0:1])[0]) if len(wf_table.dt) else 1.0
+            if not len(wf_table.dt):
+                # (the sampling period is the first entry of the per-event `dt` column, reference :2286)
+                raise ProcessingChainError(f"waveform table of {variable.name} is empty: it carries no sampling period")
+            dt0 = float(np.asarray(_host_view(wf_table.dt.nda)[0:1])[0])
             self.wf_var.update_auto(
                 grid=CoordinateGrid(
                     ureg.Quantity(dt0, dt_units),

@@ -512,3 +512,27 @@ def test_one_launch_million_row_path_matches_oracle():
                                                                                                    keep_waveforms=True))
         assert rep["ok"], (lo, rep["violations"])
         assert rep["max_rel_err"] <= 1e-5
+
+
+@pytest.mark.parametrize("n_rows", [0, 1, 147, 149])
+def test_degenerate_table_sizes(synth_batch, n_rows):
+    """a single event, one row less / more than the number of persistent CTAs: same results as the oracle, host-staged and
+    device-resident; an empty table is a set-up error as in the reference"""
+    from dspeed_b200.errors import ProcessingChainError
+
+    vals, bl, o = synth_batch
+    for device in (None, "cuda"):
+        if n_rows == 0:
+            # the sampling period of a waveform table is the first entry of its per-event `dt` column
+            # (reference processing_chain.py:2286 indexes dt[0]): an empty table cannot configure a chain
+            with pytest.raises(ProcessingChainError) as err:
+                run_icpc(vals[:0], bl[:0], device=device)
+            assert "no sampling period" in str(err.value) + str(err.value.__cause__)
+            continue
+        got = run_icpc(vals[:n_rows], bl[:n_rows], device=device)
+        assert all(len(v) == n_rows for v in got.values())
+        for k in EXACT:
+            ref = o[k][:n_rows] * (16.0 if k.startswith("tp_") else 1.0)
+            assert np.array_equal(got[k], ref.astype(np.float32), equal_nan=True), (k, device)
+        for k in FLOATS:
+            PT.assert_float_close(k, got[k], o[k][:n_rows], scale=float(np.nanmax(np.abs(o[k]))))
