@@ -536,3 +536,35 @@ def test_degenerate_table_sizes(synth_batch, n_rows):
             assert np.array_equal(got[k], ref.astype(np.float32), equal_nan=True), (k, device)
         for k in FLOATS:
             PT.assert_float_close(k, got[k], o[k][:n_rows], scale=float(np.nanmax(np.abs(o[k]))))
+
+
+def test_float_input_with_nan_waveforms(synth_batch):
+    """float32 raw waveforms (not integer-valued: the packed arg-extremum and exact-sum shortcuts of uint16 input must not
+    be taken) with NaN samples: a waveform with a NaN anywhere gives NaN in every output, like every reference processor
+    (`w_out[:] = nan; if isnan(w_in).any(): return`), and leaves its neighbours untouched"""
+    from oracle import chains
+
+    vals, bl, _ = synth_batch
+    n = 600
+    rng = np.random.default_rng(99)
+    v = vals[:n].astype(np.float32) + rng.uniform(-0.5, 0.5, (n, vals.shape[1])).astype(np.float32)
+    bad = {3: 100, 7: 8000, 11: None, 298: 0, 599: 8191}
+    for r, c in bad.items():
+        if c is None:
+            v[r, :] = np.nan
+        else:
+            v[r, c] = np.nan
+    o = chains.icpc_chain(v, bl[:n])
+    for device, bw in ((None, 256), ("cuda", None)):
+        got = run_icpc(v, bl[:n], block_width=bw, device=device)
+        for k, g in got.items():
+            assert np.isnan(g[list(bad)]).all(), (k, device)
+        ok = np.ones(n, bool)
+        ok[list(bad)] = False
+        for k in EXACT:
+            ref = o[k] * (16.0 if k.startswith("tp_") else 1.0)
+            assert np.array_equal(got[k][ok], ref.astype(np.float32)[ok]), (k, device)
+        for k in FLOATS:
+            PT.assert_float_close(k, got[k], o[k], mask=ok)
+        t0 = got["tp_0_est"] / 16.0
+        assert ((t0 == o["tp_0_est"]) | (np.isnan(t0) & np.isnan(o["tp_0_est"])))[ok].mean() > 0.995
