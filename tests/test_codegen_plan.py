@@ -198,3 +198,23 @@ def test_database_constants_do_not_change_the_kernel():
     for cs, tau in zip(consts, (439368.0 / 16, 431200.0 / 16)):
         tau32 = np.float64(np.float32(tau))
         assert sorted(abs(c - v) < 1e-15 for c, v in zip(sorted(cs), sorted([1 - np.exp(-1 / tau32), np.exp(-1 / tau32)]))) == [True, True]
+
+
+def test_small_chains_get_two_resident_ctas_per_sm(spec):
+    """A chain that needs few shared-memory slots is planned a second time with the pool cut to twice its logical slots,
+    so that two CTAs fit one SM (launch bounds (threads, 2), grid = 2 x SMs); the ICPC chain (6 slots of 32.9 KB) keeps
+    one CTA per SM.  The second planning pass starts from a clean state (the raw-chunk prefetch is still emitted)."""
+    from dspeed_b200 import tables
+    from dspeed_b200.processing_chain import build_processing_chain
+    from scripts.bench_configs import C1_CFG
+
+    n = 4
+    wf = tables.WaveformTable(size=n, t0=0, t0_units="ns", dt=16, dt_units="ns", values=np.zeros((n, 8192), np.uint16))
+    chain, _, _ = build_processing_chain(C1_CFG, tables.Table({"waveform": wf}, size=n), block_width=16, device="meta")
+    sc = codegen.SpecChain(chain)
+    src = sc.source()
+    assert sc.occ == 2 and sc.smem_bytes <= (codegen.MAX_SMEM - 2048) // 2
+    assert f"__launch_bounds__({512 + 32 * sc.n_swarps}, 2)" in src and "num_sms * 2" in src
+    assert src.count("pf0 = ldg_nc(g_)") == 2          # prologue + in-loop prefetch of the next row
+    assert codegen.spill_bytes(sc.lib_path) == 0
+    assert spec.smem_bytes > (codegen.MAX_SMEM - 2048) // 2 and "__launch_bounds__(576, 1)" in spec.source()
