@@ -42,6 +42,35 @@ __device__ __forceinline__ void stage_row_16(unsigned char* raw, const uint16_t*
   for (int q = lane; q < np; q += 32) cp_async16(raw + (q / PPC) * (2 * CH + 16) + (q % PPC) * 16, g + 8 * q);
   cp_async_commit();
 }
+// The same pieces through registers, for kernels whose staging buffer is aliased with the wave copy of the peak
+// finder: the next row is REQUESTED before the walk (the 64-sample register chunk is dead by then, so the pieces cost
+// no extra registers) and WRITTEN to the staging buffer after it.  N = samples per row (compile time: the loops unroll).
+template <int N>
+struct RowPieces {
+  static constexpr int NP = N >> 3, K = (NP + 31) / 32;
+  uint4 q[K];
+};
+template <int N>
+__device__ __forceinline__ void fetch_row_16(RowPieces<N>& r, const uint16_t* g, int lane, bool on) {
+#pragma unroll
+  for (int k = 0; k < RowPieces<N>::K; k++) {
+    const int q = lane + 32 * k;
+    r.q[k] = make_uint4(0u, 0u, 0u, 0u);
+    if (on && q < RowPieces<N>::NP)
+      asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                   : "=r"(r.q[k].x), "=r"(r.q[k].y), "=r"(r.q[k].z), "=r"(r.q[k].w)
+                   : "l"(reinterpret_cast<const uint4*>(g) + q));
+  }
+}
+template <int CH, int N>
+__device__ __forceinline__ void stage_pieces_16(unsigned char* raw, const RowPieces<N>& r, int lane) {
+  constexpr int PPC = CH / 8;
+#pragma unroll
+  for (int k = 0; k < RowPieces<N>::K; k++) {
+    const int q = lane + 32 * k;
+    if (q < RowPieces<N>::NP) *reinterpret_cast<uint4*>(raw + (q / PPC) * (2 * CH + 16) + (q % PPC) * 16) = r.q[k];
+  }
+}
 template <bool SIGNED>
 __device__ __forceinline__ float cvt16(unsigned h) {
   return SIGNED ? (float)(short)(unsigned short)h : (float)h;

@@ -21,12 +21,13 @@ to the other GPU tiers (``fusion.try_fuse``).
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
 
 from . import numpy_bridge
-from .codegen import _CTYPE, NotSpecializable, _flit, _lit, build_source, load_chain_lib
+from .codegen import spill_bytes, _CTYPE, NotSpecializable, _flit, _lit, build_source, load_chain_lib
 from .fusion import FusedChain, NotFusable, _storage
 
 MAX_LEN = 2048
@@ -356,9 +357,16 @@ class WarpChain(FusedChain):
         vx, vn = self._t("v"), self._t("v")
         nx, nn = self._sout(nmax_t), self._sout(nmin_t)
         prm = f"{_flit(d_max)}, {_flit(d_min)}, {_flit(ab_max)}, {_flit(ab_min)}, {m}"
+        fetch = []
+        if self._alias_wanted() and not getattr(self, "_row_fetched", False):
+            # the next row is requested now (the register chunk dies with the summary) and staged at the end of the row
+            self._row_fetched = True
+            pi = self.in_ptr
+            fetch = [f"RowPieces<{self.in_n}> nxt_row; fetch_row_16<{self.in_n}>(nxt_row, (const uint16_t*)A.p[{pi}] + "
+                     f"(row + wstride) * A.s[{pi}], lane, row + wstride < A.n_rows);"]
         self._e(f"st_chunk<CH>(S, lane, {w.reg});",
                 f"const ChunkSumm<CH> {cs} = chunk_summary<CH>({w.reg});",
-                "__syncwarp();",
+                "__syncwarp();", *fetch,
                 f"unsigned long long {bx} = 0ull, {bn} = 0ull; int {c0} = 0, {c1} = 0; (void){c0}; (void){c1};",
                 f"if (!({w.nan})) {{")
         if sdir in (0, 3):
@@ -405,14 +413,34 @@ class WarpChain(FusedChain):
     # ------------------------------------------------------------------------------------
     def _geometry(self):
         CH = self.CH
-        self.ctas_per_sm = 4 if CH >= 64 else (6 if CH == 32 else 8)
         raw = 32 * (2 * CH + 16)
         slot = 32 * (CH + 4) * 4
-        self.warp_smem = raw + slot + 128
+        # Shared memory per warp: the raw staging buffer of the next row and -- only when a peak finder walks a wave --
+        # one float copy of that wave.  The copy is dead from the end of the walk to the next row's store, the staging
+        # buffer from the register read of a row to the arrival of the next one: they are ALIASED (max instead of sum),
+        # which lets 50 % more warps be resident; the kernel is bound by the latency of dependent shuffle / ballot
+        # chains, so resident warps are what counts (C4: 16 -> 24 warps per SM, + 14 %).  The next row then travels
+        # through registers: requested before the walk, written to the staging buffer after it (_lower_extrema).
+        self.alias = self.uses_slot and self._alias_wanted()
+        if not self.uses_slot:
+            self.warp_smem, self.s_off, self.lbuf_off = raw + 128, 0, raw
+        elif self.alias:
+            self.warp_smem, self.s_off, self.lbuf_off = max(raw, slot) + 128, 0, max(raw, slot)
+        else:
+            self.warp_smem, self.s_off, self.lbuf_off = raw + slot + 128, raw, raw + slot
+        # resident CTAs of 4 warps: the register file allows 8 CTAs at 64 registers (CH <= 32: the chunk is <= 32
+        # registers) and 6 at 80 (CH = 64); shared memory may allow fewer
+        self.ctas_per_sm = int(os.environ.get("DSPEED_B200_WARP_CTAS", "0")) or (6 if CH >= 32 else 8)
+        if getattr(self, "max_ctas", None):
+            self.ctas_per_sm = min(self.ctas_per_sm, self.max_ctas)
         self.raw_bytes, self.slot_bytes = raw, slot
         self.smem_bytes = WARPS_PER_CTA * self.warp_smem
         while self.ctas_per_sm > 1 and self.ctas_per_sm * (self.smem_bytes + 1024) > 227 * 1024:
             self.ctas_per_sm -= 1
+
+    @staticmethod
+    def _alias_wanted() -> bool:
+        return os.environ.get("DSPEED_B200_WARP_ALIAS", "1") != "0"
 
     def source(self) -> str:
         if not hasattr(self, "in_ptr"):
@@ -424,6 +452,14 @@ class WarpChain(FusedChain):
         sg = "true" if self.in_signed else "false"
         align_check = "".join(f"  if (((uintptr_t)ptrs[{i}] & 15) || (strides[{i}] & 7)) return DSPB_ERR_UNSUPPORTED;\n"
                               for i in self.aligned_ptrs)
+        prefetch = (f"if (row + wstride < A.n_rows) stage_row_16<CH>(raw, (const uint16_t*)A.p[{pi}] + (row + wstride) * "
+                    f"A.s[{pi}], {n}, lane);")
+        if self.alias:
+            prefetch_early = "// (the staging buffer is aliased with the wave copy: the next row travels through registers)"
+            prefetch_late = f"stage_pieces_16<CH, {n}>(raw, nxt_row, lane);"
+        else:
+            prefetch_early = "// the raw row of this warp's next waveform travels while this one is processed\n    " + prefetch
+            prefetch_late = ""
         return f"""// generated by dspeed_b200/warpchain.py -- do not edit
 #include "warp_rt.cuh"
 using namespace wrt;
@@ -442,8 +478,8 @@ __global__ void __launch_bounds__(32 * WPC, {self.ctas_per_sm}) k_chain_warp(con
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned char* raw = smem_raw + warp * {self.warp_smem};
-  float* S = reinterpret_cast<float*>(raw + {self.raw_bytes});
-  float* lbuf = reinterpret_cast<float*>(raw + {self.raw_bytes + self.slot_bytes});
+  float* S = reinterpret_cast<float*>(raw + {self.s_off});
+  float* lbuf = reinterpret_cast<float*>(raw + {self.lbuf_off});
   (void)S; (void)lbuf;
   const long long wstride = (long long)gridDim.x * WPC;
   long long row = (long long)blockIdx.x * WPC + warp;
@@ -455,10 +491,10 @@ __global__ void __launch_bounds__(32 * WPC, {self.ctas_per_sm}) k_chain_warp(con
     read_chunk_16<CH, {sg}>(raw, lane, r_in);
     edge_extend<CH, {n}>(r_in, lane);
     __syncwarp();
-    // the raw row of this warp's next waveform travels while this one is processed
-    if (row + wstride < A.n_rows) stage_row_16<CH>(raw, (const uint16_t*)A.p[{pi}] + (row + wstride) * A.s[{pi}], {n}, lane);
+    {prefetch_early}
     {body}
     __syncwarp();
+    {prefetch_late}
   }}
 }}
 }}  // namespace
@@ -488,7 +524,14 @@ extern "C" int chain_launch(const void* const* ptrs, long long n_ptrs, long long
 """
 
     def _build(self):
-        self.lib_path, self.src_path = build_source(self.source())
+        # most resident CTAs first; a register budget that makes ptxas spill more than a few words inside the row loop
+        # costs more than the extra warps bring: step down (6 CTAs = 80 registers, 5 = 96, 4 = 128)
+        self.max_ctas = None
+        while True:
+            self.lib_path, self.src_path = build_source(self.source())
+            if spill_bytes(self.lib_path) <= 64 or self.ctas_per_sm <= 4:
+                break
+            self.max_ctas = self.ctas_per_sm - 1
         self.handle = C.c_void_p(1)
         if self.meta:
             return
