@@ -341,12 +341,23 @@ __device__ __forceinline__ void peak_walk(const float* S, int n, float d_max, fl
   int ei = WRT_IDX(p);
   float ev = S[widx<CH>(ei)];
   p += 1;
-  int cm = 0, cn = 0;
+  // Everything that depends on the state (find-max / find-min) is kept as a loop-carried "current" and "other" copy
+  // and SWAPPED when an event flips the state, instead of being selected in every iteration: the sign, the deltas,
+  // the absolute thresholds, the list counters and the signed window summaries (max' = -min, min' = -max).
+  float sg = 1.f, dl = d_max, dl_o = d_min, ab = a_max, ab_o = -a_min;
+  int cc = 0, cc_o = 0;                       // events recorded in the current / the other state
+  float smx[NWL], smn[NWL], drp[NWL], drp_o[NWL], thr[NWL], thr_o[NWL];
+#pragma unroll
+  for (int h = 0; h < NWL; h++) {
+    smx[h] = lmax[h];
+    smn[h] = lmin[h];
+    drp[h] = ldrop[h];
+    drp_o[h] = lclimb[h];
+    thr[h] = d_max - slack[h];
+    thr_o[h] = d_min - slack[h];
+  }
   while (p < p_end) {
-    if ((mode_max ? cm : cn) >= m) break;  // the list is full: this state never fires again
-    const float sg = mode_max ? 1.f : -1.f;
-    const float dl = mode_max ? d_max : d_min;
-    const float ab = mode_max ? a_max : -a_min;
+    if (cc >= m) break;  // the list is full: this state never fires again
     const int W = p / WS;
     // ---- exact examination of the rest of window W ------------------------------------------------
     {
@@ -369,12 +380,23 @@ __device__ __forceinline__ void peak_walk(const float* S, int n, float d_max, fl
           if (mode_max) bmax |= 1ull << (ei % CH);
           else bmin |= 1ull << (ei % CH);
         }
-        if (mode_max) cm++;
-        else cn++;
         ev = -__shfl_sync(FULL, v, ls);  // the event sample starts the opposite search
         ei = WRT_IDX(q0 + ls);
-        mode_max = !mode_max;
         p = q0 + ls + 1;
+        // flip the state: swap the current and the other copies
+        mode_max = !mode_max;
+        sg = -sg;
+        { const int t = cc + 1; cc = cc_o; cc_o = t; }
+        { const float t = dl; dl = dl_o; dl_o = t; }
+        { const float t = ab; ab = ab_o; ab_o = t; }
+#pragma unroll
+        for (int h = 0; h < NWL; h++) {
+          const float t = smx[h];
+          smx[h] = -smn[h];
+          smn[h] = -t;
+          const float u = drp[h]; drp[h] = drp_o[h]; drp_o[h] = u;
+          const float w = thr[h]; thr[h] = thr_o[h]; thr_o[h] = w;
+        }
         continue;
       }
       const float wm = __shfl_sync(FULL, pm, 31);
@@ -385,13 +407,11 @@ __device__ __forceinline__ void peak_walk(const float* S, int n, float d_max, fl
       }
     }
     // ---- next window that may fire (all windows at once) --------------------------------------------
-    float smx[NWL], smn[NWL], pmw[NWL];
+    float pmw[NWL];
     bool act[NWL];
     float tot = -CUDART_INF_F;
 #pragma unroll
     for (int h = 0; h < NWL; h++) {
-      smx[h] = mode_max ? lmax[h] : -lmin[h];  // signed window max / min
-      smn[h] = mode_max ? lmin[h] : -lmax[h];
       act[h] = lane * NWL + h > W;
       pmw[h] = act[h] ? smx[h] : -CUDART_INF_F;
       tot = fmaxf(tot, pmw[h]);
@@ -406,8 +426,7 @@ __device__ __forceinline__ void peak_walk(const float* S, int n, float d_max, fl
       const float m_full = fmaxf(m_in[h], smx[h]);
       // an event inside the window needs a sample below fl(carry - delta), or a drop of (almost) delta below
       // a maximum of the window itself
-      const float drop = mode_max ? ldrop[h] : lclimb[h];
-      const unsigned b = __ballot_sync(FULL, act[h] && (m_full > ab) && ((smn[h] < m_in[h] - dl) || (drop > dl - slack[h])));
+      const unsigned b = __ballot_sync(FULL, act[h] && (m_full > ab) && ((smn[h] < m_in[h] - dl) || (drp[h] > thr[h])));
       if (b) first = min(first, (__ffs(b) - 1) * NWL + h);
     }
     if (first == 0x7fffffff) break;
@@ -435,8 +454,8 @@ __device__ __forceinline__ void peak_walk(const float* S, int n, float d_max, fl
     p = W2 * WS;
   }
 #undef WRT_IDX
-  n_found_max = cm;
-  n_found_min = cn;
+  n_found_max = mode_max ? cc : cc_o;
+  n_found_min = mode_max ? cc_o : cc;
 }
 
 // extrema bit sets -> one list element per lane (NaN-padded, m <= 32), ascending or descending
