@@ -3,9 +3,10 @@
 // Short waveforms (<= 2048 samples, the SiPM / LAr chains of BASELINE.json config 4): ONE WARP owns
 // one waveform.  Lane l holds samples [CH*l, CH*l + CH) in registers (CH = 8..64, a power of two),
 // recursive filters are lane-local running sums + one warp scan, halos travel by shuffles, and the
-// only shared memory is (a) the raw row of the NEXT waveform, staged with cp.async while this one is
-// processed, and (b) one float copy of the wave the peak finder walks.  No block-wide barrier
-// anywhere: warps run rows independently, 16 warps per SM.
+// only shared memory is (a) the raw row of the NEXT waveform, staged while this one is processed, and
+// (b) one float copy of the wave the peak finder walks -- aliased with (a) when both exist, the next
+// row then travels through registers (RowPieces).  No block-wide barrier anywhere: warps run rows
+// independently, up to 24 warps per SM at CH = 64.
 #pragma once
 #include <cuda_runtime.h>
 #include <math_constants.h>
